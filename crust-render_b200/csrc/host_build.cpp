@@ -1,0 +1,781 @@
+// See host_build.h. Compiled with -ffp-contract=off: split decisions must be
+// bit-reproducible (bvh.rs:22-24 "every split decision depends only on the input").
+#include "host_build.h"
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstring>
+#include <future>
+#include <limits>
+#include <thread>
+
+namespace crt {
+namespace {
+
+constexpr float kInf = std::numeric_limits<float>::infinity();
+// bvh.rs:142-167
+constexpr size_t kMaxDepth = 60, kMinLeaf = 2, kMinLeafPacked = 4, kMaxLeaf = 8, kBins = 12, kParallelThreshold = 4096,
+                 kSbvhMaxDepth = 32;
+constexpr float kSbvhAlpha = 1e-5f;
+constexpr float kPad = 1e-4f;  // aabb.rs:50, triangle.rs:421, prim.rs:311
+
+inline Vec3 V(float x, float y, float z) { return Vec3{x, y, z}; }
+inline Vec3 add(Vec3 a, Vec3 b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
+inline Vec3 sub(Vec3 a, Vec3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+inline Vec3 mul(Vec3 a, float s) { return {a.x * s, a.y * s, a.z * s}; }
+inline Vec3 vmin(Vec3 a, Vec3 b) { return {std::min(a.x, b.x), std::min(a.y, b.y), std::min(a.z, b.z)}; }
+inline Vec3 vmax(Vec3 a, Vec3 b) { return {std::max(a.x, b.x), std::max(a.y, b.y), std::max(a.z, b.z)}; }
+inline float dot3(Vec3 a, Vec3 b) { return (a.x * b.x + a.y * b.y) + a.z * b.z; }  // glam: (x + y) + z
+inline Vec3 cross3(Vec3 a, Vec3 b) { return {a.y * b.z - b.y * a.z, a.z * b.x - b.z * a.x, a.x * b.y - b.x * a.y}; }
+inline Box unite(const Box& a, const Box& b) { return {vmin(a.lo, b.lo), vmax(a.hi, b.hi)}; }
+inline float area(const Box& b) {  // bvh.rs:811-814
+    Vec3 d = sub(b.hi, b.lo);
+    return 2.0f * (d.x * d.y + d.y * d.z + d.z * d.x);
+}
+inline bool overlap_box(const Box& a, const Box& b, Box& out) {  // bvh.rs:823-831
+    Vec3 lo = vmax(a.lo, b.lo), hi = vmin(a.hi, b.hi);
+    if (lo.x <= hi.x && lo.y <= hi.y && lo.z <= hi.z) {
+        out = {lo, hi};
+        return true;
+    }
+    return false;
+}
+inline void pad_flat_axes(Vec3& lo, Vec3& hi) {
+    for (int a = 0; a < 3; ++a)
+        if (hi[a] - lo[a] < kPad) {
+            lo[a] -= kPad;
+            hi[a] += kPad;
+        }
+}
+inline int longest_axis(Vec3 e) { return (e.x >= e.y && e.x >= e.z) ? 0 : (e.y >= e.z ? 1 : 2); }
+// Rust `as usize` on f32 saturates and maps NaN to 0 (bvh.rs:916, 988).
+inline size_t to_bin(float f) {
+    if (!(f > 0.0f)) return 0;
+    if (f >= (float)kBins) return kBins - 1;
+    return (size_t)f;
+}
+
+// glam Mat3A/Affine3A pieces used at commit (scene.rs:310, prim.rs:298-319).
+inline Vec3 xform_vec(const Xform& m, Vec3 v) { return add(add(mul(m.x, v.x), mul(m.y, v.y)), mul(m.z, v.z)); }
+inline Vec3 xform_point(const Xform& m, Vec3 p) { return add(xform_vec(m, p), m.t); }
+Xform invert(const Xform& a) {
+    Vec3 t0 = cross3(a.y, a.z), t1 = cross3(a.z, a.x), t2 = cross3(a.x, a.y);
+    float inv_det = 1.0f / dot3(a.z, t2);
+    Vec3 c0 = mul(t0, inv_det), c1 = mul(t1, inv_det), c2 = mul(t2, inv_det);
+    Xform r;
+    r.x = {c0.x, c1.x, c2.x};
+    r.y = {c0.y, c1.y, c2.y};
+    r.z = {c0.z, c1.z, c2.z};
+    Vec3 mt = xform_vec(r, a.t);
+    r.t = {-mt.x, -mt.y, -mt.z};
+    return r;
+}
+Box transformed_box(const Box& local, const Xform& m) {
+    Vec3 lo = V(kInf, kInf, kInf), hi = V(-kInf, -kInf, -kInf);
+    for (int i = 0; i < 8; ++i) {
+        Vec3 c{(i & 1) ? local.hi.x : local.lo.x, (i & 2) ? local.hi.y : local.lo.y, (i & 4) ? local.hi.z : local.lo.z};
+        Vec3 p = xform_point(m, c);
+        lo = vmin(lo, p);
+        hi = vmax(hi, p);
+    }
+    pad_flat_axes(lo, hi);
+    return {lo, hi};
+}
+
+struct Ref {  // bvh.rs:281-290 PrimRef
+    Box b;
+    uint32_t idx;
+};
+inline float centroid_axis(const Ref& r, int a) { return 0.5f * (r.b.lo[a] + r.b.hi[a]); }
+
+// ---- primitive bounds -------------------------------------------------------
+inline const float* tri_of(const PrimStore& ps, uint32_t pi) { return &ps.tri[9 * (size_t)ps.data[pi]]; }
+
+Box prim_box(const PrimStore& ps, uint32_t pi) {
+    switch (ps.kind[pi]) {
+        case P_TRI: {  // aabb.rs:47-58
+            const float* t = tri_of(ps, pi);
+            Vec3 v0 = V(t[0], t[1], t[2]), v1 = V(t[3], t[4], t[5]), v2 = V(t[6], t[7], t[8]);
+            Vec3 lo = vmin(vmin(v0, v1), v2), hi = vmax(vmax(v0, v1), v2);
+            pad_flat_axes(lo, hi);
+            return {lo, hi};
+        }
+        case P_SPHERE: {  // prim.rs:163-168
+            const float* s = &ps.sphere[4 * (size_t)ps.data[pi]];
+            return {V(s[0] - s[3], s[1] - s[3], s[2] - s[3]), V(s[0] + s[3], s[1] + s[3], s[2] + s[3])};
+        }
+        case P_CURVE: {  // prim.rs:202-206
+            const float* c = &ps.curve[8 * (size_t)ps.data[pi]];
+            Box a{V(c[0] - c[6], c[1] - c[6], c[2] - c[6]), V(c[0] + c[6], c[1] + c[6], c[2] + c[6])};
+            Box b{V(c[3] - c[7], c[4] - c[7], c[5] - c[7]), V(c[3] + c[7], c[4] + c[7], c[5] + c[7])};
+            return unite(a, b);
+        }
+        case P_CUBIC: {  // prim.rs:246-253
+            const float* c = &ps.cubic[14 * (size_t)ps.data[pi]];
+            float r = std::max(c[12], c[13]);
+            Vec3 lo = V(c[0], c[1], c[2]), hi = lo;
+            for (int k = 1; k < 4; ++k) {
+                lo = vmin(lo, V(c[3 * k], c[3 * k + 1], c[3 * k + 2]));
+                hi = vmax(hi, V(c[3 * k], c[3 * k + 1], c[3 * k + 2]));
+            }
+            return {V(lo.x - r, lo.y - r, lo.z - r), V(hi.x + r, hi.y + r, hi.z + r)};
+        }
+        default: return ps.inst[ps.data[pi]].bounds;  // prim.rs:380-382
+    }
+}
+
+// triangle.rs:367-429 — Sutherland-Hodgman against the slab's two planes.
+bool clip_triangle(const float* t, int axis, float mn, float mx, Box& out) {
+    Vec3 poly[8], tmp[8];
+    int n = 3;
+    poly[0] = V(t[0], t[1], t[2]);
+    poly[1] = V(t[3], t[4], t[5]);
+    poly[2] = V(t[6], t[7], t[8]);
+    for (int pass = 0; pass < 2; ++pass) {
+        const float bound = pass == 0 ? mn : mx;
+        int m = 0;
+        for (int i = 0; i < n; ++i) {
+            Vec3 a = poly[i], b = poly[(i + 1) % n];
+            float da = pass == 0 ? a[axis] - bound : bound - a[axis];
+            float db = pass == 0 ? b[axis] - bound : bound - b[axis];
+            if (da >= 0.0f) tmp[m++] = a;
+            if ((da > 0.0f) != (db > 0.0f) && da != db) {
+                float s = da / (da - db);
+                tmp[m++] = add(a, mul(sub(b, a), s));
+            }
+        }
+        n = m;
+        if (n == 0) return false;
+        for (int i = 0; i < n; ++i) poly[i] = tmp[i];
+    }
+    Vec3 lo = poly[0], hi = poly[0];
+    for (int i = 1; i < n; ++i) {
+        lo = vmin(lo, poly[i]);
+        hi = vmax(hi, poly[i]);
+    }
+    lo[axis] = std::max(lo[axis], mn);
+    hi[axis] = std::min(hi[axis], mx);
+    pad_flat_axes(lo, hi);
+    out = {lo, hi};
+    return true;
+}
+// prim.rs:39-48 default + :116-118 triangle override, then ∩ ref box (bvh.rs:1013, 1116, 1122)
+bool clipped_ref_box(const PrimStore& ps, const Ref& r, int axis, float mn, float mx, Box& out) {
+    Box c;
+    if (ps.kind[r.idx] == P_TRI) {
+        if (!clip_triangle(tri_of(ps, r.idx), axis, mn, mx, c)) return false;
+    } else {
+        c = prim_box(ps, r.idx);
+        if (c.lo[axis] > mx || c.hi[axis] < mn) return false;
+        c.lo[axis] = std::max(c.lo[axis], mn);
+        c.hi[axis] = std::min(c.hi[axis], mx);
+    }
+    return overlap_box(c, r.b, out);
+}
+
+// ---- binary build -----------------------------------------------------------
+struct ObjSplit {
+    int axis;
+    float cmin, scale;
+    size_t split_bin;
+    float cost;
+    Box left, right;
+};
+struct BinAcc {
+    size_t n = 0;
+    bool some = false;
+    Box b;
+    void grow(const Box& x) {
+        b = some ? unite(b, x) : x;
+        some = true;
+    }
+};
+
+// Sweep shared by both split kinds: candidate plane after bin `s` costs
+// area(∪ bounds[0..=s]) * Σ lcount[0..=s] + area(∪ bounds[s+1..]) * Σ rcount[s+1..]
+// (bvh.rs:931-967, 1020-1052); strict `<` keeps the first best.
+template <class Emit>
+void sweep(const BinAcc* bins, const size_t* lcount, const size_t* rcount, Emit&& emit) {
+    Box rb[kBins];
+    bool rsome[kBins];
+    size_t rc[kBins];
+    {
+        BinAcc acc;
+        size_t c = 0;
+        for (size_t b = kBins; b-- > 1;) {
+            if (bins[b].some) acc.grow(bins[b].b);
+            c += rcount[b];
+            rb[b] = acc.b;
+            rsome[b] = acc.some;
+            rc[b] = c;
+        }
+    }
+    BinAcc lacc;
+    size_t lc = 0;
+    for (size_t s = 0; s + 1 < kBins; ++s) {
+        if (bins[s].some) lacc.grow(bins[s].b);
+        lc += lcount[s];
+        if (lc == 0 || rc[s + 1] == 0) continue;
+        if (!lacc.some || !rsome[s + 1]) continue;  // unreachable on finite input (reference would panic)
+        float cost = area(lacc.b) * (float)lc + area(rb[s + 1]) * (float)rc[s + 1];
+        emit(s, cost, lacc.b, rb[s + 1]);
+    }
+}
+
+bool object_split(const std::vector<Ref>& refs, ObjSplit& out) {  // bvh.rs:894-969
+    Vec3 cmin, cmax;
+    for (int a = 0; a < 3; ++a) cmin[a] = cmax[a] = centroid_axis(refs[0], a);
+    for (size_t i = 1; i < refs.size(); ++i)
+        for (int a = 0; a < 3; ++a) {
+            float c = centroid_axis(refs[i], a);
+            cmin[a] = std::min(cmin[a], c);
+            cmax[a] = std::max(cmax[a], c);
+        }
+    Vec3 extent = sub(cmax, cmin);
+    int axis = longest_axis(extent);
+    if (extent[axis] <= 1e-6f) return false;
+    float scale = (float)kBins / extent[axis];
+    float c0 = cmin[axis];
+    BinAcc bins[kBins];
+    size_t counts[kBins] = {};
+    for (const Ref& r : refs) {
+        size_t b = to_bin((centroid_axis(r, axis) - c0) * scale);
+        counts[b] += 1;
+        bins[b].grow(r.b);
+    }
+    bool found = false;
+    sweep(bins, counts, counts, [&](size_t s, float cost, const Box& lb, const Box& rb) {
+        if (!found || cost < out.cost) {
+            out = ObjSplit{axis, c0, scale, s, cost, lb, rb};
+            found = true;
+        }
+    });
+    return found;
+}
+
+struct SpatSplit {
+    int axis;
+    float pos, cost;
+};
+bool spatial_split(const PrimStore& ps, const std::vector<Ref>& refs, const Box& bbox, SpatSplit& out) {  // bvh.rs:974-1054
+    Vec3 extent = sub(bbox.hi, bbox.lo);
+    int axis = longest_axis(extent);
+    if (extent[axis] <= 1e-6f) return false;
+    float lo = bbox.lo[axis];
+    float width = extent[axis] / (float)kBins;
+    BinAcc bins[kBins];
+    size_t entry[kBins] = {}, exit_[kBins] = {};
+    for (const Ref& r : refs) {
+        size_t b0 = to_bin((r.b.lo[axis] - lo) / width), b1 = to_bin((r.b.hi[axis] - lo) / width);
+        entry[b0] += 1;
+        exit_[b1] += 1;
+        if (b0 == b1) {
+            bins[b0].grow(r.b);
+            continue;
+        }
+        for (size_t b = b0; b <= b1; ++b) {
+            Box c;
+            if (clipped_ref_box(ps, r, axis, lo + (float)b * width, lo + (float)(b + 1) * width, c)) bins[b].grow(c);
+        }
+    }
+    bool found = false;
+    sweep(bins, entry, exit_, [&](size_t s, float cost, const Box&, const Box&) {
+        if (!found || cost < out.cost) {
+            out = SpatSplit{axis, lo + (float)(s + 1) * width, cost};
+            found = true;
+        }
+    });
+    return found;
+}
+
+struct Out {  // one DFS-ordered piece of the binary tree
+    std::vector<BinNode> nodes;
+    std::vector<uint32_t> indices;
+};
+struct Builder {
+    const PrimStore& ps;
+    float root_area;
+    std::atomic<int> spare_threads;
+
+    size_t min_leaf_for(const std::vector<Ref>& refs) const {  // bvh.rs:1201-1210
+        for (const Ref& r : refs)
+            if (ps.kind[r.idx] != P_TRI) return kMinLeaf;
+        return kMinLeafPacked;
+    }
+    static void emit_leaf(Out& out, const Box& bbox, const std::vector<Ref>& refs) {  // bvh.rs:833-842
+        out.nodes.push_back(BinNode{bbox, (uint32_t)out.indices.size(), (uint32_t)refs.size()});
+        for (const Ref& r : refs) out.indices.push_back(r.idx);
+    }
+    static void stable_split(std::vector<Ref>& refs, const ObjSplit& o, std::vector<Ref>& l, std::vector<Ref>& r) {  // bvh.rs:1224-1237
+        size_t nl = 0;
+        for (const Ref& x : refs) nl += to_bin((centroid_axis(x, o.axis) - o.cmin) * o.scale) <= o.split_bin;
+        l.reserve(nl);
+        r.reserve(refs.size() - nl);
+        for (const Ref& x : refs)
+            (to_bin((centroid_axis(x, o.axis) - o.cmin) * o.scale) <= o.split_bin ? l : r).push_back(x);
+        std::vector<Ref>().swap(refs);
+    }
+    // Appends `sub` (built standalone) behind `out`, rebasing like bvh.rs:846-872.
+    static void splice(Out& out, Out&& sub) {
+        uint32_t node_off = (uint32_t)out.nodes.size(), idx_off = (uint32_t)out.indices.size();
+        out.nodes.reserve(out.nodes.size() + sub.nodes.size());
+        for (BinNode n : sub.nodes) {
+            n.first_or_right += n.count == 0 ? node_off : idx_off;
+            out.nodes.push_back(n);
+        }
+        out.indices.insert(out.indices.end(), sub.indices.begin(), sub.indices.end());
+    }
+
+    void children(Out& out, size_t self, std::vector<Ref>& l, std::vector<Ref>& r, size_t depth) {
+        bool big = std::max(l.size(), r.size()) > kParallelThreshold;  // bvh.rs:1156
+        if (big && spare_threads.fetch_sub(1) > 0) {
+            auto fut = std::async(std::launch::async, [this, depth, rr = std::move(r)]() mutable {
+                Out sub;
+                build(sub, rr, depth + 1);
+                spare_threads.fetch_add(1);
+                return sub;
+            });
+            build(out, l, depth + 1);
+            Out sub = fut.get();
+            out.nodes[self].first_or_right = (uint32_t)out.nodes.size();
+            splice(out, std::move(sub));
+            return;
+        }
+        if (big) spare_threads.fetch_add(1);
+        build(out, l, depth + 1);
+        out.nodes[self].first_or_right = (uint32_t)out.nodes.size();
+        build(out, r, depth + 1);
+    }
+
+    // bvh.rs:1059-1169 — emits the subtree of `refs` in depth-first order.
+    void build(Out& out, std::vector<Ref>& refs, size_t depth) {
+        Box bbox = refs[0].b;
+        for (size_t i = 1; i < refs.size(); ++i) bbox = unite(bbox, refs[i].b);
+        const size_t count = refs.size();
+        if (count <= min_leaf_for(refs) || depth >= kMaxDepth) return emit_leaf(out, bbox, refs);
+
+        ObjSplit obj{};
+        const bool have_obj = object_split(refs, obj);
+        SpatSplit spat{};
+        bool have_spat = false;
+        if (have_obj && depth < kSbvhMaxDepth) {
+            Box ov;
+            float overlap = overlap_box(obj.left, obj.right, ov) ? area(ov) : 0.0f;
+            if (overlap / root_area > kSbvhAlpha) have_spat = spatial_split(ps, refs, bbox, spat) && spat.cost < obj.cost;
+        }
+
+        std::vector<Ref> l, r;
+        if (have_spat) {  // bvh.rs:1089-1135
+            for (const Ref& x : refs) {
+                if (x.b.hi[spat.axis] <= spat.pos)
+                    l.push_back(x);
+                else if (x.b.lo[spat.axis] >= spat.pos)
+                    r.push_back(x);
+                else {
+                    Box c;
+                    if (clipped_ref_box(ps, x, spat.axis, -kInf, spat.pos, c)) l.push_back(Ref{c, x.idx});
+                    if (clipped_ref_box(ps, x, spat.axis, spat.pos, kInf, c)) r.push_back(Ref{c, x.idx});
+                }
+            }
+            std::vector<Ref>().swap(refs);
+            if (l.empty() || r.empty()) {  // degenerate chop: bvh.rs:1130-1134, 1173-1196
+                l.insert(l.end(), r.begin(), r.end());
+                std::vector<Ref>().swap(r);
+                if (have_obj && l.size() > min_leaf_for(l)) {
+                    std::vector<Ref> a, b;
+                    stable_split(l, obj, a, b);
+                    if (a.empty() || b.empty()) {
+                        a.insert(a.end(), b.begin(), b.end());
+                        return emit_leaf(out, bbox, a);
+                    }
+                    size_t self = out.nodes.size();
+                    out.nodes.push_back(BinNode{bbox, 0, 0});
+                    build(out, a, depth + 1);  // this path never forks (bvh.rs:1190-1191)
+                    out.nodes[self].first_or_right = (uint32_t)out.nodes.size();
+                    build(out, b, depth + 1);
+                    return;
+                }
+                return emit_leaf(out, bbox, l);
+            }
+        } else if (have_obj) {
+            if (count <= kMaxLeaf && obj.cost >= area(bbox) * (float)count) return emit_leaf(out, bbox, refs);  // bvh.rs:1140
+            stable_split(refs, obj, l, r);
+        } else {  // every centroid coincides: median by input order (bvh.rs:1148-1152)
+            size_t mid = count / 2;
+            r.assign(refs.begin() + mid, refs.end());
+            refs.resize(mid);
+            l.swap(refs);
+        }
+        size_t self = out.nodes.size();
+        out.nodes.push_back(BinNode{bbox, 0, 0});
+        children(out, self, l, r, depth);
+    }
+};
+
+// ---- collapse to BVH4 + record emission --------------------------------------
+struct Flattener {
+    const PrimStore& ps;
+    const std::vector<BinNode>& bin;
+    const std::vector<uint32_t>& bidx;
+    HostTree& t;
+
+    static uint32_t fbits(float f) {
+        uint32_t u;
+        std::memcpy(&u, &f, 4);
+        return u;
+    }
+    void q(uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+        t.leafs.push_back(a);
+        t.leafs.push_back(b);
+        t.leafs.push_back(c);
+        t.leafs.push_back(d);
+    }
+    void qf(float a, float b, float c, uint32_t d) { q(fbits(a), fbits(b), fbits(c), d); }
+
+    // bvh.rs:1256-1290: triangles of the range first (packet order), then the rest.
+    uint32_t emit_leaf(const uint32_t* range, size_t n) {
+        uint32_t first_q = (uint32_t)(t.leafs.size() / 4);
+        size_t n_tri = 0;
+        for (size_t i = 0; i < n; ++i) n_tri += ps.kind[range[i]] == P_TRI;
+        const size_t n_other = n - n_tri;
+        size_t ti = 0;
+        for (size_t i = 0; i < n; ++i) {
+            uint32_t pi = range[i];
+            if (ps.kind[pi] != P_TRI) continue;
+            const float* v = tri_of(ps, pi);
+            uint32_t flags = REC_TRI | ((uint32_t)(ti & 3) << REC_LANE_SHIFT);
+            if ((ti & 3) == 3 || ti + 1 == n_tri) flags |= REC_PACKET_END;
+            if (ti + 1 == n_tri && n_other == 0) flags |= REC_LAST;
+            if (ps.tri_normal_slot[ps.data[pi]] != 0xFFFFFFFFu) {
+                flags |= REC_HAS_NORMALS;
+            } else {  // prim.rs:80-83
+                Vec3 a = V(v[0], v[1], v[2]);
+                Vec3 nrm = cross3(sub(V(v[3], v[4], v[5]), a), sub(V(v[6], v[7], v[8]), a));
+                if (nrm.x == 0.0f && nrm.y == 0.0f && nrm.z == 0.0f) flags |= REC_DEGENERATE;
+            }
+            qf(v[0], v[1], v[2], flags);
+            qf(v[3], v[4], v[5], pi);
+            qf(v[6], v[7], v[8], ps.mask[pi]);
+            ++ti;
+        }
+        size_t oi = 0;
+        for (size_t i = 0; i < n; ++i) {
+            uint32_t pi = range[i];
+            if (ps.kind[pi] == P_TRI) continue;
+            const uint32_t last = (++oi == n_other) ? (uint32_t)REC_LAST : 0u;
+            switch (ps.kind[pi]) {
+                case P_SPHERE: {
+                    const float* s = &ps.sphere[4 * (size_t)ps.data[pi]];
+                    qf(s[0], s[1], s[2], REC_SPHERE | last);
+                    q(fbits(s[3]), pi, ps.mask[pi], ps.geom_id[pi]);
+                    break;
+                }
+                case P_CURVE: {
+                    const float* c = &ps.curve[8 * (size_t)ps.data[pi]];
+                    qf(c[0], c[1], c[2], REC_CURVE | last);
+                    qf(c[3], c[4], c[5], pi);
+                    q(fbits(c[6]), fbits(c[7]), ps.mask[pi], 0);
+                    break;
+                }
+                case P_CUBIC: {
+                    const float* c = &ps.cubic[14 * (size_t)ps.data[pi]];
+                    qf(c[0], c[1], c[2], REC_CUBIC | last);
+                    qf(c[3], c[4], c[5], pi);
+                    qf(c[6], c[7], c[8], ps.mask[pi]);
+                    qf(c[9], c[10], c[11], 0);
+                    q(fbits(c[12]), fbits(c[13]), 0, 0);
+                    q(0, 0, 0, 0);
+                    break;
+                }
+                default: {
+                    const InstancePrim& I = ps.inst[ps.data[pi]];
+                    uint32_t flags = REC_INSTANCE | last;
+                    uint32_t motion = 0;
+                    if (I.has_end) {
+                        flags |= REC_MOTION;
+                        motion = (uint32_t)t.motion.size();
+                        MotionXform m;
+                        const Vec3* a = &I.l2w.x;
+                        const Vec3* b = &I.l2w_end.x;
+                        for (int k = 0; k < 4; ++k) {
+                            m.l2w[3 * k] = a[k].x, m.l2w[3 * k + 1] = a[k].y, m.l2w[3 * k + 2] = a[k].z;
+                            m.l2w_end[3 * k] = b[k].x, m.l2w_end[3 * k + 1] = b[k].y, m.l2w_end[3 * k + 2] = b[k].z;
+                        }
+                        t.motion.push_back(m);
+                    }
+                    t.instance_record_q.push_back((uint32_t)(t.leafs.size() / 4));
+                    qf(I.w2l.x.x, I.w2l.x.y, I.w2l.x.z, flags);
+                    qf(I.w2l.y.x, I.w2l.y.y, I.w2l.y.z, pi);
+                    qf(I.w2l.z.x, I.w2l.z.y, I.w2l.z.z, ps.mask[pi]);
+                    qf(I.w2l.t.x, I.w2l.t.y, I.w2l.t.z, motion);
+                    q(0, 0, ps.geom_id[pi], ps.data[pi]);  // words 0-1: child descriptor pointer, patched at upload
+                    break;
+                }
+            }
+        }
+        t.n_leaves += 1;
+        t.n_leaf_refs += n;
+        return CRT_LEAF_BIT | first_q;
+    }
+
+    static void set_lane(DevNode& w, int lane, const Box& b) {  // bvh.rs:243-251
+        w.bmin_x[lane] = b.lo.x, w.bmin_y[lane] = b.lo.y, w.bmin_z[lane] = b.lo.z;
+        w.bmax_x[lane] = b.hi.x, w.bmax_y[lane] = b.hi.y, w.bmax_z[lane] = b.hi.z;
+        w.flags |= 1u << lane;
+    }
+    static DevNode empty_node() {  // bvh.rs:230-241
+        DevNode w;
+        for (int l = 0; l < 4; ++l) {
+            w.bmin_x[l] = w.bmin_y[l] = w.bmin_z[l] = w.bmax_x[l] = w.bmax_y[l] = w.bmax_z[l] = kInf;
+            w.child[l] = CRT_EMPTY_LANE;
+        }
+        w.flags = 0;
+        w.pad[0] = w.pad[1] = w.pad[2] = 0;
+        return w;
+    }
+    // bvh.rs:1328-1375
+    uint32_t node(uint32_t b_idx) {
+        size_t slot = t.nodes.size();
+        t.nodes.push_back(empty_node());
+        uint32_t kids[4] = {b_idx + 1, bin[b_idx].first_or_right, 0, 0};
+        int n_kids = 2;
+        while (n_kids < 4) {
+            int best = -1;
+            float best_a = 0;
+            for (int i = 0; i < n_kids; ++i)
+                if (bin[kids[i]].count == 0) {
+                    float a = area(bin[kids[i]].bbox);
+                    if (best < 0 || a > best_a) best = i, best_a = a;
+                }
+            if (best < 0) break;
+            uint32_t k = kids[best];
+            kids[best] = k + 1;
+            kids[n_kids++] = bin[k].first_or_right;
+        }
+        for (int lane = 0; lane < n_kids; ++lane) {
+            const BinNode& k = bin[kids[lane]];
+            set_lane(t.nodes[slot], lane, k.bbox);
+            uint32_t c;
+            if (k.count > 0) {
+                c = emit_leaf(bidx.data() + k.first_or_right, k.count);
+                t.nodes[slot].flags |= 1u << (4 + lane);
+            } else {
+                c = node(kids[lane]);
+            }
+            t.nodes[slot].child[lane] = c;
+        }
+        return (uint32_t)slot;
+    }
+    void run() {  // bvh.rs:1299-1320
+        t.nodes.reserve(bin.size() / 2 + 1);
+        if (bin[0].count > 0) {
+            t.nodes.push_back(empty_node());
+            set_lane(t.nodes[0], 0, bin[0].bbox);
+            uint32_t c = emit_leaf(bidx.data() + bin[0].first_or_right, bin[0].count);
+            t.nodes[0].child[0] = c;
+            t.nodes[0].flags |= 1u << 4;
+        } else {
+            node(0);
+        }
+        // Kernels may over-read up to one triangle record past a leaf's end.
+        for (int i = 0; i < 4; ++i) q(0, 0, 0, REC_LAST | REC_SPHERE);
+    }
+};
+
+inline Vec3 v3at(const std::vector<float>& a, size_t i) { return V(a[3 * i], a[3 * i + 1], a[3 * i + 2]); }
+
+}  // namespace
+
+bool build_host_tree(std::vector<Geom>& geoms, ChildInfoFn child_info, int threads, HostTree& out, const char** err) {
+    auto t0 = std::chrono::steady_clock::now();
+    PrimStore& ps = out.prims;
+    // scene.rs:237-238: size the primitive arrays once.
+    size_t total = 0;
+    for (const Geom& g : geoms)
+        total += g.type == G_MESH ? g.indices.size() / 3
+                                  : (g.type == G_CURVES ? g.segs.size() / 8 : (g.type == G_CUBICS ? g.segs.size() / 14 : 1));
+    ps.kind.reserve(total), ps.geom_id.reserve(total), ps.prim_id.reserve(total), ps.mask.reserve(total), ps.data.reserve(total);
+    auto push = [&](PrimKind k, uint32_t gid, uint32_t pid, uint32_t mask, uint32_t data) {
+        ps.kind.push_back(k), ps.geom_id.push_back(gid), ps.prim_id.push_back(pid), ps.mask.push_back(mask), ps.data.push_back(data);
+    };
+    for (size_t gi = 0; gi < geoms.size(); ++gi) {  // scene.rs:240-335
+        Geom& g = geoms[gi];
+        const uint32_t gid = (uint32_t)gi;
+        switch (g.type) {
+            case G_MESH: {
+                size_t nv = g.verts.size() / 3, nn = g.normals.size() / 3, nt = g.indices.size() / 3;
+                for (size_t k = 0; k < nt; ++k) {
+                    size_t i0 = g.indices[3 * k], i1 = g.indices[3 * k + 1], i2 = g.indices[3 * k + 2];
+                    if (i0 >= nv || i1 >= nv || i2 >= nv) continue;  // scene.rs:251-253: id still consumed
+                    uint32_t slot = (uint32_t)(ps.tri.size() / 9);
+                    for (size_t i : {i0, i1, i2})
+                        for (int c = 0; c < 3; ++c) ps.tri.push_back(g.verts[3 * i + c]);
+                    if (g.has_normals && i0 < nn && i1 < nn && i2 < nn) {  // scene.rs:254-257
+                        ps.tri_normal_slot.push_back((uint32_t)(ps.tri_normals.size() / 9));
+                        for (size_t i : {i0, i1, i2})
+                            for (int c = 0; c < 3; ++c) ps.tri_normals.push_back(g.normals[3 * i + c]);
+                        ps.any_normals = true;
+                    } else {
+                        ps.tri_normal_slot.push_back(0xFFFFFFFFu);
+                    }
+                    push(P_TRI, gid, (uint32_t)k, g.mask, slot);
+                }
+                break;
+            }
+            case G_SPHERE:
+                push(P_SPHERE, gid, 0, g.mask, (uint32_t)(ps.sphere.size() / 4));
+                ps.sphere.insert(ps.sphere.end(), g.sphere, g.sphere + 4);
+                break;
+            case G_CURVES:
+                for (size_t k = 0; k < g.segs.size() / 8; ++k) {
+                    push(P_CURVE, gid, (uint32_t)k, g.mask, (uint32_t)(ps.curve.size() / 8));
+                    ps.curve.insert(ps.curve.end(), g.segs.begin() + 8 * k, g.segs.begin() + 8 * k + 8);
+                }
+                break;
+            case G_CUBICS:
+                for (size_t k = 0; k < g.segs.size() / 14; ++k) {
+                    push(P_CUBIC, gid, (uint32_t)k, g.mask, (uint32_t)(ps.cubic.size() / 14));
+                    ps.cubic.insert(ps.cubic.end(), g.segs.begin() + 14 * k, g.segs.begin() + 14 * k + 14);
+                }
+                break;
+            case G_INSTANCE: {
+                ChildInfo ci = child_info(g.child);
+                if (!ci.non_empty) break;  // scene.rs:307-309
+                if (ci.instance_depth + 1 > CRT_MAX_INSTANCE_DEPTH) {
+                    *err = "instance nesting deeper than CRT_MAX_INSTANCE_DEPTH";
+                    return false;
+                }
+                InstancePrim I;
+                I.child = g.child;
+                I.l2w = g.l2w;
+                I.w2l = invert(g.l2w);
+                I.has_end = g.has_end;
+                I.l2w_end = g.has_end ? g.l2w_end : g.l2w;
+                I.bounds = g.has_end ? unite(transformed_box(ci.bounds, g.l2w), transformed_box(ci.bounds, g.l2w_end))
+                                     : transformed_box(ci.bounds, g.l2w);
+                out.has_motion |= g.has_end || ci.has_motion;  // scene.rs:322
+                out.instance_depth = std::max(out.instance_depth, ci.instance_depth + 1);
+                push(P_INSTANCE, gid, 0, g.mask, (uint32_t)ps.inst.size());
+                ps.inst.push_back(I);
+                break;
+            }
+        }
+        // geometry inputs are dead once expanded
+        std::vector<float>().swap(g.verts);
+        std::vector<uint32_t>().swap(g.indices);
+        std::vector<float>().swap(g.normals);
+        std::vector<float>().swap(g.segs);
+    }
+
+    const size_t n = ps.size();
+    out.prim_ids.resize(2 * n);
+    for (size_t i = 0; i < n; ++i) {
+        out.prim_ids[2 * i] = ps.geom_id[i];
+        out.prim_ids[2 * i + 1] = ps.prim_id[i];
+    }
+    if (ps.any_normals) {
+        out.normals.assign(9 * n, 0.0f);
+        for (size_t i = 0; i < n; ++i)
+            if (ps.kind[i] == P_TRI && ps.tri_normal_slot[ps.data[i]] != 0xFFFFFFFFu)
+                std::memcpy(&out.normals[9 * i], &ps.tri_normals[9 * (size_t)ps.tri_normal_slot[ps.data[i]]], 36);
+    }
+    if (n == 0) {  // bvh.rs:310-311
+        out.non_empty = false;
+        for (int i = 0; i < 4; ++i) {
+            out.leafs.push_back(0), out.leafs.push_back(0), out.leafs.push_back(0), out.leafs.push_back(REC_LAST | REC_SPHERE);
+        }
+        out.build_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        return true;
+    }
+
+    std::vector<Ref> refs(n);
+    Box root;
+    for (size_t i = 0; i < n; ++i) {
+        refs[i] = Ref{prim_box(ps, (uint32_t)i), (uint32_t)i};
+        root = i == 0 ? refs[0].b : unite(root, refs[i].b);
+        Vec3 e = sub(refs[i].b.hi, refs[i].b.lo);
+        float diag = std::sqrt(dot3(e, e));
+        out.extent_sum += diag;
+        out.extent_max = std::max(out.extent_max, diag);
+    }
+    if (threads <= 0) threads = (int)std::max(1u, std::thread::hardware_concurrency());
+    Builder bld{ps, area(root), {threads - 1}};
+    Out bin;
+    bld.build(bin, refs, 0);
+    out.n_binary = bin.nodes.size();
+    out.non_empty = true;
+    out.root = root;
+
+    out.leafs.reserve(bin.indices.size() * 12 + 16);
+    Flattener fl{ps, bin.nodes, bin.indices, out};
+    fl.run();
+    out.build_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    return true;
+}
+
+// ---- canonical export ---------------------------------------------------------
+namespace {
+uint32_t rec_quads(uint32_t flags) {
+    switch (flags & REC_KIND_MASK) {
+        case REC_TRI: return REC_TRI_Q;
+        case REC_SPHERE: return REC_SPHERE_Q;
+        case REC_CURVE: return REC_CURVE_Q;
+        case REC_CUBIC: return REC_CUBIC_Q;
+        default: return REC_INSTANCE_Q;
+    }
+}
+}  // namespace
+
+void export_sizes(const HostTree& t, uint64_t out4[4]) {
+    out4[0] = t.nodes.size();
+    out4[1] = t.n_leaves;
+    out4[2] = t.n_leaf_refs;
+    out4[3] = t.n_binary;
+}
+
+void export_tree(const HostTree& t, void* nodes_out, uint32_t* tri_counts, uint32_t* other_counts, uint32_t* refs) {
+    // Leaves were emitted in the same DFS order the nodes reference them, so
+    // walking nodes/lanes in array order numbers them in creation order.
+    uint32_t* w = (uint32_t*)nodes_out;
+    uint32_t leaf_no = 0;
+    size_t k = 0;
+    // creation order == order of first_q; collect and sort to be safe
+    std::vector<std::pair<uint32_t, std::pair<size_t, int>>> lanes;
+    for (size_t ni = 0; ni < t.nodes.size(); ++ni)
+        for (int l = 0; l < 4; ++l) {
+            uint32_t c = t.nodes[ni].child[l];
+            if (c != CRT_EMPTY_LANE && (c & CRT_LEAF_BIT)) lanes.push_back({c & ~CRT_LEAF_BIT, {ni, l}});
+        }
+    std::sort(lanes.begin(), lanes.end());
+    std::vector<uint32_t> ordinal_of(t.nodes.size() * 4, 0);
+    for (auto& e : lanes) {
+        ordinal_of[e.second.first * 4 + e.second.second] = leaf_no;
+        uint32_t qo = e.first, nt = 0, no = 0;
+        for (;;) {
+            uint32_t flags = t.leafs[4 * (size_t)qo + 3];
+            uint32_t kind = flags & REC_KIND_MASK;
+            uint32_t pi = kind == REC_SPHERE ? t.leafs[4 * (size_t)(qo + 1) + 1] : t.leafs[4 * (size_t)(qo + 1) + 3];
+            refs[k++] = pi;
+            (kind == REC_TRI ? nt : no)++;
+            qo += rec_quads(flags);
+            if (flags & REC_LAST) break;
+        }
+        tri_counts[leaf_no] = nt;
+        other_counts[leaf_no] = no;
+        leaf_no++;
+    }
+    for (size_t ni = 0; ni < t.nodes.size(); ++ni) {
+        const DevNode& n = t.nodes[ni];
+        uint32_t* o = w + 32 * ni;
+        std::memcpy(o, n.bmin_x, 96);
+        for (int l = 0; l < 4; ++l) {
+            uint32_t c = n.child[l];
+            o[24 + l] = (c != CRT_EMPTY_LANE && (c & CRT_LEAF_BIT)) ? ordinal_of[ni * 4 + l] : c;
+        }
+        o[28] = n.flags;
+        o[29] = o[30] = o[31] = 0;
+    }
+}
+
+}  // namespace crt

@@ -1,0 +1,407 @@
+// ORACLE — TEST INFRASTRUCTURE, NOT PRODUCT CODE (see crt_oracle.hpp header).
+// Plain C entry points over the restatement so Python tests (ctypes), smoke()
+// and bench.py's CPU arm can drive it. Ray / hit records use the same 32-byte
+// layouts as include/crt.h so identical buffers can be fed to both sides.
+#include "crt_oracle.hpp"
+
+#include <chrono>
+#include <cstdio>
+
+using namespace orc;
+
+namespace {
+struct SceneHandle {
+    std::shared_ptr<Scene> scene;
+};
+struct RayRec {  // == crt_ray
+    float ox, oy, oz, tmin, dx, dy, dz, tmax;
+};
+struct HitRec {  // == crt_hit
+    float t, u, v;
+    uint32_t geom_id, prim_id;
+    float nx, ny, nz;
+};
+Affine affine_from12(const float* m) {  // glam column order: x_axis, y_axis, z_axis, translation
+    Affine a;
+    a.x_axis = {m[0], m[1], m[2]};
+    a.y_axis = {m[3], m[4], m[5]};
+    a.z_axis = {m[6], m[7], m[8]};
+    a.translation = {m[9], m[10], m[11]};
+    return a;
+}
+Geometry mesh_geom(const float* verts, size_t nverts, const uint32_t* idx, size_t ntris, const float* normals,
+                   size_t n_normals) {
+    Geometry g;
+    g.type = Geometry::Type::TriangleMesh;
+    g.vertices.resize(nverts);
+    for (size_t i = 0; i < nverts; ++i) g.vertices[i] = {verts[3 * i], verts[3 * i + 1], verts[3 * i + 2]};
+    g.indices.assign(idx, idx + 3 * ntris);
+    if (normals) {
+        g.has_normals = true;
+        g.normals.resize(n_normals);
+        for (size_t i = 0; i < n_normals; ++i) g.normals[i] = {normals[3 * i], normals[3 * i + 1], normals[3 * i + 2]};
+    }
+    return g;
+}
+Geometry sphere_geom(float cx, float cy, float cz, float r) {
+    Geometry g;
+    g.type = Geometry::Type::Sphere;
+    g.center = {cx, cy, cz};
+    g.radius = r;
+    return g;
+}
+Geometry curves_geom(const float* segs, size_t n) {
+    Geometry g;
+    g.type = Geometry::Type::RoundCurves;
+    g.segments.resize(n);
+    for (size_t i = 0; i < n; ++i) {
+        const float* s = segs + 8 * i;
+        g.segments[i] = {{s[0], s[1], s[2]}, {s[3], s[4], s[5]}, s[6], s[7]};
+    }
+    return g;
+}
+Geometry cubic_geom(const float* segs, size_t n) {
+    Geometry g;
+    g.type = Geometry::Type::CubicCurves;
+    g.cubic.resize(n);
+    for (size_t i = 0; i < n; ++i) {
+        const float* s = segs + 14 * i;
+        for (int k = 0; k < 4; ++k) g.cubic[i].cp[k] = {s[3 * k], s[3 * k + 1], s[3 * k + 2]};
+        g.cubic[i].r0 = s[12];
+        g.cubic[i].r1 = s[13];
+    }
+    return g;
+}
+Geometry instance_geom(SceneHandle* child, const float* l2w, const float* l2w_end) {
+    Geometry g;
+    g.type = Geometry::Type::Instance;
+    g.scene = child->scene;
+    g.transform = affine_from12(l2w);
+    if (l2w_end) {
+        g.has_end = true;
+        g.transform_end = affine_from12(l2w_end);
+    }
+    return g;
+}
+int resolve_threads(int threads) {
+    if (threads > 0) return threads;
+    unsigned hc = std::thread::hardware_concurrency();
+    return hc ? (int)hc : 1;
+}
+template <class F>
+void parallel_ranges(size_t n, int threads, F&& f) {
+    threads = resolve_threads(threads);
+    if (threads <= 1 || n < 1024) {
+        f(0, n, 0);
+        return;
+    }
+    // Contiguous slices, one per thread: the reference's rayon-over-pixels model
+    // (crust-core/src/tracer.rs:428-489).
+    std::vector<std::thread> th;
+    size_t chunk = (n + threads - 1) / threads;
+    for (int t = 0; t < threads; ++t) {
+        size_t a = std::min(n, chunk * t), b = std::min(n, a + chunk);
+        if (a >= b) break;
+        th.emplace_back([=, &f] { f(a, b, t); });
+    }
+    for (auto& x : th) x.join();
+}
+}  // namespace
+
+extern "C" {
+
+void* orc_builder_new() { return new SceneBuilder(); }
+void orc_builder_free(void* b) { delete (SceneBuilder*)b; }
+uint64_t orc_builder_count(void* b) { return ((SceneBuilder*)b)->geoms.size(); }
+
+uint32_t orc_attach_triangle_mesh(void* b, const float* verts, size_t nverts, const uint32_t* idx, size_t ntris,
+                                  const float* normals, size_t n_normals, uint32_t mask) {
+    return ((SceneBuilder*)b)->attach_masked(mesh_geom(verts, nverts, idx, ntris, normals, n_normals), mask);
+}
+uint32_t orc_attach_sphere(void* b, float cx, float cy, float cz, float r, uint32_t mask) {
+    return ((SceneBuilder*)b)->attach_masked(sphere_geom(cx, cy, cz, r), mask);
+}
+uint32_t orc_attach_round_curves(void* b, const float* segs, size_t n, uint32_t mask) {
+    return ((SceneBuilder*)b)->attach_masked(curves_geom(segs, n), mask);
+}
+uint32_t orc_attach_cubic_curves(void* b, const float* segs, size_t n, uint32_t mask) {
+    return ((SceneBuilder*)b)->attach_masked(cubic_geom(segs, n), mask);
+}
+uint32_t orc_attach_instance(void* b, void* child, const float* l2w, const float* l2w_end, uint32_t mask) {
+    return ((SceneBuilder*)b)->attach_masked(instance_geom((SceneHandle*)child, l2w, l2w_end), mask);
+}
+uint32_t orc_attach_empty(void* b, uint32_t mask) { return ((SceneBuilder*)b)->attach_masked(Geometry{}, mask); }
+int orc_set_triangle_mesh(void* b, uint32_t id, const float* verts, size_t nverts, const uint32_t* idx, size_t ntris,
+                          const float* normals, size_t n_normals) {
+    return ((SceneBuilder*)b)->set_geometry(id, mesh_geom(verts, nverts, idx, ntris, normals, n_normals)) ? 0 : 1;
+}
+int orc_set_sphere(void* b, uint32_t id, float cx, float cy, float cz, float r) {
+    return ((SceneBuilder*)b)->set_geometry(id, sphere_geom(cx, cy, cz, r)) ? 0 : 1;
+}
+int orc_set_instance(void* b, uint32_t id, void* child, const float* l2w, const float* l2w_end) {
+    return ((SceneBuilder*)b)->set_geometry(id, instance_geom((SceneHandle*)child, l2w, l2w_end)) ? 0 : 1;
+}
+
+// Consumes the builder (scene.rs:226 `commit(self)`).
+void* orc_commit(void* b, int threads) {
+    SceneBuilder* sb = (SceneBuilder*)b;
+    auto* h = new SceneHandle{sb->commit(resolve_threads(threads))};
+    delete sb;
+    return h;
+}
+void orc_scene_release(void* s) { delete (SceneHandle*)s; }
+
+uint32_t orc_geometry_count(void* s) { return ((SceneHandle*)s)->scene->n_geoms; }
+uint64_t orc_primitive_count(void* s) { return ((SceneHandle*)s)->scene->bvh.prims.size(); }
+int orc_has_motion(void* s) { return ((SceneHandle*)s)->scene->has_motion ? 1 : 0; }
+int orc_bounds(void* s, float* out6) {
+    const auto& rb = ((SceneHandle*)s)->scene->bvh.root_bbox;
+    if (!rb) return 0;
+    out6[0] = rb->minimum.x;
+    out6[1] = rb->minimum.y;
+    out6[2] = rb->minimum.z;
+    out6[3] = rb->maximum.x;
+    out6[4] = rb->maximum.y;
+    out6[5] = rb->maximum.z;
+    return 1;
+}
+// triangles, spheres, curve_segments, cubic_curve_spans, instances (bvh.rs:347-359)
+void orc_primitive_breakdown(void* s, uint64_t* out5) {
+    for (int i = 0; i < 5; ++i) out5[i] = 0;
+    for (const PrimNode& p : ((SceneHandle*)s)->scene->bvh.prims) out5[(int)p.kind]++;
+}
+static void unique_into(const Scene& sc, std::unordered_set<const Scene*>& visited, uint64_t* acc) {  // bvh.rs:397-416
+    for (const PrimNode& p : sc.bvh.prims) {
+        acc[(int)p.kind]++;
+        if (p.kind == Kind::Instance && visited.insert(p.inst->scene.get()).second) unique_into(*p.inst->scene, visited, acc);
+    }
+}
+void orc_unique_primitive_breakdown(void* s, uint64_t* out5) {
+    for (int i = 0; i < 5; ++i) out5[i] = 0;
+    std::unordered_set<const Scene*> visited;
+    unique_into(*((SceneHandle*)s)->scene, visited, out5);
+}
+
+// ---- tree export (for builder-equivalence tests) ---------------------------
+// sizes: wide nodes, leaves, packets, scalar indices, leaf references, binary nodes
+void orc_tree_sizes(void* s, uint64_t* out6) {
+    const Bvh& b = ((SceneHandle*)s)->scene->bvh;
+    out6[0] = b.wide.size();
+    out6[1] = b.leaves.size();
+    out6[2] = b.packets.size();
+    out6[3] = b.indices.size();
+    out6[4] = b.leaf_ref_count();
+    out6[5] = b.binary_nodes;
+}
+// Raw 128-byte wide nodes (bvh.rs:196-215 layout; 3 trailing pad words zero).
+void orc_tree_nodes(void* s, void* out) {
+    const Bvh& b = ((SceneHandle*)s)->scene->bvh;
+    std::memcpy(out, b.wide.data(), b.wide.size() * sizeof(WideNode));
+}
+// Per leaf: number of packed triangle lanes and of scalar prims; then one flat
+// list of prim indices, leaf by leaf (packet lanes in order, then scalars).
+void orc_tree_leaves(void* s, uint32_t* tri_counts, uint32_t* other_counts, uint32_t* refs) {
+    const Bvh& b = ((SceneHandle*)s)->scene->bvh;
+    size_t k = 0;
+    for (size_t li = 0; li < b.leaves.size(); ++li) {
+        const Leaf& l = b.leaves[li];
+        uint32_t nt = 0;
+        for (uint32_t p = l.pkt_first; p < l.pkt_first + l.pkt_count; ++p)
+            for (int lane = 0; lane < 4; ++lane)
+                if (b.packets[p].active & (1u << lane)) {
+                    refs[k++] = b.packets[p].prim[lane];
+                    nt++;
+                }
+        for (uint32_t i = l.idx_first; i < l.idx_first + l.idx_count; ++i) refs[k++] = b.indices[i];
+        tri_counts[li] = nt;
+        other_counts[li] = l.idx_count;
+    }
+}
+// Average packet occupancy inputs (bvh.rs:1571-1579)
+uint64_t orc_packet_lanes(void* s) {
+    const Bvh& b = ((SceneHandle*)s)->scene->bvh;
+    uint64_t n = 0;
+    for (const Tri4& p : b.packets) n += __builtin_popcount(p.active);
+    return n;
+}
+
+// ---- queries ---------------------------------------------------------------
+// stats_out (optional, 16 u64): queries[2], nodes[2], leaves[2], packets[2],
+// prim_tests[2], tri_lanes, sphere, curve, cubic, instance tests, stack high water.
+static void write_stats(const Stats& st, uint64_t* o) {
+    o[0] = st.queries[0];
+    o[1] = st.queries[1];
+    o[2] = st.nodes[0];
+    o[3] = st.nodes[1];
+    o[4] = st.leaves[0];
+    o[5] = st.leaves[1];
+    o[6] = st.packets[0];
+    o[7] = st.packets[1];
+    o[8] = st.prim_tests[0];
+    o[9] = st.prim_tests[1];
+    o[10] = st.tri_lanes;
+    o[11] = st.sphere_tests;
+    o[12] = st.curve_tests;
+    o[13] = st.cubic_tests;
+    o[14] = st.instance_tests;
+    o[15] = st.stack_high_water;
+}
+
+// Closest hit for n rays. time/mask may be NULL (0 / MASK_ALL). A miss writes
+// t = +inf, ids = INVALID_ID, zero normal. Returns seconds spent in the loop.
+double orc_intersect_n(void* s, uint64_t n, const void* rays_, const float* time, const uint32_t* mask, void* hits_,
+                       uint8_t* front_face, int threads, uint64_t* stats_out) {
+    const Scene& sc = *((SceneHandle*)s)->scene;
+    const RayRec* rays = (const RayRec*)rays_;
+    HitRec* hits = (HitRec*)hits_;
+    int nt = resolve_threads(threads);
+    std::vector<Stats> per(stats_out ? nt : 0);
+    auto t0 = std::chrono::steady_clock::now();
+    parallel_ranges(n, nt, [&](size_t a, size_t b, int tid) {
+        Ctx cx;
+        if (stats_out) cx.stats = &per[tid];
+        for (size_t i = a; i < b; ++i) {
+            const RayRec& r = rays[i];
+            Ray ray{{r.ox, r.oy, r.oz}, {r.dx, r.dy, r.dz}, time ? time[i] : 0.0f, mask ? mask[i] : MASK_ALL};
+            auto h = scene_intersect(sc, ray, r.tmin, r.tmax, cx);
+            if (h) {
+                hits[i] = {h->t, h->u, h->v, h->geom_id, h->prim_id, h->normal.x, h->normal.y, h->normal.z};
+                if (front_face) front_face[i] = h->front_face ? 1 : 0;
+            } else {
+                hits[i] = {INF, 0, 0, INVALID_ID, INVALID_ID, 0, 0, 0};
+                if (front_face) front_face[i] = 0;
+            }
+        }
+    });
+    double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    if (stats_out) {
+        Stats tot;
+        for (auto& p : per) tot.add(p);
+        write_stats(tot, stats_out);
+    }
+    return secs;
+}
+
+double orc_occluded_n(void* s, uint64_t n, const void* rays_, const float* time, const uint32_t* mask, uint8_t* out,
+                      int threads, uint64_t* stats_out) {
+    const Scene& sc = *((SceneHandle*)s)->scene;
+    const RayRec* rays = (const RayRec*)rays_;
+    int nt = resolve_threads(threads);
+    std::vector<Stats> per(stats_out ? nt : 0);
+    auto t0 = std::chrono::steady_clock::now();
+    parallel_ranges(n, nt, [&](size_t a, size_t b, int tid) {
+        Ctx cx;
+        if (stats_out) cx.stats = &per[tid];
+        for (size_t i = a; i < b; ++i) {
+            const RayRec& r = rays[i];
+            Ray ray{{r.ox, r.oy, r.oz}, {r.dx, r.dy, r.dz}, time ? time[i] : 0.0f, mask ? mask[i] : MASK_ALL};
+            out[i] = sc.occluded(ray, r.tmin, r.tmax, cx) ? 1 : 0;
+        }
+    });
+    double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    if (stats_out) {
+        Stats tot;
+        for (auto& p : per) tot.add(p);
+        write_stats(tot, stats_out);
+    }
+    return secs;
+}
+
+// Linear scan over the scene's primitives in input order (bvh.rs:1460-1470),
+// the reference's own cross-check for the BVH.
+int orc_linear_scan(void* s, const void* ray_, float time, uint32_t mask, void* hit_) {
+    const Scene& sc = *((SceneHandle*)s)->scene;
+    const RayRec& r = *(const RayRec*)ray_;
+    Ray ray{{r.ox, r.oy, r.oz}, {r.dx, r.dy, r.dz}, time, mask};
+    Ctx cx;
+    float closest = r.tmax;
+    std::optional<PrimHit> best;
+    for (const PrimNode& p : sc.bvh.prims) {
+        auto h = p.hit(ray, r.tmin, closest, cx);
+        if (h) {
+            closest = h->t;
+            best = h;
+        }
+    }
+    HitRec* out = (HitRec*)hit_;
+    if (!best) {
+        *out = {INF, 0, 0, INVALID_ID, INVALID_ID, 0, 0, 0};
+        return 0;
+    }
+    *out = {best->t, best->u, best->v, best->geom_id, best->prim_id, best->outward.x, best->outward.y, best->outward.z};
+    return 1;
+}
+
+// ---- unit hooks for the known-answer tests ---------------------------------
+int orc_test_triangle_intersect(const float* o, const float* d, const float* v9, float t_min, float t_max, float* tuv) {
+    Ray ray{{o[0], o[1], o[2]}, {d[0], d[1], d[2]}};
+    auto r = triangle_intersect(ray, {v9[0], v9[1], v9[2]}, {v9[3], v9[4], v9[5]}, {v9[6], v9[7], v9[8]}, t_min, t_max);
+    if (!r) return 0;
+    tuv[0] = r->t;
+    tuv[1] = r->u;
+    tuv[2] = r->v;
+    return 1;
+}
+// tris: n x (9 floats), masks: n; out: hits, fallback, t[4], u[4], v[4], active
+void orc_test_tri4_intersect(const float* o, const float* d, const float* tris, const uint32_t* masks, int n,
+                             uint32_t ray_mask, float t_min, float t_max, uint32_t* bits3, float* tuv12) {
+    TriIn in[4];
+    for (int i = 0; i < n; ++i) {
+        const float* v = tris + 9 * i;
+        in[i] = TriIn{{v[0], v[1], v[2]}, {v[3], v[4], v[5]}, {v[6], v[7], v[8]}, (uint32_t)i, masks[i]};
+    }
+    Tri4 pk(in, n);
+    Ray ray{{o[0], o[1], o[2]}, {d[0], d[1], d[2]}};
+    Hit4 h = pk.intersect(RayShear(ray), ray_mask, t_min, t_max);
+    bits3[0] = h.hits;
+    bits3[1] = h.fallback;
+    bits3[2] = pk.active;
+    for (int l = 0; l < 4; ++l) {
+        tuv12[l] = h.t[l];
+        tuv12[4 + l] = h.u[l];
+        tuv12[8 + l] = h.v[l];
+    }
+}
+int orc_test_rounded_cone(const float* o, const float* d, const float* p0, const float* p1, float r0, float r1,
+                          float t_min, float t_max, float* tn4) {
+    Ray ray{{o[0], o[1], o[2]}, {d[0], d[1], d[2]}};
+    auto r = rounded_cone_intersect(ray, {p0[0], p0[1], p0[2]}, {p1[0], p1[1], p1[2]}, r0, r1, t_min, t_max);
+    if (!r) return 0;
+    tn4[0] = r->t;
+    tn4[1] = r->n.x;
+    tn4[2] = r->n.y;
+    tn4[3] = r->n.z;
+    return 1;
+}
+int orc_test_cubic_curve(const float* o, const float* d, const float* cp12, float r0, float r1, float t_min, float t_max,
+                         float* tn4) {
+    Ray ray{{o[0], o[1], o[2]}, {d[0], d[1], d[2]}};
+    V3 cp[4];
+    for (int k = 0; k < 4; ++k) cp[k] = {cp12[3 * k], cp12[3 * k + 1], cp12[3 * k + 2]};
+    auto r = cubic_curve_intersect(ray, cp, r0, r1, t_min, t_max);
+    if (!r) return 0;
+    tn4[0] = r->t;
+    tn4[1] = r->n.x;
+    tn4[2] = r->n.y;
+    tn4[3] = r->n.z;
+    return 1;
+}
+uint32_t orc_test_flatness_depth(const float* cp12, float max_width) {
+    V3 cp[4];
+    for (int k = 0; k < 4; ++k) cp[k] = {cp12[3 * k], cp12[3 * k + 1], cp12[3 * k + 2]};
+    return flatness_depth(cp, max_width);
+}
+int orc_test_clip_triangle_aabb(const float* v9, int axis, float mn, float mx, float* out6) {
+    auto r = clip_triangle_aabb({v9[0], v9[1], v9[2]}, {v9[3], v9[4], v9[5]}, {v9[6], v9[7], v9[8]}, axis, mn, mx);
+    if (!r) return 0;
+    out6[0] = r->minimum.x;
+    out6[1] = r->minimum.y;
+    out6[2] = r->minimum.z;
+    out6[3] = r->maximum.x;
+    out6[4] = r->maximum.y;
+    out6[5] = r->maximum.z;
+    return 1;
+}
+uint32_t orc_sizeof_wide_node() { return (uint32_t)sizeof(WideNode); }
+
+}  // extern "C"

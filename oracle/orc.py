@@ -1,0 +1,316 @@
+"""ORACLE BINDING — TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+
+ctypes wrapper over oracle/liborc.so (the C++ restatement of crust-rt) exposing
+the same duck-typed surface as ``crust_render_b200`` (SceneBuilder / Scene /
+Geometry / Ray) so a test can run the reference's scenario against both and
+compare. Only tests/, ``__graft_entry__.smoke()`` and bench.py's CPU arm import
+this module.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from typing import Optional
+
+import numpy as np
+
+from crust_render_b200.rt_types import (  # value types only — no product code paths
+    HIT_DTYPE,
+    MASK_ALL,
+    RAY_DTYPE,
+    Geometry,
+    PrimitiveBreakdown,
+    Ray,
+    RayHit,
+    make_rays,
+)
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_lib = None
+
+STAT_NAMES = ["queries_top", "queries_inst", "nodes_top", "nodes_inst", "leaves_top", "leaves_inst", "packets_top",
+              "packets_inst", "prim_tests_top", "prim_tests_inst", "tri_lanes", "sphere_tests", "curve_tests",
+              "cubic_tests", "instance_tests", "stack_high_water"]
+
+
+def build() -> str:
+    """Compiles liborc.so with the committed Makefile (idempotent)."""
+    subprocess.run(["make", "-C", _HERE, "-s"], check=True)
+    return os.path.join(_HERE, "liborc.so")
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = os.path.join(_HERE, "liborc.so")
+    if not os.path.exists(path):
+        build()
+    L = C.CDLL(path)
+    vp, u32, u64, sz, f = C.c_void_p, C.c_uint32, C.c_uint64, C.c_size_t, C.c_float
+    L.orc_builder_new.restype = vp
+    L.orc_builder_free.argtypes = [vp]
+    L.orc_builder_count.argtypes = [vp]
+    L.orc_builder_count.restype = u64
+    L.orc_attach_triangle_mesh.argtypes = [vp, vp, sz, vp, sz, vp, sz, u32]
+    L.orc_attach_sphere.argtypes = [vp, f, f, f, f, u32]
+    L.orc_attach_round_curves.argtypes = [vp, vp, sz, u32]
+    L.orc_attach_cubic_curves.argtypes = [vp, vp, sz, u32]
+    L.orc_attach_instance.argtypes = [vp, vp, vp, vp, u32]
+    L.orc_attach_empty.argtypes = [vp, u32]
+    for n in ("orc_attach_triangle_mesh", "orc_attach_sphere", "orc_attach_round_curves", "orc_attach_cubic_curves",
+              "orc_attach_instance", "orc_attach_empty"):
+        getattr(L, n).restype = u32
+    L.orc_set_triangle_mesh.argtypes = [vp, u32, vp, sz, vp, sz, vp, sz]
+    L.orc_set_sphere.argtypes = [vp, u32, f, f, f, f]
+    L.orc_set_instance.argtypes = [vp, u32, vp, vp, vp]
+    L.orc_commit.argtypes = [vp, C.c_int]
+    L.orc_commit.restype = vp
+    L.orc_scene_release.argtypes = [vp]
+    L.orc_geometry_count.argtypes = [vp]
+    L.orc_geometry_count.restype = u32
+    L.orc_primitive_count.argtypes = [vp]
+    L.orc_primitive_count.restype = u64
+    L.orc_has_motion.argtypes = [vp]
+    L.orc_bounds.argtypes = [vp, vp]
+    L.orc_primitive_breakdown.argtypes = [vp, vp]
+    L.orc_unique_primitive_breakdown.argtypes = [vp, vp]
+    L.orc_tree_sizes.argtypes = [vp, vp]
+    L.orc_tree_nodes.argtypes = [vp, vp]
+    L.orc_tree_leaves.argtypes = [vp, vp, vp, vp]
+    L.orc_packet_lanes.argtypes = [vp]
+    L.orc_packet_lanes.restype = u64
+    L.orc_intersect_n.argtypes = [vp, u64, vp, vp, vp, vp, vp, C.c_int, vp]
+    L.orc_intersect_n.restype = C.c_double
+    L.orc_occluded_n.argtypes = [vp, u64, vp, vp, vp, vp, C.c_int, vp]
+    L.orc_occluded_n.restype = C.c_double
+    L.orc_linear_scan.argtypes = [vp, vp, f, u32, vp]
+    L.orc_test_triangle_intersect.argtypes = [vp, vp, vp, f, f, vp]
+    L.orc_test_tri4_intersect.argtypes = [vp, vp, vp, vp, C.c_int, u32, f, f, vp, vp]
+    L.orc_test_rounded_cone.argtypes = [vp, vp, vp, vp, f, f, f, f, vp]
+    L.orc_test_cubic_curve.argtypes = [vp, vp, vp, f, f, f, f, vp]
+    L.orc_test_flatness_depth.argtypes = [vp, f]
+    L.orc_test_flatness_depth.restype = u32
+    L.orc_test_clip_triangle_aabb.argtypes = [vp, C.c_int, f, f, vp]
+    L.orc_sizeof_wide_node.restype = u32
+    _lib = L
+    return L
+
+
+def _p(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _f3(v) -> np.ndarray:
+    return np.ascontiguousarray(np.asarray(v, dtype=np.float32).reshape(-1))
+
+
+class SceneBuilder:
+    def __init__(self):
+        self._h = C.c_void_p(lib().orc_builder_new())
+        self._keep = []
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().orc_builder_free(self._h)
+            self._h = None
+
+    def attach(self, g: Geometry) -> int:
+        return self.attach_masked(g, MASK_ALL)
+
+    def attach_masked(self, g: Geometry, mask: int) -> int:
+        L, h = lib(), self._h
+        if g.kind == "mesh":
+            n = g.normals
+            return L.orc_attach_triangle_mesh(h, _p(g.vertices), len(g.vertices), _p(g.indices), len(g.indices), _p(n),
+                                              0 if n is None else len(n), mask)
+        if g.kind == "sphere":
+            c = g.center
+            return L.orc_attach_sphere(h, float(c[0]), float(c[1]), float(c[2]), g.radius, mask)
+        if g.kind == "curves":
+            return L.orc_attach_round_curves(h, _p(g.segments), len(g.segments), mask)
+        if g.kind == "cubics":
+            return L.orc_attach_cubic_curves(h, _p(g.segments), len(g.segments), mask)
+        if g.kind == "instance":
+            self._keep.append(g.scene)
+            return L.orc_attach_instance(h, g.scene._h, _p(g.transform.m), None if g.transform_end is None else _p(g.transform_end.m), mask)
+        if g.kind == "empty":
+            return L.orc_attach_empty(h, mask)
+        raise ValueError(g.kind)
+
+    def count(self) -> int:
+        return int(lib().orc_builder_count(self._h))
+
+    def reserve(self, additional: int) -> None:
+        pass
+
+    def set_geometry(self, id: int, g: Geometry) -> None:
+        L, h = lib(), self._h
+        if g.kind == "mesh":
+            n = g.normals
+            rc = L.orc_set_triangle_mesh(h, id, _p(g.vertices), len(g.vertices), _p(g.indices), len(g.indices), _p(n), 0 if n is None else len(n))
+        elif g.kind == "sphere":
+            c = g.center
+            rc = L.orc_set_sphere(h, id, float(c[0]), float(c[1]), float(c[2]), g.radius)
+        elif g.kind == "instance":
+            self._keep.append(g.scene)
+            rc = L.orc_set_instance(h, id, g.scene._h, _p(g.transform.m), None if g.transform_end is None else _p(g.transform_end.m))
+        else:
+            raise ValueError(g.kind)
+        if rc:
+            raise IndexError("set_geometry: id was never attached")
+
+    @staticmethod
+    def empty_geometry() -> Geometry:
+        return Geometry.Empty()
+
+    def commit(self, flags: int = 0, host_threads: int = 0) -> "Scene":
+        h, self._h = self._h, None
+        s = Scene(C.c_void_p(lib().orc_commit(h, host_threads)))
+        s._keep = self._keep
+        return s
+
+
+class Scene:
+    def __init__(self, h):
+        self._h = h
+        self._keep = []
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().orc_scene_release(self._h)
+            self._h = None
+
+    def intersect_n(self, rays, time=None, mask=None, threads: int = 1, stats: bool = False):
+        rays = np.ascontiguousarray(rays, dtype=RAY_DTYPE)
+        n = len(rays)
+        time = None if time is None else np.ascontiguousarray(time, dtype=np.float32)
+        mask = None if mask is None else np.ascontiguousarray(mask, dtype=np.uint32)
+        hits = np.empty(n, dtype=HIT_DTYPE)
+        ff = np.empty(n, dtype=np.uint8)
+        st = np.zeros(16, dtype=np.uint64) if stats else None
+        secs = lib().orc_intersect_n(self._h, n, _p(rays), _p(time), _p(mask), _p(hits), _p(ff), threads, _p(st))
+        self.last_seconds = secs
+        if stats:
+            return hits, ff, dict(zip(STAT_NAMES, (int(x) for x in st)))
+        return hits, ff
+
+    def occluded_n(self, rays, time=None, mask=None, threads: int = 1, stats: bool = False):
+        rays = np.ascontiguousarray(rays, dtype=RAY_DTYPE)
+        n = len(rays)
+        time = None if time is None else np.ascontiguousarray(time, dtype=np.float32)
+        mask = None if mask is None else np.ascontiguousarray(mask, dtype=np.uint32)
+        occ = np.empty(n, dtype=np.uint8)
+        st = np.zeros(16, dtype=np.uint64) if stats else None
+        secs = lib().orc_occluded_n(self._h, n, _p(rays), _p(time), _p(mask), _p(occ), threads, _p(st))
+        self.last_seconds = secs
+        if stats:
+            return occ, dict(zip(STAT_NAMES, (int(x) for x in st)))
+        return occ
+
+    def intersect(self, ray: Ray, t_min: float, t_max: float) -> Optional[RayHit]:
+        r = make_rays([ray.origin], [ray.dir], t_min, t_max)
+        hits, ff = self.intersect_n(r, np.array([ray.time], np.float32), np.array([ray.mask & 0xFFFFFFFF], np.uint32))
+        h = hits[0]
+        if h["geom_id"] == 0xFFFFFFFF:
+            return None
+        return RayHit(float(h["t"]), h["normal"].copy(), bool(ff[0]), float(h["u"]), float(h["v"]), int(h["geom_id"]), int(h["prim_id"]))
+
+    def occluded(self, ray: Ray, t_min: float, t_max: float) -> bool:
+        r = make_rays([ray.origin], [ray.dir], t_min, t_max)
+        return bool(self.occluded_n(r, np.array([ray.time], np.float32), np.array([ray.mask & 0xFFFFFFFF], np.uint32))[0])
+
+    def linear_scan(self, ray: Ray, t_min: float, t_max: float):
+        """bvh.rs:1460-1470: closest hit by testing every primitive in input order (outward normal)."""
+        r = make_rays([ray.origin], [ray.dir], t_min, t_max)
+        hit = np.zeros(1, dtype=HIT_DTYPE)
+        got = lib().orc_linear_scan(self._h, _p(r), np.float32(ray.time), ray.mask & 0xFFFFFFFF, _p(hit))
+        return hit[0] if got else None
+
+    def bounds(self):
+        o = np.zeros(6, np.float32)
+        if not lib().orc_bounds(self._h, _p(o)):
+            return None
+        from crust_render_b200.rt_types import _v3  # noqa
+
+        class _B:
+            minimum = o[:3].copy()
+            maximum = o[3:].copy()
+
+        return _B
+
+    def geometry_count(self) -> int:
+        return int(lib().orc_geometry_count(self._h))
+
+    def primitive_count(self) -> int:
+        return int(lib().orc_primitive_count(self._h))
+
+    def has_motion(self) -> bool:
+        return bool(lib().orc_has_motion(self._h))
+
+    def primitive_breakdown(self) -> PrimitiveBreakdown:
+        o = np.zeros(5, np.uint64)
+        lib().orc_primitive_breakdown(self._h, _p(o))
+        return PrimitiveBreakdown(*(int(x) for x in o))
+
+    def unique_primitive_breakdown(self) -> PrimitiveBreakdown:
+        o = np.zeros(5, np.uint64)
+        lib().orc_unique_primitive_breakdown(self._h, _p(o))
+        return PrimitiveBreakdown(*(int(x) for x in o))
+
+    def tree(self):
+        """Canonical tree export, same shape as crust_render_b200.Scene.debug_tree()."""
+        sz = np.zeros(6, np.uint64)
+        lib().orc_tree_sizes(self._h, _p(sz))
+        n_wide, n_leaves, n_pk, n_idx, n_refs, n_bin = (int(x) for x in sz)
+        nodes = np.zeros((n_wide, 32), np.uint32)
+        lib().orc_tree_nodes(self._h, _p(nodes))
+        tri = np.zeros(n_leaves, np.uint32)
+        oth = np.zeros(n_leaves, np.uint32)
+        refs = np.zeros(n_refs, np.uint32)
+        lib().orc_tree_leaves(self._h, _p(tri), _p(oth), _p(refs))
+        return {"nodes": nodes, "tri_counts": tri, "other_counts": oth, "refs": refs, "binary_nodes": n_bin,
+                "packets": n_pk, "indices": n_idx, "packet_lanes": int(lib().orc_packet_lanes(self._h))}
+
+
+# ---- unit hooks -----------------------------------------------------------------
+def triangle_intersect(o, d, v0, v1, v2, t_min, t_max):
+    """triangle.rs:97-106 -> (t, u, v) or None."""
+    out = np.zeros(3, np.float32)
+    v9 = _f3([v0, v1, v2])
+    ok = lib().orc_test_triangle_intersect(_p(_f3(o)), _p(_f3(d)), _p(v9), t_min, t_max, _p(out))
+    return tuple(out) if ok else None
+
+
+def tri4_intersect(o, d, tris, masks, ray_mask, t_min, t_max):
+    """triangle.rs:217-348: tris = list of (v0, v1, v2). Returns dict hits/fallback/active/t/u/v."""
+    n = len(tris)
+    t9 = _f3([[v for v in tri] for tri in tris])
+    m = np.asarray(masks, np.uint32)
+    bits = np.zeros(3, np.uint32)
+    tuv = np.zeros(12, np.float32)
+    lib().orc_test_tri4_intersect(_p(_f3(o)), _p(_f3(d)), _p(t9), _p(m), n, ray_mask & 0xFFFFFFFF, t_min, t_max, _p(bits), _p(tuv))
+    return {"hits": int(bits[0]), "fallback": int(bits[1]), "active": int(bits[2]), "t": tuv[0:4], "u": tuv[4:8], "v": tuv[8:12]}
+
+
+def rounded_cone_intersect(o, d, p0, p1, r0, r1, t_min, t_max):
+    out = np.zeros(4, np.float32)
+    ok = lib().orc_test_rounded_cone(_p(_f3(o)), _p(_f3(d)), _p(_f3(p0)), _p(_f3(p1)), r0, r1, t_min, t_max, _p(out))
+    return (float(out[0]), out[1:4].copy()) if ok else None
+
+
+def cubic_curve_intersect(o, d, cp, r0, r1, t_min, t_max):
+    out = np.zeros(4, np.float32)
+    ok = lib().orc_test_cubic_curve(_p(_f3(o)), _p(_f3(d)), _p(_f3(cp)), r0, r1, t_min, t_max, _p(out))
+    return (float(out[0]), out[1:4].copy()) if ok else None
+
+
+def flatness_depth(cp, max_width) -> int:
+    return int(lib().orc_test_flatness_depth(_p(_f3(cp)), max_width))
+
+
+def clip_triangle_aabb(v0, v1, v2, axis, mn, mx):
+    out = np.zeros(6, np.float32)
+    ok = lib().orc_test_clip_triangle_aabb(_p(_f3([v0, v1, v2])), axis, mn, mx, _p(out))
+    return (out[:3].copy(), out[3:].copy()) if ok else None
