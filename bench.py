@@ -1,0 +1,387 @@
+#!/usr/bin/env python
+"""bench.py — rays/s of the closest-hit + occlusion hot path on the 10 M-triangle stress mesh.
+
+One step = one pass of the traversal kernels over five resident ray sets on the K1 scene
+(SURVEY.md §8(d)): closest-hit on (i) LCG box rays, (ii) camera rays, (iii) cosine bounce
+rays; occlusion on (i) and on (iv) RectLight shadow rays. `value` = rays of all five
+launches / device time, inputs resident in HBM. `e2e` = the same five queries through the
+host-buffer C ABI (crt_*_host_n) with pinned host rays in and hits out, copies inside the
+timed region. `--impl reference` times the CPU restatement of crust-rt (oracle/) on all
+host threads on a bounded sample of the same sets.
+
+Contract: python bench.py --gpus N --steps K --warmup W [--impl reference]; one JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "oracle")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+METRIC = "Mrays/s closest-hit+occlusion per GPU"
+SETS = ["closest_lcg", "closest_camera", "closest_bounce", "occluded_lcg", "occluded_shadow"]
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--grid", type=int, default=32, help="stress-scene sphere grid (32 = K1, 10.07 M triangles)")
+    ap.add_argument("--rays-log2", type=int, default=24, help="rays per set (camera set: 3840x2160x2 spp when 24)")
+    ap.add_argument("--cpu-sample-log2", type=int, default=20, help="rays per set for the CPU baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------
+# workload
+# ---------------------------------------------------------------------------
+def camera_dims(rays_log2):
+    # 3840x2160 x 2 spp = 16.6 M ~ 2^24; smaller runs shrink the image, keeping 16:9 and 2 spp
+    n = 1 << rays_log2
+    h = max(9, int(round((n / 2 / (16 / 9)) ** 0.5)))
+    if rays_log2 == 24:
+        return 3840, 2160, 2
+    return int(h * 16 / 9), h, 2
+
+
+def build_ray_sets(W, scene_bounds, rays_log2, rank, trace_closest):
+    """Returns dict name -> (rays RAY_DTYPE[n], mask or None). `trace_closest(rays)` gives hits (HIT_DTYPE)."""
+    n = 1 << rays_log2
+    ext = W.scene_extent(scene_bounds)
+    sets = {}
+    lcg = W.ray_batch(n, ext, seed=(0x2545F491 + 7919 * rank) & 0xFFFFFFFF)
+    sets["closest_lcg"] = (lcg, None)
+    sets["occluded_lcg"] = (lcg, None)
+    w, h, spp = camera_dims(rays_log2)
+    cam = W.stress_camera(w, h)
+    parts = [cam.rays(spp, seed=rank, rows=(j, min(j + 256, h))) for j in range(0, h, 256)]
+    cam_rays = np.concatenate(parts)
+    sets["closest_camera"] = (cam_rays, None)
+    hits = trace_closest(cam_rays)
+    sets["closest_bounce"] = (W.bounce_rays(cam_rays, hits, seed=1 + rank), None)
+    sr, sm = W.shadow_rays(cam_rays, hits, seed=2 + rank)
+    sets["occluded_shadow"] = (sr, sm)
+    return sets, {"lcg_extent": ext, "camera": [w, h, spp]}
+
+
+def bytes_per_ray(stats, n, any_hit):
+    """B_ray = 128 N_node + 48 N_tri + 32 N_sph + 48 N_curve + 64 N_inst + 32 (ray in) + B_out."""
+    per = lambda k: stats[k] / n  # noqa: E731
+    nodes = per("nodes_top") + per("nodes_inst")
+    b = 128 * nodes + 48 * per("tri_lanes") + 32 * per("sphere_tests") + 48 * (per("curve_tests") + per("cubic_tests")) + 64 * per("instance_tests")
+    return b + 32 + (1 if any_hit else 32), nodes, per("tri_lanes")
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        self.t.join(timeout=2)
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(len(r) >= 7 and r[3 + k].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------
+# reference arm: the CPU restatement of crust-rt on all host threads
+# ---------------------------------------------------------------------------
+def cpu_sample(sets, sample_log2):
+    out = {}
+    m = 1 << sample_log2
+    for name in SETS:
+        rays, mask = sets[name]
+        stride = max(1, len(rays) // m)
+        out[name] = (np.ascontiguousarray(rays[::stride][:m]), None if mask is None else np.ascontiguousarray(mask[::stride][:m]))
+    return out
+
+
+def run_cpu(o_scene, sample, threads, with_stats=False):
+    """One pass of the five queries on the oracle. Returns (rays, seconds, per-set dict)."""
+    total_rays, total_s, per = 0, 0.0, {}
+    for name in SETS:
+        rays, mask = sample[name]
+        if name.startswith("closest"):
+            res = o_scene.intersect_n(rays, None, mask, threads=threads, stats=with_stats)
+        else:
+            res = o_scene.occluded_n(rays, None, mask, threads=threads, stats=with_stats)
+        s = o_scene.last_seconds
+        per[name] = {"rays": len(rays), "seconds": s, "stats": res[-1] if with_stats else None}
+        total_rays += len(rays)
+        total_s += s
+    return total_rays, total_s, per
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import orc
+    from crust_render_b200 import workloads as W
+
+    cores = os.cpu_count() or 1
+    t0 = time.time()
+    b, n_tris = W.stress_scene(orc, grid=args.grid, shards=30000, jitter=True)
+    o_scene = b.commit(host_threads=0)
+    log(f"[reference] oracle commit of {n_tris} triangles: {time.time() - t0:.1f}s")
+    sets, info = build_ray_sets(W, o_scene.bounds(), args.rays_log2, 0, lambda r: o_scene.intersect_n(r, threads=0)[0])
+    sample = cpu_sample(sets, args.cpu_sample_log2)
+    for _ in range(args.warmup):
+        run_cpu(o_scene, sample, 0)
+    rays = secs = 0
+    for _ in range(args.steps):
+        r, s, _per = run_cpu(o_scene, sample, 0)
+        rays, secs = rays + r, secs + s
+    v = rays / secs / 1e6
+    desc = f"{rays // args.steps} rays/step: 2^{args.cpu_sample_log2} strided rays of each of the 5 ray sets, {cores} threads, contiguous slices"
+    line = {"metric": METRIC, "value": v, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": secs / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "impl": "reference",
+            "config": {"workload": f"K1 stress mesh ({n_tris} triangles, flat BVH4), ray sets (i)-(iv) of SURVEY 8(d)", "triangles": n_tris,
+                       "rays_per_set": 1 << args.rays_log2, **info},
+            "cpu_baseline": {"value": v, "unit": "Mrays/s", "cores": cores, "kind": "port", "sample": desc},
+            "e2e": {"value": v, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------
+# B200 arm
+# ---------------------------------------------------------------------------
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return reference_arm(args)
+
+    import torch
+    import torch.distributed as dist
+
+    import crust_render_b200 as crt
+    from crust_render_b200 import workloads as W
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    crt.init(local)
+    dev = torch.device("cuda", local)
+    cores = os.cpu_count() or 1
+
+    # ---- scene: replicated on every GPU -------------------------
+    t0 = time.time()
+    b, n_tris = W.stress_scene(crt, grid=args.grid, shards=30000, jitter=True)
+    scene = b.commit(host_threads=max(1, cores // world))
+    bi = scene.build_info()
+    if rank == 0:
+        log(f"[bench] commit of {n_tris} triangles: {time.time() - t0:.1f}s (host build {bi.build_seconds:.1f}s, upload {bi.upload_seconds:.2f}s), "
+            f"{bi.wide_nodes} BVH4 nodes ({bi.node_bytes / 1e6:.0f} MB), {bi.leaf_refs} leaf refs ({bi.leaf_bytes / 1e6:.0f} MB)")
+
+    t0 = time.time()
+    sets, info = build_ray_sets(W, scene.bounds(), args.rays_log2, rank, lambda r: scene.intersect_n(r)[0])
+    if rank == 0:
+        log(f"[bench] ray sets: " + ", ".join(f"{k}={len(v[0])}" for k, v in sets.items()) + f" ({time.time() - t0:.1f}s)")
+
+    # ---- device-resident inputs / outputs ------------------------------------
+    d_in, d_mask, d_out, h_in, h_mask, h_out = {}, {}, {}, {}, {}, {}
+    for name in SETS:
+        rays, mask = sets[name]
+        h = torch.from_numpy(rays.view(np.float32).reshape(-1, 8)).pin_memory()
+        h_in[name] = h
+        d_in[name] = h.to(dev, non_blocking=True)
+        if mask is not None:
+            hm = torch.from_numpy(mask.view(np.int32)).pin_memory()
+            h_mask[name] = hm
+            d_mask[name] = hm.to(dev, non_blocking=True)
+        if name.startswith("closest"):
+            d_out[name] = torch.empty((len(rays), 8), dtype=torch.float32, device=dev)
+            h_out[name] = torch.empty((len(rays), 8), dtype=torch.float32).pin_memory()
+        else:
+            d_out[name] = torch.empty(len(rays), dtype=torch.uint8, device=dev)
+            h_out[name] = torch.empty(len(rays), dtype=torch.uint8).pin_memory()
+    torch.cuda.synchronize()
+    rays_per_step = sum(len(sets[n][0]) for n in SETS)
+    stream = torch.cuda.current_stream()
+
+    def launch(name):
+        n = len(sets[name][0])
+        mk = d_mask[name].data_ptr() if name in d_mask else 0
+        if name.startswith("closest"):
+            scene.intersect_ptr(n, d_in[name].data_ptr(), 0, mk, d_out[name].data_ptr(), 0, stream.cuda_stream)
+        else:
+            scene.occluded_ptr(n, d_in[name].data_ptr(), 0, mk, d_out[name].data_ptr(), stream.cuda_stream)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        for name in SETS:
+            launch(name)
+    barrier()
+
+    # ---- timed region: K steps, CUDA events on the launching stream ------------
+    ev = [[(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in SETS] for _ in range(args.steps)]
+    e_start, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    clocks = ClockSampler(local)
+    clocks.start()
+    launches0 = crt.launch_count()
+    barrier()
+    e_start.record(stream)
+    for k in range(args.steps):
+        for j, name in enumerate(SETS):
+            ev[k][j][0].record(stream)
+            launch(name)
+            ev[k][j][1].record(stream)
+    e_end.record(stream)
+    barrier()
+    launches = crt.launch_count() - launches0
+    clk = clocks.stop()
+    total_ms = e_start.elapsed_time(e_end)
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms_max = float(t.item())
+    ms_per_step = total_ms_max / args.steps
+    value = rays_per_step * world / (ms_per_step * 1e-3) / 1e6
+    k_ms = {name: float(np.mean([ev[k][j][0].elapsed_time(ev[k][j][1]) for k in range(args.steps)])) for j, name in enumerate(SETS)}
+    status = crt.device_status()
+
+    # ---- e2e: host buffers through the C ABI, copies inside the timed region ----
+    e2e = None
+    if not args.no_e2e:
+        def e2e_step():
+            for name in SETS:
+                n = len(sets[name][0])
+                mk = h_mask[name].data_ptr() if name in h_mask else 0
+                if name.startswith("closest"):
+                    scene.intersect_host_ptr(n, h_in[name].data_ptr(), 0, mk, h_out[name].data_ptr(), 0)
+                else:
+                    scene.occluded_host_ptr(n, h_in[name].data_ptr(), 0, mk, h_out[name].data_ptr())
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            e2e_step()
+        barrier()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt.item())
+        h2d = sum(len(sets[n][0]) * 32 + (len(sets[n][0]) * 4 if n in h_mask else 0) for n in SETS)
+        d2h = sum(len(sets[n][0]) * (32 if n.startswith("closest") else 1) for n in SETS)
+        e2e = {"value": rays_per_step * world * args.steps / dt / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "ms_per_step": dt / args.steps * 1e3}
+
+    # ---- CPU baseline + algorithmic bytes per ray (rank 0, N = 1 only) -----------
+    cpu_baseline, roofline, per_set = None, None, {}
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except OSError:
+            pass
+        peak, peak_src = (float(peaks["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)") if "hbm_gbs" in peaks else (6650.0, "fallback (B200_PROFILING.md)")
+        stats_by_set = None
+        if world == 1 and not args.no_cpu_baseline:
+            import orc
+            t0 = time.time()
+            ob, _ = W.stress_scene(orc, grid=args.grid, shards=30000, jitter=True)
+            o_scene = ob.commit(host_threads=0)
+            log(f"[bench] oracle commit: {time.time() - t0:.1f}s")
+            sample = cpu_sample(sets, args.cpu_sample_log2)
+            # parity spot-check on the sample (checker role only)
+            for name in SETS:
+                rays, mask = sample[name]
+                if name.startswith("closest"):
+                    g = scene.intersect_n(rays, None, mask)[0]
+                    c = o_scene.intersect_n(rays, None, mask, threads=0)[0]
+                    agree = float(((g["geom_id"] == c["geom_id"]) & (g["prim_id"] == c["prim_id"]) & (g["t"] == c["t"])).mean())
+                else:
+                    agree = float((scene.occluded_n(rays, None, mask) == o_scene.occluded_n(rays, None, mask, threads=0)).mean())
+                per_set.setdefault(name, {})["oracle_agreement_on_sample"] = agree
+            run_cpu(o_scene, sample, 0)
+            r_all, s_all, _ = run_cpu(o_scene, sample, 0)
+            r_1, s_1, _ = run_cpu(o_scene, {k: (v[0][: 1 << 17], None if v[1] is None else v[1][: 1 << 17]) for k, v in sample.items()}, 1)
+            _, _, st = run_cpu(o_scene, {k: (v[0][: 1 << 17], None if v[1] is None else v[1][: 1 << 17]) for k, v in sample.items()}, 0, with_stats=True)
+            stats_by_set = {k: (v["stats"], v["rays"]) for k, v in st.items()}
+            cpu_baseline = {"value": r_all / s_all / 1e6, "unit": "Mrays/s", "cores": cores, "kind": "port",
+                            "sample": f"2^{args.cpu_sample_log2} strided rays of each of the 5 sets ({r_all} rays, {s_all:.1f}s of CPU work); "
+                                      f"C++ restatement of crust-rt, one ray per call, contiguous slices per thread",
+                            "one_thread_mrays": r_1 / s_1 / 1e6}
+        # roofline of the dominant kernel (closest-hit): algorithmic bytes / measured duration
+        closest = [n for n in SETS if n.startswith("closest")]
+        if stats_by_set:
+            tot_bytes = 0.0
+            for name in SETS:
+                bpr, nodes, tris = bytes_per_ray(stats_by_set[name][0], stats_by_set[name][1], not name.startswith("closest"))
+                per_set.setdefault(name, {}).update({"bytes_per_ray": bpr, "nodes_per_ray": nodes, "tri_lanes_per_ray": tris})
+            for name in closest:
+                tot_bytes += per_set[name]["bytes_per_ray"] * len(sets[name][0])
+            dur = sum(k_ms[n] for n in closest) * 1e-3
+            ach = tot_bytes / dur / 1e9
+            roofline = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                        "kernel": "trace_kernel<closest-hit, triangles>", "peak_source": peak_src,
+                        "bytes_per_launch": tot_bytes / len(closest), "launch_ms": dur * 1e3 / len(closest)}
+        for name in SETS:
+            per_set.setdefault(name, {}).update({"rays": len(sets[name][0]), "kernel_ms": k_ms[name], "mrays": len(sets[name][0]) / k_ms[name] / 1e3})
+
+        line = {"metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": f"K1 stress mesh ({n_tris} triangles, flat BVH4), ray sets (i)-(iv) of SURVEY 8(d)", "triangles": n_tris,
+                           "rays_per_set": 1 << args.rays_log2, "rays_per_step_per_gpu": rays_per_step, "l2": "inputs larger than L2 (rays+hits 2.7 GB, BVH 0.9 GB per step)",
+                           "scene": "replicated per GPU", **info},
+                "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
+                "sets": per_set, "closest_hit_mrays": sum(len(sets[n][0]) for n in closest) / sum(k_ms[n] for n in closest) / 1e3,
+                "occlusion_mrays": sum(len(sets[n][0]) for n in SETS if n not in closest) / sum(k_ms[n] for n in SETS if n not in closest) / 1e3,
+                "device_status": status, "host_cores": cores}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

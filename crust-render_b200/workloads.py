@@ -234,3 +234,112 @@ def scene_extent(bounds) -> float:
     """Half-diagonal of the scene bounds (the `extent` SURVEY §8(d) feeds ray_batch)."""
     d = np.asarray(bounds.maximum, np.float64) - np.asarray(bounds.minimum, np.float64)
     return float(0.5 * np.sqrt((d * d).sum()))
+
+
+# ---------------------------------------------------------------------------
+# ray sets (ii)-(iv) of SURVEY §8(d): camera, bounce and shadow rays for the stress scene
+# ---------------------------------------------------------------------------
+def _hash_u01(idx: np.ndarray, salt: int) -> np.ndarray:
+    """Stateless 32-bit integer hash -> [0,1) f32 (input generation only; the
+    integrator's Sobol sampler is a separate component)."""
+    x = (idx.astype(np.uint64) * np.uint64(0x9E3779B1) + np.uint64(salt & 0xFFFFFFFF)).astype(np.uint32)
+    with np.errstate(over="ignore"):
+        x ^= x >> np.uint32(16)
+        x *= np.uint32(0x7FEB352D)
+        x ^= x >> np.uint32(15)
+        x *= np.uint32(0x846CA68B)
+        x ^= x >> np.uint32(16)
+    return (x >> np.uint32(8)).astype(np.float32) / np.float32(1 << 24)
+
+
+class PinholeCamera:
+    """crust-core/src/camera.rs:25-84 with the importer's USD mapping
+    (scene/usd_import.rs:2174-2220), pinhole case (fStop 0). f32 throughout."""
+
+    def __init__(self, lookfrom, forward, up, focal_length, horiz_aperture, width, height, focus_dist=10.0):
+        f = np.float32
+        lookfrom, forward, up = (np.asarray(v, f) for v in (lookfrom, forward, up))
+        vert_aperture = f(horiz_aperture) * f(height) / f(width)
+        vfov = f(2.0) * np.degrees(np.arctan(vert_aperture / (f(2.0) * f(focal_length))), dtype=f)
+        theta = np.radians(vfov, dtype=f)
+        h = np.tan(theta / f(2.0), dtype=f)
+        vh = f(2.0) * h
+        vw = f(width) / f(height) * vh
+
+        def nrm(v):
+            return (v / np.sqrt((v * v).sum(dtype=f), dtype=f)).astype(f)
+
+        lookat = lookfrom + nrm(forward) * f(focus_dist)
+        w = nrm(lookfrom - lookat)
+        u = nrm(np.cross(nrm(up), w).astype(f))
+        v = np.cross(w, u).astype(f)
+        self.origin = lookfrom
+        self.horizontal = (f(focus_dist) * vw * u).astype(f)
+        self.vertical = (f(focus_dist) * vh * v).astype(f)
+        self.lower_left = (lookfrom - self.horizontal / f(2.0) - self.vertical / f(2.0) - f(focus_dist) * w).astype(f)
+        self.width, self.height = width, height
+
+    def rays(self, spp: int, seed: int = 0, rows=None) -> np.ndarray:
+        """Scanline-ordered camera rays (pixel-major, sample-minor); u = (i + fx) / w, v = (j + fy) / h
+        (tracer.rs:574-575). `rows` = (j0, j1) restricts to a band of image rows."""
+        j0, j1 = rows if rows is not None else (0, self.height)
+        jj, ii, ss = np.meshgrid(np.arange(j0, j1), np.arange(self.width), np.arange(spp), indexing="ij")
+        idx = ((jj * self.width + ii) * spp + ss).ravel()
+        fx, fy = _hash_u01(idx, seed * 2 + 1), _hash_u01(idx, seed * 2 + 2)
+        s = ((ii.ravel().astype(np.float32) + fx) / np.float32(self.width))[:, None]
+        t = ((jj.ravel().astype(np.float32) + fy) / np.float32(self.height))[:, None]
+        d = self.lower_left + s * self.horizontal + t * self.vertical - self.origin
+        r = np.empty(len(idx), dtype=RAY_DTYPE)
+        r["o"], r["d"] = self.origin, d.astype(np.float32)
+        r["tmin"], r["tmax"] = np.float32(0.001), np.float32(np.inf)
+        return r
+
+
+def stress_camera(width: int, height: int) -> PinholeCamera:
+    """gen_stress_scene.py:88-93: translate (0, 9, 20), rotateX -22 deg, focalLength 24, aperture 20.955."""
+    a = math.radians(-22.0)
+    forward = (0.0, math.sin(a), -math.cos(a))  # Rx(a) * (0, 0, -1)
+    up = (0.0, math.cos(a), math.sin(a))        # Rx(a) * (0, 1, 0)
+    return PinholeCamera((0.0, 9.0, 20.0), forward, up, 24.0, 20.955, width, height)
+
+
+def bounce_rays(rays: np.ndarray, hits: np.ndarray, seed: int = 1) -> np.ndarray:
+    """Set (iii): cosine-hemisphere directions (utils/src/common.rs:128-135) about the ray-facing
+    normal at each hit point of `rays`; misses are dropped. t_min = 0.001 (tracer.rs:1152)."""
+    f = np.float32
+    ok = hits["geom_id"] != 0xFFFFFFFF
+    o = (rays["o"][ok] + hits["t"][ok, None] * rays["d"][ok]).astype(f)
+    n = hits["normal"][ok]
+    idx = np.nonzero(ok)[0]
+    u, v = _hash_u01(idx, seed * 2 + 101), _hash_u01(idx, seed * 2 + 102)
+    z = np.sqrt(f(1.0) - v, dtype=f)
+    phi = f(2.0 * math.pi) * u
+    x, y = np.cos(phi, dtype=f) * np.sqrt(v, dtype=f), np.sin(phi, dtype=f) * np.sqrt(v, dtype=f)
+    # any orthonormal frame around n (input generation; not the reference's align_to_normal)
+    a = np.where(np.abs(n[:, :1]) > 0.9, np.array([[0, 1, 0]], f), np.array([[1, 0, 0]], f))
+    t = np.cross(n, a)
+    t /= np.linalg.norm(t, axis=1, keepdims=True)
+    b = np.cross(n, t)
+    d = (x[:, None] * t + y[:, None] * b + z[:, None] * n).astype(f)
+    r = np.empty(len(o), dtype=RAY_DTYPE)
+    r["o"], r["d"] = o, d
+    r["tmin"], r["tmax"] = f(0.001), f(np.inf)
+    return r
+
+
+def shadow_rays(rays: np.ndarray, hits: np.ndarray, seed: int = 2, half: float = 6.0, y: float = 12.0):
+    """Set (iv): from each hit point of `rays` to a uniform point on the stress scene's 12x12
+    RectLight; range [0.001, dist - 0.001] (tracer.rs:1016-1028). Returns (rays, mask=SHADOW)."""
+    f = np.float32
+    ok = hits["geom_id"] != 0xFFFFFFFF
+    o = (rays["o"][ok] + hits["t"][ok, None] * rays["d"][ok]).astype(f)
+    idx = np.nonzero(ok)[0]
+    u, v = _hash_u01(idx, seed * 2 + 201), _hash_u01(idx, seed * 2 + 202)
+    target = np.stack([(u * f(2.0) - f(1.0)) * f(half), np.full(len(o), y, f), (v * f(2.0) - f(1.0)) * f(half)], 1).astype(f)
+    d = target - o
+    dist = np.sqrt((d * d).sum(1, dtype=f), dtype=f)
+    d = (d / dist[:, None]).astype(f)
+    r = np.empty(len(o), dtype=RAY_DTYPE)
+    r["o"], r["d"] = o, d
+    r["tmin"], r["tmax"] = f(0.001), dist - f(0.001)
+    return r, np.full(len(o), 2, np.uint32)

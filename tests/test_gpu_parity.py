@@ -1,0 +1,191 @@
+"""-m gpu: CUDA traversal vs the CPU oracle on identical seeded ray batches.
+
+Bar (BASELINE.json north_star): per-ray geom_id/prim_id agreement >= 99.99 %,
+hit t within 1e-5 relative. Because the tree, the visiting order and the f32
+arithmetic are reproduced exactly, these tests demand the stronger property the
+design aims for — bit-identical (t, u, v, ids) — and report the weaker one on
+failure.
+"""
+import numpy as np
+import pytest
+
+from crust_render_b200 import workloads
+from crust_render_b200.rt_types import (MASK_CAMERA, MASK_SHADOW, Affine3A, CubicCurveSegment, CurveSegment, Geometry,
+                                        make_rays)
+
+pytestmark = pytest.mark.gpu
+INF = np.float32(np.inf)
+
+
+def _compare_closest(p_scene, o_scene, rays, time=None, mask=None, exact=True, normals_tol=1e-5):
+    ph, pf = p_scene.intersect_n(rays, time, mask)
+    oh, of = o_scene.intersect_n(rays, time, mask, threads=0)
+    n = len(rays)
+    ids_ok = (ph["geom_id"] == oh["geom_id"]) & (ph["prim_id"] == oh["prim_id"])
+    agree = ids_ok.mean()
+    both = (ph["geom_id"] != 0xFFFFFFFF) & (oh["geom_id"] != 0xFFFFFFFF)
+    rel = np.abs(ph["t"][both] - oh["t"][both]) / np.maximum(np.abs(oh["t"][both]), 1e-30)
+    assert agree >= 0.9999, f"id agreement {agree:.6f} over {n} rays"
+    assert rel.size == 0 or rel.max() <= 1e-5, f"max relative t error {rel.max():.3e}"
+    if exact:
+        assert np.array_equal(ph["geom_id"], oh["geom_id"]) and np.array_equal(ph["prim_id"], oh["prim_id"])
+        for k in ("t", "u", "v"):
+            assert ph[k].tobytes() == oh[k].tobytes(), f"{k} not bit-identical"
+        assert np.array_equal(pf, of)
+    m = both & ids_ok
+    assert np.abs(ph["normal"][m] - oh["normal"][m]).max(initial=0.0) <= normals_tol
+    return int(both.sum())
+
+
+def _compare_occluded(p_scene, o_scene, rays, time=None, mask=None):
+    a = p_scene.occluded_n(rays, time, mask)
+    b = o_scene.occluded_n(rays, time, mask, threads=0)
+    assert np.array_equal(a, b), f"{int((a != b).sum())} of {len(rays)} occlusion answers differ"
+    return int(a.sum())
+
+
+def _pair(gpu, orc, make):
+    return make(gpu).commit(), make(orc).commit()
+
+
+def test_reference_probe_batches(gpu, orc):
+    """ray_throughput.rs: the three probe scenes x the 4096-ray LCG batch, closest + occluded."""
+    for make, extent in ((workloads.triangle_scene, 6.0), (workloads.sphere_grid_scene, 14.0), (workloads.instance_scene, 7.0)):
+        p, o = _pair(gpu, orc, make)
+        rays = workloads.ray_batch(4096, extent)
+        hits = _compare_closest(p, o, rays)
+        assert hits > 100
+        assert _compare_occluded(p, o, rays) == hits  # hit_any == hit.is_some() (bvh.rs:1583-1607)
+
+
+def test_tri_spheres_one_million_rays(gpu, orc):
+    p, o = _pair(gpu, orc, workloads.triangle_scene)
+    rays = workloads.ray_batch(1 << 20, 6.0, seed=0x1234567)
+    assert _compare_closest(p, o, rays) > 10000
+    _compare_occluded(p, o, rays)
+    # finite ranges: occlusion with t_max short of / beyond the first hit
+    rays["tmax"] = np.float32(9.0)
+    _compare_closest(p, o, rays)
+    _compare_occluded(p, o, rays)
+
+
+def test_stress_scene_with_spatial_splits(gpu, orc):
+    """gen_stress_scene.py at 1/9 size: flat spheres + thin shards (SBVH duplicates) + floor + slab."""
+    make = lambda api: workloads.stress_scene(api, grid=2, shards=30000)[0]  # noqa: E731
+    p, o = _pair(gpu, orc, make)
+    ext = workloads.scene_extent(p.bounds())
+    rays = workloads.ray_batch(1 << 19, ext, seed=99)
+    assert _compare_closest(p, o, rays) > 1000
+    _compare_occluded(p, o, rays)
+    # rays started on the floor going up (bounce-like, t_min = 0.001), and axis-aligned ones
+    rng = np.random.default_rng(3)
+    n = 1 << 18
+    org = np.stack([rng.uniform(-16, 16, n), np.zeros(n), rng.uniform(-16, 16, n)], 1).astype(np.float32)
+    d = rng.normal(size=(n, 3)).astype(np.float32)
+    d[:, 1] = np.abs(d[:, 1])
+    d[: n // 8] = (0, 1, 0)
+    rays = make_rays(org, d, 0.001, np.inf)
+    _compare_closest(p, o, rays)
+    _compare_occluded(p, o, rays)
+
+
+def test_watertight_edges_and_vertices_on_gpu(gpu, orc):
+    """Rays aimed exactly at mesh vertices and edge midpoints: the f64 tie-break lanes
+    (triangle.rs:141-145, bvh.rs:551-561) must resolve identically. (The reference's slab
+    test is not conservative — bvh.rs:790-808 has no ulp padding — so a ray through a vertex
+    that is also a box corner can miss in the BVH while a linear scan hits; the oracle
+    reproduces that, and the GPU must reproduce the oracle.)"""
+    v, i = workloads.uv_sphere((0, 0, 0), 1.0, 40, 20)
+    make = lambda api: (lambda b: (b.attach(Geometry.TriangleMesh(v, i)), b)[1])(api.SceneBuilder())  # noqa: E731
+    p, o = _pair(gpu, orc, make)
+    tri = v[i]  # [m,3,3]
+    targets = np.concatenate([tri[:, 0], (tri[:, 0] + tri[:, 1]) * np.float32(0.5), (tri[:, 1] + tri[:, 2]) * np.float32(0.5)])
+    for origin in ((0.0, 0.0, 0.0), (3.0, 0.5, -2.0)):
+        org = np.tile(np.asarray(origin, np.float32), (len(targets), 1))
+        rays = make_rays(org, targets - org, 0.001, np.inf)
+        hits = _compare_closest(p, o, rays)
+        if origin == (0.0, 0.0, 0.0):
+            assert hits >= 0.98 * len(rays)
+
+
+def test_all_primitive_kinds_masks_motion_nesting(gpu, orc):
+    rng = np.random.default_rng(11)
+    cache = {}
+
+    def make(api):
+        r = np.random.default_rng(5)
+        ball = api.SceneBuilder()
+        ball.attach(Geometry.TriangleMesh(*workloads.uv_sphere((0, 0, 0), 1.0, 24, 12)))
+        ball.attach_masked(Geometry.Sphere((0, 1.5, 0), 0.5), MASK_CAMERA | MASK_SHADOW)
+        ball = ball.commit()
+        hair = api.SceneBuilder()
+        hair.attach(Geometry.RoundCurves([CurveSegment(r.uniform(-1, 1, 3), r.uniform(-1, 1, 3), 0.08, 0.02) for _ in range(60)]))
+        hair.attach(Geometry.CubicCurves([CubicCurveSegment(r.uniform(-1.5, 1.5, (4, 3)), 0.06, 0.03) for _ in range(40)]))
+        hair = hair.commit()
+        mid = api.SceneBuilder()
+        mid.attach(Geometry.Instance(ball, Affine3A.from_translation((-2, 0, 0))))
+        mid.attach(Geometry.Instance(hair, Affine3A.from_translation((2, 0, 0)) * Affine3A.from_scale((1, 2, 1))))
+        mid.attach_masked(Geometry.Instance(ball, Affine3A.from_translation((0, 3, 0))), MASK_SHADOW)
+        mid = mid.commit()
+        cache[api.__name__] = (ball, hair, mid)
+        b = api.SceneBuilder()
+        b.attach(Geometry.TriangleMesh([(-30, -3, -30), (30, -3, -30), (30, -3, 30), (-30, -3, 30)], [(0, 1, 2), (0, 2, 3)]))
+        for k in range(12):
+            rot = Affine3A.from_rotation_y(0.5 * k) * Affine3A.from_rotation_x(0.1 * k)
+            t = Affine3A.from_translation((6.0 * (k % 4) - 9.0, 0.0, 6.0 * (k // 4) - 6.0)) * rot
+            end = Affine3A.from_translation((1.0, 0.5, 0.0)) * t if k % 3 == 0 else None
+            b.attach(Geometry.Instance(mid, t, end))
+        for k in range(20):
+            b.attach(Geometry.Sphere(r.uniform(-12, 12, 3), float(r.uniform(0.2, 1.0))))
+        b.attach(Geometry.RoundCurves([CurveSegment(r.uniform(-12, 12, 3), r.uniform(-12, 12, 3), 0.2, 0.1) for _ in range(30)]))
+        return b
+
+    p, o = _pair(gpu, orc, make)
+    assert p.has_motion() and o.has_motion()
+    n = 1 << 18
+    rays = workloads.ray_batch(n, 16.0, seed=2024)
+    time = rng.uniform(0, 1, n).astype(np.float32)
+    time[: n // 4] = 0.0
+    mask = rng.choice(np.array([0xFFFFFFFF, MASK_CAMERA, MASK_SHADOW, 4], np.uint32), n)
+    # curves / instance normals go through sqrt+div chains: ids and t must still be exact
+    assert _compare_closest(p, o, rays, time, mask) > 5000
+    _compare_occluded(p, o, rays, time, mask)
+
+
+def test_ragged_and_empty_batches(gpu, orc):
+    p, o = _pair(gpu, orc, workloads.sphere_grid_scene)
+    for n in (0, 1, 31, 33, 127, 129, 4097):
+        rays = workloads.ray_batch(max(n, 1), 14.0)[:n]
+        ph, _ = p.intersect_n(rays)
+        oh, _ = o.intersect_n(rays, threads=1)
+        assert ph.tobytes() == oh.tobytes()
+    empty = gpu.SceneBuilder().commit()
+    h, _ = empty.intersect_n(workloads.ray_batch(100, 1.0))
+    assert np.all(h["geom_id"] == 0xFFFFFFFF) and np.all(np.isinf(h["t"]))
+    assert not empty.occluded_n(workloads.ray_batch(100, 1.0)).any()
+
+
+def test_device_pointer_entry_points(gpu, orc):
+    """crt_intersect_n / crt_occluded_n with DEVICE buffers on a torch stream."""
+    import torch
+
+    p, o = _pair(gpu, orc, workloads.triangle_scene)
+    rays = workloads.ray_batch(1 << 16, 6.0, seed=7)
+    d_rays = torch.from_numpy(rays.view(np.float32).reshape(-1, 8)).cuda()
+    d_hits = torch.empty((len(rays), 8), dtype=torch.float32, device="cuda")
+    d_ff = torch.empty(len(rays), dtype=torch.uint8, device="cuda")
+    d_occ = torch.empty(len(rays), dtype=torch.uint8, device="cuda")
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    before = gpu.launch_count()
+    with torch.cuda.stream(s):
+        p.intersect_ptr(len(rays), d_rays.data_ptr(), 0, 0, d_hits.data_ptr(), d_ff.data_ptr(), s.cuda_stream)
+        p.occluded_ptr(len(rays), d_rays.data_ptr(), 0, 0, d_occ.data_ptr(), s.cuda_stream)
+    s.synchronize()
+    assert gpu.launch_count() == before + 2
+    oh, of = o.intersect_n(rays, threads=0)
+    got = d_hits.cpu().numpy().view(gpu.HIT_DTYPE).reshape(-1)
+    assert got.tobytes() == oh.tobytes()
+    assert np.array_equal(d_ff.cpu().numpy(), of)
+    assert np.array_equal(d_occ.cpu().numpy(), o.occluded_n(rays, threads=0))
+    assert gpu.device_status() == 0
