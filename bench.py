@@ -42,7 +42,7 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--grid", type=int, default=32, help="stress-scene sphere grid (32 = K1, 10.07 M triangles)")
     ap.add_argument("--rays-log2", type=int, default=24, help="rays per set (camera set: 3840x2160x2 spp when 24)")
-    ap.add_argument("--cpu-sample-log2", type=int, default=20, help="rays per set for the CPU baseline sample")
+    ap.add_argument("--cpu-sample-log2", type=int, default=22, help="rays per set for the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()

@@ -24,9 +24,23 @@ struct TraceParams {
     uint32_t n;
 };
 
+// Tunables (overridable with -D for the tuning harness, tools/tune_trace.py)
+#ifndef CRT_BLOCK
 #define CRT_BLOCK 128
+#endif
+#ifndef CRT_SSTACK
 #define CRT_SSTACK 16  // shared-memory stack entries per thread
-#define CRT_LSTACK 112  // local-memory spill entries per thread
+#endif
+#define CRT_LSTACK (128 - CRT_SSTACK)  // local-memory spill entries per thread
+#ifndef CRT_MINBLOCKS_CLOSEST
+#define CRT_MINBLOCKS_CLOSEST 8  // resident blocks per SM the closest-hit variants are compiled for (64 registers)
+#endif
+#ifndef CRT_MINBLOCKS_ANY
+#define CRT_MINBLOCKS_ANY 8
+#endif
+#ifndef CRT_REFILL
+#define CRT_REFILL 16  // a warp refills its idle lanes when fewer than this many are active
+#endif
 
 // Resident blocks per SM of the kernel variant a scene with `feat` uses.
 int trace_blocks_per_sm(bool any_hit, uint32_t feat);

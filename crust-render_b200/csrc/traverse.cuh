@@ -87,7 +87,7 @@ __device__ __forceinline__ const DevScene* instance_child(const float4* rec) {
 }
 
 __device__ __forceinline__ float safe_inv(float d) {  // bvh.rs:662-668
-    return fabsf(d) < 1e-20f ? copysignf(1e20f, d) : 1.0f / d;
+    return fabsf(d) < 1e-20f ? copysignf(1e20f, d) : __frcp_rn(d);  // correctly rounded: same bits as 1.0f / d
 }
 
 // Per-level ray: origin/direction in the current scene's space plus the
@@ -113,7 +113,7 @@ struct LevelRay {
             }
             sx = pick(dir, kx) / dz;
             sy = pick(dir, ky) / dz;
-            sz = 1.0f / dz;
+            sz = __frcp_rn(dz);
         }
     }
 };

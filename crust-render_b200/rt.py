@@ -53,7 +53,8 @@ class CrtError(RuntimeError):
 
 
 def lib_path() -> str:
-    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "libcrt_b200.so")
+    """In-tree library; CRT_B200_LIB selects another build of the same sources (tuning harness only)."""
+    return os.environ.get("CRT_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libcrt_b200.so")
 
 
 class _PrimitiveBreakdown(C.Structure):
