@@ -1,0 +1,71 @@
+// Library-internal declarations shared by scene.cu (crust-rt seam) and render.cu (integrator).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <string>
+#include <vector>
+
+#include "crt.h"
+#include "host_build.h"
+#include "launch.h"
+
+struct crt_scene {
+    std::atomic<int> refs{1};
+    crt::HostTree* host = nullptr;  // kept only with CRT_COMMIT_KEEP_HOST_TREE
+    bool non_empty = false;
+    crt::Box root{};
+    bool has_motion = false;
+    uint32_t n_geoms = 0;
+    uint64_t n_prims = 0;
+    crt_primitive_breakdown breakdown{};
+    uint32_t instance_depth = 0;
+    uint32_t features = 0;  // FEAT_* over this scene and everything below it
+    float extent_sum = 0, extent_max = 0;
+    std::vector<crt_scene*> children;  // distinct instanced scenes, retained
+    crt_build_info info{};
+    // device
+    bool host_only = false;
+    void *d_nodes = nullptr, *d_leafs = nullptr, *d_prim_ids = nullptr, *d_normals = nullptr, *d_motion = nullptr;
+    DevScene desc{};
+    DevScene* d_desc = nullptr;
+    crt_memory_footprint footprint{};
+
+    ~crt_scene() {
+        delete host;
+        cudaFree(d_nodes);
+        cudaFree(d_leafs);
+        cudaFree(d_prim_ids);
+        cudaFree(d_normals);
+        cudaFree(d_motion);
+        cudaFree(d_desc);
+        for (crt_scene* c : children) crt_scene_release(c);
+    }
+};
+
+namespace crt {
+
+// Sets the calling thread's crt_last_error() message and returns `code`.
+int set_error(int code, const std::string& msg);
+int set_cuda_error(cudaError_t e, const char* what);
+// crt_init side effects (device properties, counter ring); CRT_ERR_NO_DEVICE without a GPU.
+int require_device();
+int device_sm_count();
+unsigned int* device_status_word();
+void count_launches(uint64_t n);
+
+// One persistent traversal launch whose ray count lives in device memory (wavefront queues).
+// `counter` must be zero when the kernel starts. No host synchronisation.
+struct QueueTrace {
+    const float4* rays;
+    const float* time;         // or null (time 0)
+    uint32_t mask_uniform;     // every ray of one queue has the same category mask
+    float4* hits;              // closest-hit
+    uint8_t* flag;             // closest-hit: front_face; any-hit: occluded
+    const uint32_t* n_dev;     // queue length
+    uint32_t capacity;         // upper bound of *n_dev
+    unsigned int* counter;     // persistent-fetch ray counter
+};
+int enqueue_queue_trace(const crt_scene* s, bool any_hit, const QueueTrace& q, cudaStream_t stream);
+
+}  // namespace crt

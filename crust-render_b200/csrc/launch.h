@@ -21,7 +21,9 @@ struct TraceParams {
     uint8_t* flag;        // closest-hit: front_face (optional); any-hit: occluded
     unsigned int* counter;  // ray counter for persistent fetch (zeroed before launch)
     unsigned int* status;   // sticky error bits (bit 0: traversal stack overflow)
-    uint32_t n;
+    uint32_t n;               // ray count, or the capacity bound when n_dev is set
+    const uint32_t* n_dev;    // optional: ray count in device memory (read at kernel start)
+    uint32_t mask_uniform;    // ray mask of every ray when `mask` is null
 };
 
 // Tunables (overridable with -D for the tuning harness, tools/tune_trace.py)

@@ -1,0 +1,874 @@
+// Wavefront path tracer for sm_100a (include/crt_render.h).
+//
+// Restates crust-core's integrator (crates/crust-core/src/tracer.rs:515-636 render_pixel,
+// :1086-1558 trace_path) as a queue-driven wavefront instead of one recursive walk per pixel:
+//
+//   raygen  -> extend queue 0                      camera.rs:71-84, filter.rs, tracer.rs:559-584
+//   loop k = 0 .. max_depth:
+//     trace   closest-hit over extend queue k      traverse.cu (persistent BVH4 kernel), count read on device
+//     shade   per hit: emission + MIS ownership, NEE sample -> shadow queue k, BSDF sample + Russian
+//             roulette -> extend queue k+1         tracer.rs:1321-1530 (queues fed through global atomics)
+//     trace   any-hit over shadow queue k
+//     resolve unoccluded NEE contributions          tracer.rs:1416-1443
+//   accumulate the finished samples per pixel IN SAMPLE ORDER, then the adaptive test every 4th
+//   sample (tracer.rs:602-617) decides which pixels enter the next round.
+//
+// The reference records a VertexRec per vertex and gathers backwards (tracer.rs:1537-1556); here the
+// same sum is accumulated forwards with the running throughput `beta` (identical terms, different
+// float association). Path state lives in HBM as structure-of-arrays indexed by path slot; queues
+// hold (ray, path slot) so the traversal kernels read contiguous 32-byte ray records. Nothing in a
+// round synchronises with the host; the host reads one counter per adaptive round.
+//
+// Out of scope here: volume regions, path guiding, environment maps, Ptex.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <mutex>
+#include <vector>
+
+#include "crt_render.h"
+#include "internal.h"
+#include "shade/abi_convert.h"
+
+using namespace shade;
+
+namespace {
+
+#define CKR(call)                                                  \
+    do {                                                           \
+        cudaError_t _e = (call);                                   \
+        if (_e != cudaSuccess) return crt::set_cuda_error(_e, #call); \
+    } while (0)
+
+constexpr int kBlock = 128;
+constexpr uint32_t FLAG_HAS_PREV = 1u, FLAG_PREV_DELTA = 2u;  // PrevBounce, tracer.rs:898-905
+constexpr float kTMin = 0.001f;                               // tracer.rs:1152 / 1029
+
+struct PathState {       // structure of arrays, one slot per path in flight
+    float4* beta_pdf;    // throughput (tracer.rs:1113) + pdf of the bounce that produced the current ray
+    float4* L_w;         // radiance accumulated so far + the sample's FIS weight wx*wy (tracer.rs:565-566)
+    float4* prevp;       // previous vertex position (MIS `from`, tracer.rs:945) + flag word
+    uint2* sampler;      // K_PATH domain pattern, sample index (tracer.rs:1101)
+    float* time;         // shutter time of the path
+};
+struct Queues {
+    float4* rays[2];     // extend queue, double-buffered: 2 x float4 per ray (crt_ray)
+    uint32_t* path[2];   // path slot of each queued ray
+    float* time[2];      // shutter time per queued ray (null when nothing moves)
+    float4* hits;        // closest-hit records of the current extend queue
+    uint8_t* ff;         // front_face of the current extend queue
+    float4* srays;       // shadow queue
+    float* stime;
+    uint32_t* spath;
+    float4* scontrib;    // NEE contribution that lands if the shadow ray is unoccluded
+    uint8_t* occ;
+    // per wavefront, all zeroed by one memset: ext_count[D+2] | sh_count[D+2] | ext_fetch[D+2] | sh_fetch[D+2]
+    uint32_t* counts;
+};
+struct PixelState {      // one entry per pixel this process renders (position in `pixels`)
+    const uint32_t* pixels;  // pixel id = j * width + i
+    float4* sum_w;           // Σ w·L, Σ w (tracer.rs:526-531)
+    double2* lum;            // Σ lum, Σ lum² in f64 (tracer.rs:533-534)
+    uint32_t* taken;
+};
+struct RenderParams {
+    Camera cam;
+    Filter filter;
+    RenderSettings st;
+    const Material* materials;
+    const uint32_t* geom_material;
+    const Light* lights;
+    const int32_t* geom_light;  // LightList::find_by_geom (light.rs:436-440) as a table
+    int n_lights;
+    int motion;
+    PathState ps;
+    Queues q;
+    PixelState px;
+    unsigned long long* stats;  // crt_ray_stats
+};
+
+__device__ __forceinline__ V3 xyz(float4 a) { return v3(a.x, a.y, a.z); }
+__device__ __forceinline__ float4 f4(V3 a, float w) { return make_float4(a.x, a.y, a.z, w); }
+
+// Warp-aggregated queue slot allocation (one global atomic per warp per push site).
+__device__ __forceinline__ uint32_t queue_push(uint32_t* counter) {
+    unsigned m = __activemask();
+    unsigned lane = threadIdx.x & 31u;
+    int leader = __ffs(m) - 1;
+    uint32_t base = 0;
+    if ((int)lane == leader) base = atomicAdd(counter, (uint32_t)__popc(m));
+    base = __shfl_sync(m, base, leader);
+    return base + (uint32_t)__popc(m & ((1u << lane) - 1u));
+}
+__device__ __forceinline__ void stat_add(unsigned long long* dst, uint32_t v) {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xFFFFFFFFu, v, o);
+    if ((threadIdx.x & 31u) == 0 && v) atomicAdd(dst, (unsigned long long)v);
+}
+
+// ---- raygen (tracer.rs:543-584) --------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock) raygen_kernel(const RenderParams P, const uint32_t* __restrict__ active, uint32_t nb, uint32_t s_base,
+                                                        uint32_t s_count) {
+    const uint32_t total = nb * s_count;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        P.q.counts[0] = total;
+        atomicAdd(P.stats + 0, (unsigned long long)total);  // camera_rays
+    }
+    for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < total; p += gridDim.x * blockDim.x) {
+        uint32_t a = p % nb, sl = p / nb;  // sample-major: a warp covers neighbouring pixels of one sample index
+        uint32_t pixel = P.px.pixels[active[a]];
+        uint32_t i = pixel % P.st.width, j = pixel / P.st.width;
+        uint32_t sample = s_base + sl;
+        int32_t tile = (int32_t)(i >> 8) + (int32_t)(j >> 8) * 4096;
+        PathSampler root = new_domain(sampler_new((int32_t)i, (int32_t)j, P.st.frame, (int32_t)sample), tile);
+        float cs[4];
+        draw_sample4(new_domain(root, K_CAMERA), cs);
+        float fx, wx, fy, wy;
+        filter_sample(P.filter, cs[0], fx, wx);
+        filter_sample(P.filter, cs[1], fy, wy);
+        float u = ((float)i + fx) / (float)P.st.width;
+        float v = ((float)j + fy) / (float)P.st.height;
+        float time = 0.0f;
+        if (P.motion) {
+            float ts[4];
+            draw_sample4(new_domain(root, K_TIME), ts);
+            time = ts[0];
+        }
+        V3 o, d;
+        camera_get_ray(P.cam, u, v, cs[2], cs[3], o, d);
+        P.q.rays[0][2 * (size_t)p] = f4(o, kTMin);
+        P.q.rays[0][2 * (size_t)p + 1] = f4(d, INFINITY);
+        P.q.path[0][p] = p;
+        if (P.q.time[0]) P.q.time[0][p] = time;
+        PathSampler path = new_domain(root, K_PATH);
+        P.ps.beta_pdf[p] = make_float4(1.0f, 1.0f, 1.0f, 0.0f);
+        P.ps.L_w[p] = make_float4(0.0f, 0.0f, 0.0f, wx * wy);
+        P.ps.prevp[p] = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(0u));
+        P.ps.sampler[p] = make_uint2(path.pattern, path.index);
+        P.ps.time[p] = time;
+    }
+}
+
+// bounce_emission_weight, tracer.rs:930-953. A surface bounce that produced a sample always has an
+// evaluable material (scatter and eval share the `v_local.z <= 0` gate, openpbr.rs:1033-1037,
+// 1148-1151), so "eval is None" reduces to the delta flag.
+__device__ __forceinline__ float bounce_emission_weight(const RenderParams& P, uint32_t flags, float prev_pdf, V3 prev_p, uint32_t geom_id, V3 hit_p) {
+    if (flags & FLAG_PREV_DELTA) return 1.0f;
+    int li = P.geom_light[geom_id];
+    if (li < 0) return 1.0f;
+    float light_pdf = fmaxf(light_pdf_at_point(P.lights[li], prev_p, hit_p) / (float)P.n_lights, 1e-6f);
+    return strategy_bounce_weight(P.st.sampling_strategy, prev_pdf, light_pdf);
+}
+
+// ---- shade: one path vertex per queue entry (tracer.rs:1118-1535) --------------------------------
+__global__ void __launch_bounds__(kBlock) shade_kernel(const RenderParams P, int k, int cur) {
+    const int D = (int)P.st.max_depth;
+    const uint32_t n = P.q.counts[k];
+    uint32_t* next_count = P.q.counts + k + 1;
+    uint32_t* sh_count = P.q.counts + (D + 2) + k;
+    const int nxt = cur ^ 1;
+    uint32_t c_vertices = 0, c_rr_tested = 0, c_rr_killed = 0, c_escaped = 0, c_depth = 0;
+
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t path = P.q.path[cur][i];
+        const float4 ra = P.q.rays[cur][2 * (size_t)i], rb = P.q.rays[cur][2 * (size_t)i + 1];
+        const V3 ro = xyz(ra), rd = xyz(rb);
+        const float4 h0 = P.q.hits[2 * (size_t)i], h1 = P.q.hits[2 * (size_t)i + 1];
+        const uint32_t geom_id = __float_as_uint(h0.w);
+        const bool have_hit = geom_id != CRT_INVALID_ID;
+        const float t_surf = h0.x;
+        const float4 bp = P.ps.beta_pdf[path];
+        V3 beta = xyz(bp);
+        const float prev_pdf = bp.w;
+        const float4 pp = P.ps.prevp[path];
+        const uint32_t flags = __float_as_uint(pp.w);
+        const bool has_prev = (flags & FLAG_HAS_PREV) != 0;
+        const int medium = (int)((flags >> 8) & 0xFFFFu) - 1;
+        const uint2 smp = P.ps.sampler[path];
+        const PathSampler v = new_domain(PathSampler{smp.x, smp.y}, k);
+        const float time = P.ps.time[path];
+        V3 add = splat(0.0f);
+        const Medium* med = medium >= 0 ? &P.materials[medium].medium : nullptr;
+
+        if (k >= D) {
+            // Depth exhausted (tracer.rs:1123-1148): the ray was traced for bounce-hit emission only.
+            ++c_depth;
+            if (have_hit) {
+                const Material& mat = P.materials[P.geom_material[geom_id]];
+                V3 normal = v3(h1.y, h1.z, h1.w);
+                float cos_o = fabsf(dot(normalize(rd), normal));
+                V3 emitted = material_emitted_directional(mat, cos_o);
+                if (length_squared(emitted) > 0.0f) {
+                    if (med) emitted *= medium_transmittance(*med, t_surf);
+                    float w = bounce_emission_weight(P, flags, prev_pdf, xyz(pp), geom_id, ro + t_surf * rd);
+                    add = beta * (emitted * w);
+                }
+            }
+        } else {
+            // Free flight in a scattering carried medium (tracer.rs:1158-1164).
+            float t_med = INFINITY;
+            if (med && medium_is_scattering(*med)) {
+                float sigma_t_max = fmaxf(medium_sigma_t_max(*med), 1e-4f);
+                t_med = -logf(draw_rnd1(new_domain(v, K_MEDIUM))) / sigma_t_max;
+            }
+            bool cont = false;      // does the path continue with a new extend ray?
+            V3 no = splat(0.0f), nd = splat(0.0f);
+            float new_pdf = 0.0f;
+            V3 new_prevp = splat(0.0f);
+            uint32_t new_flags = 0;
+
+            if (t_med < t_surf) {
+                // Carried-medium scatter vertex (tracer.rs:1251-1318): no NEE, prev = None afterwards.
+                float sigma_bar = fmaxf(medium_sigma_t_max(*med), 1e-4f);
+                V3 pos = ro + t_med * rd;
+                float ph[4];
+                draw_sample4(new_domain(v, K_PHASE), ph);
+                V3 dir = sample_henyey_greenstein(normalize(rd), med->g, ph[0], ph[1]);
+                V3 e = (splat(sigma_bar) - (med->sigma_a + med->sigma_s)) * t_med;
+                V3 factor = med->sigma_s / sigma_bar * v3(expf(e.x), expf(e.y), expf(e.z));
+                beta *= factor;
+                bool survived = true;
+                if (k >= RR_START_BOUNCE) {
+                    ++c_rr_tested;
+                    float p_survive = clampf(max_element(beta), RR_MIN_PROB, 1.0f);
+                    if (p_survive < 1.0f) {
+                        if (draw_rnd1(new_domain(v, K_RR)) >= p_survive) {
+                            survived = false;
+                            ++c_rr_killed;
+                        } else {
+                            beta = beta / p_survive;
+                        }
+                    }
+                }
+                ++c_vertices;
+                if (survived) {
+                    if (k + 1 >= D) {
+                        ++c_depth;  // remaining <= 0 with prev = None: the reference ends without tracing (:1123-1128)
+                    } else {
+                        cont = true;
+                        no = pos;
+                        nd = dir;
+                        new_flags = (uint32_t)(medium + 1) << 8;
+                    }
+                }
+            } else if (!have_hit) {
+                // Background (tracer.rs:1321-1342) with escaped_emission (:966-1009).
+                ++c_escaped;
+                V3 unit = normalize(rd);
+                V3 background = splat(0.0f);
+                bool covered = false;
+                if (P.n_lights > 0) {
+                    bool competing = has_prev && !(flags & FLAG_PREV_DELTA);
+                    for (int l = 0; l < P.n_lights; ++l) {
+                        V3 emitted;
+                        float pdf;
+                        if (!light_escaped(P.lights[l], unit, emitted, pdf)) continue;
+                        covered = true;
+                        float w = 1.0f;
+                        if (competing && strategy_samples_lights(P.st.sampling_strategy))
+                            w = strategy_bounce_weight(P.st.sampling_strategy, prev_pdf, fmaxf(pdf / (float)P.n_lights, 1e-6f));
+                        background += emitted * w;
+                    }
+                }
+                if (!covered) {
+                    float t = 0.5f * (unit.y + 1.0f);
+                    background += (1.0f - t) * v3(1.0f, 1.0f, 1.0f) + t * v3(0.5f, 0.7f, 1.0f);
+                }
+                add = beta * background;
+            } else {
+                // Surface vertex.
+                const uint32_t mat_index = P.geom_material[geom_id];
+                const Material& mat = P.materials[mat_index];
+                SurfaceHit rec;
+                rec.p = ro + t_surf * rd;  // rt_world.rs:221
+                rec.normal = v3(h1.y, h1.z, h1.w);
+                rec.t = t_surf;
+                rec.front_face = P.q.ff[i] != 0;
+                // attenuation over the arriving segment (tracer.rs:1352-1361)
+                V3 atten = splat(1.0f);
+                if (med) {
+                    if (medium_is_scattering(*med)) {
+                        float sigma_bar = fmaxf(medium_sigma_t_max(*med), 1e-4f);
+                        V3 e = (splat(sigma_bar) - (med->sigma_a + med->sigma_s)) * rec.t;
+                        atten = v3(expf(e.x), expf(e.y), expf(e.z));
+                    } else {
+                        atten = medium_transmittance(*med, rec.t);
+                    }
+                }
+                // emission ownership (tracer.rs:1369-1381)
+                float cos_o = fabsf(dot(normalize(rd), rec.normal));
+                V3 emitted = material_emitted_directional(mat, cos_o);
+                if (has_prev) {
+                    if (length_squared(emitted) > 0.0f) {
+                        float w = bounce_emission_weight(P, flags, prev_pdf, xyz(pp), geom_id, rec.p);
+                        add = beta * ((atten * emitted) * w);
+                    }
+                } else {
+                    add = beta * (atten * emitted);
+                }
+                // 1. light sampling (tracer.rs:1394-1445): the shadow ray is queued with the contribution
+                //    it would deliver; every sampled light costs one occlusion query like the reference.
+                float nee_s[4];
+                draw_sample4(new_domain(v, K_NEE), nee_s);
+                int li = strategy_samples_lights(P.st.sampling_strategy) ? light_pick(P.n_lights, nee_s[0]) : -1;
+                LightSample ls;
+                if (li >= 0 && light_sample_li(P.lights[li], rec.p, nee_s[1], nee_s[2], ls)) {
+                    V3 contrib = splat(0.0f);
+                    float cosine = fabsf(dot(rec.normal, ls.direction));
+                    float light_pdf = fmaxf(ls.pdf / (float)P.n_lights, 1e-6f);
+                    V3 brdf_value;
+                    float brdf_pdf;
+                    if (material_eval(mat, rd, rec, ls.direction, brdf_value, brdf_pdf)) {
+                        float weight = strategy_light_weight(P.st.sampling_strategy, light_pdf, brdf_pdf);
+                        V3 nee = ls.radiance * brdf_value * cosine * weight / light_pdf;
+                        contrib = beta * (atten * nee);
+                    }
+                    uint32_t s = queue_push(sh_count);
+                    P.q.srays[2 * (size_t)s] = f4(rec.p, kTMin);
+                    P.q.srays[2 * (size_t)s + 1] = f4(ls.direction, ls.distance - 0.001f);
+                    if (P.q.stime) P.q.stime[s] = time;
+                    P.q.spath[s] = path;
+                    P.q.scontrib[s] = f4(contrib, 0.0f);
+                }
+                // 2. BSDF sampling + Russian roulette (tracer.rs:1459-1530)
+                float bs[4];
+                draw_sample4(new_domain(v, K_BSDF), bs);
+                ScatterSample sample;
+                if (material_scatter(mat, rd, rec, bs, sample)) {
+                    V3 dir = normalize(sample.dir);
+                    float cosine = sample.delta ? 1.0f : fabsf(dot(rec.normal, dir));
+                    V3 factor = sample.value * cosine / sample.pdf;
+                    beta *= atten * factor;
+                    bool survived = true;
+                    if (k >= RR_START_BOUNCE) {
+                        ++c_rr_tested;
+                        float p_survive = clampf(max_element(beta), RR_MIN_PROB, 1.0f);
+                        if (p_survive < 1.0f) {
+                            if (draw_rnd1(new_domain(v, K_RR)) >= p_survive) {
+                                survived = false;
+                                ++c_rr_killed;
+                            } else {
+                                beta = beta / p_survive;
+                            }
+                        }
+                    }
+                    if (survived) {
+                        cont = true;
+                        no = sample.origin;
+                        nd = sample.dir;
+                        new_pdf = sample.pdf;
+                        new_prevp = rec.p;
+                        new_flags = FLAG_HAS_PREV | (sample.delta ? FLAG_PREV_DELTA : 0u) | (sample.enters_medium ? (mat_index + 1u) << 8 : 0u);
+                    }
+                }
+                ++c_vertices;
+            }
+            if (cont) {
+                P.ps.beta_pdf[path] = f4(beta, new_pdf);
+                P.ps.prevp[path] = f4(new_prevp, __uint_as_float(new_flags));
+                uint32_t s = queue_push(next_count);
+                P.q.rays[nxt][2 * (size_t)s] = f4(no, kTMin);
+                P.q.rays[nxt][2 * (size_t)s + 1] = f4(nd, INFINITY);
+                P.q.path[nxt][s] = path;
+                if (P.q.time[nxt]) P.q.time[nxt][s] = time;
+            }
+        }
+        if (add.x != 0.0f || add.y != 0.0f || add.z != 0.0f) {
+            float4 lw = P.ps.L_w[path];
+            P.ps.L_w[path] = make_float4(lw.x + add.x, lw.y + add.y, lw.z + add.z, lw.w);
+        }
+    }
+    stat_add(P.stats + 3, c_vertices);
+    stat_add(P.stats + 4, c_rr_tested);
+    stat_add(P.stats + 5, c_rr_killed);
+    stat_add(P.stats + 6, c_escaped);
+    stat_add(P.stats + 7, c_depth);
+}
+
+// ---- NEE resolve: unoccluded contributions land on their path (tracer.rs:1416-1443) ---------------
+__global__ void __launch_bounds__(kBlock) nee_resolve_kernel(const RenderParams P, int k) {
+    const int D = (int)P.st.max_depth;
+    const uint32_t n = P.q.counts[(D + 2) + k];
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        if (P.q.occ[i]) continue;
+        float4 c = P.q.scontrib[i];
+        if (c.x == 0.0f && c.y == 0.0f && c.z == 0.0f) continue;
+        uint32_t path = P.q.spath[i];
+        float4 lw = P.ps.L_w[path];
+        P.ps.L_w[path] = make_float4(lw.x + c.x, lw.y + c.y, lw.z + c.z, lw.w);
+    }
+}
+
+// closest_hit / shadow_rays = lengths of the queues that were traced (stats.rs:133-136)
+__global__ void ray_stats_kernel(const RenderParams P) {
+    const int D = (int)P.st.max_depth;
+    unsigned long long ch = 0, sh = 0;
+    for (int k = 0; k <= D; ++k) {
+        ch += P.q.counts[k];
+        sh += P.q.counts[(D + 2) + k];
+    }
+    atomicAdd(P.stats + 1, ch);
+    atomicAdd(P.stats + 2, sh);
+}
+
+// ---- film: add the finished samples of each pixel in sample order (tracer.rs:599-607) -----------
+__global__ void __launch_bounds__(kBlock) accumulate_kernel(const RenderParams P, const uint32_t* __restrict__ active, uint32_t nb, uint32_t s_count) {
+    for (uint32_t a = blockIdx.x * blockDim.x + threadIdx.x; a < nb; a += gridDim.x * blockDim.x) {
+        uint32_t pos = active[a];
+        float4 sw = P.px.sum_w[pos];
+        double2 lum = P.px.lum[pos];
+        for (uint32_t sl = 0; sl < s_count; ++sl) {
+            float4 lw = P.ps.L_w[(size_t)sl * nb + a];
+            V3 color = xyz(lw) * lw.w;
+            sw.x += color.x;
+            sw.y += color.y;
+            sw.z += color.z;
+            sw.w += lw.w;
+            double l = (double)luminance(color);
+            lum.x += l;
+            lum.y += l * l;
+        }
+        P.px.sum_w[pos] = sw;
+        P.px.lum[pos] = lum;
+        P.px.taken[pos] += s_count;
+    }
+}
+
+// ---- adaptive early stop (tracer.rs:609-617): which pixels enter the next round -------------------
+__global__ void __launch_bounds__(kBlock) adaptive_kernel(const RenderParams P, const uint32_t* __restrict__ active_in, uint32_t n_in, uint32_t* __restrict__ active_out,
+                                                          uint32_t* __restrict__ count_out) {
+    const double threshold = (double)P.st.variance_threshold;
+    const uint32_t min_spp = max(P.st.min_samples_per_pixel, 2u);
+    for (uint32_t a = blockIdx.x * blockDim.x + threadIdx.x; a < n_in; a += gridDim.x * blockDim.x) {
+        uint32_t pos = active_in[a];
+        uint32_t taken = P.px.taken[pos];
+        bool done = taken >= P.st.samples_per_pixel;
+        if (!done && P.st.adaptive && threshold > 0.0 && taken >= min_spp && taken % 4u == 0u) {
+            double2 lum = P.px.lum[pos];
+            double nn = (double)taken;
+            double var_of_mean = fmax((lum.y - lum.x * lum.x / nn) / (nn - 1.0) / nn, 0.0);
+            double mean = fmax(lum.x / nn, 1e-4);
+            done = sqrt(var_of_mean) / mean < threshold;
+        }
+        if (!done) active_out[queue_push(count_out)] = pos;
+    }
+}
+
+// ---- resolve the film (tracer.rs:627-634) ------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock) film_kernel(const RenderParams P, uint32_t n, float4* __restrict__ fb) {
+    for (uint32_t pos = blockIdx.x * blockDim.x + threadIdx.x; pos < n; pos += gridDim.x * blockDim.x) {
+        float4 sw = P.px.sum_w[pos];
+        uint32_t taken = P.px.taken[pos];
+        V3 mean = sw.w > 0.0f ? xyz(sw) / sw.w : xyz(sw) / (float)taken;
+        fb[P.px.pixels[pos]] = f4(mean, (float)taken);
+    }
+}
+
+struct Scratch {  // grow-only device buffers reused across crt_render calls on one world
+    size_t cap_paths = 0, cap_pixels = 0, cap_counts = 0;
+    void* paths = nullptr;   // everything sized by the path pool
+    void* pixels = nullptr;  // everything sized by the pixel count
+    uint32_t* counts = nullptr;
+    unsigned long long* stats = nullptr;
+    uint32_t* active_count = nullptr;  // 2 words
+    uint32_t* h_pinned = nullptr;      // pinned host mirror for small read-backs
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    ~Scratch() {
+        cudaFree(paths);
+        cudaFree(pixels);
+        cudaFree(counts);
+        cudaFree(stats);
+        cudaFree(active_count);
+        if (h_pinned) cudaFreeHost(h_pinned);
+        if (ev0) cudaEventDestroy(ev0);
+        if (ev1) cudaEventDestroy(ev1);
+    }
+};
+
+thread_local uint64_t t_last_launches = 0, t_last_rounds = 0;
+thread_local double t_last_ms = 0.0;
+
+}  // namespace
+
+struct crt_world {
+    crt_scene* scene = nullptr;
+    std::vector<Material> materials;
+    std::vector<uint32_t> geom_material;
+    std::vector<Light> lights;
+    Material* d_materials = nullptr;
+    uint32_t* d_geom_material = nullptr;
+    Light* d_lights = nullptr;
+    int32_t* d_geom_light = nullptr;
+    std::mutex mu;
+    Scratch scratch;
+    ~crt_world() {
+        cudaFree(d_materials);
+        cudaFree(d_geom_material);
+        cudaFree(d_lights);
+        cudaFree(d_geom_light);
+        if (scene) crt_scene_release(scene);
+    }
+};
+
+extern "C" {
+
+void crt_material_default(crt_material* out) {
+    if (!out) return;
+    Material m = material_default();
+    material_to_abi(m, out);
+}
+
+int crt_world_new(crt_scene* scene, const crt_material* materials, size_t n_materials, const uint32_t* geom_material, size_t n_geoms,
+                  const crt_light* lights, size_t n_lights, crt_world** out) {
+    if (!scene || !out || (n_materials && !materials) || (n_geoms && !geom_material) || (n_lights && !lights))
+        return crt::set_error(CRT_ERR_INVALID_ARG, "crt_world_new: null argument");
+    if (n_geoms != scene->n_geoms) return crt::set_error(CRT_ERR_INVALID_ARG, "crt_world_new: geom_material must have one entry per geometry of the scene");
+    for (size_t g = 0; g < n_geoms; ++g)
+        if (geom_material[g] >= n_materials) return crt::set_error(CRT_ERR_INVALID_ARG, "crt_world_new: material index out of range");
+    if (n_materials > 0xFFFEu) return crt::set_error(CRT_ERR_INVALID_ARG, "crt_world_new: at most 65534 distinct materials");
+    for (size_t l = 0; l < n_lights; ++l)
+        if (lights[l].kind > CRT_LIGHT_DOME) return crt::set_error(CRT_ERR_INVALID_ARG, "crt_world_new: unknown light kind");
+    int rc = crt::require_device();
+    if (rc) return rc;
+    auto* w = new crt_world();
+    crt_scene_retain(scene);
+    w->scene = scene;
+    for (size_t i = 0; i < n_materials; ++i) w->materials.push_back(material_from_abi(materials[i]));
+    w->geom_material.assign(geom_material, geom_material + n_geoms);
+    for (size_t i = 0; i < n_lights; ++i) w->lights.push_back(light_from_abi(lights[i]));
+    std::vector<int32_t> geom_light(n_geoms, -1);
+    for (size_t g = 0; g < n_geoms; ++g) geom_light[g] = light_find_by_geom(w->lights.data(), (int)w->lights.size(), (uint32_t)g);
+    auto up = [&](void** dst, const void* src, size_t bytes) -> cudaError_t {
+        cudaError_t e = cudaMalloc(dst, bytes ? bytes : 16);
+        if (e != cudaSuccess) return e;
+        return bytes ? cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice) : cudaSuccess;
+    };
+    cudaError_t e;
+    if ((e = up((void**)&w->d_materials, w->materials.data(), w->materials.size() * sizeof(Material))) != cudaSuccess ||
+        (e = up((void**)&w->d_geom_material, w->geom_material.data(), n_geoms * sizeof(uint32_t))) != cudaSuccess ||
+        (e = up((void**)&w->d_lights, w->lights.data(), w->lights.size() * sizeof(Light))) != cudaSuccess ||
+        (e = up((void**)&w->d_geom_light, geom_light.data(), n_geoms * sizeof(int32_t))) != cudaSuccess) {
+        delete w;
+        return crt::set_cuda_error(e, "crt_world_new upload");
+    }
+    *out = w;
+    return CRT_OK;
+}
+
+void crt_world_release(crt_world* w) { delete w; }
+
+int crt_render_last_info(uint64_t* launches, double* device_ms, uint64_t* rounds) {
+    if (launches) *launches = t_last_launches;
+    if (device_ms) *device_ms = t_last_ms;
+    if (rounds) *rounds = t_last_rounds;
+    return CRT_OK;
+}
+
+}  // extern "C"
+
+namespace {
+
+template <typename T>
+T* carve(char*& p, size_t count) {
+    T* r = (T*)p;
+    p += (count * sizeof(T) + 255) & ~(size_t)255;
+    return r;
+}
+size_t carve_bytes(size_t count, size_t elem) { return (count * elem + 255) & ~(size_t)255; }
+
+int render_impl(crt_world* w, const crt_camera* camera, const crt_render_settings* s, float* d_fb, crt_ray_stats* stats_out, cudaStream_t stream) {
+    if (!w || !camera || !s || !d_fb) return crt::set_error(CRT_ERR_INVALID_ARG, "crt_render: null argument");
+    if (s->width == 0 || s->height == 0 || (uint64_t)s->width * s->height > 0x7FFFFFFFu) return crt::set_error(CRT_ERR_INVALID_ARG, "crt_render: bad image size");
+    if (s->samples_per_pixel == 0 || s->samples_per_pixel > 65536u) return crt::set_error(CRT_ERR_INVALID_ARG, "crt_render: samples_per_pixel must be in 1..65536 (sampler index range)");
+    if (s->max_depth > 4096u) return crt::set_error(CRT_ERR_INVALID_ARG, "crt_render: max_depth too large");
+    if (s->pixel_filter > CRT_FILTER_MITCHELL || s->sampling_strategy > CRT_STRATEGY_BSDF_ONLY) return crt::set_error(CRT_ERR_INVALID_ARG, "crt_render: unknown filter or strategy");
+    if (s->tile_world > 1 && (s->tile_size == 0 || s->tile_rank >= s->tile_world)) return crt::set_error(CRT_ERR_INVALID_ARG, "crt_render: bad tile split");
+    int rc = crt::require_device();
+    if (rc) return rc;
+    if (w->scene->host_only) return crt::set_error(CRT_ERR_NO_DEVICE, "scene was committed host-only: nothing to render with");
+    std::lock_guard<std::mutex> lk(w->mu);
+    Scratch& sc = w->scratch;
+    const int sms = crt::device_sm_count();
+    const int D = (int)s->max_depth;
+    uint64_t launches = 0, trace_launches = 0, rounds = 0;
+
+    // ---- the pixels this process owns, tile by tile (interleaved tiles) ----
+    std::vector<uint32_t> pixels;
+    {
+        const uint32_t W = s->width, H = s->height;
+        if (s->tile_world <= 1) {
+            // whole image, in 8x4 blocks so a warp of camera rays covers a compact footprint
+            pixels.reserve((size_t)W * H);
+            for (uint32_t by = 0; by < H; by += 4)
+                for (uint32_t bx = 0; bx < W; bx += 8)
+                    for (uint32_t y = by; y < std::min(by + 4, H); ++y)
+                        for (uint32_t x = bx; x < std::min(bx + 8, W); ++x) pixels.push_back(y * W + x);
+        } else {
+            const uint32_t T = s->tile_size, tx = (W + T - 1) / T, ty = (H + T - 1) / T;
+            for (uint32_t t = s->tile_rank; t < tx * ty; t += s->tile_world) {
+                uint32_t x0 = (t % tx) * T, y0 = (t / tx) * T;
+                for (uint32_t by = y0; by < std::min(y0 + T, H); by += 4)
+                    for (uint32_t bx = x0; bx < std::min(x0 + T, W); bx += 8)
+                        for (uint32_t y = by; y < std::min({by + 4, y0 + T, H}); ++y)
+                            for (uint32_t x = bx; x < std::min({bx + 8, x0 + T, W}); ++x) pixels.push_back(y * W + x);
+            }
+        }
+    }
+    const uint32_t n_pix = (uint32_t)pixels.size();
+    if (!sc.ev0) {
+        CKR(cudaEventCreate(&sc.ev0));
+        CKR(cudaEventCreate(&sc.ev1));
+        CKR(cudaMalloc(&sc.stats, 8 * sizeof(unsigned long long)));
+        CKR(cudaMalloc(&sc.active_count, 2 * sizeof(uint32_t)));
+        CKR(cudaMallocHost(&sc.h_pinned, 64 * sizeof(uint32_t)));
+    }
+    CKR(cudaEventRecord(sc.ev0, stream));
+    CKR(cudaMemsetAsync(sc.stats, 0, 8 * sizeof(unsigned long long), stream));
+    if (n_pix == 0) {
+        CKR(cudaEventRecord(sc.ev1, stream));
+        CKR(cudaStreamSynchronize(stream));
+        if (stats_out) *stats_out = crt_ray_stats{};
+        t_last_launches = 0;
+        t_last_rounds = 0;
+        t_last_ms = 0.0;
+        return CRT_OK;
+    }
+
+    // ---- buffers ----
+    size_t cap = s->max_paths ? s->max_paths : ((size_t)1 << 22);
+    cap = std::max<size_t>(cap, 1024);
+    cap = std::min<size_t>(cap, (size_t)n_pix * s->samples_per_pixel);
+    cap = std::max<size_t>(cap, 1);
+    const bool motion = w->scene->has_motion;
+    {
+        size_t need = 3 * carve_bytes(cap, 16) + carve_bytes(cap, 8) + carve_bytes(cap, 4)                        // path state
+                      + 2 * (carve_bytes(2 * cap, 16) + 2 * carve_bytes(cap, 4)) + carve_bytes(2 * cap, 16) + carve_bytes(cap, 1)  // extend
+                      + carve_bytes(2 * cap, 16) + 2 * carve_bytes(cap, 4) + carve_bytes(cap, 16) + carve_bytes(cap, 1);          // shadow
+        if (need > sc.cap_paths) {
+            cudaFree(sc.paths);
+            sc.paths = nullptr;
+            sc.cap_paths = 0;
+            CKR(cudaMalloc(&sc.paths, need));
+            sc.cap_paths = need;
+        }
+        size_t need_px = carve_bytes(n_pix, 4) * 4 + carve_bytes(n_pix, 16) * 2;
+        if (need_px > sc.cap_pixels) {
+            cudaFree(sc.pixels);
+            sc.pixels = nullptr;
+            sc.cap_pixels = 0;
+            CKR(cudaMalloc(&sc.pixels, need_px));
+            sc.cap_pixels = need_px;
+        }
+        size_t need_counts = 4 * (size_t)(D + 2);
+        if (need_counts > sc.cap_counts) {
+            cudaFree(sc.counts);
+            sc.counts = nullptr;
+            sc.cap_counts = 0;
+            CKR(cudaMalloc(&sc.counts, need_counts * sizeof(uint32_t)));
+            sc.cap_counts = need_counts;
+        }
+    }
+    RenderParams P;
+    P.cam = camera_from_abi(*camera);
+    P.filter = filter_new(s->pixel_filter, s->filter_radius);
+    P.st = settings_from_abi(*s);
+    P.materials = w->d_materials;
+    P.geom_material = w->d_geom_material;
+    P.lights = w->d_lights;
+    P.geom_light = w->d_geom_light;
+    P.n_lights = (int)w->lights.size();
+    P.motion = motion ? 1 : 0;
+    P.stats = sc.stats;
+    {
+        char* p = (char*)sc.paths;
+        P.ps.beta_pdf = carve<float4>(p, cap);
+        P.ps.L_w = carve<float4>(p, cap);
+        P.ps.prevp = carve<float4>(p, cap);
+        P.ps.sampler = carve<uint2>(p, cap);
+        P.ps.time = carve<float>(p, cap);
+        for (int b = 0; b < 2; ++b) {
+            P.q.rays[b] = carve<float4>(p, 2 * cap);
+            P.q.path[b] = carve<uint32_t>(p, cap);
+            float* t = carve<float>(p, cap);
+            P.q.time[b] = motion ? t : nullptr;
+        }
+        P.q.hits = carve<float4>(p, 2 * cap);
+        P.q.ff = carve<uint8_t>(p, cap);
+        P.q.srays = carve<float4>(p, 2 * cap);
+        float* st = carve<float>(p, cap);
+        P.q.stime = motion ? st : nullptr;
+        P.q.spath = carve<uint32_t>(p, cap);
+        P.q.scontrib = carve<float4>(p, cap);
+        P.q.occ = carve<uint8_t>(p, cap);
+        P.q.counts = sc.counts;
+    }
+    uint32_t* d_active[2];
+    {
+        char* p = (char*)sc.pixels;
+        uint32_t* d_pixels = carve<uint32_t>(p, n_pix);
+        d_active[0] = carve<uint32_t>(p, n_pix);
+        d_active[1] = carve<uint32_t>(p, n_pix);
+        P.px.taken = carve<uint32_t>(p, n_pix);
+        P.px.sum_w = carve<float4>(p, n_pix);
+        P.px.lum = (double2*)carve<float4>(p, n_pix);
+        P.px.pixels = d_pixels;
+        CKR(cudaMemcpyAsync(d_pixels, pixels.data(), (size_t)n_pix * 4, cudaMemcpyHostToDevice, stream));
+        std::vector<uint32_t> iota(n_pix);
+        for (uint32_t i = 0; i < n_pix; ++i) iota[i] = i;
+        CKR(cudaMemcpyAsync(d_active[0], iota.data(), (size_t)n_pix * 4, cudaMemcpyHostToDevice, stream));
+        CKR(cudaStreamSynchronize(stream));  // the staging vectors die with this scope
+        CKR(cudaMemsetAsync(P.px.taken, 0, (size_t)n_pix * 4, stream));
+        CKR(cudaMemsetAsync(P.px.sum_w, 0, (size_t)n_pix * 16, stream));
+        CKR(cudaMemsetAsync(P.px.lum, 0, (size_t)n_pix * 16, stream));
+    }
+    auto grid_for = [&](size_t n) {
+        size_t blocks = (n + kBlock - 1) / kBlock;
+        return (int)std::max<size_t>(1, std::min<size_t>(blocks, (size_t)sms * 8));
+    };
+
+    // ---- one wavefront: `nb` pixels (active[off .. off+nb)) x samples [s_base, s_base + s_count) ----
+    auto wavefront = [&](const uint32_t* active, uint32_t nb, uint32_t s_base, uint32_t s_count) -> int {
+        const uint32_t total = nb * s_count;
+        CKR(cudaMemsetAsync(sc.counts, 0, 4 * (size_t)(D + 2) * sizeof(uint32_t), stream));
+        raygen_kernel<<<grid_for(total), kBlock, 0, stream>>>(P, active, nb, s_base, s_count);
+        ++launches;
+        if (D == 0) {
+            // max_depth 0: every path ends at `remaining <= 0` before tracing anything (tracer.rs:1123-1148)
+            return CRT_OK;
+        }
+        for (int k = 0; k <= D; ++k) {
+            const int cur = k & 1;
+            crt::QueueTrace qt;
+            qt.rays = P.q.rays[cur];
+            qt.time = P.q.time[cur];
+            qt.mask_uniform = k == 0 ? CRT_MASK_CAMERA : CRT_MASK_INDIRECT;
+            qt.hits = P.q.hits;
+            qt.flag = P.q.ff;
+            qt.n_dev = sc.counts + k;
+            qt.capacity = total;
+            qt.counter = sc.counts + 2 * (D + 2) + k;
+            int r = crt::enqueue_queue_trace(w->scene, false, qt, stream);
+            if (r) return r;
+            shade_kernel<<<grid_for(total), kBlock, 0, stream>>>(P, k, cur);
+            launches += 2;
+            ++trace_launches;
+            if (k < D && P.n_lights > 0 && strategy_samples_lights(P.st.sampling_strategy)) {
+                crt::QueueTrace qs;
+                qs.rays = P.q.srays;
+                qs.time = P.q.stime;
+                qs.mask_uniform = CRT_MASK_SHADOW;
+                qs.hits = nullptr;
+                qs.flag = P.q.occ;
+                qs.n_dev = sc.counts + (D + 2) + k;
+                qs.capacity = total;
+                qs.counter = sc.counts + 3 * (D + 2) + k;
+                r = crt::enqueue_queue_trace(w->scene, true, qs, stream);
+                if (r) return r;
+                nee_resolve_kernel<<<grid_for(total), kBlock, 0, stream>>>(P, k);
+                launches += 2;
+                ++trace_launches;
+            }
+            // Every few bounces look at the next queue's length so a dead wavefront stops launching.
+            if (k >= 5 && k < D && ((k - 5) % 4) == 0) {
+                CKR(cudaMemcpyAsync(sc.h_pinned, sc.counts + k + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+                CKR(cudaStreamSynchronize(stream));
+                if (sc.h_pinned[0] == 0) break;
+            }
+        }
+        ray_stats_kernel<<<1, 1, 0, stream>>>(P);
+        ++launches;
+        return CRT_OK;
+    };
+
+    // ---- rounds (tracer.rs:558-618): samples are taken in order; the adaptive test runs after every
+    //      4th sample once min_spp is reached, so rounds end on those boundaries ----
+    const uint32_t spp = s->samples_per_pixel;
+    const bool adaptive = s->adaptive && s->variance_threshold > 0.0f;
+    const uint32_t min_spp = std::max(s->min_samples_per_pixel, 2u);
+    uint32_t n_active = n_pix, s_base = 0;
+    int cur_list = 0;
+    while (n_active > 0 && s_base < spp) {
+        uint32_t round_samples;
+        if (!adaptive)
+            round_samples = spp - s_base;
+        else if (s_base == 0)
+            round_samples = std::min(spp, (min_spp + 3u) / 4u * 4u);
+        else
+            round_samples = std::min(spp - s_base, 4u);
+        // split the round into wavefronts that fit the pool
+        uint32_t sub = (uint32_t)std::max<size_t>(1, std::min<size_t>(round_samples, cap / n_active));
+        uint32_t block_px = (uint32_t)std::min<size_t>(n_active, cap / sub);
+        for (uint32_t s0 = 0; s0 < round_samples; s0 += sub) {
+            uint32_t sc_count = std::min(sub, round_samples - s0);
+            for (uint32_t off = 0; off < n_active; off += block_px) {
+                uint32_t nb = std::min(block_px, n_active - off);
+                int r = wavefront(d_active[cur_list] + off, nb, s_base + s0, sc_count);
+                if (r) return r;
+                accumulate_kernel<<<grid_for(nb), kBlock, 0, stream>>>(P, d_active[cur_list] + off, nb, sc_count);
+                ++launches;
+            }
+        }
+        s_base += round_samples;
+        ++rounds;
+        if (s_base >= spp) break;
+        CKR(cudaMemsetAsync(sc.active_count, 0, sizeof(uint32_t), stream));
+        adaptive_kernel<<<grid_for(n_active), kBlock, 0, stream>>>(P, d_active[cur_list], n_active, d_active[cur_list ^ 1], sc.active_count);
+        ++launches;
+        CKR(cudaMemcpyAsync(sc.h_pinned, sc.active_count, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+        CKR(cudaStreamSynchronize(stream));
+        n_active = sc.h_pinned[0];
+        cur_list ^= 1;
+    }
+    film_kernel<<<grid_for(n_pix), kBlock, 0, stream>>>(P, n_pix, (float4*)d_fb);
+    ++launches;
+    CKR(cudaGetLastError());
+    CKR(cudaMemcpyAsync(sc.h_pinned + 16, sc.stats, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
+    CKR(cudaEventRecord(sc.ev1, stream));
+    CKR(cudaStreamSynchronize(stream));
+    float ms = 0.0f;
+    CKR(cudaEventElapsedTime(&ms, sc.ev0, sc.ev1));
+    crt::count_launches(launches - trace_launches);  // traversal launches were already counted by enqueue_queue_trace
+    if (stats_out) {
+        const unsigned long long* st = (const unsigned long long*)(sc.h_pinned + 16);
+        stats_out->camera_rays = st[0];
+        stats_out->closest_hit = st[1];
+        stats_out->shadow_rays = st[2];
+        stats_out->vertices = st[3];
+        stats_out->rr_tested = st[4];
+        stats_out->rr_killed = st[5];
+        stats_out->ended_escaped = st[6];
+        stats_out->ended_depth = st[7];
+        if (D == 0) stats_out->ended_depth = st[0];
+    }
+    t_last_launches = launches;
+    t_last_rounds = rounds;
+    t_last_ms = (double)ms;
+    return CRT_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int crt_render(const crt_world* w, const crt_camera* camera, const crt_render_settings* settings, float* framebuffer, crt_ray_stats* stats, void* stream) {
+    return render_impl(const_cast<crt_world*>(w), camera, settings, framebuffer, stats, (cudaStream_t)stream);
+}
+
+int crt_render_host(const crt_world* w, const crt_camera* camera, const crt_render_settings* settings, float* framebuffer, crt_ray_stats* stats) {
+    if (!settings || !framebuffer) return crt::set_error(CRT_ERR_INVALID_ARG, "crt_render_host: null argument");
+    int rc = crt::require_device();
+    if (rc) return rc;
+    size_t bytes = (size_t)settings->width * settings->height * 16;
+    float* d = nullptr;
+    CKR(cudaMalloc(&d, bytes ? bytes : 16));
+    cudaError_t e = cudaMemcpy(d, framebuffer, bytes, cudaMemcpyHostToDevice);  // pixels of other ranks stay as given
+    if (e == cudaSuccess) {
+        rc = render_impl(const_cast<crt_world*>(w), camera, settings, d, stats, nullptr);
+        if (rc == CRT_OK) e = cudaMemcpy(framebuffer, d, bytes, cudaMemcpyDeviceToHost);
+    }
+    cudaFree(d);
+    if (e != cudaSuccess) return crt::set_cuda_error(e, "crt_render_host copy");
+    return rc;
+}
+
+}  // extern "C"

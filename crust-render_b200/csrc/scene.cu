@@ -15,6 +15,7 @@
 #include "crt.h"
 #include "host_build.h"
 #include "launch.h"
+#include "internal.h"
 
 using namespace crt;
 
@@ -87,38 +88,6 @@ struct crt_builder {
     std::vector<Geom> geoms;
 };
 
-struct crt_scene {
-    std::atomic<int> refs{1};
-    HostTree* host = nullptr;  // kept only with CRT_COMMIT_KEEP_HOST_TREE
-    bool non_empty = false;
-    Box root{};
-    bool has_motion = false;
-    uint32_t n_geoms = 0;
-    uint64_t n_prims = 0;
-    crt_primitive_breakdown breakdown{};
-    uint32_t instance_depth = 0;
-    uint32_t features = 0;  // FEAT_* over this scene and everything below it
-    float extent_sum = 0, extent_max = 0;
-    std::vector<crt_scene*> children;  // distinct instanced scenes, retained
-    crt_build_info info{};
-    // device
-    bool host_only = false;
-    void *d_nodes = nullptr, *d_leafs = nullptr, *d_prim_ids = nullptr, *d_normals = nullptr, *d_motion = nullptr;
-    DevScene desc{};
-    DevScene* d_desc = nullptr;
-    crt_memory_footprint footprint{};
-
-    ~crt_scene() {
-        delete host;
-        cudaFree(d_nodes);
-        cudaFree(d_leafs);
-        cudaFree(d_prim_ids);
-        cudaFree(d_normals);
-        cudaFree(d_motion);
-        cudaFree(d_desc);
-        for (crt_scene* c : children) crt_scene_release(c);
-    }
-};
 
 namespace {
 ChildInfo child_info_of(crt_scene* s) { return ChildInfo{s->non_empty, s->root, s->has_motion, s->instance_depth}; }
@@ -545,6 +514,8 @@ static int launch_query(const crt_scene* s, bool any_hit, size_t n, const crt_ra
         p.counter = g_dev.counters + (g_dev.next_counter.fetch_add(1) % kCounterRing);
         p.status = g_dev.status;
         p.n = (uint32_t)cnt;
+        p.n_dev = nullptr;
+        p.mask_uniform = CRT_MASK_ALL;
         int grid = g_dev.sm_count * per_sm;
         size_t need = (cnt + CRT_BLOCK - 1) / CRT_BLOCK;
         if ((size_t)grid > need) grid = (int)need;
@@ -736,3 +707,35 @@ int crt_debug_tree_export(const crt_scene* s, void* nodes, uint32_t* tri_counts,
 }
 
 }  // extern "C"
+
+// ---- library-internal interface (internal.h) -----------------------------------------------
+namespace crt {
+int set_error(int code, const std::string& msg) { return fail(code, msg); }
+int set_cuda_error(cudaError_t e, const char* what) { return fail_cuda(e, what); }
+int require_device() { return ensure_device(); }
+int device_sm_count() { return g_dev.sm_count; }
+unsigned int* device_status_word() { return g_dev.status; }
+void count_launches(uint64_t n) { g_dev.launches.fetch_add(n); }
+
+int enqueue_queue_trace(const crt_scene* s, bool any_hit, const QueueTrace& q, cudaStream_t stream) {
+    if (!s || s->host_only) return fail(CRT_ERR_NO_DEVICE, "scene has no device data");
+    TraceParams p;
+    p.scene = s->desc;
+    p.rays = q.rays;
+    p.time = q.time;
+    p.mask = nullptr;
+    p.mask_uniform = q.mask_uniform;
+    p.hits = q.hits;
+    p.flag = q.flag;
+    p.counter = q.counter;
+    p.status = g_dev.status;
+    p.n = q.capacity;
+    p.n_dev = q.n_dev;
+    int grid = g_dev.sm_count * trace_blocks_per_sm(any_hit, s->features);
+    size_t need = ((size_t)q.capacity + CRT_BLOCK - 1) / CRT_BLOCK;
+    if ((size_t)grid > need) grid = (int)(need ? need : 1);
+    CK(launch_trace(any_hit, s->features, p, grid, stream));
+    g_dev.launches.fetch_add(1);
+    return CRT_OK;
+}
+}  // namespace crt

@@ -34,6 +34,8 @@ __global__ void __launch_bounds__(CRT_BLOCK, ANY_HIT ? CRT_MINBLOCKS_ANY : CRT_M
 
     const unsigned lane = threadIdx.x & 31u;
     const unsigned tid = threadIdx.x;
+    // wavefront queues pass their length by device pointer (written by the producing kernel)
+    const uint32_t n_rays = p.n_dev ? min(__ldg(p.n_dev), p.n) : p.n;
     constexpr bool INST = (FEAT & FEAT_INSTANCE) != 0;
 
     // ---- per-ray state -------------------------------------------------------
@@ -387,13 +389,13 @@ __global__ void __launch_bounds__(CRT_BLOCK, ANY_HIT ? CRT_MINBLOCKS_ANY : CRT_M
                 base = __shfl_sync(0xFFFFFFFFu, base, leader);
                 if (state == IDLE) {
                     uint32_t idx = base + __popc(idle & ((1u << lane) - 1u));
-                    if (idx < p.n) {
+                    if (idx < n_rays) {
                         float4 a = __ldg(p.rays + 2 * (size_t)idx), b = __ldg(p.rays + 2 * (size_t)idx + 1);
                         ray_idx = idx;
                         t_min = a.w;
                         closest = b.w;
                         time = p.time ? __ldg(p.time + idx) : 0.0f;
-                        ray_mask = p.mask ? __ldg(p.mask + idx) : 0xFFFFFFFFu;
+                        ray_mask = p.mask ? __ldg(p.mask + idx) : p.mask_uniform;
                         world_o = f3(a.x, a.y, a.z);
                         world_d = f3(b.x, b.y, b.z);
                         r.set(world_o, world_d, p.scene.has_triangles != 0);
@@ -410,8 +412,8 @@ __global__ void __launch_bounds__(CRT_BLOCK, ANY_HIT ? CRT_MINBLOCKS_ANY : CRT_M
                         if (p.scene.n_nodes != 0) push(make_entry(0u, t_min));
                     }
                 }
-                if (base + (unsigned)__popc(idle) >= p.n) exhausted = true;
-                if (base >= p.n && act == 0u) break;  // nothing left anywhere in this warp
+                if (base + (unsigned)__popc(idle) >= n_rays) exhausted = true;
+                if (base >= n_rays && act == 0u) break;  // nothing left anywhere in this warp
             }
         }
 

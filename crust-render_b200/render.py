@@ -1,0 +1,112 @@
+"""Engine side of the seam over libcrt_b200.so: `WorldBuilder` / `World` (crates/crust-core/src/
+rt_world.rs:142-293) and `Renderer` (tracer.rs:136-212), bound to include/crt_render.h. The render
+itself is the CUDA wavefront integrator (csrc/render.cu); there is no host fallback."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import numpy as np
+
+from . import rt
+from .render_types import (  # noqa: F401
+    LIGHT_DTYPE,
+    MATERIAL_DTYPE,
+    STATS_DTYPE,
+    Camera,
+    DistantLight,
+    DomeLight,
+    Emissive,
+    LightList,
+    OpenPBR,
+    PixelFilter,
+    PixelFilterKind,
+    RayStats,
+    RectLight,
+    RenderSettings,
+    SamplingStrategy,
+    SphereLight,
+    WorldBuilderBase,
+)
+
+__all__ = ["World", "WorldBuilder", "Renderer", "Camera", "RenderSettings", "SamplingStrategy", "PixelFilter", "PixelFilterKind",
+           "RayStats", "LightList", "OpenPBR", "Emissive", "SphereLight", "RectLight", "DistantLight", "DomeLight"]
+
+
+def _p(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class World:
+    """rt_world.rs:244-293 (+ the LightList, which the reference hands to the Renderer separately)."""
+
+    def __init__(self, scene: "rt.Scene", materials: np.ndarray, geom_material: np.ndarray, lights: LightList):
+        self.scene = scene
+        self._lights = lights.records()
+        h = C.c_void_p()
+        rt._ck(rt.lib().crt_world_new(scene._h, _p(materials), len(materials), _p(geom_material), len(geom_material), _p(self._lights),
+                                      len(self._lights), C.byref(h)))
+        self._h = h
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            rt.lib().crt_world_release(self._h)
+            self._h = None
+
+    def count(self) -> int:
+        return self.scene.geometry_count()
+
+    def has_motion(self) -> bool:
+        return self.scene.has_motion()
+
+    def bounds(self):
+        return self.scene.bounds()
+
+    def primitive_count(self) -> int:
+        return self.scene.primitive_count()
+
+
+class WorldBuilder(WorldBuilderBase):
+    def _new_scene_builder(self):
+        return rt.SceneBuilder()
+
+    def commit(self, lights: Optional[LightList] = None) -> World:  # rt_world.rs:235-241
+        mats, gm = self.material_table()
+        return World(self._sb.commit(), mats, gm, lights or LightList())
+
+
+class Renderer:
+    """`Renderer::new(camera, world, lights, settings)` (tracer.rs:149-163); lights live in the World here."""
+
+    def __init__(self, camera: Camera, world: World, settings: RenderSettings):
+        self.camera, self.world, self.settings = camera, world, settings
+        self.device_ms = 0.0
+        self.launches = 0
+        self.rounds = 0
+
+    def _info(self):
+        n, ms, r = C.c_uint64(), C.c_double(), C.c_uint64()
+        rt.lib().crt_render_last_info(C.byref(n), C.byref(ms), C.byref(r))
+        self.launches, self.device_ms, self.rounds = n.value, ms.value, r.value
+
+    def render_with_stats(self, out: Optional[np.ndarray] = None):
+        """tracer.rs:194-200. Returns (framebuffer[h, w, 4] with row 0 = bottom row, RayStats)."""
+        st = self.settings
+        fb = out if out is not None else np.zeros((st.height, st.width, 4), dtype=np.float32)
+        assert fb.dtype == np.float32 and fb.shape == (st.height, st.width, 4) and fb.flags.c_contiguous
+        stats = np.zeros((), dtype=STATS_DTYPE)
+        cam, rec = self.camera.record(), st.record()
+        rt._ck(rt.lib().crt_render_host(self.world._h, _p(cam), _p(rec), _p(fb), _p(stats)))
+        self._info()
+        return fb, RayStats.from_record(stats)
+
+    def render(self) -> np.ndarray:  # tracer.rs:172-174
+        return self.render_with_stats()[0]
+
+    def render_device(self, fb_ptr: int, stream: int = 0) -> RayStats:
+        """Same with a device framebuffer (width*height float4) and a CUDA stream."""
+        stats = np.zeros((), dtype=STATS_DTYPE)
+        cam, rec = self.camera.record(), self.settings.record()
+        rt._ck(rt.lib().crt_render(self.world._h, _p(cam), _p(rec), C.c_void_p(fb_ptr), _p(stats), C.c_void_p(stream)))
+        self._info()
+        return RayStats.from_record(stats)

@@ -128,12 +128,17 @@ def lib() -> C.CDLL:
         "crt_device_status": [u32p],
         "crt_debug_tree_sizes": [vp, C.POINTER(u64)],
         "crt_debug_tree_export": [vp, vp, u32p, u32p, u32p],
+        # include/crt_render.h
+        "crt_world_new": [vp, vp, sz, vp, sz, vp, sz, C.POINTER(vp)],
+        "crt_render": [vp, vp, vp, vp, vp, vp],
+        "crt_render_host": [vp, vp, vp, vp, vp],
+        "crt_render_last_info": [C.POINTER(u64), C.POINTER(C.c_double), C.POINTER(u64)],
     }
     for name, args in sig.items():
         fn = getattr(L, name)
         fn.argtypes = args
         fn.restype = C.c_int
-    for name in ("crt_builder_free", "crt_scene_retain", "crt_scene_release"):
+    for name in ("crt_builder_free", "crt_scene_retain", "crt_scene_release", "crt_world_release", "crt_material_default"):
         getattr(L, name).argtypes = [vp]
         getattr(L, name).restype = None
     L.crt_launch_count.restype = u64

@@ -7,4 +7,7 @@ __path__.insert(0, _os.path.join(_os.path.dirname(_os.path.dirname(_os.path.absp
 from .rt import *  # noqa: E402,F401,F403
 from .rt import __all__ as _rt_all  # noqa: E402
 
-__all__ = list(_rt_all)
+from .render import *  # noqa: E402,F401,F403
+from .render import __all__ as _render_all  # noqa: E402
+
+__all__ = list(_rt_all) + list(_render_all)

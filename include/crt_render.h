@@ -1,0 +1,148 @@
+/* crt_render.h — C ABI of the wavefront path tracer that sits on top of crt.h.
+ *
+ * BASELINE.json's north_star moves crust-core's integrator loop onto the device
+ * (a one-ray-per-call CPU seam cannot feed a GPU), so besides the crust-rt seam
+ * (crt.h) the library exports the engine-side records the integrator reads and
+ * one render entry. Every `file:line` is relative to
+ * /root/reference/crates/crust-core/src.
+ *
+ *   crt_world      rt_world.rs:142-293   World: committed scene + geom_id-indexed material table
+ *                  light.rs:404-446      LightList
+ *   crt_material   material/openpbr.rs:66-173 OpenPBR parameters (spec defaults), material/emissive.rs
+ *   crt_light      light.rs:21-304       AreaLight{Sphere,Rect}, DistantLight, uniform DomeLight
+ *   crt_camera     camera.rs:27-59       Camera::new arguments
+ *   crt_render_settings tracer.rs:639-661 RenderSettings + filter.rs:28-60 PixelFilter
+ *   crt_ray_stats  stats.rs:128-146      RayStats
+ *   crt_render     tracer.rs:194-212     Renderer::render_with_stats (non-guided pass)
+ *
+ * No CPU fallback: crt_render fails with CRT_ERR_NO_DEVICE without a CUDA device.
+ */
+#ifndef CRT_RENDER_H
+#define CRT_RENDER_H
+#include "crt.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CRT_MAT_OPENPBR 0u
+#define CRT_MAT_EMISSIVE 1u
+
+/* openpbr.rs:66-128 (field order), defaults :130-173 via crt_material_default(). 236 bytes. */
+typedef struct crt_material {
+    uint32_t kind;
+    float base_weight;
+    float base_color[3];
+    float base_diffuse_roughness, base_metalness;
+    float specular_weight;
+    float specular_color[3];
+    float specular_roughness, specular_ior, specular_roughness_anisotropy;
+    float transmission_weight;
+    float transmission_color[3];
+    float transmission_depth;
+    float transmission_scatter[3];
+    float transmission_scatter_anisotropy, transmission_dispersion_scale, transmission_dispersion_abbe_number;
+    float subsurface_weight;
+    float subsurface_color[3];
+    float subsurface_radius;
+    float subsurface_radius_scale[3];
+    float subsurface_scatter_anisotropy;
+    float fuzz_weight;
+    float fuzz_color[3];
+    float fuzz_roughness;
+    float coat_weight;
+    float coat_color[3];
+    float coat_roughness, coat_roughness_anisotropy, coat_ior, coat_darkening;
+    float thin_film_weight, thin_film_thickness, thin_film_ior;
+    float emission_luminance;
+    float emission_color[3];
+    float geometry_opacity;
+    uint32_t geometry_thin_walled;
+    float emissive_color[3]; /* CRT_MAT_EMISSIVE: Emissive::color (emissive.rs:12-14) */
+} crt_material;
+
+#define CRT_LIGHT_SPHERE 0u  /* light.rs:21-44  SphereShape: a = center, r = radius */
+#define CRT_LIGHT_RECT 1u    /* light.rs:55-81  RectShape: a = origin, b = edge_u, c = edge_v, n = unit normal */
+#define CRT_LIGHT_DISTANT 2u /* light.rs:234-304: n = unit travel direction, r = cos(half angle), s = cone solid angle */
+#define CRT_LIGHT_DOME 3u    /* light.rs:320-389, uniform (no environment map): radiance = tint */
+#define CRT_NO_GEOM 0xFFFFFFFFu
+
+/* 76 bytes */
+typedef struct crt_light {
+    uint32_t kind;
+    uint32_t geom_id; /* world geom_id of the emissive geometry an area light shares (light.rs:150-160), else CRT_NO_GEOM */
+    float radiance[3];
+    float a[3], b[3], c[3], n[3];
+    float r, s;
+} crt_light;
+
+/* camera.rs:27-35 */
+typedef struct crt_camera {
+    float lookfrom[3], lookat[3], vup[3];
+    float vfov_deg, aspect, aperture, focus_dist;
+} crt_camera;
+
+#define CRT_FILTER_BOX 0u
+#define CRT_FILTER_TRIANGLE 1u
+#define CRT_FILTER_GAUSSIAN 2u
+#define CRT_FILTER_BLACKMAN 3u
+#define CRT_FILTER_MITCHELL 4u
+#define CRT_STRATEGY_POWER_MIS 0u
+#define CRT_STRATEGY_BALANCE_MIS 1u
+#define CRT_STRATEGY_LIGHT_ONLY 2u
+#define CRT_STRATEGY_BSDF_ONLY 3u
+
+typedef struct crt_render_settings {
+    /* tracer.rs:639-661 */
+    uint32_t width, height;
+    uint32_t samples_per_pixel, max_depth, min_samples_per_pixel;
+    float variance_threshold; /* 0 disables adaptive early stopping */
+    int32_t frame;            /* sampler seed */
+    uint32_t sampling_strategy;
+    uint32_t adaptive; /* 1 = final-pass behaviour (tracer.rs:216-223) */
+    uint32_t pixel_filter;
+    float filter_radius;
+    /* multi-GPU image split: square tiles of `tile_size` pixels, tile t rendered by the
+     * process with tile_rank == t % tile_world. tile_world <= 1: the whole image. Pixels of other
+     * ranks are left untouched in the framebuffer. */
+    uint32_t tile_size, tile_rank, tile_world;
+    /* wavefront pool: at most this many paths in flight (0 = library default). */
+    uint32_t max_paths;
+    uint32_t reserved;
+} crt_render_settings;
+
+/* stats.rs:128-146 */
+typedef struct crt_ray_stats {
+    uint64_t camera_rays, closest_hit, shadow_rays, vertices, rr_tested, rr_killed, ended_escaped, ended_depth;
+} crt_ray_stats;
+
+typedef struct crt_world crt_world;
+
+/* openpbr.rs:130-173 Default for OpenPBR */
+void crt_material_default(crt_material* out);
+/* World (rt_world.rs:142-242 WorldBuilder::commit) + LightList. Retains `scene`; inputs are copied.
+ * geom_material[g] = index into `materials` of the material bound to geom_id g (n_geoms must equal
+ * the scene's geometry count). */
+int crt_world_new(crt_scene* scene, const crt_material* materials, size_t n_materials, const uint32_t* geom_material,
+                  size_t n_geoms, const crt_light* lights, size_t n_lights, crt_world** out);
+void crt_world_release(crt_world* w);
+
+/* Renderer::render_with_stats (tracer.rs:194-212): one non-guided pass. `framebuffer` is a DEVICE
+ * pointer to width*height float4 {r, g, b, samples taken}; row j is image row j counted from the
+ * bottom (buffer.rs:40-44; the reference flips on read, :74-77). Work is enqueued on `stream`;
+ * the call synchronises that stream before returning because adaptive rounds are decided from
+ * device-side counts. `stats` may be NULL. */
+int crt_render(const crt_world* w, const crt_camera* camera, const crt_render_settings* settings, float* framebuffer,
+               crt_ray_stats* stats, void* stream);
+/* Same with a HOST framebuffer (D2H inside). */
+int crt_render_host(const crt_world* w, const crt_camera* camera, const crt_render_settings* settings,
+                    float* framebuffer, crt_ray_stats* stats);
+
+/* Kernel launches issued by the last crt_render* call of this thread, and the device time it took
+ * (CUDA events on the render stream), for bench.py. */
+int crt_render_last_info(uint64_t* launches, double* device_ms, uint64_t* rounds);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CRT_RENDER_H */

@@ -405,3 +405,142 @@ int orc_test_clip_triangle_aabb(const float* v9, int axis, float mn, float mx, f
 uint32_t orc_sizeof_wide_node() { return (uint32_t)sizeof(WideNode); }
 
 }  // extern "C"
+
+// ---- integrator (crt_oracle_render.hpp) -----------------------------------------------------
+#include "../crust-render_b200/csrc/shade/abi_convert.h"
+#include "crt_oracle_render.hpp"
+
+namespace {
+struct WorldHandle {
+    orcr::World world;
+};
+shade::V3 sv(const float* p) { return shade::v3(p[0], p[1], p[2]); }
+void put3(float* o, shade::V3 v) {
+    o[0] = v.x;
+    o[1] = v.y;
+    o[2] = v.z;
+}
+shade::SurfaceHit surface(const float* p, const float* n, int front_face) {
+    shade::SurfaceHit r;
+    r.p = sv(p);
+    r.normal = sv(n);
+    r.t = 1.0f;
+    r.front_face = front_face != 0;
+    return r;
+}
+}  // namespace
+
+extern "C" {
+void* orc_world_new(void* scene, const crt_material* materials, size_t n_materials, const uint32_t* geom_material, size_t n_geoms,
+                    const crt_light* lights, size_t n_lights) {
+    auto* h = new WorldHandle();
+    h->world.scene = ((SceneHandle*)scene)->scene;
+    for (size_t i = 0; i < n_materials; ++i) h->world.materials.push_back(shade::material_from_abi(materials[i]));
+    h->world.geom_material.assign(geom_material, geom_material + n_geoms);
+    for (size_t i = 0; i < n_lights; ++i) h->world.lights.push_back(shade::light_from_abi(lights[i]));
+    return h;
+}
+void orc_world_free(void* w) { delete (WorldHandle*)w; }
+// returns seconds
+double orc_render(void* w, const crt_camera* cam, const crt_render_settings* st, float* fb, double* var_map, uint64_t* stats8, int threads) {
+    shade::Camera c = shade::camera_from_abi(*cam);
+    shade::Filter f = shade::filter_new(st->pixel_filter, st->filter_radius);
+    shade::RenderSettings s = shade::settings_from_abi(*st);
+    auto t0 = std::chrono::steady_clock::now();
+    orcr::RayStats rs = orcr::render(((WorldHandle*)w)->world, c, f, s, fb, var_map, threads, st->tile_size, st->tile_rank, st->tile_world);
+    double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    if (stats8) {
+        uint64_t v[8] = {rs.camera_rays, rs.closest_hit, rs.shadow_rays, rs.vertices, rs.rr_tested, rs.rr_killed, rs.ended_escaped, rs.ended_depth};
+        for (int i = 0; i < 8; ++i) stats8[i] = v[i];
+    }
+    return dt;
+}
+
+// ---- shading-math hooks for the known-answer tests (tests/test_shade_kats.py) ----------------
+void orc_material_default(crt_material* out) {
+    shade::Material m = shade::material_default();
+    shade::material_to_abi(m, out);
+}
+void orc_material_pmf(const crt_material* m, float* out5) {
+    shade::Material mm = shade::material_from_abi(*m);
+    out5[0] = mm.pmf.p_diffuse;
+    out5[1] = mm.pmf.p_specular;
+    out5[2] = mm.pmf.p_coat;
+    out5[3] = mm.pmf.p_fuzz;
+    out5[4] = mm.pmf.p_transmission;
+}
+int orc_material_medium(const crt_material* m, float* sigma_a3, float* sigma_s3, float* g) {
+    shade::Material mm = shade::material_from_abi(*m);
+    put3(sigma_a3, mm.medium.sigma_a);
+    put3(sigma_s3, mm.medium.sigma_s);
+    *g = mm.medium.g;
+    return (int)mm.has_medium;
+}
+int orc_material_eval(const crt_material* m, const float* ray_dir, const float* p, const float* normal, int front_face, const float* wi, float* value3,
+                      float* pdf) {
+    shade::Material mm = shade::material_from_abi(*m);
+    shade::V3 v;
+    bool ok = shade::material_eval(mm, sv(ray_dir), surface(p, normal, front_face), sv(wi), v, *pdf);
+    if (ok) put3(value3, v);
+    return ok ? 1 : 0;
+}
+// out: origin3, dir3, value3, pdf, delta, enters_medium (11 floats)
+int orc_material_scatter(const crt_material* m, const float* ray_dir, const float* p, const float* normal, int front_face, const float* s4, float* out11) {
+    shade::Material mm = shade::material_from_abi(*m);
+    shade::ScatterSample ss;
+    if (!shade::material_scatter(mm, sv(ray_dir), surface(p, normal, front_face), s4, ss)) return 0;
+    put3(out11, ss.origin);
+    put3(out11 + 3, ss.dir);
+    put3(out11 + 6, ss.value);
+    out11[9] = ss.pdf;
+    out11[10] = (ss.delta ? 1.0f : 0.0f) + (ss.enters_medium ? 2.0f : 0.0f);
+    return 1;
+}
+void orc_material_emitted_directional(const crt_material* m, float cos_o, float* out3) {
+    put3(out3, shade::material_emitted_directional(shade::material_from_abi(*m), cos_o));
+}
+// out: direction3, radiance3, distance, pdf
+int orc_light_sample_li(const crt_light* l, const float* from, float u, float v, float* out8) {
+    shade::LightSample ls;
+    if (!shade::light_sample_li(shade::light_from_abi(*l), sv(from), u, v, ls)) return 0;
+    put3(out8, ls.direction);
+    put3(out8 + 3, ls.radiance);
+    out8[6] = ls.distance;
+    out8[7] = ls.pdf;
+    return 1;
+}
+float orc_light_pdf_at_point(const crt_light* l, const float* from, const float* point) {
+    return shade::light_pdf_at_point(shade::light_from_abi(*l), sv(from), sv(point));
+}
+int orc_light_escaped(const crt_light* l, const float* dir, float* radiance3, float* pdf) {
+    shade::V3 r;
+    if (!shade::light_escaped(shade::light_from_abi(*l), sv(dir), r, *pdf)) return 0;
+    put3(radiance3, r);
+    return 1;
+}
+int orc_light_pick(int n, float u) { return shade::light_pick(n, u); }
+void orc_camera_ray(const crt_camera* cam, float s, float t, float lu, float lv, float* origin3, float* dir3) {
+    shade::V3 o, d;
+    shade::camera_get_ray(shade::camera_from_abi(*cam), s, t, lu, lv, o, d);
+    put3(origin3, o);
+    put3(dir3, d);
+}
+void orc_filter_sample(uint32_t kind, float radius, float u, float* offset, float* weight) {
+    shade::Filter f = shade::filter_new(kind, radius);
+    shade::filter_sample(f, u, *offset, *weight);
+}
+float orc_filter_eval(uint32_t kind, float radius, float x) {
+    shade::Filter f = shade::filter_new(kind, radius);
+    return shade::filter_eval(f, x);
+}
+// sampler: root = new(x, y, frame, index); then new_domain for each key; draws one 4-D block + one rnd.
+void orc_sampler_draw(int32_t x, int32_t y, int32_t frame, int32_t index, const int32_t* keys, int n_keys, float* out4, float* rnd) {
+    shade::PathSampler s = shade::sampler_new(x, y, frame, index);
+    for (int i = 0; i < n_keys; ++i) s = shade::new_domain(s, keys[i]);
+    shade::draw_sample4(s, out4);
+    *rnd = shade::draw_rnd1(s);
+}
+float orc_mis_weight(uint32_t strategy, int light_side, float a, float b) {
+    return light_side ? shade::strategy_light_weight(strategy, a, b) : shade::strategy_bounce_weight(strategy, a, b);
+}
+}  // extern "C"

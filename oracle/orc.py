@@ -94,6 +94,30 @@ def lib() -> C.CDLL:
     L.orc_test_flatness_depth.restype = u32
     L.orc_test_clip_triangle_aabb.argtypes = [vp, C.c_int, f, f, vp]
     L.orc_sizeof_wide_node.restype = u32
+    # integrator + shading hooks (crt_oracle_render.hpp)
+    L.orc_world_new.argtypes = [vp, vp, sz, vp, sz, vp, sz]
+    L.orc_world_new.restype = vp
+    L.orc_world_free.argtypes = [vp]
+    L.orc_render.argtypes = [vp, vp, vp, vp, vp, vp, C.c_int]
+    L.orc_render.restype = C.c_double
+    L.orc_material_default.argtypes = [vp]
+    L.orc_material_pmf.argtypes = [vp, vp]
+    L.orc_material_medium.argtypes = [vp, vp, vp, vp]
+    L.orc_material_eval.argtypes = [vp, vp, vp, vp, C.c_int, vp, vp, vp]
+    L.orc_material_scatter.argtypes = [vp, vp, vp, vp, C.c_int, vp, vp]
+    L.orc_material_emitted_directional.argtypes = [vp, f, vp]
+    L.orc_light_sample_li.argtypes = [vp, vp, f, f, vp]
+    L.orc_light_pdf_at_point.argtypes = [vp, vp, vp]
+    L.orc_light_pdf_at_point.restype = f
+    L.orc_light_escaped.argtypes = [vp, vp, vp, vp]
+    L.orc_light_pick.argtypes = [C.c_int, f]
+    L.orc_camera_ray.argtypes = [vp, f, f, f, f, vp, vp]
+    L.orc_filter_sample.argtypes = [u32, f, f, vp, vp]
+    L.orc_filter_eval.argtypes = [u32, f, f]
+    L.orc_filter_eval.restype = f
+    L.orc_sampler_draw.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp, C.c_int, vp, vp]
+    L.orc_mis_weight.argtypes = [u32, C.c_int, f, f]
+    L.orc_mis_weight.restype = f
     _lib = L
     return L
 
@@ -314,3 +338,65 @@ def clip_triangle_aabb(v0, v1, v2, axis, mn, mx):
     out = np.zeros(6, np.float32)
     ok = lib().orc_test_clip_triangle_aabb(_p(_f3([v0, v1, v2])), axis, mn, mx, _p(out))
     return (out[:3].copy(), out[3:].copy()) if ok else None
+
+
+# ---- engine side: World / Renderer over the oracle (crt_oracle_render.hpp) -----------------------
+from crust_render_b200.render_types import (  # noqa: E402  value types only
+    LIGHT_DTYPE,
+    MATERIAL_DTYPE,
+    STATS_DTYPE,
+    Camera,
+    LightList,
+    RayStats,
+    RenderSettings,
+    WorldBuilderBase,
+)
+
+
+class World:
+    def __init__(self, scene: "Scene", materials: np.ndarray, geom_material: np.ndarray, lights: LightList):
+        self.scene = scene
+        self._lights = lights.records()
+        self._h = C.c_void_p(lib().orc_world_new(scene._h, _p(materials), len(materials), _p(geom_material), len(geom_material),
+                                                 _p(self._lights), len(self._lights)))
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().orc_world_free(self._h)
+            self._h = None
+
+    def count(self) -> int:
+        return self.scene.geometry_count()
+
+    def has_motion(self) -> bool:
+        return self.scene.has_motion()
+
+
+class WorldBuilder(WorldBuilderBase):
+    def _new_scene_builder(self):
+        return SceneBuilder()
+
+    def commit(self, lights: Optional[LightList] = None) -> World:
+        mats, gm = self.material_table()
+        return World(self._sb.commit(), mats, gm, lights or LightList())
+
+
+class Renderer:
+    """`Renderer::new(camera, world, lights, settings)` (tracer.rs:149-163); the LightList travels in the World here."""
+
+    def __init__(self, camera: Camera, world: World, settings: RenderSettings):
+        self.camera, self.world, self.settings = camera, world, settings
+        self.seconds = 0.0
+
+    def render_with_stats(self, threads: int = 0, var_map: bool = False):
+        st = self.settings
+        fb = np.zeros((st.height, st.width, 4), dtype=np.float32)
+        vm = np.zeros((st.height, st.width), dtype=np.float64) if var_map else None
+        stats = np.zeros((), dtype=STATS_DTYPE)
+        cam, rec = self.camera.record(), st.record()
+        self.seconds = lib().orc_render(self.world._h, _p(cam), _p(rec), _p(fb), _p(vm), _p(stats), threads)
+        self.var_map = vm
+        return fb, RayStats.from_record(stats)
+
+    def render(self, threads: int = 0) -> np.ndarray:
+        return self.render_with_stats(threads)[0]
