@@ -1,0 +1,65 @@
+"""Multi-GPU rendering: image-space split with a replicated scene.
+
+The reference shards a frame over rayon workers by pixel / 16x16 tile with no shared mutable state
+(crates/crust-core/src/tracer.rs:423-502). Here the workers are processes, one per GPU: square tiles
+are dealt round-robin (tile t -> rank t % world, so adaptive-sampling cost is decorrelated from
+rank), every rank renders its tiles into a zero-initialised full-frame buffer, and one collective —
+a sum-reduce to rank 0 over NCCL/NVLink, exact because pixel ownership is disjoint — assembles the
+frame. Per-pixel sampler streams depend only on (i, j, frame, sample), so the image is bit-identical
+for every world size. Traversal and shading never communicate.
+"""
+from __future__ import annotations
+
+import copy
+import dataclasses
+
+import numpy as np
+
+from .render_types import RayStats, STATS_DTYPE
+
+
+def rank_settings(settings, rank: int, world: int, tile_size: int = 32):
+    s = copy.copy(settings)
+    s.tile_size, s.tile_rank, s.tile_world = tile_size, rank, world
+    return s
+
+
+def owned_mask(width: int, height: int, tile_size: int, rank: int, world: int) -> np.ndarray:
+    """[h, w] bool: pixels whose tile id % world == rank (the split crt_render applies)."""
+    if world <= 1:
+        return np.ones((height, width), dtype=bool)
+    tx = (width + tile_size - 1) // tile_size
+    jj, ii = np.meshgrid(np.arange(height), np.arange(width), indexing="ij")
+    return ((jj // tile_size) * tx + ii // tile_size) % world == rank
+
+
+def render_distributed(renderer, dist=None, tile_size: int = 32, fb=None, stream: int = 0):
+    """Renders this rank's tiles and sum-reduces frame + RayStats to rank 0.
+
+    `renderer` is a Renderer (CUDA binding; the oracle's in CPU tests). With `fb` a CUDA torch tensor
+    [h, w, 4] the render writes device memory and the reduce runs on it (NCCL); otherwise host
+    buffers are used (gloo). Returns (frame, RayStats) — complete on rank 0, this rank's share elsewhere.
+    """
+    import torch
+
+    world = dist.get_world_size() if dist is not None and dist.is_initialized() else 1
+    rank = dist.get_rank() if world > 1 else 0
+    base = renderer.settings
+    renderer.settings = rank_settings(base, rank, world, tile_size)
+    try:
+        if fb is not None:
+            fb.zero_()
+            stats = renderer.render_device(fb.data_ptr(), stream)
+            frame = fb
+        else:
+            host, stats = renderer.render_with_stats()
+            frame = torch.from_numpy(host)
+    finally:
+        renderer.settings = base
+    if world > 1:
+        dist.reduce(frame, dst=0, op=dist.ReduceOp.SUM)
+        st = torch.tensor([getattr(stats, n) for n in STATS_DTYPE.names], dtype=torch.int64, device=frame.device)
+        dist.reduce(st, dst=0, op=dist.ReduceOp.SUM)
+        if rank == 0:
+            stats = RayStats(*[int(v) for v in st.tolist()])
+    return (frame if fb is not None else frame.numpy()), stats

@@ -49,8 +49,9 @@ class World:
         self._h = h
 
     def __del__(self):
-        if getattr(self, "_h", None):
-            rt.lib().crt_world_release(self._h)
+        L = getattr(rt, "_lib", None) if rt is not None else None  # module globals are gone at interpreter shutdown
+        if getattr(self, "_h", None) and L is not None:
+            L.crt_world_release(self._h)
             self._h = None
 
     def count(self) -> int:

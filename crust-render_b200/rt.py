@@ -199,8 +199,8 @@ class SceneBuilder:
         self._keep = []  # instanced Scene objects stay alive at least until commit
 
     def __del__(self):
-        if getattr(self, "_h", None):
-            lib().crt_builder_free(self._h)
+        if getattr(self, "_h", None) and _lib is not None:
+            _lib.crt_builder_free(self._h)
             self._h = None
 
     def _handle(self):
@@ -283,8 +283,8 @@ class Scene:
         self._h = handle
 
     def __del__(self):
-        if getattr(self, "_h", None):
-            lib().crt_scene_release(self._h)
+        if getattr(self, "_h", None) and _lib is not None:  # module globals are gone at interpreter shutdown
+            _lib.crt_scene_release(self._h)
             self._h = None
 
     # -- single-ray calls in the reference's shape (scene.rs:354, 370) ---------

@@ -544,3 +544,61 @@ float orc_mis_weight(uint32_t strategy, int light_side, float a, float b) {
     return light_side ? shade::strategy_light_weight(strategy, a, b) : shade::strategy_bounce_weight(strategy, a, b);
 }
 }  // extern "C"
+
+// Generic hook over the leaf shading functions (shade/brdf.h, material.h), addressed by name so
+// tests/test_shade_kats.py can restate crust-core's unit tests. Returns the number of floats written,
+// -1 for an unknown name.
+extern "C" int orc_shade_fn(const char* name, const crt_material* mat, const float* a, float* out) {
+    using namespace shade;
+    std::string n(name);
+    Material m = mat ? material_from_abi(*mat) : material_default();
+    auto put = [&](shade::V3 v) { put3(out, v); return 3; };
+    if (n == "fresnel_dielectric") { out[0] = fresnel_dielectric(a[0], a[1], a[2]); return 1; }
+    if (n == "f0_from_ior") { out[0] = f0_from_ior(a[0]); return 1; }
+    if (n == "roughness_to_alpha_aniso") { roughness_to_alpha_aniso(a[0], a[1], out[0], out[1]); return 2; }
+    if (n == "sheen_charlie") { out[0] = sheen_charlie(a[0], a[1], a[2], a[3]); return 1; }
+    if (n == "coat_darkening_factor") return put(coat_darkening_factor(sv(a), a[3], a[4]));
+    if (n == "thin_film_fresnel") return put(thin_film_fresnel(a[0], a[1], a[2], a[3], a[4]));
+    if (n == "thin_film_fresnel_metal") return put(thin_film_fresnel_metal(a[0], a[1], a[2], sv(a + 3), a[6]));
+    if (n == "dispersive_ior") return put(dispersive_ior(a[0], a[1], a[2]));
+    if (n == "cauchy_ior") { out[0] = cauchy_ior(a[0], a[1], a[2]); return 1; }
+    if (n == "eon_diffuse") return put(eon_diffuse(sv(a), a[3], sv(a + 4), sv(a + 7)));
+    if (n == "eon_albedo_exact") { out[0] = eon_albedo_exact(a[0], a[1]); return 1; }
+    if (n == "eon_albedo_approx") { out[0] = eon_albedo_approx(a[0], a[1]); return 1; }
+    if (n == "fresnel_f82_tint") return put(fresnel_f82_tint(a[0], sv(a + 1), sv(a + 4)));
+    if (n == "fresnel_schlick") return put(fresnel_schlick(a[0], sv(a + 1)));
+    if (n == "eval_all") return put(eval_all(m, sv(a), sv(a + 3), a[6] != 0.0f));
+    if (n == "pdf_all") { out[0] = pdf_all(m, sv(a), sv(a + 3), a[6] != 0.0f); return 1; }
+    if (n == "eval_coat") return put(eval_coat(m, sv(a), sv(a + 3), sv(a + 6), a[9], a[10]));
+    if (n == "coat_attenuation") return put(coat_attenuation(m, a[0], a[1]));
+    if (n == "coat_passage") return put(coat_passage(m, a[0]));
+    if (n == "transmission_iors") return put(transmission_iors(m));
+    if (n == "material_emitted") return put(material_emitted(m));
+    if (n == "medium_from_transmission") {
+        Medium md = medium_from_transmission(sv(a), a[3], sv(a + 4), a[7]);
+        put3(out, md.sigma_a); put3(out + 3, md.sigma_s); out[6] = md.g; return 7;
+    }
+    if (n == "medium_from_subsurface") {
+        Medium md = medium_from_subsurface(sv(a), a[3], sv(a + 4), a[7]);
+        put3(out, md.sigma_a); put3(out + 3, md.sigma_s); out[6] = md.g; return 7;
+    }
+    if (n == "medium_transmittance") {
+        Medium md{sv(a), sv(a + 3), a[6]};
+        return put(medium_transmittance(md, a[7]));
+    }
+    if (n == "sample_henyey_greenstein") return put(sample_henyey_greenstein(sv(a), a[3], a[4], a[5]));
+    if (n == "ggx_d_aniso") { out[0] = ggx_d_aniso(a[0], a[1], a[2], a[3], a[4]); return 1; }
+    if (n == "ggx_g2_smith_aniso") { out[0] = ggx_g2_smith_aniso(a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7]); return 1; }
+    if (n == "sample_vndf_ggx_aniso_local") return put(sample_vndf_ggx_aniso_local(sv(a), a[3], a[4], a[5], a[6]));
+    if (n == "pdf_vndf_ggx_aniso_local") { out[0] = pdf_vndf_ggx_aniso_local(sv(a), sv(a + 3), a[6], a[7]); return 1; }
+    if (n == "cosine_hemisphere") return put(cosine_hemisphere(a[0], a[1]));
+    if (n == "concentric_disk") return put(concentric_disk(a[0], a[1]));
+    if (n == "align_to_normal") return put(align_to_normal(sv(a), sv(a + 3)));
+    if (n == "power_heuristic") { out[0] = power_heuristic(a[0], a[1]); return 1; }
+    if (n == "balance_heuristic") { out[0] = balance_heuristic(a[0], a[1]); return 1; }
+    return -1;
+}
+extern "C" void orc_filter_sample_n(uint32_t kind, float radius, size_t n, const float* u, float* offset, float* weight) {
+    shade::Filter f = shade::filter_new(kind, radius);
+    for (size_t i = 0; i < n; ++i) shade::filter_sample(f, u[i], offset[i], weight[i]);
+}

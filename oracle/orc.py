@@ -118,6 +118,8 @@ def lib() -> C.CDLL:
     L.orc_sampler_draw.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp, C.c_int, vp, vp]
     L.orc_mis_weight.argtypes = [u32, C.c_int, f, f]
     L.orc_mis_weight.restype = f
+    L.orc_shade_fn.argtypes = [C.c_char_p, vp, vp, vp]
+    L.orc_filter_sample_n.argtypes = [u32, f, sz, vp, vp, vp]
     _lib = L
     return L
 
@@ -400,3 +402,106 @@ class Renderer:
 
     def render(self, threads: int = 0) -> np.ndarray:
         return self.render_with_stats(threads)[0]
+
+
+# ---- leaf shading math hooks (tests/test_shade_kats.py, test_sampler.py) ---------------------------
+def shade_fn(name: str, args, material: Optional[np.ndarray] = None) -> np.ndarray:
+    a = np.ascontiguousarray(np.asarray(args, dtype=np.float32).reshape(-1))
+    out = np.zeros(16, dtype=np.float32)
+    n = lib().orc_shade_fn(name.encode(), _p(material), _p(a), _p(out))
+    if n < 0:
+        raise KeyError(name)
+    return out[:n].copy()
+
+
+def material_eval(material, ray_dir, normal, front_face, wi, p=(0, 0, 0)):
+    """Material::eval (material.rs:64-69): (value, pdf) or None."""
+    v, pdf = np.zeros(3, np.float32), C.c_float()
+    ok = lib().orc_material_eval(_p(material), _p(_f3(ray_dir)), _p(_f3(p)), _p(_f3(normal)), int(front_face), _p(_f3(wi)), _p(v), C.byref(pdf))
+    return (v, pdf.value) if ok else None
+
+
+def material_scatter(material, ray_dir, normal, front_face, s4, p=(0, 0, 0)):
+    """Material::scatter_importance with an explicit 4-D block: dict(origin, dir, value, pdf, delta, enters_medium) or None."""
+    out = np.zeros(11, np.float32)
+    s = np.ascontiguousarray(np.asarray(s4, np.float32))
+    if not lib().orc_material_scatter(_p(material), _p(_f3(ray_dir)), _p(_f3(p)), _p(_f3(normal)), int(front_face), _p(s), _p(out)):
+        return None
+    fl = int(out[10])
+    return dict(origin=out[0:3].copy(), dir=out[3:6].copy(), value=out[6:9].copy(), pdf=float(out[9]), delta=bool(fl & 1), enters_medium=bool(fl & 2))
+
+
+def material_medium(material):
+    sa, ss, g = np.zeros(3, np.float32), np.zeros(3, np.float32), C.c_float()
+    has = lib().orc_material_medium(_p(material), _p(sa), _p(ss), C.byref(g))
+    return (sa, ss, g.value) if has else None
+
+
+def material_pmf(material) -> np.ndarray:
+    out = np.zeros(5, np.float32)
+    lib().orc_material_pmf(_p(material), _p(out))
+    return out
+
+
+def material_emitted_directional(material, cos_o: float) -> np.ndarray:
+    out = np.zeros(3, np.float32)
+    lib().orc_material_emitted_directional(_p(material), cos_o, _p(out))
+    return out
+
+
+def light_sample_li(light, from_, u, v):
+    out = np.zeros(8, np.float32)
+    if not lib().orc_light_sample_li(_p(light), _p(_f3(from_)), u, v, _p(out)):
+        return None
+    return dict(direction=out[0:3].copy(), radiance=out[3:6].copy(), distance=float(out[6]), pdf=float(out[7]))
+
+
+def light_pdf_at_point(light, from_, point) -> float:
+    return lib().orc_light_pdf_at_point(_p(light), _p(_f3(from_)), _p(_f3(point)))
+
+
+def light_escaped(light, direction):
+    r, pdf = np.zeros(3, np.float32), C.c_float()
+    if not lib().orc_light_escaped(_p(light), _p(_f3(direction)), _p(r), C.byref(pdf)):
+        return None
+    return r, pdf.value
+
+
+def light_pick(n: int, u: float) -> int:
+    return lib().orc_light_pick(n, u)
+
+
+def camera_ray(camera: Camera, s, t, lu=0.0, lv=0.0):
+    o, d = np.zeros(3, np.float32), np.zeros(3, np.float32)
+    rec = camera.record()
+    lib().orc_camera_ray(_p(rec), s, t, lu, lv, _p(o), _p(d))
+    return o, d
+
+
+def filter_sample(kind: int, radius: float, u: float):
+    off, w = C.c_float(), C.c_float()
+    lib().orc_filter_sample(kind, radius, u, C.byref(off), C.byref(w))
+    return off.value, w.value
+
+
+def filter_eval(kind: int, radius: float, x: float) -> float:
+    return lib().orc_filter_eval(kind, radius, x)
+
+
+def sampler_draw(x: int, y: int, frame: int, index: int, keys=()):
+    """PathSampler::new(x, y, frame, index).new_domain(k)... -> (4-D block, rnd)."""
+    k = np.ascontiguousarray(np.asarray(list(keys), dtype=np.int32))
+    out, rnd = np.zeros(4, np.float32), C.c_float()
+    lib().orc_sampler_draw(x, y, frame, index, _p(k) if len(k) else None, len(k), _p(out), C.byref(rnd))
+    return out, rnd.value
+
+
+def mis_weight(strategy: int, light_side: bool, a: float, b: float) -> float:
+    return lib().orc_mis_weight(int(strategy), int(light_side), a, b)
+
+
+def filter_sample_n(kind: int, radius: float, u: np.ndarray):
+    u = np.ascontiguousarray(u, dtype=np.float32)
+    off, w = np.zeros_like(u), np.zeros_like(u)
+    lib().orc_filter_sample_n(kind, radius, len(u), _p(u), _p(off), _p(w))
+    return off, w

@@ -1,0 +1,185 @@
+"""-m gpu: the CUDA wavefront integrator (csrc/render.cu, through the C ABI of include/crt_render.h)
+against the CPU oracle (oracle/crt_oracle_render.hpp) on identical scenes, settings and sampler
+seeds. BASELINE.json's bar is "at equal spp and identical Sobol seeds, images match within a stated
+relative-MSE tolerance": the tolerance stated here is relMSE <= 1e-6 with <= 1% of pixels off by more
+than 1e-3 relative (measured on B200: relMSE 4e-12 .. 1.2e-7, see profiles/r01_render_parity.jsonl).
+Differences come from CUDA's vs glibc's transcendental functions and the forward-vs-backward
+summation order; a handful of paths per million flip a discrete decision (lobe pick, roulette)."""
+import numpy as np
+import pytest
+
+from crust_render_b200 import scenes
+from crust_render_b200.distributed import owned_mask, rank_settings
+from crust_render_b200.render_types import PixelFilter, PixelFilterKind, SamplingStrategy
+
+pytestmark = pytest.mark.gpu
+
+RELMSE_TOL = 1e-6
+
+
+def compare(a, b, frac_tol=0.01):
+    a3, b3 = a[..., :3].astype(np.float64), b[..., :3].astype(np.float64)
+    relmse = float(((a3 - b3) ** 2 / (b3 ** 2 + 1e-4)).mean())
+    rel = (np.abs(a3 - b3) / (np.abs(b3) + 1e-3)).max(axis=-1)
+    assert np.all(np.isfinite(a)), "NaN/Inf in the GPU frame"
+    assert relmse <= RELMSE_TOL, relmse
+    assert (rel > 1e-3).mean() <= frac_tol, (rel > 1e-3).mean()
+    return relmse
+
+
+def stats_close(g, c, tol=1e-4):
+    assert g.camera_rays == c.camera_rays
+    for name in ("closest_hit", "shadow_rays", "vertices", "rr_tested", "rr_killed", "ended_escaped", "ended_depth"):
+        a, b = getattr(g, name), getattr(c, name)
+        assert abs(a - b) <= max(4, tol * max(a, b)), (name, a, b)
+
+
+def both(gpu, orc, fn, **kw):
+    wg, cam, st = fn(gpu, **kw)[:3]
+    wo = fn(orc, **kw)[0]
+    rg = gpu.Renderer(cam, wg, st)
+    fg, sg = rg.render_with_stats()
+    fo, so = orc.Renderer(cam, wo, st).render_with_stats()
+    return fg, sg, fo, so, rg
+
+
+def test_every_integrator_branch_scene(gpu, orc):
+    """Diffuse, metal, coat, thick glass with an absorbing medium, thin-walled delta lobe, fuzz on
+    instanced meshes, sphere + rect lights, lens sampling."""
+    fg, sg, fo, so, rg = both(gpu, orc, scenes.furnace_room, width=192, height=128, spp=16, variance_threshold=0.0)
+    compare(fg, fo)
+    stats_close(sg, so)
+    assert np.array_equal(fg[..., 3], fo[..., 3]) and rg.launches > 0 and gpu.device_status() == 0
+
+
+def test_adaptive_sampling_decisions_match(gpu, orc):
+    fg, sg, fo, so, rg = both(gpu, orc, scenes.furnace_room, width=192, height=128, spp=64, variance_threshold=0.05, min_samples_per_pixel=16)
+    assert (fg[..., 3] == fo[..., 3]).mean() >= 0.999  # a 1-ulp luminance difference may move a threshold decision
+    same = fg[..., 3] == fo[..., 3]
+    compare(fg[same], fo[same])
+    assert rg.rounds > 1 and fg[..., 3].min() >= 16 and (fg[..., 3] < 64).any()
+    stats_close(sg, so, tol=2e-3)
+
+
+def test_config2_veach_mis(gpu, orc):
+    fg, sg, fo, so, _ = both(gpu, orc, scenes.veach_mis, width=240, height=135, spp=16)
+    compare(fg, fo)
+    stats_close(sg, so)
+
+
+@pytest.mark.parametrize("strategy", list(SamplingStrategy))
+def test_sampling_strategies(gpu, orc, strategy):
+    fg, sg, fo, so, _ = both(gpu, orc, scenes.veach_mis, width=96, height=54, spp=8, sampling_strategy=strategy)
+    compare(fg, fo)
+    stats_close(sg, so)
+    assert (sg.shadow_rays == 0) == (strategy == SamplingStrategy.BsdfOnly)
+
+
+def test_config3_openpbr_showcase_adaptive(gpu, orc):
+    fg, sg, fo, so, _ = both(gpu, orc, scenes.openpbr_showcase, width=320, height=180, spp=64)
+    same = fg[..., 3] == fo[..., 3]
+    assert same.mean() >= 0.999
+    compare(fg[same], fo[same])
+    stats_close(sg, so, tol=2e-3)
+
+
+def test_config5_stress_scene_small(gpu, orc):
+    fn = lambda api, **kw: scenes.stress(api, **kw)  # noqa: E731
+    fg, sg, fo, so, _ = both(gpu, orc, fn, grid=2, shards=2000, width=160, height=90, spp=8)
+    compare(fg, fo)
+    stats_close(sg, so)
+
+
+@pytest.mark.parametrize("kind,radius", [(PixelFilterKind.Box, 0.5), (PixelFilterKind.Gaussian, 1.5), (PixelFilterKind.Mitchell, 2.0)])
+def test_pixel_filters(gpu, orc, kind, radius):
+    fg, _, fo, _, _ = both(gpu, orc, scenes.furnace_room, width=64, height=48, spp=8, variance_threshold=0.0, pixel_filter=PixelFilter(kind, radius))
+    compare(fg, fo)
+
+
+def test_motion_blur_and_depth_limits(gpu, orc):
+    """A moving instance makes has_motion() true, so the shutter dimension is drawn (tracer.rs:556,
+    579-583); max_depth 1 and 2 exercise the depth-exhausted emission-only trace (:1123-1148)."""
+    from crust_render_b200.render_types import Camera, LightList, OpenPBR, RenderSettings
+    from crust_render_b200.rt_types import Affine3A, Geometry
+    from crust_render_b200 import workloads as W
+
+    def build(api, depth):
+        wb = api.WorldBuilder()
+        lights = LightList()
+        wb.attach(Geometry.TriangleMesh(np.array([(-6, 0, -6), (6, 0, -6), (6, 0, 6), (-6, 0, 6)], np.float32), np.array([[0, 2, 1], [0, 3, 2]], np.uint32)), OpenPBR())
+        sv, si = W.uv_sphere((0, 0, 0), 0.7, 12, 6)
+        sb = api.SceneBuilder()
+        sb.attach(Geometry.TriangleMesh(sv, si))
+        child = sb.commit()
+        wb.attach(Geometry.Instance(child, Affine3A.from_translation((-1, 0.7, 0)), Affine3A.from_translation((1.5, 0.7, 0))), OpenPBR(base_color=(0.9, 0.2, 0.2)))
+        scenes._sphere_light(wb, lights, (0, 4, 1), 0.6, (1, 1, 1), 25.0, True)
+        return wb.commit(lights), Camera((0, 2, 6), (0, 0.7, 0), (0, 1, 0), 40.0, 1.5), RenderSettings(8, depth, 96, 64, variance_threshold=0.0)
+
+    for depth in (1, 2, 5):
+        wg, cam, st = build(gpu, depth)
+        wo, _, _ = build(orc, depth)
+        assert wg.has_motion() and wo.has_motion()
+        fg, sg = gpu.Renderer(cam, wg, st).render_with_stats()
+        fo, so = orc.Renderer(cam, wo, st).render_with_stats()
+        compare(fg, fo)
+        stats_close(sg, so)
+        assert sg.ended_depth > 0
+
+
+def test_max_depth_zero_and_empty_world(gpu, orc):
+    from crust_render_b200.render_types import Camera, RenderSettings
+    wg, cam, st = scenes.furnace_room(gpu, width=32, height=16, spp=2, max_depth=0, variance_threshold=0.0)
+    fg, sg = gpu.Renderer(cam, wg, st).render_with_stats()
+    assert np.all(fg[..., :3] == 0) and np.all(fg[..., 3] == 2) and sg.ended_depth == sg.camera_rays == 32 * 16 * 2 and sg.closest_hit == 0
+    for api in (gpu, orc):  # nothing attached: every ray sees the sky gradient (tracer.rs:1330-1337)
+        w = api.WorldBuilder().commit()
+        f, s = api.Renderer(Camera((0, 0, 0), (0, 0, -1), (0, 1, 0), 60.0, 2.0), w, RenderSettings(2, 4, 32, 16, variance_threshold=0.0)).render_with_stats()
+        assert s.ended_escaped == s.camera_rays == s.closest_hit and s.shadow_rays == 0
+        if api is gpu:
+            sky = f
+    compare(sky, f)
+
+
+def test_bit_determinism_pool_size_and_tile_split(gpu):
+    """GPU vs GPU, bit for bit: repeated renders, a path pool so small that every round is cut into
+    many wavefronts, and the multi-GPU tile deal (each rank's tiles == the same pixels of the full frame)."""
+    world, cam, st = scenes.furnace_room(gpu, width=96, height=64, spp=12, variance_threshold=0.05, min_samples_per_pixel=4)
+    full, sf = gpu.Renderer(cam, world, st).render_with_stats()
+    again, sa = gpu.Renderer(cam, world, st).render_with_stats()
+    assert full.tobytes() == again.tobytes() and sf == sa
+    st_small = scenes.furnace_room(gpu, width=96, height=64, spp=12, variance_threshold=0.05, min_samples_per_pixel=4)[2]
+    st_small.max_paths = 1500
+    small, ss = gpu.Renderer(cam, world, st_small).render_with_stats()
+    assert full.tobytes() == small.tobytes() and sf == ss
+    acc = np.zeros_like(full)
+    rays = 0
+    for rank in range(3):
+        part, sp = gpu.Renderer(cam, world, rank_settings(st, rank, 3, tile_size=16)).render_with_stats()
+        m = owned_mask(96, 64, 16, rank, 3)
+        assert np.all(part[~m] == 0) and np.array_equal(part[m], full[m])
+        acc += part
+        rays += sp.total_rays()
+    assert acc.tobytes() == full.tobytes() and rays == sf.total_rays()
+
+
+def test_device_framebuffer_entry_and_distributed_wrapper(gpu):
+    import torch
+    from crust_render_b200.distributed import render_distributed
+    world, cam, st = scenes.furnace_room(gpu, width=64, height=48, spp=4, variance_threshold=0.0)
+    host, sh = gpu.Renderer(cam, world, st).render_with_stats()
+    fb = torch.empty((48, 64, 4), dtype=torch.float32, device="cuda")
+    frame, sd = render_distributed(gpu.Renderer(cam, world, st), None, fb=fb, stream=torch.cuda.current_stream().cuda_stream)
+    assert frame.cpu().numpy().tobytes() == host.tobytes() and sd == sh
+
+
+def test_render_argument_errors(gpu):
+    world, cam, st = scenes.furnace_room(gpu, width=16, height=16, spp=1)
+    for field, value in (("width", 0), ("samples_per_pixel", 0), ("samples_per_pixel", 70000)):
+        bad = scenes.furnace_room(gpu, width=16, height=16, spp=1)[2]
+        setattr(bad, field, value)
+        with pytest.raises(gpu.CrtError) as e:
+            gpu.Renderer(cam, world, bad).render_device(0)
+        assert e.value.status == 1
+    bad = rank_settings(st, 3, 2)
+    with pytest.raises(gpu.CrtError):
+        gpu.Renderer(cam, world, bad).render_with_stats()
