@@ -27,9 +27,10 @@ def compare(a, b, frac_tol=0.01):
     return relmse
 
 
-def stats_close(g, c, tol=1e-4):
-    assert g.camera_rays == c.camera_rays
-    for name in ("closest_hit", "shadow_rays", "vertices", "rr_tested", "rr_killed", "ended_escaped", "ended_depth"):
+def stats_close(g, c, tol=1e-4, adaptive=False):
+    if not adaptive:  # with adaptive stopping a 1-ulp luminance difference can move one pixel's stop by 4 samples
+        assert g.camera_rays == c.camera_rays
+    for name in ("camera_rays", "closest_hit", "shadow_rays", "vertices", "rr_tested", "rr_killed", "ended_escaped", "ended_depth"):
         a, b = getattr(g, name), getattr(c, name)
         assert abs(a - b) <= max(4, tol * max(a, b)), (name, a, b)
 
@@ -58,7 +59,7 @@ def test_adaptive_sampling_decisions_match(gpu, orc):
     same = fg[..., 3] == fo[..., 3]
     compare(fg[same], fo[same])
     assert rg.rounds > 1 and fg[..., 3].min() >= 16 and (fg[..., 3] < 64).any()
-    stats_close(sg, so, tol=2e-3)
+    stats_close(sg, so, tol=2e-3, adaptive=True)
 
 
 def test_config2_veach_mis(gpu, orc):
@@ -80,7 +81,7 @@ def test_config3_openpbr_showcase_adaptive(gpu, orc):
     same = fg[..., 3] == fo[..., 3]
     assert same.mean() >= 0.999
     compare(fg[same], fo[same])
-    stats_close(sg, so, tol=2e-3)
+    stats_close(sg, so, tol=2e-3, adaptive=True)
 
 
 def test_config5_stress_scene_small(gpu, orc):
