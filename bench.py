@@ -9,6 +9,12 @@ host-buffer C ABI (crt_*_host_n) with pinned host rays in and hits out, copies i
 timed region. `--impl reference` times the CPU restatement of crust-rt (oracle/) on all
 host threads on a bounded sample of the same sets.
 
+The same line carries the second half of BASELINE.json's metric, spp/s, under "render": config 5
+(the stress mesh lit by its RectLight, 3840x2160, depth 6) rendered by the wavefront integrator
+(crt_render) `--render-spp` samples per pixel per step; with N GPUs the frame is dealt out in
+interleaved 32x32 tiles and sum-reduced to rank 0 over NCCL inside the timed region (strong scaling:
+the frame is fixed). spp_per_s = samples per pixel of the whole 4K frame per second.
+
 Contract: python bench.py --gpus N --steps K --warmup W [--impl reference]; one JSON line on rank 0.
 """
 import argparse
@@ -34,6 +40,25 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+# stdout carries exactly one JSON line: native libraries (NCCL's version banner) write to fd 1, so fd 1
+# is pointed at stderr for the whole run and the line goes to a private duplicate of the real stdout.
+_REAL_STDOUT = None
+
+
+def protect_stdout():
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -42,10 +67,34 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--grid", type=int, default=32, help="stress-scene sphere grid (32 = K1, 10.07 M triangles)")
     ap.add_argument("--rays-log2", type=int, default=24, help="rays per set (camera set: 3840x2160x2 spp when 24)")
-    ap.add_argument("--cpu-sample-log2", type=int, default=22, help="rays per set for the CPU baseline sample")
+    ap.add_argument("--cpu-sample-log2", type=int, default=24, help="rays per set for the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-render", action="store_true")
+    ap.add_argument("--render-spp", type=int, default=8, help="samples per pixel per render step (a 256-spp frame is 32 such steps)")
+    ap.add_argument("--render-steps", type=int, default=3)
+    ap.add_argument("--render-width", type=int, default=3840)
+    ap.add_argument("--render-height", type=int, default=2160)
+    ap.add_argument("--cpu-render", default="1920x1080x6", help="bounded sample of the render workload for the CPU baseline: WxHxSPP")
     return ap.parse_args()
+
+
+def cpu_render_sample(args, log_prefix):
+    """The oracle integrator on all host threads over a bounded sample of config 5 (same scene, camera
+    and settings at reduced resolution / spp). Returns the `render.cpu_baseline` object."""
+    import orc
+    from crust_render_b200 import scenes
+
+    w, h, spp = (int(v) for v in args.cpu_render.lower().split("x"))
+    t0 = time.time()
+    world, cam, st, n_tris = scenes.stress(orc, grid=args.grid, jitter=True, width=w, height=h, spp=spp)
+    log(f"{log_prefix} oracle world commit ({n_tris} triangles): {time.time() - t0:.1f}s")
+    r = orc.Renderer(cam, world, st)
+    _, stats = r.render_with_stats(threads=0)
+    cores = os.cpu_count() or 1
+    return {"value": spp / r.seconds * (w * h) / (args.render_width * args.render_height), "unit": "spp/s of the 4K frame (scaled from the sample by pixel count)",
+            "msamples_per_s": w * h * spp / r.seconds / 1e6, "mrays_per_s": stats.total_rays() / r.seconds / 1e6, "cores": cores, "kind": "port",
+            "sample": f"{w}x{h} x {spp} spp of the same scene/camera/settings, {r.seconds:.1f}s on {cores} threads (rows dealt to threads)"}
 
 
 # ---------------------------------------------------------------------------
@@ -181,7 +230,11 @@ def reference_arm(args):
             "cpu_baseline": {"value": v, "unit": "Mrays/s", "cores": cores, "kind": "port", "sample": desc},
             "e2e": {"value": v, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    if not args.no_render:
+        del o_scene, sets, sample
+        line["render"] = {"cpu_baseline": cpu_render_sample(args, "[reference]")}
+        line["render"]["spp_per_s"] = line["render"]["cpu_baseline"]["value"]
+    emit(line)
 
 
 # ---------------------------------------------------------------------------
@@ -189,6 +242,7 @@ def reference_arm(args):
 # ---------------------------------------------------------------------------
 def main():
     args = parse()
+    protect_stdout()
     if args.impl == "reference":
         return reference_arm(args)
 
@@ -315,6 +369,72 @@ def main():
         e2e = {"value": rays_per_step * world * args.steps / dt / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                "ms_per_step": dt / args.steps * 1e3}
 
+    # ---- render: config 5 through the wavefront integrator, frame split over the ranks ----------
+    render = None
+    if not args.no_render:
+        from crust_render_b200 import scenes
+        from crust_render_b200.distributed import render_distributed
+
+        sample_sets = cpu_sample(sets, args.cpu_sample_log2) if (rank == 0 and world == 1 and not args.no_cpu_baseline) else None
+        del d_in, d_out, d_mask, h_in, h_out, h_mask
+        full_sets_sizes = {n: len(sets[n][0]) for n in SETS}
+        torch.cuda.empty_cache()
+        rw, rh, rspp = args.render_width, args.render_height, args.render_spp
+        t0 = time.time()
+        r_world, r_cam, r_st, r_tris = scenes.stress(crt, grid=args.grid, jitter=True, width=rw, height=rh, spp=rspp)
+        if rank == 0:
+            log(f"[bench] render world commit ({r_tris} triangles incl. the RectLight): {time.time() - t0:.1f}s")
+        renderer = crt.Renderer(r_cam, r_world, r_st)
+        fb = torch.zeros((rh, rw, 4), dtype=torch.float32, device=dev)
+        r_launches = 0
+        render_distributed(renderer, dist if world > 1 else None, fb=fb, stream=stream.cuda_stream)  # warm-up
+        barrier()
+        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        r_stats = []
+        dev_ms = 0.0
+        r0.record(stream)
+        for _ in range(args.render_steps):
+            _, st_k = render_distributed(renderer, dist if world > 1 else None, fb=fb, stream=stream.cuda_stream)
+            r_stats.append(st_k)
+            r_launches += renderer.launches
+            dev_ms += renderer.device_ms
+        r1.record(stream)
+        barrier()
+        tt = torch.tensor([r0.elapsed_time(r1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        r_ms = float(tt.item()) / args.render_steps
+        mean_rgb = [float(v) for v in fb[..., :3].mean(dim=(0, 1)).tolist()] if rank == 0 else None
+        # e2e: the same frame through crt_render_host (framebuffer copied back to host memory every step)
+        host_fb = np.zeros((rh, rw, 4), dtype=np.float32)
+        from crust_render_b200.distributed import rank_settings
+        renderer.settings = rank_settings(r_st, rank, world)
+        barrier()
+        t0 = time.perf_counter()
+        renderer.render_with_stats(out=host_fb)
+        barrier()
+        e2e_s = time.perf_counter() - t0
+        te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e_s = float(te.item())
+        renderer.settings = r_st
+        if rank == 0:
+            st0 = r_stats[-1]
+            render = {"workload": f"config 5: stress mesh ({r_tris} triangles) + 12x12 RectLight, {rw}x{rh}, depth 6, {rspp} spp per step, power MIS, triangle filter",
+                      "spp_per_s": rspp / (r_ms * 1e-3), "msamples_per_s": rw * rh * rspp / r_ms / 1e3, "mrays_per_s": st0.total_rays() / r_ms / 1e3,
+                      "ms_per_step": r_ms, "steps": args.render_steps, "rays_per_sample": st0.total_rays() / max(1, st0.camera_rays), "n_gpus": world,
+                      "split": "whole frame" if world == 1 else f"32x32 tiles dealt round-robin over {world} ranks, NCCL sum-reduce to rank 0 inside the timed region",
+                      "scaling": "strong", "gpu_launches_per_step_rank0": r_launches // args.render_steps, "device_ms_rank0_render_only": dev_ms / args.render_steps,
+                      "e2e": {"spp_per_s": rspp / e2e_s, "unit": "spp/s", "d2h_bytes_per_step": rw * rh * 16, "h2d_bytes_per_step": rw * rh * 16,
+                              "note": "crt_render_host: frame in/out of host memory, no cross-rank gather"},
+                      "mean_rgb": mean_rgb, "ray_stats": st0.__dict__}
+        del fb, renderer, r_world
+        torch.cuda.empty_cache()
+    else:
+        sample_sets = cpu_sample(sets, args.cpu_sample_log2) if (rank == 0 and world == 1 and not args.no_cpu_baseline) else None
+        full_sets_sizes = {n: len(sets[n][0]) for n in SETS}
+
     # ---- CPU baseline + algorithmic bytes per ray (rank 0, N = 1 only) -----------
     cpu_baseline, roofline, per_set = None, None, {}
     if rank == 0:
@@ -331,7 +451,7 @@ def main():
             ob, _ = W.stress_scene(orc, grid=args.grid, shards=30000, jitter=True)
             o_scene = ob.commit(host_threads=0)
             log(f"[bench] oracle commit: {time.time() - t0:.1f}s")
-            sample = cpu_sample(sets, args.cpu_sample_log2)
+            sample = sample_sets
             # parity spot-check on the sample (checker role only)
             for name in SETS:
                 rays, mask = sample[name]
@@ -377,7 +497,13 @@ def main():
                 "sets": per_set, "closest_hit_mrays": sum(len(sets[n][0]) for n in closest) / sum(k_ms[n] for n in closest) / 1e3,
                 "occlusion_mrays": sum(len(sets[n][0]) for n in SETS if n not in closest) / sum(k_ms[n] for n in SETS if n not in closest) / 1e3,
                 "device_status": status, "host_cores": cores}
-        print(json.dumps(line), flush=True)
+        if render is not None:
+            if world == 1 and not args.no_cpu_baseline:
+                del o_scene
+                render["cpu_baseline"] = cpu_render_sample(args, "[bench]")
+            line["render"] = render
+            line["spp_per_s"] = render["spp_per_s"]
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
