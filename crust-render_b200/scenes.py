@@ -1,12 +1,13 @@
 """Render scenes for BASELINE.json's configs, built through the WorldBuilder API.
 
 The bundled samples are transcribed the way crust-core's USD importer would hand them to the
-engine (crates/crust-core/src/scene/usd_import.rs): geometry in prim order so `geom_id`s match
-(meshes and lights are attached as the stage walk meets them, :140-269), quads fan-triangulated
+engine (crates/crust-core/src/scene/usd_import.rs): geometry in the importer's visiting order so `geom_id`s and the light order match
+(the stage walk is a LIFO stack: siblings in reverse authored order, :140-269), quads fan-triangulated
 (:1164-1214), lights as geometry + AreaLight sharing a geom_id with mask SHADOW|INDIRECT[|CAMERA]
 (:747-753, 2259-2349), cameras from focal length / aperture (:2174-2220), unbound prims on the
-default grey OpenPBR. A USD reader is SURVEY §8(f) rank 1; until it exists these builders ARE the
-ingest for configs 2, 3 and 5, and `cornellbox()` / `medcity()` read compact binary fixtures.
+default grey OpenPBR. The text-USD importer (usd/importer.py) reads the real files where /root/reference exists;
+tests/test_usd_import.py proves these transcriptions equal what it produces, and the GPU box — which
+has no reference tree — uses them plus the binary fixture behind `cornellbox()`.
 
 Every builder takes an ``api`` namespace exposing ``WorldBuilder`` and ``Geometry`` (the CUDA
 binding, or the oracle binding in tests) and returns (world, camera, settings).
@@ -41,22 +42,20 @@ def _f32(x):
 
 
 def usd_camera(translate, rotate_x_deg: float, focal_length: float, horizontal_aperture: float, width: int, height: int,
-               vertical_aperture=None, f_stop: float = 0.0, focus_distance: float = 10.0, basis=None) -> Camera:
-    """`build_camera` (usd_import.rs:2174-2220): a USD camera looks down -Z with +Y up."""
-    if basis is None:
-        a = math.radians(rotate_x_deg)
-        forward = np.array([0.0, math.sin(a), -math.cos(a)], np.float32)  # Rx(a) * (0, 0, -1)
-        up = np.array([0.0, math.cos(a), math.sin(a)], np.float32)        # Rx(a) * (0, 1, 0)
-    else:
-        forward, up = (np.asarray(b, np.float32) for b in basis)
-    forward = forward / np.sqrt((forward * forward).sum(dtype=np.float32))
-    up = up / np.sqrt((up * up).sum(dtype=np.float32))
-    va = vertical_aperture if vertical_aperture is not None else _f32(horizontal_aperture) * _f32(height) / _f32(width)
-    vfov = _f32(2.0) * np.degrees(np.arctan(_f32(va) / (_f32(2.0) * _f32(focal_length)), dtype=np.float32), dtype=np.float32)
-    aperture = focal_length / f_stop if f_stop > 0 else 0.0
-    lookfrom = np.asarray(translate, np.float32)
-    lookat = lookfrom + forward * _f32(focus_distance)
-    return Camera(lookfrom, lookat, up, float(vfov), float(_f32(width) / _f32(height)), float(aperture), float(focus_distance))
+               vertical_aperture=None, f_stop: float = 0.0, focus_distance: float = 10.0, matrix=None) -> Camera:
+    """`build_camera` (usd_import.rs:2174-2220) for a camera authored as translate + rotateX (or a full
+    row-vector `xformOp:transform` matrix), through the importer's own f32 arithmetic."""
+    from .usd.importer import _mul, _rot, _translate, build_camera
+    from .usd.usda import Attribute, Prim
+
+    world = np.asarray(matrix, np.float32).reshape(4, 4).T.copy() if matrix is not None else _mul(_translate(translate), _rot(0, rotate_x_deg))
+    prim = Prim("def", "Camera", "Cam", "/World/Cam")
+    vals = {"focalLength": focal_length, "horizontalAperture": horizontal_aperture, "fStop": f_stop, "focusDistance": focus_distance}
+    if vertical_aperture is not None:
+        vals["verticalAperture"] = vertical_aperture
+    for k, v in vals.items():
+        prim.attributes[k] = Attribute(k, "float", v)
+    return build_camera(prim, world, RenderSettings(1, 1, width, height))
 
 
 def _light_mask(camera_visible: bool) -> int:  # usd_import.rs:747-753
@@ -120,22 +119,23 @@ def furnace_room(api, width: int = 96, height: int = 64, spp: int = 8, max_depth
 def veach_mis(api, width: int = 960, height: int = 540, spp: int = 128, **settings_kw):
     wb = api.WorldBuilder()
     lights = LightList()
-    # lights first: they precede the meshes in the stage (geom_ids 0..3), all cameraVisible
-    for pos, radius, color, intensity in (((-3.375, 6, -3), 0.05, (1.0, 0.45, 0.35), 8748.0), ((-1.125, 6, -3), 0.15, (1.0, 0.85, 0.45), 972.0),
-                                           ((1.125, 6, -3), 0.45, (0.45, 1.0, 0.55), 108.0), ((3.375, 6, -3), 1.35, (0.4, 0.6, 1.0), 12.0)):
-        _sphere_light(wb, lights, pos, radius, color, intensity, True)
+    # The importer's stage walk pops siblings off a stack, i.e. visits them in REVERSE authored order
+    # (usd_import.rs:140-269): BackWall, Floor, Plate3..Plate0, then LightBig..LightTiny.
     plates = [
         ([(-4.5, 1.845, -0.896), (4.5, 1.845, -0.896), (4.5, 2.555, -2.104), (-4.5, 2.555, -2.104)], 0.01),
         ([(-4.5, 1.161, 1.158), (4.5, 1.161, 1.158), (4.5, 1.639, -0.158), (-4.5, 1.639, -0.158)], 0.05),
         ([(-4.5, 0.450, 3.184), (4.5, 0.450, 3.184), (4.5, 0.750, 1.816), (-4.5, 0.750, 1.816)], 0.12),
         ([(-4.5, -0.263, 5.197), (4.5, -0.263, 5.197), (4.5, -0.137, 3.803), (-4.5, -0.137, 3.803)], 0.25),
     ]
-    for pts, rough in plates:
+    backdrop = OpenPBR(base_color=(0.05, 0.05, 0.05), specular_weight=0.0)
+    wb.attach(Geometry.TriangleMesh(np.asarray([(-12, -2.5, -10), (12, -2.5, -10), (12, 14, -10), (-12, 14, -10)], np.float32), QUAD), backdrop)
+    wb.attach(Geometry.TriangleMesh(np.asarray([(-12, -2.5, 14), (12, -2.5, 14), (12, -2.5, -10), (-12, -2.5, -10)], np.float32), QUAD), backdrop)
+    for pts, rough in reversed(plates):
         wb.attach(Geometry.TriangleMesh(np.asarray(pts, np.float32), QUAD),
                   OpenPBR(base_color=(0.9, 0.9, 0.9), base_metalness=1.0, specular_roughness=rough))
-    backdrop = OpenPBR(base_color=(0.05, 0.05, 0.05), specular_weight=0.0)
-    wb.attach(Geometry.TriangleMesh(np.asarray([(-12, -2.5, 14), (12, -2.5, 14), (12, -2.5, -10), (-12, -2.5, -10)], np.float32), QUAD), backdrop)
-    wb.attach(Geometry.TriangleMesh(np.asarray([(-12, -2.5, -10), (12, -2.5, -10), (12, 14, -10), (-12, 14, -10)], np.float32), QUAD), backdrop)
+    for pos, radius, color, intensity in (((3.375, 6, -3), 1.35, (0.4, 0.6, 1.0), 12.0), ((1.125, 6, -3), 0.45, (0.45, 1.0, 0.55), 108.0),
+                                           ((-1.125, 6, -3), 0.15, (1.0, 0.85, 0.45), 972.0), ((-3.375, 6, -3), 0.05, (1.0, 0.45, 0.35), 8748.0)):
+        _sphere_light(wb, lights, pos, radius, color, intensity, True)
     world = wb.commit(lights)
     cam = usd_camera((0, 4, 12), -10.0, 16.0, 20.955, width, height)
     kw = dict(min_samples_per_pixel=32, variance_threshold=0.0, sampling_strategy=SamplingStrategy.BalanceMis)
@@ -149,7 +149,9 @@ def veach_mis(api, width: int = 960, height: int = 540, spp: int = 128, **settin
 def openpbr_showcase(api, width: int = 640, height: int = 360, spp: int = 128, **settings_kw):
     wb = api.WorldBuilder()
     lights = LightList()
-    wb.attach(Geometry.Sphere((0, -1000, 0), 1000.0), OpenPBR())  # ground, unbound
+    # reverse sibling order (see veach_mis): Light2, Light1, then Scene's spheres soap bubble .. chrome, ground
+    _sphere_light(wb, lights, (4, 8, -2), 1.5, (18, 12, 9), 1.0, True)
+    _sphere_light(wb, lights, (-2, 8, 3), 1.5, (15, 15, 15), 1.0, True)
     mats = [
         OpenPBR(base_color=(0.95, 0.95, 0.95), base_metalness=1.0, specular_roughness=0.02),
         OpenPBR(base_color=(0.8, 0.1, 0.1)),
@@ -161,13 +163,12 @@ def openpbr_showcase(api, width: int = 640, height: int = 360, spp: int = 128, *
         OpenPBR(base_color=(0.8, 0.8, 0.8), specular_roughness=0.02, specular_ior=1.33, transmission_weight=0.4, transmission_color=(0.95, 0.95, 1.0),
                 thin_film_weight=1.0, thin_film_thickness=0.55, geometry_thin_walled=1),
     ]
-    for k, m in enumerate(mats):
-        wb.attach(Geometry.Sphere((-7.5 + 2.5 * k, 1, 0), 1.0), m)
-    _sphere_light(wb, lights, (-2, 8, 3), 1.5, (15, 15, 15), 1.0, True)
-    _sphere_light(wb, lights, (4, 8, -2), 1.5, (18, 12, 9), 1.0, True)
+    for k in reversed(range(len(mats))):
+        wb.attach(Geometry.Sphere((-7.5 + 2.5 * k, 1, 0), 1.0), mats[k])
+    wb.attach(Geometry.Sphere((0, -1000, 0), 1000.0), OpenPBR())  # ground, unbound
     world = wb.commit(lights)
-    cam = usd_camera((0, 3, 22), 0.0, 50.0, 73.63848, width, height, vertical_aperture=41.42165, f_stop=1000.0, focus_distance=22.0,
-                     basis=((0.0, -0.09053575, -0.9958932), (0.0, 0.9958932, -0.09053575)))
+    cam = usd_camera(None, 0.0, 50.0, 73.63848, width, height, vertical_aperture=41.42165, f_stop=1000.0, focus_distance=22.0,
+                     matrix=((1, 0, 0, 0), (0, 0.9958932, -0.09053575, 0), (0, 0.09053575, 0.9958932, 0), (0, 3, 22, 1)))
     kw = dict(min_samples_per_pixel=32, variance_threshold=0.05)
     kw.update(settings_kw)
     return world, cam, RenderSettings(spp, 32, width, height, **kw)
@@ -181,14 +182,104 @@ def stress(api, grid: int = 6, shards: int = 30000, jitter: bool = False, width:
     lights = LightList()
     grey = OpenPBR(base_color=(0.55, 0.55, 0.6), specular_roughness=0.4)  # UsdPreviewSurface mapping, README.md:102-106
     meshes = W.stress_meshes(grid, shards, jitter)
+    # reverse sibling order (see veach_mis): the RectLight "Key" first, then OccluderSlab, Floor, Shards, Ball_{G-1}_{G-1} .. Ball_0_0.
+    # Key: 12 x 12 at (0, 12, 0), rotateX -90 => emits along -Y
+    _rect_light(wb, lights, (-6.0, 12.0, 6.0), (12.0, 0.0, 0.0), (0.0, 0.0, -12.0), (0.0, -1.0, 0.0), (6.0, 6.0, 6.0), False)
     n_tris = 0
-    for k, (v, i) in enumerate(meshes):
+    for k in reversed(range(len(meshes))):
+        v, i = meshes[k]
         wb.attach(Geometry.TriangleMesh(v, i), grey if k < grid * grid else OpenPBR())
         n_tris += len(i)
-    # RectLight "Key": 12 x 12 at (0, 12, 0), rotateX -90 => emits along -Y
-    _rect_light(wb, lights, (-6.0, 12.0, 6.0), (12.0, 0.0, 0.0), (0.0, 0.0, -12.0), (0.0, -1.0, 0.0), (6.0, 6.0, 6.0), False)
     world = wb.commit(lights)
     cam = usd_camera((0, 9, 20), -22.0, 24.0, 20.955, width, height)
     kw = dict(min_samples_per_pixel=16, variance_threshold=0.0)
     kw.update(settings_kw)
     return world, cam, RenderSettings(spp, 6, width, height, **kw), n_tris + 2
+
+
+# ---------------------------------------------------------------------------------------------
+# config 1: samples/cornellbox.usda (from the binary fixture the importer wrote)
+# ---------------------------------------------------------------------------------------------
+GOLDEN = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+
+def cornellbox(api, width: int = 512, height: int = 512, spp: int = 64, **settings_kw):
+    """5 meshes / 2 342 triangles, no lights (sky gradient only), importer defaults (depth 32, min 32,
+    threshold 0.05, triangle filter) with BASELINE.json's 512x512 / 64 spp override."""
+    from .usd.importer import DEFAULTS, build_camera, world_from_meshes
+    from .usd.usda import Attribute, Prim
+
+    z = np.load(os.path.join(GOLDEN, "cornellbox_scene.npz"))
+    kw = dict(min_samples_per_pixel=DEFAULTS["min_spp"], variance_threshold=DEFAULTS["variance"])
+    kw.update(settings_kw)
+    st = RenderSettings(spp, DEFAULTS["max_depth"], width, height, **kw)
+    meshes = [(z[f"mesh{k}_points"], z[f"mesh{k}_tris"].astype(np.uint32), z[f"mesh{k}_l2w"]) for k in range(int(z["n_meshes"]))]
+    world = world_from_meshes(api, meshes, st)
+    fl, hap, vap, fstop, focus = (float(v) for v in z["camera_params"])
+    cam_prim = Prim("def", "Camera", "camera1", "/scene/camera1")
+    for name, val in (("focalLength", fl), ("horizontalAperture", hap), ("verticalAperture", vap), ("fStop", fstop), ("focusDistance", focus)):
+        cam_prim.attributes[name] = Attribute(name, "float", val)
+    return world, build_camera(cam_prim, z["camera_l2w"], st), st
+
+
+# ---------------------------------------------------------------------------------------------
+# config 4 stand-in: a point-instanced city (two-level BVH)
+# ---------------------------------------------------------------------------------------------
+def _building(rng, floors: int, sides: int):
+    """A closed prism tower with setbacks: ~1.1-1.3 k triangles like the MedCity prototypes."""
+    verts, tris = [], []
+    rings = floors * 6
+    r0 = 1.0
+    for k in range(rings + 1):
+        y = k / rings * floors * 0.6
+        r = r0 * (1.0 - 0.35 * (k // (rings // 3 + 1)) / 3.0) * (1.0 + 0.04 * math.sin(k * 1.7))
+        for s in range(sides):
+            a = 2.0 * math.pi * s / sides
+            verts.append((r * math.cos(a), y, r * math.sin(a)))
+    for k in range(rings):
+        for s in range(sides):
+            a, b = k * sides + s, k * sides + (s + 1) % sides
+            c, d = a + sides, b + sides
+            tris += [(a, c, b), (b, c, d)]
+    top = len(verts)
+    verts.append((0.0, floors * 0.6, 0.0))
+    for s in range(sides):
+        tris.append((rings * sides + s, top, rings * sides + (s + 1) % sides))
+    return np.asarray(verts, np.float32), np.asarray(tris, np.uint32)
+
+
+def point_instanced_city(api, n_instances: int = 40000, width: int = 640, height: int = 360, spp: int = 128, seed: int = 7, **settings_kw):
+    """STAND-IN for samples/PointInstancedMedCity.usd (binary USDC; a crate reader is SURVEY §8f): the
+    same shape of work — one top-level scene of `n_instances` instances (T * R * S per instance,
+    usd_import.rs:1775-1782) over 4 distinct ~1.1-1.3 k-triangle prototype BLASes, Z-up like the file,
+    default grey OpenPBR, no lights (sky only, no shadow rays), importer default settings."""
+    rng = np.random.default_rng(seed)
+    protos = []
+    for floors, sides in ((9, 10), (8, 11), (10, 10), (9, 11)):
+        v, t = _building(rng, floors, sides)
+        v = v[:, [0, 2, 1]].copy()  # Z-up
+        t = t[:, [0, 2, 1]].copy()
+        sb = api.SceneBuilder()
+        sb.attach(Geometry.TriangleMesh(v, t))
+        protos.append((sb.commit(), len(t)))
+    wb = api.WorldBuilder()
+    side = int(math.ceil(math.sqrt(n_instances)))
+    grey = OpenPBR()
+    k = 0
+    for iy in range(side):
+        for ix in range(side):
+            if k >= n_instances:
+                break
+            yaw = float(rng.uniform(0.0, 2.0 * math.pi))
+            s = float(rng.uniform(0.7, 1.3))
+            pos = ((ix - side / 2) * 3.0 + float(rng.uniform(-0.5, 0.5)), (iy - side / 2) * 3.0 + float(rng.uniform(-0.5, 0.5)), 0.0)
+            xf = Affine3A.from_translation(pos) * Affine3A.from_rotation_z(yaw) * Affine3A.from_scale((s, s, s * float(rng.uniform(0.6, 1.8))))
+            wb.attach(Geometry.Instance(protos[int(rng.integers(0, 4))][0], xf), grey)
+            k += 1
+    wb.attach(Geometry.TriangleMesh(np.asarray([(-side * 2, -side * 2, 0), (side * 2, -side * 2, 0), (side * 2, side * 2, 0), (-side * 2, side * 2, 0)], np.float32), QUAD), grey)
+    world = wb.commit(LightList())
+    ext = side * 1.5
+    cam = Camera((-ext * 0.9, -ext * 1.1, ext * 0.55), (0.0, 0.0, 0.0), (0.0, 0.0, 1.0), 40.0, width / height, 0.0, 10.0)
+    kw = dict(min_samples_per_pixel=32, variance_threshold=0.05)
+    kw.update(settings_kw)
+    return world, cam, RenderSettings(spp, 32, width, height, **kw), sum(n for _, n in protos)

@@ -91,6 +91,26 @@ def test_config5_stress_scene_small(gpu, orc):
     stats_close(sg, so)
 
 
+def test_config1_cornellbox(gpu, orc):
+    """samples/cornellbox.usda via the importer's fixture: 822 baked triangles + two instances of one
+    760-triangle BLAS, no lights (no shadow rays at all), depth 32 with Russian roulette, adaptive on."""
+    fg, sg, fo, so, _ = both(gpu, orc, scenes.cornellbox, width=128, height=128, spp=48)
+    same = fg[..., 3] == fo[..., 3]
+    assert same.mean() >= 0.999
+    compare(fg[same], fo[same])
+    stats_close(sg, so, tol=2e-3, adaptive=True)
+    assert sg.shadow_rays == 0 and sg.rr_tested > 0
+
+
+def test_config4_point_instanced_city_stand_in(gpu, orc):
+    """Two-level traversal: thousands of instances over four shared BLASes, sky light only."""
+    fn = lambda api, **kw: scenes.point_instanced_city(api, **kw)  # noqa: E731
+    fg, sg, fo, so, _ = both(gpu, orc, fn, n_instances=2500, width=160, height=90, spp=8, variance_threshold=0.0)
+    compare(fg, fo)
+    stats_close(sg, so)
+    assert sg.shadow_rays == 0
+
+
 @pytest.mark.parametrize("kind,radius", [(PixelFilterKind.Box, 0.5), (PixelFilterKind.Gaussian, 1.5), (PixelFilterKind.Mitchell, 2.0)])
 def test_pixel_filters(gpu, orc, kind, radius):
     fg, _, fo, _, _ = both(gpu, orc, scenes.furnace_room, width=64, height=48, spp=8, variance_threshold=0.0, pixel_filter=PixelFilter(kind, radius))
