@@ -42,6 +42,9 @@ namespace {
     } while (0)
 
 constexpr int kBlock = 128;
+#ifndef CRT_SHADE_MINBLOCKS
+#define CRT_SHADE_MINBLOCKS 8  // resident blocks per SM shade_kernel is compiled for: 64 registers with spills beat 128 registers at half the occupancy (measured 4/5/6/8 on B200)
+#endif
 constexpr uint32_t FLAG_HAS_PREV = 1u, FLAG_PREV_DELTA = 2u;  // PrevBounce, tracer.rs:898-905
 constexpr float kTMin = 0.001f;                               // tracer.rs:1152 / 1029
 
@@ -161,7 +164,7 @@ __device__ __forceinline__ float bounce_emission_weight(const RenderParams& P, u
 }
 
 // ---- shade: one path vertex per queue entry (tracer.rs:1118-1535) --------------------------------
-__global__ void __launch_bounds__(kBlock) shade_kernel(const RenderParams P, int k, int cur) {
+__global__ void __launch_bounds__(kBlock, CRT_SHADE_MINBLOCKS) shade_kernel(const RenderParams P, int k, int cur) {
     const int D = (int)P.st.max_depth;
     const uint32_t n = P.q.counts[k];
     uint32_t* next_count = P.q.counts + k + 1;
@@ -635,7 +638,7 @@ int render_impl(crt_world* w, const crt_camera* camera, const crt_render_setting
     }
 
     // ---- buffers ----
-    size_t cap = s->max_paths ? s->max_paths : ((size_t)1 << 22);
+    size_t cap = s->max_paths ? s->max_paths : ((size_t)1 << 24);  // 16 Mi paths (~5.8 GB of queues + state): fewer, longer launches; measured 4..64 Mi on B200
     cap = std::max<size_t>(cap, 1024);
     cap = std::min<size_t>(cap, (size_t)n_pix * s->samples_per_pixel);
     cap = std::max<size_t>(cap, 1);
