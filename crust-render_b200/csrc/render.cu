@@ -24,6 +24,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstring>
 #include <mutex>
 #include <vector>
 
@@ -467,6 +468,10 @@ __global__ void __launch_bounds__(kBlock) film_kernel(const RenderParams P, uint
     }
 }
 
+// crt_steal_cursor: one u32 in device memory of the creating process; peers map it through CUDA IPC and bump
+// it with system-scope atomics (over NVLink / NVSwitch peer access).
+__global__ void fetch_chunk_kernel(unsigned int* cursor, uint32_t* out) { *out = atomicAdd_system(cursor, 1u); }
+
 struct Scratch {  // grow-only device buffers reused across crt_render calls on one world
     size_t cap_paths = 0, cap_pixels = 0, cap_counts = 0;
     void* paths = nullptr;   // everything sized by the path pool
@@ -488,10 +493,15 @@ struct Scratch {  // grow-only device buffers reused across crt_render calls on 
     }
 };
 
-thread_local uint64_t t_last_launches = 0, t_last_rounds = 0;
+thread_local uint64_t t_last_launches = 0, t_last_rounds = 0, t_last_chunks = 0;
 thread_local double t_last_ms = 0.0;
 
 }  // namespace
+
+struct crt_steal_cursor {
+    unsigned int* dev = nullptr;
+    bool owner = false;
+};
 
 struct crt_world {
     crt_scene* scene = nullptr;
@@ -560,6 +570,63 @@ int crt_world_new(crt_scene* scene, const crt_material* materials, size_t n_mate
 
 void crt_world_release(crt_world* w) { delete w; }
 
+int crt_steal_cursor_create(crt_steal_cursor** out, unsigned char ipc_handle[64]) {
+    if (!out) return crt::set_error(CRT_ERR_INVALID_ARG, "crt_steal_cursor_create: null argument");
+    int rc = crt::require_device();
+    if (rc) return rc;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "ipc handle size");
+    auto* c = new crt_steal_cursor();
+    c->owner = true;
+    cudaError_t e = cudaMalloc(&c->dev, sizeof(unsigned int));
+    if (e == cudaSuccess) e = cudaMemset(c->dev, 0, sizeof(unsigned int));
+    if (e == cudaSuccess && ipc_handle) {
+        cudaIpcMemHandle_t h;
+        e = cudaIpcGetMemHandle(&h, c->dev);
+        if (e == cudaSuccess) memcpy(ipc_handle, &h, 64);
+    }
+    if (e != cudaSuccess) {
+        cudaFree(c->dev);
+        delete c;
+        return crt::set_cuda_error(e, "crt_steal_cursor_create");
+    }
+    *out = c;
+    return CRT_OK;
+}
+
+int crt_steal_cursor_open(const unsigned char ipc_handle[64], crt_steal_cursor** out) {
+    if (!out || !ipc_handle) return crt::set_error(CRT_ERR_INVALID_ARG, "crt_steal_cursor_open: null argument");
+    int rc = crt::require_device();
+    if (rc) return rc;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, ipc_handle, 64);
+    auto* c = new crt_steal_cursor();
+    cudaError_t e = cudaIpcOpenMemHandle((void**)&c->dev, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+        delete c;
+        return crt::set_cuda_error(e, "cudaIpcOpenMemHandle (peer access between the two GPUs is required)");
+    }
+    *out = c;
+    return CRT_OK;
+}
+
+int crt_steal_cursor_reset(crt_steal_cursor* c) {
+    if (!c || !c->owner) return crt::set_error(CRT_ERR_INVALID_ARG, "crt_steal_cursor_reset: only the creating process resets the cursor");
+    CKR(cudaMemset(c->dev, 0, sizeof(unsigned int)));
+    return CRT_OK;
+}
+
+void crt_steal_cursor_close(crt_steal_cursor* c) {
+    if (!c) return;
+    if (c->owner)
+        cudaFree(c->dev);
+    else
+        cudaIpcCloseMemHandle(c->dev);
+    delete c;
+}
+
+int crt_render_steal(const crt_world* w, const crt_camera* camera, const crt_render_settings* settings, float* framebuffer, crt_ray_stats* stats, void* stream,
+                     crt_steal_cursor* cursor);
+
 int crt_render_last_info(uint64_t* launches, double* device_ms, uint64_t* rounds) {
     if (launches) *launches = t_last_launches;
     if (device_ms) *device_ms = t_last_ms;
@@ -579,7 +646,8 @@ T* carve(char*& p, size_t count) {
 }
 size_t carve_bytes(size_t count, size_t elem) { return (count * elem + 255) & ~(size_t)255; }
 
-int render_impl(crt_world* w, const crt_camera* camera, const crt_render_settings* s, float* d_fb, crt_ray_stats* stats_out, cudaStream_t stream) {
+int render_impl(crt_world* w, const crt_camera* camera, const crt_render_settings* s, float* d_fb, crt_ray_stats* stats_out, cudaStream_t stream,
+                crt_steal_cursor* cursor) {
     if (!w || !camera || !s || !d_fb) return crt::set_error(CRT_ERR_INVALID_ARG, "crt_render: null argument");
     if (s->width == 0 || s->height == 0 || (uint64_t)s->width * s->height > 0x7FFFFFFFu) return crt::set_error(CRT_ERR_INVALID_ARG, "crt_render: bad image size");
     if (s->samples_per_pixel == 0 || s->samples_per_pixel > 65536u) return crt::set_error(CRT_ERR_INVALID_ARG, "crt_render: samples_per_pixel must be in 1..65536 (sampler index range)");
@@ -593,31 +661,37 @@ int render_impl(crt_world* w, const crt_camera* camera, const crt_render_setting
     Scratch& sc = w->scratch;
     const int sms = crt::device_sm_count();
     const int D = (int)s->max_depth;
-    uint64_t launches = 0, trace_launches = 0, rounds = 0;
+    uint64_t launches = 0, trace_launches = 0, rounds = 0, chunks_done = 0;
 
-    // ---- the pixels this process owns, tile by tile (interleaved tiles) ----
+    // ---- which pixels this process renders ----
+    // Tiles are walked in 8x4 pixel blocks so a warp of camera rays covers a compact footprint.
+    const uint32_t W = s->width, H = s->height;
+    const uint32_t T = s->tile_size ? s->tile_size : 32u, tiles_x = (W + T - 1) / T, tiles_y = (H + T - 1) / T, n_tiles = tiles_x * tiles_y;
+    auto append_tile = [&](uint32_t t, std::vector<uint32_t>& out) {
+        uint32_t x0 = (t % tiles_x) * T, y0 = (t / tiles_x) * T;
+        for (uint32_t by = y0; by < std::min(y0 + T, H); by += 4)
+            for (uint32_t bx = x0; bx < std::min(x0 + T, W); bx += 8)
+                for (uint32_t y = by; y < std::min({by + 4, y0 + T, H}); ++y)
+                    for (uint32_t x = bx; x < std::min({bx + 8, x0 + T, W}); ++x) out.push_back(y * W + x);
+    };
     std::vector<uint32_t> pixels;
-    {
-        const uint32_t W = s->width, H = s->height;
-        if (s->tile_world <= 1) {
-            // whole image, in 8x4 blocks so a warp of camera rays covers a compact footprint
-            pixels.reserve((size_t)W * H);
-            for (uint32_t by = 0; by < H; by += 4)
-                for (uint32_t bx = 0; bx < W; bx += 8)
-                    for (uint32_t y = by; y < std::min(by + 4, H); ++y)
-                        for (uint32_t x = bx; x < std::min(bx + 8, W); ++x) pixels.push_back(y * W + x);
-        } else {
-            const uint32_t T = s->tile_size, tx = (W + T - 1) / T, ty = (H + T - 1) / T;
-            for (uint32_t t = s->tile_rank; t < tx * ty; t += s->tile_world) {
-                uint32_t x0 = (t % tx) * T, y0 = (t / tx) * T;
-                for (uint32_t by = y0; by < std::min(y0 + T, H); by += 4)
-                    for (uint32_t bx = x0; bx < std::min(x0 + T, W); bx += 8)
-                        for (uint32_t y = by; y < std::min({by + 4, y0 + T, H}); ++y)
-                            for (uint32_t x = bx; x < std::min({bx + 8, x0 + T, W}); ++x) pixels.push_back(y * W + x);
-            }
-        }
+    const uint32_t steal_chunk = cursor ? std::max(1u, s->steal_chunk_tiles) : 0u;
+    const uint32_t n_chunks = steal_chunk ? (n_tiles + steal_chunk - 1) / steal_chunk : 0u;
+    size_t max_pixels;  // largest pixel set one render_pixel_set call will see (buffer sizing)
+    if (cursor) {
+        max_pixels = std::min<size_t>((size_t)steal_chunk * T * T, (size_t)W * H);
+    } else if (s->tile_world <= 1) {
+        pixels.reserve((size_t)W * H);
+        for (uint32_t by = 0; by < H; by += 4)
+            for (uint32_t bx = 0; bx < W; bx += 8)
+                for (uint32_t y = by; y < std::min(by + 4, H); ++y)
+                    for (uint32_t x = bx; x < std::min(bx + 8, W); ++x) pixels.push_back(y * W + x);
+        max_pixels = pixels.size();
+    } else {
+        // static deal: tile t belongs to rank t % world (interleaved, so adaptive cost is decorrelated from rank)
+        for (uint32_t t = s->tile_rank; t < n_tiles; t += s->tile_world) append_tile(t, pixels);
+        max_pixels = pixels.size();
     }
-    const uint32_t n_pix = (uint32_t)pixels.size();
     if (!sc.ev0) {
         CKR(cudaEventCreate(&sc.ev0));
         CKR(cudaEventCreate(&sc.ev1));
@@ -627,7 +701,7 @@ int render_impl(crt_world* w, const crt_camera* camera, const crt_render_setting
     }
     CKR(cudaEventRecord(sc.ev0, stream));
     CKR(cudaMemsetAsync(sc.stats, 0, 8 * sizeof(unsigned long long), stream));
-    if (n_pix == 0) {
+    if (max_pixels == 0) {
         CKR(cudaEventRecord(sc.ev1, stream));
         CKR(cudaStreamSynchronize(stream));
         if (stats_out) *stats_out = crt_ray_stats{};
@@ -640,7 +714,7 @@ int render_impl(crt_world* w, const crt_camera* camera, const crt_render_setting
     // ---- buffers ----
     size_t cap = s->max_paths ? s->max_paths : ((size_t)1 << 24);  // 16 Mi paths (~5.8 GB of queues + state): fewer, longer launches; measured 4..64 Mi on B200
     cap = std::max<size_t>(cap, 1024);
-    cap = std::min<size_t>(cap, (size_t)n_pix * s->samples_per_pixel);
+    cap = std::min<size_t>(cap, max_pixels * s->samples_per_pixel);
     cap = std::max<size_t>(cap, 1);
     const bool motion = w->scene->has_motion;
     {
@@ -654,7 +728,7 @@ int render_impl(crt_world* w, const crt_camera* camera, const crt_render_setting
             CKR(cudaMalloc(&sc.paths, need));
             sc.cap_paths = need;
         }
-        size_t need_px = carve_bytes(n_pix, 4) * 4 + carve_bytes(n_pix, 16) * 2;
+        size_t need_px = carve_bytes(max_pixels, 4) * 4 + carve_bytes(max_pixels, 16) * 2;
         if (need_px > sc.cap_pixels) {
             cudaFree(sc.pixels);
             sc.pixels = nullptr;
@@ -704,25 +778,6 @@ int render_impl(crt_world* w, const crt_camera* camera, const crt_render_setting
         P.q.scontrib = carve<float4>(p, cap);
         P.q.occ = carve<uint8_t>(p, cap);
         P.q.counts = sc.counts;
-    }
-    uint32_t* d_active[2];
-    {
-        char* p = (char*)sc.pixels;
-        uint32_t* d_pixels = carve<uint32_t>(p, n_pix);
-        d_active[0] = carve<uint32_t>(p, n_pix);
-        d_active[1] = carve<uint32_t>(p, n_pix);
-        P.px.taken = carve<uint32_t>(p, n_pix);
-        P.px.sum_w = carve<float4>(p, n_pix);
-        P.px.lum = (double2*)carve<float4>(p, n_pix);
-        P.px.pixels = d_pixels;
-        CKR(cudaMemcpyAsync(d_pixels, pixels.data(), (size_t)n_pix * 4, cudaMemcpyHostToDevice, stream));
-        std::vector<uint32_t> iota(n_pix);
-        for (uint32_t i = 0; i < n_pix; ++i) iota[i] = i;
-        CKR(cudaMemcpyAsync(d_active[0], iota.data(), (size_t)n_pix * 4, cudaMemcpyHostToDevice, stream));
-        CKR(cudaStreamSynchronize(stream));  // the staging vectors die with this scope
-        CKR(cudaMemsetAsync(P.px.taken, 0, (size_t)n_pix * 4, stream));
-        CKR(cudaMemsetAsync(P.px.sum_w, 0, (size_t)n_pix * 16, stream));
-        CKR(cudaMemsetAsync(P.px.lum, 0, (size_t)n_pix * 16, stream));
     }
     auto grid_for = [&](size_t n) {
         size_t blocks = (n + kBlock - 1) / kBlock;
@@ -783,47 +838,92 @@ int render_impl(crt_world* w, const crt_camera* camera, const crt_render_setting
         return CRT_OK;
     };
 
-    // ---- rounds (tracer.rs:558-618): samples are taken in order; the adaptive test runs after every
-    //      4th sample once min_spp is reached, so rounds end on those boundaries ----
-    const uint32_t spp = s->samples_per_pixel;
-    const bool adaptive = s->adaptive && s->variance_threshold > 0.0f;
-    const uint32_t min_spp = std::max(s->min_samples_per_pixel, 2u);
-    uint32_t n_active = n_pix, s_base = 0;
-    int cur_list = 0;
-    while (n_active > 0 && s_base < spp) {
-        uint32_t round_samples;
-        if (!adaptive)
-            round_samples = spp - s_base;
-        else if (s_base == 0)
-            round_samples = std::min(spp, (min_spp + 3u) / 4u * 4u);
-        else
-            round_samples = std::min(spp - s_base, 4u);
-        // split the round into wavefronts that fit the pool
-        uint32_t sub = (uint32_t)std::max<size_t>(1, std::min<size_t>(round_samples, cap / n_active));
-        uint32_t block_px = (uint32_t)std::min<size_t>(n_active, cap / sub);
-        for (uint32_t s0 = 0; s0 < round_samples; s0 += sub) {
-            uint32_t sc_count = std::min(sub, round_samples - s0);
-            for (uint32_t off = 0; off < n_active; off += block_px) {
-                uint32_t nb = std::min(block_px, n_active - off);
-                int r = wavefront(d_active[cur_list] + off, nb, s_base + s0, sc_count);
-                if (r) return r;
-                accumulate_kernel<<<grid_for(nb), kBlock, 0, stream>>>(P, d_active[cur_list] + off, nb, sc_count);
-                ++launches;
-            }
+    // ---- one pixel set: all rounds of all its pixels, then its film pixels ----
+    uint32_t* d_active[2] = {nullptr, nullptr};
+    auto render_pixel_set = [&](const std::vector<uint32_t>& pixels) -> int {
+        const uint32_t n_pix = (uint32_t)pixels.size();
+        if (n_pix == 0) return CRT_OK;
+        {
+            char* p = (char*)sc.pixels;
+            uint32_t* d_pixels = carve<uint32_t>(p, n_pix);
+            d_active[0] = carve<uint32_t>(p, n_pix);
+            d_active[1] = carve<uint32_t>(p, n_pix);
+            P.px.taken = carve<uint32_t>(p, n_pix);
+            P.px.sum_w = carve<float4>(p, n_pix);
+            P.px.lum = (double2*)carve<float4>(p, n_pix);
+            P.px.pixels = d_pixels;
+            CKR(cudaMemcpyAsync(d_pixels, pixels.data(), (size_t)n_pix * 4, cudaMemcpyHostToDevice, stream));
+            std::vector<uint32_t> iota(n_pix);
+            for (uint32_t i = 0; i < n_pix; ++i) iota[i] = i;
+            CKR(cudaMemcpyAsync(d_active[0], iota.data(), (size_t)n_pix * 4, cudaMemcpyHostToDevice, stream));
+            CKR(cudaStreamSynchronize(stream));  // the staging vectors die with this scope
+            CKR(cudaMemsetAsync(P.px.taken, 0, (size_t)n_pix * 4, stream));
+            CKR(cudaMemsetAsync(P.px.sum_w, 0, (size_t)n_pix * 16, stream));
+            CKR(cudaMemsetAsync(P.px.lum, 0, (size_t)n_pix * 16, stream));
         }
-        s_base += round_samples;
-        ++rounds;
-        if (s_base >= spp) break;
-        CKR(cudaMemsetAsync(sc.active_count, 0, sizeof(uint32_t), stream));
-        adaptive_kernel<<<grid_for(n_active), kBlock, 0, stream>>>(P, d_active[cur_list], n_active, d_active[cur_list ^ 1], sc.active_count);
+        // ---- rounds (tracer.rs:558-618): samples are taken in order; the adaptive test runs after every
+        //      4th sample once min_spp is reached, so rounds end on those boundaries ----
+        const uint32_t spp = s->samples_per_pixel;
+        const bool adaptive = s->adaptive && s->variance_threshold > 0.0f;
+        const uint32_t min_spp = std::max(s->min_samples_per_pixel, 2u);
+        uint32_t n_active = n_pix, s_base = 0;
+        int cur_list = 0;
+        while (n_active > 0 && s_base < spp) {
+            uint32_t round_samples;
+            if (!adaptive)
+                round_samples = spp - s_base;
+            else if (s_base == 0)
+                round_samples = std::min(spp, (min_spp + 3u) / 4u * 4u);
+            else
+                round_samples = std::min(spp - s_base, 4u);
+            // split the round into wavefronts that fit the pool
+            uint32_t sub = (uint32_t)std::max<size_t>(1, std::min<size_t>(round_samples, cap / n_active));
+            uint32_t block_px = (uint32_t)std::min<size_t>(n_active, cap / sub);
+            for (uint32_t s0 = 0; s0 < round_samples; s0 += sub) {
+                uint32_t sc_count = std::min(sub, round_samples - s0);
+                for (uint32_t off = 0; off < n_active; off += block_px) {
+                    uint32_t nb = std::min(block_px, n_active - off);
+                    int r = wavefront(d_active[cur_list] + off, nb, s_base + s0, sc_count);
+                    if (r) return r;
+                    accumulate_kernel<<<grid_for(nb), kBlock, 0, stream>>>(P, d_active[cur_list] + off, nb, sc_count);
+                    ++launches;
+                }
+            }
+            s_base += round_samples;
+            ++rounds;
+            if (s_base >= spp) break;
+            CKR(cudaMemsetAsync(sc.active_count, 0, sizeof(uint32_t), stream));
+            adaptive_kernel<<<grid_for(n_active), kBlock, 0, stream>>>(P, d_active[cur_list], n_active, d_active[cur_list ^ 1], sc.active_count);
+            ++launches;
+            CKR(cudaMemcpyAsync(sc.h_pinned, sc.active_count, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+            CKR(cudaStreamSynchronize(stream));
+            n_active = sc.h_pinned[0];
+            cur_list ^= 1;
+        }
+        film_kernel<<<grid_for(n_pix), kBlock, 0, stream>>>(P, n_pix, (float4*)d_fb);
         ++launches;
-        CKR(cudaMemcpyAsync(sc.h_pinned, sc.active_count, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
-        CKR(cudaStreamSynchronize(stream));
-        n_active = sc.h_pinned[0];
-        cur_list ^= 1;
+        return CRT_OK;
+    };
+    if (cursor) {
+        // work stealing: every process pulls chunks of `steal_chunk` tiles off one system-scope cursor until the
+        // frame is exhausted; chunk c = tiles {c + k * n_chunks}, i.e. spread over the whole image
+        for (;;) {
+            fetch_chunk_kernel<<<1, 1, 0, stream>>>(cursor->dev, sc.active_count + 1);
+            ++launches;
+            CKR(cudaMemcpyAsync(sc.h_pinned + 1, sc.active_count + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+            CKR(cudaStreamSynchronize(stream));
+            const uint32_t c = sc.h_pinned[1];
+            if (c >= n_chunks) break;
+            pixels.clear();
+            for (uint32_t t = c; t < n_tiles; t += n_chunks) append_tile(t, pixels);
+            int r = render_pixel_set(pixels);
+            if (r) return r;
+            ++chunks_done;
+        }
+    } else {
+        int r = render_pixel_set(pixels);
+        if (r) return r;
     }
-    film_kernel<<<grid_for(n_pix), kBlock, 0, stream>>>(P, n_pix, (float4*)d_fb);
-    ++launches;
     CKR(cudaGetLastError());
     CKR(cudaMemcpyAsync(sc.h_pinned + 16, sc.stats, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
     CKR(cudaEventRecord(sc.ev1, stream));
@@ -846,6 +946,7 @@ int render_impl(crt_world* w, const crt_camera* camera, const crt_render_setting
     t_last_launches = launches;
     t_last_rounds = rounds;
     t_last_ms = (double)ms;
+    t_last_chunks = chunks_done;
     return CRT_OK;
 }
 
@@ -854,7 +955,13 @@ int render_impl(crt_world* w, const crt_camera* camera, const crt_render_setting
 extern "C" {
 
 int crt_render(const crt_world* w, const crt_camera* camera, const crt_render_settings* settings, float* framebuffer, crt_ray_stats* stats, void* stream) {
-    return render_impl(const_cast<crt_world*>(w), camera, settings, framebuffer, stats, (cudaStream_t)stream);
+    return render_impl(const_cast<crt_world*>(w), camera, settings, framebuffer, stats, (cudaStream_t)stream, nullptr);
+}
+
+int crt_render_steal(const crt_world* w, const crt_camera* camera, const crt_render_settings* settings, float* framebuffer, crt_ray_stats* stats, void* stream,
+                     crt_steal_cursor* cursor) {
+    if (!cursor) return crt::set_error(CRT_ERR_INVALID_ARG, "crt_render_steal: null cursor");
+    return render_impl(const_cast<crt_world*>(w), camera, settings, framebuffer, stats, (cudaStream_t)stream, cursor);
 }
 
 int crt_render_host(const crt_world* w, const crt_camera* camera, const crt_render_settings* settings, float* framebuffer, crt_ray_stats* stats) {
@@ -866,7 +973,7 @@ int crt_render_host(const crt_world* w, const crt_camera* camera, const crt_rend
     CKR(cudaMalloc(&d, bytes ? bytes : 16));
     cudaError_t e = cudaMemcpy(d, framebuffer, bytes, cudaMemcpyHostToDevice);  // pixels of other ranks stay as given
     if (e == cudaSuccess) {
-        rc = render_impl(const_cast<crt_world*>(w), camera, settings, d, stats, nullptr);
+        rc = render_impl(const_cast<crt_world*>(w), camera, settings, d, stats, nullptr, nullptr);
         if (rc == CRT_OK) e = cudaMemcpy(framebuffer, d, bytes, cudaMemcpyDeviceToHost);
     }
     cudaFree(d);

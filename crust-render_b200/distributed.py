@@ -33,8 +33,39 @@ def owned_mask(width: int, height: int, tile_size: int, rank: int, world: int) -
     return ((jj // tile_size) * tx + ii // tile_size) % world == rank
 
 
-def render_distributed(renderer, dist=None, tile_size: int = 32, fb=None, stream: int = 0):
+_CURSORS = {}
+
+
+def shared_cursor(dist, device):
+    """One StealCursor per process group: rank 0 creates it, the 64-byte CUDA IPC handle is broadcast, the other
+    ranks open it (peer access over NVLink). Cached for the life of the process."""
+    import torch
+
+    from .render import StealCursor
+
+    key = id(dist.group.WORLD) if dist is not None and dist.is_initialized() else None
+    if key in _CURSORS:
+        return _CURSORS[key]
+    world = dist.get_world_size() if key is not None else 1
+    rank = dist.get_rank() if world > 1 else 0
+    cur = StealCursor() if rank == 0 else None
+    if world > 1:
+        t = torch.zeros(64, dtype=torch.uint8, device=device)
+        if rank == 0:
+            t.copy_(torch.frombuffer(bytearray(cur.handle), dtype=torch.uint8))
+        dist.broadcast(t, src=0)
+        if rank != 0:
+            cur = StealCursor(bytes(t.cpu().numpy().tobytes()))
+    _CURSORS[key] = cur
+    return cur
+
+
+def render_distributed(renderer, dist=None, tile_size: int = 32, fb=None, stream: int = 0, steal: bool = False):
     """Renders this rank's tiles and sum-reduces frame + RayStats to rank 0.
+
+    steal=True (device framebuffer only): instead of the static round-robin deal, every rank pulls chunks of
+    `settings.steal_chunk_tiles` tiles off a cursor shared through CUDA IPC until the frame is exhausted —
+    balances adaptive sampling, whose cost per tile is not known in advance. The image is the same either way.
 
     `renderer` is a Renderer (CUDA binding; the oracle's in CPU tests). With `fb` a CUDA torch tensor
     [h, w, 4] the render writes device memory and the reduce runs on it (NCCL); otherwise host
@@ -47,7 +78,18 @@ def render_distributed(renderer, dist=None, tile_size: int = 32, fb=None, stream
     base = renderer.settings
     renderer.settings = rank_settings(base, rank, world, tile_size)
     try:
-        if fb is not None:
+        if fb is not None and steal:
+            cursor = shared_cursor(dist, fb.device)
+            fb.zero_()
+            if world > 1:
+                dist.barrier()          # nobody is still pulling from the previous frame
+            if rank == 0:
+                cursor.reset()
+            if world > 1:
+                dist.barrier()          # the cursor is zero before anyone pulls
+            stats = renderer.render_steal(fb.data_ptr(), cursor, stream)
+            frame = fb
+        elif fb is not None:
             fb.zero_()
             stats = renderer.render_device(fb.data_ptr(), stream)
             frame = fb

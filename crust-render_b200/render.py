@@ -29,7 +29,7 @@ from .render_types import (  # noqa: F401
     WorldBuilderBase,
 )
 
-__all__ = ["World", "WorldBuilder", "Renderer", "Camera", "RenderSettings", "SamplingStrategy", "PixelFilter", "PixelFilterKind",
+__all__ = ["World", "WorldBuilder", "Renderer", "StealCursor", "Camera", "RenderSettings", "SamplingStrategy", "PixelFilter", "PixelFilterKind",
            "RayStats", "LightList", "OpenPBR", "Emissive", "SphereLight", "RectLight", "DistantLight", "DomeLight"]
 
 
@@ -76,6 +76,32 @@ class WorldBuilder(WorldBuilderBase):
         return World(self._sb.commit(), mats, gm, lights or LightList())
 
 
+class StealCursor:
+    """The shared tile cursor of crt_render_steal (include/crt_render.h): created by one process, opened by the
+    others from its 64-byte CUDA IPC handle."""
+
+    def __init__(self, handle: Optional[bytes] = None):
+        h = C.c_void_p()
+        if handle is None:
+            buf = (C.c_ubyte * 64)()
+            rt._ck(rt.lib().crt_steal_cursor_create(C.byref(h), buf))
+            self.handle, self.owner = bytes(buf), True
+        else:
+            buf = (C.c_ubyte * 64).from_buffer_copy(handle)
+            rt._ck(rt.lib().crt_steal_cursor_open(buf, C.byref(h)))
+            self.handle, self.owner = bytes(handle), False
+        self._h = h
+
+    def reset(self) -> None:
+        rt._ck(rt.lib().crt_steal_cursor_reset(self._h))
+
+    def __del__(self):
+        L = getattr(rt, "_lib", None) if rt is not None else None
+        if getattr(self, "_h", None) and L is not None:
+            L.crt_steal_cursor_close(self._h)
+            self._h = None
+
+
 class Renderer:
     """`Renderer::new(camera, world, lights, settings)` (tracer.rs:149-163); lights live in the World here."""
 
@@ -103,6 +129,14 @@ class Renderer:
 
     def render(self) -> np.ndarray:  # tracer.rs:172-174
         return self.render_with_stats()[0]
+
+    def render_steal(self, fb_ptr: int, cursor: StealCursor, stream: int = 0) -> RayStats:
+        """crt_render_steal: renders the chunks of tiles this process wins off the shared cursor."""
+        stats = np.zeros((), dtype=STATS_DTYPE)
+        cam, rec = self.camera.record(), self.settings.record()
+        rt._ck(rt.lib().crt_render_steal(self.world._h, _p(cam), _p(rec), C.c_void_p(fb_ptr), _p(stats), C.c_void_p(stream), cursor._h))
+        self._info()
+        return RayStats.from_record(stats)
 
     def render_device(self, fb_ptr: int, stream: int = 0) -> RayStats:
         """Same with a device framebuffer (width*height float4) and a CUDA stream."""

@@ -34,7 +34,7 @@ SETTINGS_DTYPE = np.dtype([("width", "<u4"), ("height", "<u4"), ("samples_per_pi
                            ("min_samples_per_pixel", "<u4"), ("variance_threshold", "<f4"), ("frame", "<i4"),
                            ("sampling_strategy", "<u4"), ("adaptive", "<u4"), ("pixel_filter", "<u4"), ("filter_radius", "<f4"),
                            ("tile_size", "<u4"), ("tile_rank", "<u4"), ("tile_world", "<u4"), ("max_paths", "<u4"),
-                           ("reserved", "<u4")])  # crt_render_settings
+                           ("steal_chunk_tiles", "<u4")])  # crt_render_settings
 STATS_DTYPE = np.dtype([(n, "<u8") for n in ("camera_rays", "closest_hit", "shadow_rays", "vertices", "rr_tested", "rr_killed",
                                               "ended_escaped", "ended_depth")])  # crt_ray_stats
 assert MATERIAL_DTYPE.itemsize == 236 and LIGHT_DTYPE.itemsize == 76 and CAMERA_DTYPE.itemsize == 52
@@ -175,6 +175,7 @@ class RenderSettings:
     tile_rank: int = 0
     tile_world: int = 1
     max_paths: int = 0
+    steal_chunk_tiles: int = 64
 
     def with_samples_per_pixel(self, spp: int) -> "RenderSettings":
         self.samples_per_pixel = max(int(spp), 1)
@@ -198,6 +199,7 @@ class RenderSettings:
         s["variance_threshold"], s["frame"], s["sampling_strategy"] = self.variance_threshold, self.frame, int(self.sampling_strategy)
         s["adaptive"], s["pixel_filter"], s["filter_radius"] = int(self.adaptive), int(self.pixel_filter.kind), self.pixel_filter.radius
         s["tile_size"], s["tile_rank"], s["tile_world"], s["max_paths"] = self.tile_size, self.tile_rank, self.tile_world, self.max_paths
+        s["steal_chunk_tiles"] = self.steal_chunk_tiles
         return s
 
 

@@ -133,12 +133,16 @@ def lib() -> C.CDLL:
         "crt_render": [vp, vp, vp, vp, vp, vp],
         "crt_render_host": [vp, vp, vp, vp, vp],
         "crt_render_last_info": [C.POINTER(u64), C.POINTER(C.c_double), C.POINTER(u64)],
+        "crt_steal_cursor_create": [C.POINTER(vp), vp],
+        "crt_steal_cursor_open": [vp, C.POINTER(vp)],
+        "crt_steal_cursor_reset": [vp],
+        "crt_render_steal": [vp, vp, vp, vp, vp, vp, vp],
     }
     for name, args in sig.items():
         fn = getattr(L, name)
         fn.argtypes = args
         fn.restype = C.c_int
-    for name in ("crt_builder_free", "crt_scene_retain", "crt_scene_release", "crt_world_release", "crt_material_default"):
+    for name in ("crt_builder_free", "crt_scene_retain", "crt_scene_release", "crt_world_release", "crt_material_default", "crt_steal_cursor_close"):
         getattr(L, name).argtypes = [vp]
         getattr(L, name).restype = None
     L.crt_launch_count.restype = u64

@@ -108,7 +108,8 @@ typedef struct crt_render_settings {
     uint32_t tile_size, tile_rank, tile_world;
     /* wavefront pool: at most this many paths in flight (0 = library default). */
     uint32_t max_paths;
-    uint32_t reserved;
+    /* crt_render_steal only: tiles per stolen chunk (0 = 1). Chunk c = tiles {c + k * n_chunks}: spread over the image. */
+    uint32_t steal_chunk_tiles;
 } crt_render_settings;
 
 /* stats.rs:128-146 */
@@ -137,6 +138,20 @@ int crt_render(const crt_world* w, const crt_camera* camera, const crt_render_se
 /* Same with a HOST framebuffer (D2H inside). */
 int crt_render_host(const crt_world* w, const crt_camera* camera, const crt_render_settings* settings,
                     float* framebuffer, crt_ray_stats* stats);
+
+/* Work stealing across the per-GPU processes (the reference balances tiles over rayon workers,
+ * tracer.rs:423-468): one process creates a cursor in its device memory and hands the 64-byte CUDA IPC handle to
+ * the others (e.g. a torch.distributed broadcast); all then call crt_render_steal on the same frame and pull
+ * chunks of tiles off the cursor with system-scope atomics until it is exhausted. Whole tiles only, so per-pixel
+ * sampler streams — and therefore the image — do not depend on who rendered what. The owner resets the cursor
+ * between frames (with a barrier on either side). Pixels this process did not render are left untouched. */
+typedef struct crt_steal_cursor crt_steal_cursor;
+int crt_steal_cursor_create(crt_steal_cursor** out, unsigned char ipc_handle[64]);
+int crt_steal_cursor_open(const unsigned char ipc_handle[64], crt_steal_cursor** out);
+int crt_steal_cursor_reset(crt_steal_cursor* c);
+void crt_steal_cursor_close(crt_steal_cursor* c);
+int crt_render_steal(const crt_world* w, const crt_camera* camera, const crt_render_settings* settings, float* framebuffer,
+                     crt_ray_stats* stats, void* stream, crt_steal_cursor* cursor);
 
 /* Kernel launches issued by the last crt_render* call of this thread, and the device time it took
  * (CUDA events on the render stream), for bench.py. */

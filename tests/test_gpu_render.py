@@ -193,6 +193,33 @@ def test_device_framebuffer_entry_and_distributed_wrapper(gpu):
     assert frame.cpu().numpy().tobytes() == host.tobytes() and sd == sh
 
 
+def test_work_stealing_cursor_single_process(gpu):
+    """crt_render_steal with a local cursor: the frame is pulled chunk by chunk (strided tile sets) and is
+    bit-identical to the one-shot render, adaptive sampling included; a second frame needs a reset."""
+    import torch
+    from crust_render_b200.distributed import render_distributed
+    world, cam, st = scenes.furnace_room(gpu, width=160, height=96, spp=24, variance_threshold=0.05, min_samples_per_pixel=8)
+    full, sf = gpu.Renderer(cam, world, st).render_with_stats()
+    fb = torch.zeros((96, 160, 4), dtype=torch.float32, device="cuda")
+    for chunk in (1, 4, 1000):
+        st.steal_chunk_tiles = chunk
+        r = gpu.Renderer(cam, world, st)
+        frame, ss = render_distributed(r, None, tile_size=32, fb=fb, stream=torch.cuda.current_stream().cuda_stream, steal=True)
+        assert frame.cpu().numpy().tobytes() == full.tobytes(), chunk
+        assert ss.camera_rays == sf.camera_rays and ss.total_rays() == sf.total_rays()
+    # an exhausted cursor hands out nothing: the frame stays as it was given
+    cur = gpu.StealCursor()
+    r = gpu.Renderer(cam, world, rank_settings(st, 0, 1, 32))
+    fb.fill_(7.0)
+    r.render_steal(fb.data_ptr(), cur)
+    assert not bool((fb == 7.0).any())
+    fb.fill_(7.0)
+    s2 = r.render_steal(fb.data_ptr(), cur)
+    assert bool((fb == 7.0).all()) and s2.camera_rays == 0
+    cur.reset()
+    assert r.render_steal(fb.data_ptr(), cur).camera_rays == sf.camera_rays
+
+
 def test_render_argument_errors(gpu):
     world, cam, st = scenes.furnace_room(gpu, width=16, height=16, spp=1)
     for field, value in (("width", 0), ("samples_per_pixel", 0), ("samples_per_pixel", 70000)):
