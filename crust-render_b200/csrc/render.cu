@@ -675,7 +675,10 @@ int render_impl(crt_world* w, const crt_camera* camera, const crt_render_setting
                     for (uint32_t x = bx; x < std::min({bx + 8, x0 + T, W}); ++x) out.push_back(y * W + x);
     };
     std::vector<uint32_t> pixels;
-    const uint32_t steal_chunk = cursor ? std::max(1u, s->steal_chunk_tiles) : 0u;
+    // 0 = auto: about four chunks per participating process — coarse enough that each chunk's adaptive rounds still
+    // fill the GPU (small chunks are launch-latency-bound), fine enough to absorb a slow or busy GPU
+    const uint32_t auto_chunk = std::max(1u, n_tiles / (4u * std::max(1u, s->tile_world)));
+    const uint32_t steal_chunk = cursor ? (s->steal_chunk_tiles ? s->steal_chunk_tiles : auto_chunk) : 0u;
     const uint32_t n_chunks = steal_chunk ? (n_tiles + steal_chunk - 1) / steal_chunk : 0u;
     size_t max_pixels;  // largest pixel set one render_pixel_set call will see (buffer sizing)
     if (cursor) {

@@ -175,7 +175,7 @@ class RenderSettings:
     tile_rank: int = 0
     tile_world: int = 1
     max_paths: int = 0
-    steal_chunk_tiles: int = 64
+    steal_chunk_tiles: int = 0
 
     def with_samples_per_pixel(self, spp: int) -> "RenderSettings":
         self.samples_per_pixel = max(int(spp), 1)

@@ -108,7 +108,8 @@ typedef struct crt_render_settings {
     uint32_t tile_size, tile_rank, tile_world;
     /* wavefront pool: at most this many paths in flight (0 = library default). */
     uint32_t max_paths;
-    /* crt_render_steal only: tiles per stolen chunk (0 = 1). Chunk c = tiles {c + k * n_chunks}: spread over the image. */
+    /* crt_render_steal only: tiles per stolen chunk (0 = auto: about 4 chunks per process of tile_world). Chunk c = tiles
+     * {c + k * n_chunks}: spread over the image. */
     uint32_t steal_chunk_tiles;
 } crt_render_settings;
 

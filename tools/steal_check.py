@@ -20,7 +20,6 @@ from crust_render_b200.distributed import render_distributed  # noqa: E402
 
 local = int(os.environ.get("LOCAL_RANK", "0"))
 world_size = int(os.environ.get("WORLD_SIZE", "1"))
-os.dup2(2, 1) if False else None
 if world_size > 1:
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 torch.cuda.set_device(local)
@@ -28,7 +27,7 @@ crt.init(local)
 rank = dist.get_rank() if world_size > 1 else 0
 W, H, SPP = int(os.environ.get("STEAL_W", 1920)), int(os.environ.get("STEAL_H", 1080)), 128
 world, cam, st = scenes.openpbr_showcase(crt, width=W, height=H, spp=SPP)
-st.steal_chunk_tiles = 32
+st.steal_chunk_tiles = int(os.environ.get("STEAL_CHUNK", 0))
 r = crt.Renderer(cam, world, st)
 fb = torch.zeros((H, W, 4), dtype=torch.float32, device="cuda")
 stream = torch.cuda.current_stream().cuda_stream
