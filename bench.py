@@ -97,6 +97,32 @@ def cpu_render_sample(args, log_prefix):
             "sample": f"{w}x{h} x {spp} spp of the same scene/camera/settings, {r.seconds:.1f}s on {cores} threads (rows dealt to threads)"}
 
 
+def time_sample_configs(crt, torch, stream):
+    """BASELINE.json configs 1-4 through crt_render at the sizes the config list names (device framebuffer,
+    best of 3 after a warm-up): spp/s of the frame, Msamples/s, Mrays/s."""
+    from crust_render_b200 import scenes
+
+    out = {}
+    cases = [("1 cornellbox 512x512 64spp (adaptive, depth 32, sky only)", lambda: scenes.cornellbox(crt)),
+             ("2 veach_mis 960x540 128spp (balance MIS, 4 sphere lights)", lambda: scenes.veach_mis(crt)),
+             ("3 openpbr_showcase 640x360 128spp (adaptive, all OpenPBR lobes)", lambda: scenes.openpbr_showcase(crt)),
+             ("4 point-instanced city stand-in 40000 instances 640x360 128spp (adaptive, two-level BVH)", lambda: scenes.point_instanced_city(crt)[:3])]
+    for name, build in cases:
+        world_k, cam_k, st_k = build()
+        r = crt.Renderer(cam_k, world_k, st_k)
+        fb = torch.zeros((st_k.height, st_k.width, 4), dtype=torch.float32, device="cuda")
+        best, stats = None, None
+        for k in range(4):
+            stats = r.render_device(fb.data_ptr(), stream.cuda_stream)
+            if k and (best is None or r.device_ms < best):
+                best = r.device_ms
+        taken = stats.camera_rays / (st_k.width * st_k.height)
+        out[name] = {"ms": best, "spp_per_s": taken / (best * 1e-3), "mean_spp_taken": taken, "msamples_per_s": stats.camera_rays / best / 1e3,
+                     "mrays_per_s": stats.total_rays() / best / 1e3, "launches": r.launches, "rounds": r.rounds}
+        del fb, r, world_k
+    return out
+
+
 # ---------------------------------------------------------------------------
 # workload
 # ---------------------------------------------------------------------------
@@ -431,6 +457,9 @@ def main():
                       "mean_rgb": mean_rgb, "ray_stats": st0.__dict__}
         del fb, renderer, r_world
         torch.cuda.empty_cache()
+        # configs 1-4 of BASELINE.json at their own sizes (parity-test cases; timed here so every config has a number)
+        if rank == 0 and world == 1:
+            render["configs"] = time_sample_configs(crt, torch, stream)
     else:
         sample_sets = cpu_sample(sets, args.cpu_sample_log2) if (rank == 0 and world == 1 and not args.no_cpu_baseline) else None
         full_sets_sizes = {n: len(sets[n][0]) for n in SETS}

@@ -48,6 +48,9 @@ constexpr int kBlock = 128;
 #endif
 constexpr uint32_t FLAG_HAS_PREV = 1u, FLAG_PREV_DELTA = 2u;  // PrevBounce, tracer.rs:898-905
 constexpr float kTMin = 0.001f;                               // tracer.rs:1152 / 1029
+// per-sample RayStats (stats.rs:128-146), packed into the path slot: x = closest_hit (12 bits) | shadow_rays (12) |
+// rr_killed (1) | ended_escaped (1) | ended_depth (1); y = vertices (12) | rr_tested (12). max_depth <= 4095.
+constexpr uint32_t CNT_SHADOW_SHIFT = 12, CNT_RR_KILLED = 1u << 24, CNT_ESCAPED = 1u << 25, CNT_DEPTH = 1u << 26, CNT_RR_TESTED_SHIFT = 12;
 
 struct PathState {       // structure of arrays, one slot per path in flight
     float4* beta_pdf;    // throughput (tracer.rs:1113) + pdf of the bounce that produced the current ray
@@ -55,6 +58,7 @@ struct PathState {       // structure of arrays, one slot per path in flight
     float4* prevp;       // previous vertex position (MIS `from`, tracer.rs:945) + flag word
     uint2* sampler;      // K_PATH domain pattern, sample index (tracer.rs:1101)
     float* time;         // shutter time of the path
+    uint2* counts;       // RayStats of this sample, packed (see CNT_*): only accepted samples are counted
 };
 struct Queues {
     float4* rays[2];     // extend queue, double-buffered: 2 x float4 per ray (crt_ray)
@@ -74,8 +78,9 @@ struct PixelState {      // one entry per pixel this process renders (position i
     const uint32_t* pixels;  // pixel id = j * width + i
     float4* sum_w;           // Σ w·L, Σ w (tracer.rs:526-531)
     double2* lum;            // Σ lum, Σ lum² in f64 (tracer.rs:533-534)
-    uint32_t* taken;
+    uint32_t* taken;         // samples accumulated so far; bit 31 = the adaptive test has stopped this pixel
 };
+constexpr uint32_t PX_DONE = 0x80000000u;
 struct RenderParams {
     Camera cam;
     Filter filter;
@@ -114,10 +119,7 @@ __device__ __forceinline__ void stat_add(unsigned long long* dst, uint32_t v) {
 __global__ void __launch_bounds__(kBlock) raygen_kernel(const RenderParams P, const uint32_t* __restrict__ active, uint32_t nb, uint32_t s_base,
                                                         uint32_t s_count) {
     const uint32_t total = nb * s_count;
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        P.q.counts[0] = total;
-        atomicAdd(P.stats + 0, (unsigned long long)total);  // camera_rays
-    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) P.q.counts[0] = total;
     for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < total; p += gridDim.x * blockDim.x) {
         uint32_t a = p % nb, sl = p / nb;  // sample-major: a warp covers neighbouring pixels of one sample index
         uint32_t pixel = P.px.pixels[active[a]];
@@ -150,6 +152,7 @@ __global__ void __launch_bounds__(kBlock) raygen_kernel(const RenderParams P, co
         P.ps.prevp[p] = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(0u));
         P.ps.sampler[p] = make_uint2(path.pattern, path.index);
         P.ps.time[p] = time;
+        P.ps.counts[p] = make_uint2(P.st.max_depth == 0 ? CNT_DEPTH : 0u, 0u);
     }
 }
 
@@ -171,7 +174,6 @@ __global__ void __launch_bounds__(kBlock, CRT_SHADE_MINBLOCKS) shade_kernel(cons
     uint32_t* next_count = P.q.counts + k + 1;
     uint32_t* sh_count = P.q.counts + (D + 2) + k;
     const int nxt = cur ^ 1;
-    uint32_t c_vertices = 0, c_rr_tested = 0, c_rr_killed = 0, c_escaped = 0, c_depth = 0;
 
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const uint32_t path = P.q.path[cur][i];
@@ -192,11 +194,13 @@ __global__ void __launch_bounds__(kBlock, CRT_SHADE_MINBLOCKS) shade_kernel(cons
         const PathSampler v = new_domain(PathSampler{smp.x, smp.y}, k);
         const float time = P.ps.time[path];
         V3 add = splat(0.0f);
+        uint2 cnt = P.ps.counts[path];
+        cnt.x += 1u;  // this entry is one traced closest-hit query (stats.rs:133)
         const Medium* med = medium >= 0 ? &P.materials[medium].medium : nullptr;
 
         if (k >= D) {
             // Depth exhausted (tracer.rs:1123-1148): the ray was traced for bounce-hit emission only.
-            ++c_depth;
+            cnt.x |= CNT_DEPTH;
             if (have_hit) {
                 const Material& mat = P.materials[P.geom_material[geom_id]];
                 V3 normal = v3(h1.y, h1.z, h1.w);
@@ -233,21 +237,21 @@ __global__ void __launch_bounds__(kBlock, CRT_SHADE_MINBLOCKS) shade_kernel(cons
                 beta *= factor;
                 bool survived = true;
                 if (k >= RR_START_BOUNCE) {
-                    ++c_rr_tested;
+                    cnt.y += 1u << CNT_RR_TESTED_SHIFT;
                     float p_survive = clampf(max_element(beta), RR_MIN_PROB, 1.0f);
                     if (p_survive < 1.0f) {
                         if (draw_rnd1(new_domain(v, K_RR)) >= p_survive) {
                             survived = false;
-                            ++c_rr_killed;
+                            cnt.x |= CNT_RR_KILLED;
                         } else {
                             beta = beta / p_survive;
                         }
                     }
                 }
-                ++c_vertices;
+                cnt.y += 1u;
                 if (survived) {
                     if (k + 1 >= D) {
-                        ++c_depth;  // remaining <= 0 with prev = None: the reference ends without tracing (:1123-1128)
+                        cnt.x |= CNT_DEPTH;  // remaining <= 0 with prev = None: the reference ends without tracing (:1123-1128)
                     } else {
                         cont = true;
                         no = pos;
@@ -257,7 +261,7 @@ __global__ void __launch_bounds__(kBlock, CRT_SHADE_MINBLOCKS) shade_kernel(cons
                 }
             } else if (!have_hit) {
                 // Background (tracer.rs:1321-1342) with escaped_emission (:966-1009).
-                ++c_escaped;
+                cnt.x |= CNT_ESCAPED;
                 V3 unit = normalize(rd);
                 V3 background = splat(0.0f);
                 bool covered = false;
@@ -327,6 +331,7 @@ __global__ void __launch_bounds__(kBlock, CRT_SHADE_MINBLOCKS) shade_kernel(cons
                         V3 nee = ls.radiance * brdf_value * cosine * weight / light_pdf;
                         contrib = beta * (atten * nee);
                     }
+                    cnt.x += 1u << CNT_SHADOW_SHIFT;
                     uint32_t s = queue_push(sh_count);
                     P.q.srays[2 * (size_t)s] = f4(rec.p, kTMin);
                     P.q.srays[2 * (size_t)s + 1] = f4(ls.direction, ls.distance - 0.001f);
@@ -345,12 +350,12 @@ __global__ void __launch_bounds__(kBlock, CRT_SHADE_MINBLOCKS) shade_kernel(cons
                     beta *= atten * factor;
                     bool survived = true;
                     if (k >= RR_START_BOUNCE) {
-                        ++c_rr_tested;
+                        cnt.y += 1u << CNT_RR_TESTED_SHIFT;
                         float p_survive = clampf(max_element(beta), RR_MIN_PROB, 1.0f);
                         if (p_survive < 1.0f) {
                             if (draw_rnd1(new_domain(v, K_RR)) >= p_survive) {
                                 survived = false;
-                                ++c_rr_killed;
+                                cnt.x |= CNT_RR_KILLED;
                             } else {
                                 beta = beta / p_survive;
                             }
@@ -365,7 +370,7 @@ __global__ void __launch_bounds__(kBlock, CRT_SHADE_MINBLOCKS) shade_kernel(cons
                         new_flags = FLAG_HAS_PREV | (sample.delta ? FLAG_PREV_DELTA : 0u) | (sample.enters_medium ? (mat_index + 1u) << 8 : 0u);
                     }
                 }
-                ++c_vertices;
+                cnt.y += 1u;
             }
             if (cont) {
                 P.ps.beta_pdf[path] = f4(beta, new_pdf);
@@ -377,16 +382,12 @@ __global__ void __launch_bounds__(kBlock, CRT_SHADE_MINBLOCKS) shade_kernel(cons
                 if (P.q.time[nxt]) P.q.time[nxt][s] = time;
             }
         }
+        P.ps.counts[path] = cnt;
         if (add.x != 0.0f || add.y != 0.0f || add.z != 0.0f) {
             float4 lw = P.ps.L_w[path];
             P.ps.L_w[path] = make_float4(lw.x + add.x, lw.y + add.y, lw.z + add.z, lw.w);
         }
     }
-    stat_add(P.stats + 3, c_vertices);
-    stat_add(P.stats + 4, c_rr_tested);
-    stat_add(P.stats + 5, c_rr_killed);
-    stat_add(P.stats + 6, c_escaped);
-    stat_add(P.stats + 7, c_depth);
 }
 
 // ---- NEE resolve: unoccluded contributions land on their path (tracer.rs:1416-1443) ---------------
@@ -403,26 +404,25 @@ __global__ void __launch_bounds__(kBlock) nee_resolve_kernel(const RenderParams 
     }
 }
 
-// closest_hit / shadow_rays = lengths of the queues that were traced (stats.rs:133-136)
-__global__ void ray_stats_kernel(const RenderParams P) {
-    const int D = (int)P.st.max_depth;
-    unsigned long long ch = 0, sh = 0;
-    for (int k = 0; k <= D; ++k) {
-        ch += P.q.counts[k];
-        sh += P.q.counts[(D + 2) + k];
-    }
-    atomicAdd(P.stats + 1, ch);
-    atomicAdd(P.stats + 2, sh);
-}
-
-// ---- film: add the finished samples of each pixel in sample order (tracer.rs:599-607) -----------
+// ---- film: add the finished samples of each pixel in sample order and apply the adaptive stop
+// (tracer.rs:599-617). A round may hold more samples than the reference would have taken for a pixel: the
+// test runs after every 4th sample exactly where the reference runs it, and samples past the stopping point
+// are discarded — neither their radiance nor their RayStats count — so results do not depend on the round size.
 __global__ void __launch_bounds__(kBlock) accumulate_kernel(const RenderParams P, const uint32_t* __restrict__ active, uint32_t nb, uint32_t s_count) {
+    const double threshold = (double)P.st.variance_threshold;
+    const bool adaptive = P.st.adaptive && threshold > 0.0;
+    const uint32_t min_spp = max(P.st.min_samples_per_pixel, 2u);
+    uint32_t c[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     for (uint32_t a = blockIdx.x * blockDim.x + threadIdx.x; a < nb; a += gridDim.x * blockDim.x) {
         uint32_t pos = active[a];
         float4 sw = P.px.sum_w[pos];
         double2 lum = P.px.lum[pos];
-        for (uint32_t sl = 0; sl < s_count; ++sl) {
-            float4 lw = P.ps.L_w[(size_t)sl * nb + a];
+        uint32_t taken = P.px.taken[pos];
+        bool done = (taken & PX_DONE) != 0;
+        taken &= ~PX_DONE;
+        for (uint32_t sl = 0; sl < s_count && !done; ++sl) {
+            const size_t p = (size_t)sl * nb + a;
+            float4 lw = P.ps.L_w[p];
             V3 color = xyz(lw) * lw.w;
             sw.x += color.x;
             sw.y += color.y;
@@ -431,30 +431,38 @@ __global__ void __launch_bounds__(kBlock) accumulate_kernel(const RenderParams P
             double l = (double)luminance(color);
             lum.x += l;
             lum.y += l * l;
+            ++taken;
+            uint2 cnt = P.ps.counts[p];
+            c[0] += 1u;
+            c[1] += cnt.x & 0xFFFu;
+            c[2] += (cnt.x >> CNT_SHADOW_SHIFT) & 0xFFFu;
+            c[3] += cnt.y & 0xFFFu;
+            c[4] += (cnt.y >> CNT_RR_TESTED_SHIFT) & 0xFFFu;
+            c[5] += (cnt.x & CNT_RR_KILLED) ? 1u : 0u;
+            c[6] += (cnt.x & CNT_ESCAPED) ? 1u : 0u;
+            c[7] += (cnt.x & CNT_DEPTH) ? 1u : 0u;
+            if (taken >= P.st.samples_per_pixel) {
+                done = true;
+            } else if (adaptive && taken >= min_spp && taken % 4u == 0u) {
+                double nn = (double)taken;
+                double var_of_mean = fmax((lum.y - lum.x * lum.x / nn) / (nn - 1.0) / nn, 0.0);
+                double mean = fmax(lum.x / nn, 1e-4);
+                done = sqrt(var_of_mean) / mean < threshold;
+            }
         }
         P.px.sum_w[pos] = sw;
         P.px.lum[pos] = lum;
-        P.px.taken[pos] += s_count;
+        P.px.taken[pos] = taken | (done ? PX_DONE : 0u);
     }
+    for (int k = 0; k < 8; ++k) stat_add(P.stats + k, c[k]);
 }
 
-// ---- adaptive early stop (tracer.rs:609-617): which pixels enter the next round -------------------
+// ---- which pixels enter the next round ----------------------------------------------------------
 __global__ void __launch_bounds__(kBlock) adaptive_kernel(const RenderParams P, const uint32_t* __restrict__ active_in, uint32_t n_in, uint32_t* __restrict__ active_out,
                                                           uint32_t* __restrict__ count_out) {
-    const double threshold = (double)P.st.variance_threshold;
-    const uint32_t min_spp = max(P.st.min_samples_per_pixel, 2u);
     for (uint32_t a = blockIdx.x * blockDim.x + threadIdx.x; a < n_in; a += gridDim.x * blockDim.x) {
         uint32_t pos = active_in[a];
-        uint32_t taken = P.px.taken[pos];
-        bool done = taken >= P.st.samples_per_pixel;
-        if (!done && P.st.adaptive && threshold > 0.0 && taken >= min_spp && taken % 4u == 0u) {
-            double2 lum = P.px.lum[pos];
-            double nn = (double)taken;
-            double var_of_mean = fmax((lum.y - lum.x * lum.x / nn) / (nn - 1.0) / nn, 0.0);
-            double mean = fmax(lum.x / nn, 1e-4);
-            done = sqrt(var_of_mean) / mean < threshold;
-        }
-        if (!done) active_out[queue_push(count_out)] = pos;
+        if (!(P.px.taken[pos] & PX_DONE)) active_out[queue_push(count_out)] = pos;
     }
 }
 
@@ -462,7 +470,7 @@ __global__ void __launch_bounds__(kBlock) adaptive_kernel(const RenderParams P, 
 __global__ void __launch_bounds__(kBlock) film_kernel(const RenderParams P, uint32_t n, float4* __restrict__ fb) {
     for (uint32_t pos = blockIdx.x * blockDim.x + threadIdx.x; pos < n; pos += gridDim.x * blockDim.x) {
         float4 sw = P.px.sum_w[pos];
-        uint32_t taken = P.px.taken[pos];
+        uint32_t taken = P.px.taken[pos] & ~PX_DONE;
         V3 mean = sw.w > 0.0f ? xyz(sw) / sw.w : xyz(sw) / (float)taken;
         fb[P.px.pixels[pos]] = f4(mean, (float)taken);
     }
@@ -651,7 +659,7 @@ int render_impl(crt_world* w, const crt_camera* camera, const crt_render_setting
     if (!w || !camera || !s || !d_fb) return crt::set_error(CRT_ERR_INVALID_ARG, "crt_render: null argument");
     if (s->width == 0 || s->height == 0 || (uint64_t)s->width * s->height > 0x7FFFFFFFu) return crt::set_error(CRT_ERR_INVALID_ARG, "crt_render: bad image size");
     if (s->samples_per_pixel == 0 || s->samples_per_pixel > 65536u) return crt::set_error(CRT_ERR_INVALID_ARG, "crt_render: samples_per_pixel must be in 1..65536 (sampler index range)");
-    if (s->max_depth > 4096u) return crt::set_error(CRT_ERR_INVALID_ARG, "crt_render: max_depth too large");
+    if (s->max_depth > 4000u) return crt::set_error(CRT_ERR_INVALID_ARG, "crt_render: max_depth must be <= 4000 (12-bit per-sample ray counters)");
     if (s->pixel_filter > CRT_FILTER_MITCHELL || s->sampling_strategy > CRT_STRATEGY_BSDF_ONLY) return crt::set_error(CRT_ERR_INVALID_ARG, "crt_render: unknown filter or strategy");
     if (s->tile_world > 1 && (s->tile_size == 0 || s->tile_rank >= s->tile_world)) return crt::set_error(CRT_ERR_INVALID_ARG, "crt_render: bad tile split");
     int rc = crt::require_device();
@@ -721,7 +729,7 @@ int render_impl(crt_world* w, const crt_camera* camera, const crt_render_setting
     cap = std::max<size_t>(cap, 1);
     const bool motion = w->scene->has_motion;
     {
-        size_t need = 3 * carve_bytes(cap, 16) + carve_bytes(cap, 8) + carve_bytes(cap, 4)                        // path state
+        size_t need = 3 * carve_bytes(cap, 16) + 2 * carve_bytes(cap, 8) + carve_bytes(cap, 4)                       // path state
                       + 2 * (carve_bytes(2 * cap, 16) + 2 * carve_bytes(cap, 4)) + carve_bytes(2 * cap, 16) + carve_bytes(cap, 1)  // extend
                       + carve_bytes(2 * cap, 16) + 2 * carve_bytes(cap, 4) + carve_bytes(cap, 16) + carve_bytes(cap, 1);          // shadow
         if (need > sc.cap_paths) {
@@ -766,6 +774,7 @@ int render_impl(crt_world* w, const crt_camera* camera, const crt_render_setting
         P.ps.prevp = carve<float4>(p, cap);
         P.ps.sampler = carve<uint2>(p, cap);
         P.ps.time = carve<float>(p, cap);
+        P.ps.counts = carve<uint2>(p, cap);
         for (int b = 0; b < 2; ++b) {
             P.q.rays[b] = carve<float4>(p, 2 * cap);
             P.q.path[b] = carve<uint32_t>(p, cap);
@@ -836,8 +845,6 @@ int render_impl(crt_world* w, const crt_camera* camera, const crt_render_setting
                 if (sc.h_pinned[0] == 0) break;
             }
         }
-        ray_stats_kernel<<<1, 1, 0, stream>>>(P);
-        ++launches;
         return CRT_OK;
     };
 
@@ -877,8 +884,12 @@ int render_impl(crt_world* w, const crt_camera* camera, const crt_render_setting
                 round_samples = spp - s_base;
             else if (s_base == 0)
                 round_samples = std::min(spp, (min_spp + 3u) / 4u * 4u);
-            else
-                round_samples = std::min(spp - s_base, 4u);
+            else {
+                // later rounds: a multiple of 4 large enough to keep ~1 Mi paths in flight (samples a pixel turns out
+                // not to need are discarded by accumulate_kernel, so this only trades a little work for fewer rounds)
+                uint32_t groups = (uint32_t)std::min<size_t>(8, std::max<size_t>(1, ((size_t)1 << 20) / ((size_t)n_active * 4)));
+                round_samples = std::min(spp - s_base, 4u * groups);
+            }
             // split the round into wavefronts that fit the pool
             uint32_t sub = (uint32_t)std::max<size_t>(1, std::min<size_t>(round_samples, cap / n_active));
             uint32_t block_px = (uint32_t)std::min<size_t>(n_active, cap / sub);
@@ -944,7 +955,6 @@ int render_impl(crt_world* w, const crt_camera* camera, const crt_render_setting
         stats_out->rr_killed = st[5];
         stats_out->ended_escaped = st[6];
         stats_out->ended_depth = st[7];
-        if (D == 0) stats_out->ended_depth = st[0];
     }
     t_last_launches = launches;
     t_last_rounds = rounds;
