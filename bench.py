@@ -106,7 +106,7 @@ def time_sample_configs(crt, torch, stream):
     cases = [("1 cornellbox 512x512 64spp (adaptive, depth 32, sky only)", lambda: scenes.cornellbox(crt)),
              ("2 veach_mis 960x540 128spp (balance MIS, 4 sphere lights)", lambda: scenes.veach_mis(crt)),
              ("3 openpbr_showcase 640x360 128spp (adaptive, all OpenPBR lobes)", lambda: scenes.openpbr_showcase(crt)),
-             ("4 point-instanced city stand-in 40000 instances 640x360 128spp (adaptive, two-level BVH)", lambda: scenes.point_instanced_city(crt)[:3])]
+             ("4 PointInstancedMedCity 40000 instances 640x360 128spp (adaptive, two-level BVH, sky only)", lambda: scenes.medcity(crt))]
     for name, build in cases:
         world_k, cam_k, st_k = build()
         r = crt.Renderer(cam_k, world_k, st_k)

@@ -223,6 +223,53 @@ def cornellbox(api, width: int = 512, height: int = 512, spp: int = 64, **settin
 
 
 # ---------------------------------------------------------------------------------------------
+# config 4: samples/PointInstancedMedCity.usd (from the binary fixture the crate reader wrote)
+# ---------------------------------------------------------------------------------------------
+def medcity(api, width: int = 640, height: int = 360, spp: int = 128, n_instances=None, **settings_kw):
+    """One PointInstancer, 40 000 instances (T * R * S) over 8 prototype meshes (9 832 unique triangles), Z-up,
+    default grey OpenPBR, no lights (sky only), importer default settings. The fixture is replayed through the
+    importer itself as a synthesised stage, so placement arithmetic and ids are the importer's."""
+    from .usd.importer import import_stage
+    from .usd.usda import Attribute, Prim, Stage
+
+    z = np.load(os.path.join(GOLDEN, "medcity_scene.npz"))
+
+    def prim(ptype, name, parent, **attrs):
+        p = Prim("def", ptype, name, (parent.path if parent else "") + "/" + name, parent=parent)
+        for k, v in attrs.items():
+            p.attributes[k] = Attribute(k, "", v)
+        if parent is not None:
+            parent.children.append(p)
+        return p
+
+    def xf(m):  # column-vector f32 matrix -> a row-vector `xformOp:transform`
+        return {"xformOp:transform": np.asarray(m, np.float64).T.copy(), "xformOpOrder": ["xformOp:transform"]}
+
+    cams = prim("Xform", "Cameras", None)
+    fl, hap, vap, fstop, focus = (float(v) for v in z["camera_params"])
+    cam_attrs = dict(focalLength=fl, horizontalAperture=hap, fStop=fstop, focusDistance=focus, **xf(z["camera_l2w"]))
+    if vap > 0:
+        cam_attrs["verticalAperture"] = vap
+    prim("Camera", "main_cam", cams, **cam_attrs)
+    hills = prim("Xform", "MediterraneanHills", None)
+    n = len(z["positions"]) if n_instances is None else min(int(n_instances), len(z["positions"]))
+    inst = prim("PointInstancer", "Buildings", hills, positions=z["positions"][:n], orientations=z["orientations_wxyz"][:n], scales=z["scales"][:n],
+                protoIndices=z["proto_indices"][:n].astype(np.int32), **xf(z["instancer_l2w"]))
+    protos = prim("Xform", "Prototypes", inst)
+    targets = []
+    for k in range(int(z["n_protos"])):
+        root = prim("Xform", f"prototype_{k}", protos)
+        tris = z[f"proto{k}_tris"].astype(np.int64)
+        prim("Mesh", "mesh_0", root, points=z[f"proto{k}_points"], faceVertexCounts=np.full(len(tris), 3, np.int64), faceVertexIndices=tris.reshape(-1),
+             **xf(z[f"proto{k}_local"]))
+        targets.append(root.path)
+    inst.relationships["prototypes"] = targets
+    kw = dict(width=width, height=height, samples_per_pixel=spp)
+    kw.update(settings_kw)
+    return import_stage(api, Stage({"upAxis": "Z"}, [cams, hills]), "tests/golden/medcity_scene.npz", **kw)
+
+
+# ---------------------------------------------------------------------------------------------
 # config 4 stand-in: a point-instanced city (two-level BVH)
 # ---------------------------------------------------------------------------------------------
 def _building(rng, floors: int, sides: int):
@@ -249,10 +296,9 @@ def _building(rng, floors: int, sides: int):
 
 
 def point_instanced_city(api, n_instances: int = 40000, width: int = 640, height: int = 360, spp: int = 128, seed: int = 7, **settings_kw):
-    """STAND-IN for samples/PointInstancedMedCity.usd (binary USDC; a crate reader is SURVEY §8f): the
-    same shape of work — one top-level scene of `n_instances` instances (T * R * S per instance,
-    usd_import.rs:1775-1782) over 4 distinct ~1.1-1.3 k-triangle prototype BLASes, Z-up like the file,
-    default grey OpenPBR, no lights (sky only, no shadow rays), importer default settings."""
+    """A synthetic, scalable relative of config 4 (the real file is `medcity()`): one top-level scene of
+    `n_instances` instances (T * R * S per instance, usd_import.rs:1775-1782) over 4 distinct ~1.1-1.3 k-triangle
+    prototype BLASes, Z-up, default grey OpenPBR, no lights (sky only, no shadow rays), importer default settings."""
     rng = np.random.default_rng(seed)
     protos = []
     for floors, sides in ((9, 10), (8, 11), (10, 10), (9, 11)):

@@ -14,7 +14,9 @@ What is reproduced, with the reference lines it follows:
   * camera from focal length / apertures / fStop / focusDistance (:2174-2220);
   * materials: `crust:openpbr` decoded 1:1 (:2902-2975), `UsdPreviewSurface` mapped (:2661-2705),
     unbound => default grey OpenPBR; RenderSettings and the crust:* attributes (:3015-3100).
-Not reproduced yet: PointInstancer / native instancing, BasisCurves, volumes, environment-map domes,
+  * PointInstancer (:1674-1875): T * R * S placements, one Instance per prototype part, `invisibleIds`;
+    binary crate files through usdc.py.
+Not reproduced yet: native instancing, nested instancers, BasisCurves, volumes, environment-map domes,
 Ptex, references/payloads/variants.
 """
 from __future__ import annotations
@@ -305,7 +307,8 @@ class _Import:
             world = local if resets else _mul(parent_world, local)
             t = prim.type
             if t == "PointInstancer":
-                continue  # prototypes are drawn through the instancer only; instancing is a later row
+                self.emit_point_instancer(prim, world)
+                continue  # prototypes are drawn through the instancer, never on their own (:197-208)
             if t == "Mesh":
                 self.emit_mesh(prim, world)
             elif t == "Sphere":
@@ -370,6 +373,98 @@ class _Import:
                     end = _affine(_mul(_translate(p["motion"]), l2w))
                 self.wb.set_geometry(p["geom_id"], Geometry.Instance(slot["scene"], _affine(l2w), end))
 
+    # -- PointInstancer (:1674-1875) ---------------------------------------------------------------
+    def proto_parts(self, root: usda.Prim):
+        """collect_proto_parts (:1379-1540): every mesh / sphere under a prototype root as (BLAS, local matrix,
+        material, mask). Nested instancers and curves inside prototypes are not expanded yet."""
+        key = root.path
+        cache = self.__dict__.setdefault("_protos", {})
+        if key in cache:
+            return cache[key]
+        parts = []
+        stack = [(root, _ident())]
+        while stack:
+            prim, parent_local = stack.pop()
+            if not prim.is_active():
+                continue
+            if prim is root:
+                local = _ident()
+            else:
+                m, resets = local_matrix(prim)
+                local = m if resets else _mul(parent_local, m)
+            mask = _ray_mask(prim)
+            if prim.type == "Mesh":
+                pts, counts, idx = prim.attr("points"), prim.attr("faceVertexCounts"), prim.attr("faceVertexIndices")
+                if pts is not None and counts is not None and idx is not None:
+                    pts = np.asarray(pts, np.float64).reshape(-1, 3).astype(F)
+                    counts = np.asarray(counts).astype(np.int64).ravel()
+                    idx = np.asarray(idx).astype(np.int64).ravel()
+                    mat_id, mat = self.materials.resolve(prim)
+                    skey = (pts.tobytes(), counts.tobytes(), idx.tobytes(), mat_id)
+                    slot = self.slots.get(skey)
+                    if slot is None:
+                        tris = triangulate(counts, idx, len(pts))
+                        slot = self.slots[skey] = dict(verts=pts, tris=tris, n_place=0, scene=None) if len(tris) else None
+                    if slot is not None:
+                        if slot["scene"] is None:
+                            sb = self.api.SceneBuilder()
+                            sb.attach(Geometry.TriangleMesh(slot["verts"], slot["tris"]))
+                            slot["scene"] = sb.commit()
+                        parts.append((slot["scene"], local, mat, mask))
+            elif prim.type == "Sphere":
+                r = prim.attr("radius")
+                sb = self.api.SceneBuilder()
+                sb.attach(Geometry.Sphere((0.0, 0.0, 0.0), 1.0 if r is None else float(F(r))))
+                parts.append((sb.commit(), local, self.materials.resolve(prim)[1], mask))
+            elif prim.type == "PointInstancer" and prim is not root:
+                continue
+            for c in prim.children:
+                stack.append((c, local))
+        cache[key] = parts
+        return parts
+
+    def emit_point_instancer(self, prim, world):
+        """read_instancer + emit_point_instancer (:1674-1875): placement = world * (T * R * S), one Instance per
+        prototype part; `orientationsf` wins over `orientations`; `invisibleIds` hides instances by id."""
+        targets = prim.relationships.get("prototypes") or []
+        proto_idx = prim.attr("protoIndices")
+        if not targets or proto_idx is None:
+            return
+        proto_idx = np.asarray(proto_idx).astype(np.int64).ravel()
+        positions = prim.attr("positions")
+        positions = np.zeros((0, 3), F) if positions is None else np.asarray(positions, np.float64).reshape(-1, 3).astype(F)
+        scales = prim.attr("scales")
+        scales = None if scales is None else np.asarray(scales, np.float64).reshape(-1, 3).astype(F)
+        orient = prim.attr("orientationsf")
+        if orient is None or len(orient) == 0:
+            orient = prim.attr("orientations")
+        orient = None if orient is None or len(orient) == 0 else np.asarray(orient, np.float32).reshape(-1, 4)  # (w, x, y, z)
+        ids = prim.attr("ids")
+        invisible = set(int(v) for v in (prim.attr("invisibleIds") if prim.attr("invisibleIds") is not None else []))
+        protos = []
+        for t in targets:
+            root = self.stage.prim_at(t)
+            protos.append(self.proto_parts(root) if root is not None else [])
+        for i, k in enumerate(proto_idx):
+            if i >= len(positions):
+                break
+            inst_id = int(ids[i]) if ids is not None and i < len(ids) else i
+            if inst_id in invisible:
+                continue
+            if k < 0 or k >= len(targets):
+                continue
+            m = _translate(positions[i])
+            if orient is not None and i < len(orient):
+                m = _mul(m, _quat(*orient[i]))
+            if scales is not None and i < len(scales):
+                m = _mul(m, _scale(scales[i]))
+            placement = _mul(world, m)
+            for scene, local, mat, mask in protos[int(k)]:
+                xf = _mul(placement, local)
+                if abs(float(np.linalg.det(xf.astype(np.float64)))) < 1e-12:
+                    continue
+                self.wb.attach_masked(Geometry.Instance(scene, _affine(xf)), mat, mask)
+
     def emit_sphere(self, prim, world):  # :1235-1272
         r = prim.attr("radius")
         radius = 1.0 if r is None else float(F(r))
@@ -427,7 +522,18 @@ def world_from_meshes(api, meshes, settings: RenderSettings):
 def load_scene(api, path: str, **overrides):
     """`Scene::from_usd` (scene.rs:67-85 -> usd_import.rs:287-424). Returns (world, camera, settings);
     keyword overrides replace RenderSettings fields (the CLI's -s / --strategy / --filter flags)."""
-    stage = usda.load(path)
+    with open(path, "rb") as f:
+        magic = f.read(8)
+    if magic == b"PXR-USDC":
+        from . import usdc
+        stage = usdc.load(path)
+    else:
+        stage = usda.load(path)
+    return import_stage(api, stage, path, **overrides)
+
+
+def import_stage(api, stage: usda.Stage, path: str = "<stage>", **overrides):
+    """The import proper, from an already parsed (or synthesised) Stage."""
     imp = _Import(api, stage)
     for k, v in overrides.items():
         setattr(imp.settings, k, v)

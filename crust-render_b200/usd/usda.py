@@ -28,12 +28,16 @@ class Attribute:
     metadata: Dict[str, Any] = field(default_factory=dict)
 
     def get(self):
-        """Value at the default time; falls back to the earliest time sample."""
-        if self.value is not None:
-            return self.value
+        """Value at the default time; falls back to the earliest time sample when no default is authored — or
+        when the authored default is an empty array while samples exist (PointInstancedMedCity.usd authors
+        `positions = []` next to a 40 000-element time sample; what `openusd` returns there is unpinned)."""
+        v = self.value
+        empty = v is not None and hasattr(v, "__len__") and not isinstance(v, (str, dict)) and len(v) == 0
+        if v is not None and not (empty and self.time_samples):
+            return v
         if self.time_samples:
             return self.time_samples[min(self.time_samples)]
-        return None
+        return v
 
 
 @dataclass

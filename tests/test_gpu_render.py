@@ -102,13 +102,23 @@ def test_config1_cornellbox(gpu, orc):
     assert sg.shadow_rays == 0 and sg.rr_tested > 0
 
 
-def test_config4_point_instanced_city_stand_in(gpu, orc):
-    """Two-level traversal: thousands of instances over four shared BLASes, sky light only."""
+def test_config4_point_instanced_medcity(gpu, orc):
+    """samples/PointInstancedMedCity.usd via the crate reader's fixture: one TLAS of 40 000 instances over 8
+    prototype BLASes (two-level traversal in one kernel), sky light only, importer defaults (adaptive, depth 32)."""
+    fg, sg, fo, so, _ = both(gpu, orc, scenes.medcity, width=192, height=108, spp=40)
+    same = fg[..., 3] == fo[..., 3]
+    assert same.mean() >= 0.999
+    compare(fg[same], fo[same])
+    stats_close(sg, so, tol=2e-3, adaptive=True)
+    assert sg.shadow_rays == 0 and sg.rr_tested > 0
+
+
+def test_synthetic_instanced_city(gpu, orc):
+    """The scalable stand-in generator (any instance count) used for instancing stress runs."""
     fn = lambda api, **kw: scenes.point_instanced_city(api, **kw)  # noqa: E731
     fg, sg, fo, so, _ = both(gpu, orc, fn, n_instances=2500, width=160, height=90, spp=8, variance_threshold=0.0)
     compare(fg, fo)
     stats_close(sg, so)
-    assert sg.shadow_rays == 0
 
 
 @pytest.mark.parametrize("kind,radius", [(PixelFilterKind.Box, 0.5), (PixelFilterKind.Gaussian, 1.5), (PixelFilterKind.Mitchell, 2.0)])
