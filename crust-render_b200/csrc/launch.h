@@ -40,6 +40,9 @@ struct TraceParams {
 #ifndef CRT_MINBLOCKS_ANY
 #define CRT_MINBLOCKS_ANY 8
 #endif
+#ifndef CRT_MINBLOCKS_INST
+#define CRT_MINBLOCKS_INST 5  // variants with instance descent carry more live state (level saves, hit chain): 96 registers without spills beat 64 with (measured 3/4/5/6/8 on B200)
+#endif
 #ifndef CRT_REFILL
 #define CRT_REFILL 16  // a warp refills its idle lanes when fewer than this many are active
 #endif

@@ -27,7 +27,7 @@ struct LevelSave {  // what an instance descent must restore (prim.rs:345-365 re
 };
 
 template <bool ANY_HIT, uint32_t FEAT>
-__global__ void __launch_bounds__(CRT_BLOCK, ANY_HIT ? CRT_MINBLOCKS_ANY : CRT_MINBLOCKS_CLOSEST) trace_kernel(const TraceParams p) {
+__global__ void __launch_bounds__(CRT_BLOCK, (FEAT & FEAT_INSTANCE) ? CRT_MINBLOCKS_INST : (ANY_HIT ? CRT_MINBLOCKS_ANY : CRT_MINBLOCKS_CLOSEST)) trace_kernel(const TraceParams p) {
     typedef typename StackT<ANY_HIT>::type Entry;
     __shared__ Entry sstack[CRT_SSTACK][CRT_BLOCK];
     Entry lstack[CRT_LSTACK];  // spill (local memory, touched only by deep trees)
