@@ -5,6 +5,7 @@
 #include <atomic>
 #include <chrono>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -552,7 +553,17 @@ int crt_device_status(uint32_t* bits) {
 // ---- host-buffer path ------------------------------------------------------
 namespace {
 constexpr int kSlots = 3;
-constexpr size_t kChunk = (size_t)1 << 20;  // rays per pipeline stage
+// rays per pipeline stage; CRT_HOST_CHUNK_LOG2 overrides (tuning only)
+static size_t host_chunk() {
+    static size_t v = [] {
+        const char* e = getenv("CRT_HOST_CHUNK_LOG2");
+        int l = e ? atoi(e) : 20;  // 2^20 measured best of 2^19..2^23 on B200 (PCIe-bound: 52 GB/s H2D)
+        if (l < 12 || l > 26) l = 20;
+        return (size_t)1 << l;
+    }();
+    return v;
+}
+#define kChunk host_chunk()
 struct HostPipe {
     std::mutex mu;
     bool ready = false;
@@ -565,7 +576,7 @@ struct HostPipe {
     uint32_t* d_mask[kSlots];
     uint8_t* d_flag[kSlots];
     // pinned staging per slot (only for pageable user memory)
-    crt_ray* h_rays[kSlots];
+    crt_ray* h_rays[kSlots] = {};
     crt_hit* h_hits[kSlots];
     float* h_time[kSlots];
     uint32_t* h_mask[kSlots];
@@ -582,13 +593,20 @@ int ensure_pipe() {
         CK(cudaMalloc(&g_pipe.d_time[i], kChunk * sizeof(float)));
         CK(cudaMalloc(&g_pipe.d_mask[i], kChunk * sizeof(uint32_t)));
         CK(cudaMalloc(&g_pipe.d_flag[i], kChunk));
+    }
+    g_pipe.ready = true;
+    return CRT_OK;
+}
+// Pinned staging is only needed when the caller's buffers are pageable: allocate it on first such call.
+int ensure_staging() {
+    if (g_pipe.h_rays[0]) return CRT_OK;
+    for (int i = 0; i < kSlots; ++i) {
         CK(cudaMallocHost(&g_pipe.h_rays[i], kChunk * sizeof(crt_ray)));
         CK(cudaMallocHost(&g_pipe.h_hits[i], kChunk * sizeof(crt_hit)));
         CK(cudaMallocHost(&g_pipe.h_time[i], kChunk * sizeof(float)));
         CK(cudaMallocHost(&g_pipe.h_mask[i], kChunk * sizeof(uint32_t)));
         CK(cudaMallocHost(&g_pipe.h_flag[i], kChunk));
     }
-    g_pipe.ready = true;
     return CRT_OK;
 }
 bool is_pinned(const void* p) {
@@ -618,6 +636,7 @@ int host_query(const crt_scene* s, bool any_hit, size_t n, const crt_ray* rays, 
     if ((rc = ensure_pipe())) return rc;
     const bool in_pinned = is_pinned(rays) && is_pinned(time) && is_pinned(mask);
     const bool out_pinned = is_pinned(hits) && is_pinned(flag);
+    if ((!in_pinned || !out_pinned) && (rc = ensure_staging())) return rc;
     Pending pend[kSlots];
     auto drain = [&](int sl) -> int {
         if (!pend[sl].used) return CRT_OK;
