@@ -466,6 +466,10 @@ __global__ void __launch_bounds__(kBlock) adaptive_kernel(const RenderParams P, 
     }
 }
 
+__global__ void iota_kernel(uint32_t* __restrict__ out, uint32_t n) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = i;
+}
+
 // ---- resolve the film (tracer.rs:627-634) ------------------------------------------------------------
 __global__ void __launch_bounds__(kBlock) film_kernel(const RenderParams P, uint32_t n, float4* __restrict__ fb) {
     for (uint32_t pos = blockIdx.x * blockDim.x + threadIdx.x; pos < n; pos += gridDim.x * blockDim.x) {
@@ -488,6 +492,9 @@ struct Scratch {  // grow-only device buffers reused across crt_render calls on 
     unsigned long long* stats = nullptr;
     uint32_t* active_count = nullptr;  // 2 words
     uint32_t* h_pinned = nullptr;      // pinned host mirror for small read-backs
+    // the static pixel list of the last frame stays on the device: same image size and tile deal => no host work
+    uint64_t pixel_key = 0;
+    uint32_t pixel_count = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     ~Scratch() {
         cudaFree(paths);
@@ -683,6 +690,8 @@ int render_impl(crt_world* w, const crt_camera* camera, const crt_render_setting
                     for (uint32_t x = bx; x < std::min({bx + 8, x0 + T, W}); ++x) out.push_back(y * W + x);
     };
     std::vector<uint32_t> pixels;
+    const uint64_t pixel_key = cursor ? 0 : (((uint64_t)W << 40) ^ ((uint64_t)H << 20) ^ ((uint64_t)(s->tile_world <= 1 ? 0 : T) << 52) ^ ((uint64_t)s->tile_rank << 8) ^ (uint64_t)s->tile_world) | 1ull;
+    const bool pixels_cached = !cursor && sc.pixel_key == pixel_key && sc.pixels != nullptr;
     // 0 = auto: about four chunks per participating process — coarse enough that each chunk's adaptive rounds still
     // fill the GPU (small chunks are launch-latency-bound), fine enough to absorb a slow or busy GPU
     const uint32_t auto_chunk = std::max(1u, n_tiles / (4u * std::max(1u, s->tile_world)));
@@ -691,6 +700,8 @@ int render_impl(crt_world* w, const crt_camera* camera, const crt_render_setting
     size_t max_pixels;  // largest pixel set one render_pixel_set call will see (buffer sizing)
     if (cursor) {
         max_pixels = std::min<size_t>((size_t)steal_chunk * T * T, (size_t)W * H);
+    } else if (pixels_cached) {
+        max_pixels = sc.pixel_count;
     } else if (s->tile_world <= 1) {
         pixels.reserve((size_t)W * H);
         for (uint32_t by = 0; by < H; by += 4)
@@ -744,6 +755,7 @@ int render_impl(crt_world* w, const crt_camera* camera, const crt_render_setting
             cudaFree(sc.pixels);
             sc.pixels = nullptr;
             sc.cap_pixels = 0;
+            sc.pixel_key = 0;
             CKR(cudaMalloc(&sc.pixels, need_px));
             sc.cap_pixels = need_px;
         }
@@ -850,8 +862,7 @@ int render_impl(crt_world* w, const crt_camera* camera, const crt_render_setting
 
     // ---- one pixel set: all rounds of all its pixels, then its film pixels ----
     uint32_t* d_active[2] = {nullptr, nullptr};
-    auto render_pixel_set = [&](const std::vector<uint32_t>& pixels) -> int {
-        const uint32_t n_pix = (uint32_t)pixels.size();
+    auto render_pixel_set = [&](const std::vector<uint32_t>& pixels, uint32_t n_pix, bool upload) -> int {
         if (n_pix == 0) return CRT_OK;
         {
             char* p = (char*)sc.pixels;
@@ -862,11 +873,12 @@ int render_impl(crt_world* w, const crt_camera* camera, const crt_render_setting
             P.px.sum_w = carve<float4>(p, n_pix);
             P.px.lum = (double2*)carve<float4>(p, n_pix);
             P.px.pixels = d_pixels;
-            CKR(cudaMemcpyAsync(d_pixels, pixels.data(), (size_t)n_pix * 4, cudaMemcpyHostToDevice, stream));
-            std::vector<uint32_t> iota(n_pix);
-            for (uint32_t i = 0; i < n_pix; ++i) iota[i] = i;
-            CKR(cudaMemcpyAsync(d_active[0], iota.data(), (size_t)n_pix * 4, cudaMemcpyHostToDevice, stream));
-            CKR(cudaStreamSynchronize(stream));  // the staging vectors die with this scope
+            if (upload) {
+                CKR(cudaMemcpyAsync(d_pixels, pixels.data(), (size_t)n_pix * 4, cudaMemcpyHostToDevice, stream));
+                CKR(cudaStreamSynchronize(stream));  // `pixels` may be reused by the caller
+            }
+            iota_kernel<<<(int)std::max<size_t>(1, std::min<size_t>(((size_t)n_pix + kBlock - 1) / kBlock, (size_t)sms * 8)), kBlock, 0, stream>>>(d_active[0], n_pix);
+            ++launches;
             CKR(cudaMemsetAsync(P.px.taken, 0, (size_t)n_pix * 4, stream));
             CKR(cudaMemsetAsync(P.px.sum_w, 0, (size_t)n_pix * 16, stream));
             CKR(cudaMemsetAsync(P.px.lum, 0, (size_t)n_pix * 16, stream));
@@ -930,13 +942,16 @@ int render_impl(crt_world* w, const crt_camera* camera, const crt_render_setting
             if (c >= n_chunks) break;
             pixels.clear();
             for (uint32_t t = c; t < n_tiles; t += n_chunks) append_tile(t, pixels);
-            int r = render_pixel_set(pixels);
+            sc.pixel_key = 0;  // the pixel scratch now holds a chunk's list
+            int r = render_pixel_set(pixels, (uint32_t)pixels.size(), true);
             if (r) return r;
             ++chunks_done;
         }
     } else {
-        int r = render_pixel_set(pixels);
+        int r = render_pixel_set(pixels, pixels_cached ? sc.pixel_count : (uint32_t)pixels.size(), !pixels_cached);
         if (r) return r;
+        sc.pixel_key = pixel_key;
+        sc.pixel_count = pixels_cached ? sc.pixel_count : (uint32_t)pixels.size();
     }
     CKR(cudaGetLastError());
     CKR(cudaMemcpyAsync(sc.h_pinned + 16, sc.stats, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
