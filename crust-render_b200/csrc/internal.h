@@ -68,4 +68,8 @@ struct QueueTrace {
 };
 int enqueue_queue_trace(const crt_scene* s, bool any_hit, const QueueTrace& q, cudaStream_t stream);
 
+// device_build.cu
+bool device_build_supported(const std::vector<Geom>& geoms);
+int device_build(const std::vector<Geom>& geoms, crt_scene* s);
+
 }  // namespace crt

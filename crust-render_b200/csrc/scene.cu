@@ -319,6 +319,17 @@ int crt_commit_ex(crt_builder* b, uint32_t flags, int host_threads, crt_scene** 
             crt_scene_release(s);
             return fail(CRT_ERR_INVALID_ARG, "commit: instanced scene was committed in a different mode (host-only vs device)");
         }
+    if ((flags & CRT_COMMIT_DEVICE_BUILD) && !host_only && !(flags & CRT_COMMIT_KEEP_HOST_TREE) && device_build_supported(b->geoms)) {
+        int rc = device_build(b->geoms, s);
+        crt_builder_free(b);
+        if (rc) {
+            crt_scene_release(s);
+            return rc;
+        }
+        s->info.built_on_device = 1;
+        *out = s;
+        return CRT_OK;
+    }
     HostTree* t = new HostTree();
     const char* err = nullptr;
     bool ok = build_host_tree(b->geoms, child_info_of, host_threads, *t, &err);

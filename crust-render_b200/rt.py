@@ -37,11 +37,12 @@ __all__ = [
     "AABB", "Affine3A", "CrtError", "CubicCurveSegment", "CurveSegment", "Geometry", "HIT_DTYPE", "INVALID_ID",
     "MASK_ALL", "MASK_CAMERA", "MASK_INDIRECT", "MASK_SHADOW", "PrimitiveBreakdown", "RAY_DTYPE", "Ray", "RayHit",
     "Scene", "SceneBuilder", "MemoryFootprint", "BuildInfo", "lib", "lib_path", "make_rays", "init", "device_info",
-    "launch_count", "device_status", "COMMIT_KEEP_HOST_TREE", "COMMIT_HOST_ONLY",
+    "launch_count", "device_status", "COMMIT_KEEP_HOST_TREE", "COMMIT_HOST_ONLY", "COMMIT_DEVICE_BUILD",
 ]
 
 COMMIT_KEEP_HOST_TREE = 0x1
 COMMIT_HOST_ONLY = 0x2
+COMMIT_DEVICE_BUILD = 0x4  # build the BVH on the GPU (triangle-only scenes; see include/crt.h)
 
 _STATUS = {1: "invalid argument", 2: "unknown geometry id", 3: "CUDA error", 4: "no CUDA device", 5: "instance nesting too deep", 6: "out of device memory"}
 
@@ -72,7 +73,7 @@ class MemoryFootprint(C.Structure):
 
 class BuildInfo(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ("primitives", "binary_nodes", "wide_nodes", "leaves", "leaf_refs", "node_bytes", "leaf_bytes")] + [
-        ("build_seconds", C.c_double), ("upload_seconds", C.c_double), ("instance_depth", C.c_uint32)]
+        ("build_seconds", C.c_double), ("upload_seconds", C.c_double), ("instance_depth", C.c_uint32), ("built_on_device", C.c_uint32)]
 
 
 _lib = None

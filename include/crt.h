@@ -92,6 +92,7 @@ typedef struct crt_build_info {
     uint64_t node_bytes, leaf_bytes;
     double build_seconds, upload_seconds;
     uint32_t instance_depth; /* 0 = no instances below */
+    uint32_t built_on_device; /* 1 = CRT_COMMIT_DEVICE_BUILD took effect (build_seconds is device time) */
 } crt_build_info;
 
 const char* crt_last_error(void);
@@ -136,6 +137,13 @@ int crt_commit(crt_builder* b, crt_scene** out);
 #define CRT_COMMIT_KEEP_HOST_TREE 0x1u /* keep the host copy for crt_debug_* */
 #define CRT_COMMIT_HOST_ONLY 0x2u      /* test support: build the host tree and skip the upload; every query on such
                                           a scene fails with CRT_ERR_NO_DEVICE (there is no host traversal) */
+/* Build the BVH on the device instead of the host: Morton-order radix tree collapsed to BVH4 with
+ * the reference's largest-area rule, leaves of <= 4 triangles. For scenes made only of triangle meshes without
+ * vertex normals; any other scene silently takes the host build (crt_build_info.built_on_device tells which).
+ * Milliseconds instead of seconds at 10 M triangles. The tree is NOT the reference's SAH/SBVH tree: every query
+ * returns the same closest hit except where two primitives tie at exactly equal t (the reference's "later wins"
+ * rule, bvh.rs:537-544, depends on visiting order), and traversal is somewhat slower. Deterministic. */
+#define CRT_COMMIT_DEVICE_BUILD 0x4u
 int crt_commit_ex(crt_builder* b, uint32_t flags, int host_threads /* 0 = all */, crt_scene** out);
 
 void crt_scene_retain(crt_scene* s);

@@ -1,0 +1,131 @@
+"""-m gpu: the device-side BVH build (csrc/device_build.cu, CRT_COMMIT_DEVICE_BUILD) against the oracle.
+The GPU-built tree is not the reference's SAH/SBVH tree, so the comparison is on query results: the closest hit
+of every ray must be the oracle's (same t, u, v, ids bit for bit — the primitive tests are the same code), except
+where two triangles tie at exactly equal t; occlusion must agree everywhere."""
+import numpy as np
+import pytest
+
+from crust_render_b200 import workloads as W
+from crust_render_b200.rt_types import Geometry, make_rays
+
+pytestmark = pytest.mark.gpu
+
+
+def commit_both(gpu, orc, meshes, mask=None):
+    bg, bo = gpu.SceneBuilder(), orc.SceneBuilder()
+    for k, (v, i) in enumerate(meshes):
+        m = 0xFFFFFFFF if mask is None else mask[k]
+        bg.attach_masked(Geometry.TriangleMesh(v, i), m)
+        bo.attach_masked(Geometry.TriangleMesh(v, i), m)
+    return bg.commit(flags=gpu.COMMIT_DEVICE_BUILD), bo.commit()
+
+
+def agree(g, o):
+    same = (g["geom_id"] == o["geom_id"]) & (g["prim_id"] == o["prim_id"]) & (g["t"] == o["t"]) & (g["u"] == o["u"]) & (g["v"] == o["v"])
+    tie = (~same) & (g["t"] == o["t"]) & (g["geom_id"] != 0xFFFFFFFF) & (o["geom_id"] != 0xFFFFFFFF)
+    return same, tie
+
+
+def test_probe_scene_matches_the_oracle(gpu, orc):
+    """ray_throughput.rs's tri_spheres (43 200 triangles) x 262 144 LCG rays."""
+    meshes = [W.uv_sphere(c, 0.45, 24, 12) for c in [(x * 1.2, y * 1.2, z * 1.2) for x in range(-2, 3) for y in range(-1, 2) for z in range(-2, 3)]]
+    sg, so = commit_both(gpu, orc, meshes)
+    info = sg.build_info()
+    assert info.built_on_device == 1 and info.primitives == sum(len(i) for _, i in meshes) and info.leaf_refs == info.primitives
+    assert info.leaves * 4 >= info.primitives and info.wide_nodes > 0
+    rays = W.ray_batch(1 << 18, W.scene_extent(so.bounds()))
+    hg, fg = sg.intersect_n(rays)
+    ho, fo = so.intersect_n(rays, threads=0)
+    same, tie = agree(hg, ho)
+    assert (same | tie).all() and same.mean() >= 0.9999
+    assert np.array_equal(fg[same], fo[same])
+    assert np.array_equal(sg.occluded_n(rays), so.occluded_n(rays, threads=0))
+    bg, bo = sg.bounds(), so.bounds()
+    assert np.allclose(bg.minimum, bo.minimum) and np.allclose(bg.maximum, bo.maximum)
+
+
+def test_every_triangle_is_reachable(gpu, orc):
+    """One ray per triangle, aimed at its centroid from outside the convex mesh: the hit must be that triangle."""
+    v, i = W.uv_sphere((0.0, 0.0, 0.0), 1.0, 96, 48)
+    sg, _ = commit_both(gpu, orc, [(v, i)])
+    tri = v[i.astype(np.int64)]
+    c = tri.mean(axis=1)
+    area = np.linalg.norm(np.cross(tri[:, 1] - tri[:, 0], tri[:, 2] - tri[:, 0]), axis=1)
+    keep = area > 1e-7  # the pole rows hold zero-area triangles
+    d = -c / np.linalg.norm(c, axis=1, keepdims=True)
+    rays = make_rays(c[keep] - 2.0 * d[keep], d[keep])
+    h, _ = sg.intersect_n(rays)
+    assert np.array_equal(h["prim_id"], np.nonzero(keep)[0].astype(np.uint32)) and np.all(h["geom_id"] == 0)
+
+
+def test_stress_scene_with_masks_and_bad_indices(gpu, orc):
+    meshes = W.stress_meshes(grid=2, shards=3000, jitter=True)
+    v, i = meshes[0]
+    bad = i.copy()
+    bad[5] = (0, 1, 10 ** 6)            # out-of-range index: skipped, still consumes prim_id 5 (scene.rs:251-253)
+    meshes[0] = (v, bad)
+    masks = [0xFFFFFFFF] * len(meshes)
+    masks[1] = 0x2                      # shadow rays only
+    sg, so = commit_both(gpu, orc, meshes, masks)
+    assert sg.build_info().built_on_device == 1 and sg.primitive_count() == so.primitive_count()
+    rays = W.ray_batch(1 << 17, W.scene_extent(so.bounds()), seed=99)
+    for m in (None, np.full(len(rays), 0x1, np.uint32), np.full(len(rays), 0x2, np.uint32)):
+        hg, _ = sg.intersect_n(rays, None, m)
+        ho, _ = so.intersect_n(rays, None, m, threads=0)
+        same, tie = agree(hg, ho)
+        assert (same | tie).all() and same.mean() >= 0.9999
+        assert np.array_equal(sg.occluded_n(rays, None, m), so.occluded_n(rays, None, m, threads=0))
+
+
+@pytest.mark.parametrize("n_tris", [0, 1, 3, 4, 5, 9])
+def test_tiny_and_empty_scenes(gpu, orc, n_tris):
+    rng = np.random.default_rng(n_tris)
+    v = rng.uniform(-1, 1, (max(3 * n_tris, 3), 3)).astype(np.float32)
+    i = np.arange(3 * n_tris, dtype=np.uint32).reshape(-1, 3)
+    sg, so = commit_both(gpu, orc, [(v, i)])
+    rays = W.ray_batch(4096, 2.0, seed=5)
+    hg, _ = sg.intersect_n(rays)
+    ho, _ = so.intersect_n(rays, threads=0)
+    same, tie = agree(hg, ho)
+    assert (same | tie).all()
+    assert np.array_equal(sg.occluded_n(rays), so.occluded_n(rays, threads=0))
+
+
+def test_deterministic_and_falls_back_for_other_primitives(gpu):
+    meshes = W.stress_meshes(grid=2, shards=2000, jitter=False)
+    rays = W.ray_batch(1 << 16, 30.0)
+    outs = []
+    for _ in range(2):
+        b = gpu.SceneBuilder()
+        for v, i in meshes:
+            b.attach(Geometry.TriangleMesh(v, i))
+        s = b.commit(flags=gpu.COMMIT_DEVICE_BUILD)
+        bi = s.build_info()
+        outs.append((s.intersect_n(rays)[0].tobytes(), bi.wide_nodes, bi.leaves))
+    assert outs[0] == outs[1]
+    b = gpu.SceneBuilder()
+    b.attach(Geometry.TriangleMesh(*meshes[0]))
+    b.attach(Geometry.Sphere((0, 0, 0), 1.0))
+    s = b.commit(flags=gpu.COMMIT_DEVICE_BUILD)
+    assert s.build_info().built_on_device == 0 and s.primitive_breakdown().spheres == 1
+
+
+def test_render_on_a_device_built_scene(gpu, orc):
+    """The wavefront integrator over a GPU-built tree renders the same image (ties aside) as over the host tree."""
+    from crust_render_b200.render_types import Camera, LightList, OpenPBR, RenderSettings
+    meshes = W.stress_meshes(grid=2, shards=1000, jitter=False)
+
+    def world(flags):
+        sb = gpu.SceneBuilder()
+        for v, i in meshes:
+            sb.attach(Geometry.TriangleMesh(v, i))
+        scene = sb.commit(flags=flags)
+        mats = np.zeros(1, dtype=OpenPBR().dtype)
+        mats[0] = OpenPBR()
+        return gpu.World(scene, mats, np.zeros(len(meshes), np.uint32), LightList())
+    cam = Camera((0, 9, 20), (0, 0, 0), (0, 1, 0), 40.0, 16 / 9)
+    st = RenderSettings(4, 4, 160, 90, variance_threshold=0.0)
+    a, sa = gpu.Renderer(cam, world(0), st).render_with_stats()
+    b, sb_ = gpu.Renderer(cam, world(gpu.COMMIT_DEVICE_BUILD), st).render_with_stats()
+    rel = np.abs(a[..., :3] - b[..., :3]) / (np.abs(a[..., :3]) + 1e-3)
+    assert (rel.max(axis=-1) > 1e-3).mean() < 0.002 and sa.camera_rays == sb_.camera_rays
