@@ -9,7 +9,9 @@
 //
 //   tri_setup      gather each triangle from its mesh (scene.rs:240-264: out-of-range indices skip the
 //                  triangle but still consume a prim_id), padded AABB (aabb.rs:47-58), scene bounds
-//   morton         63-bit Morton code of the AABB centre; invalid triangles sort to the end
+//   extent/count   early split clipping: triangles much larger than the mean get a regular grid over their box
+//   split          one candidate reference per grid cell: the triangle clipped to the cell (Sutherland-Hodgman),
+//                  its box, and the 63-bit Morton code of the box centre; empty cells sort to the end
 //   radix sort     cub::DeviceRadixSort (library sort, like a library GEMM)
 //   karras         binary radix tree over the sorted codes (Karras 2012), ties broken by position
 //   refit          bottom-up AABBs, one atomic counter per internal node
@@ -22,7 +24,11 @@
 #include <cub/cub.cuh>
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <chrono>
+#include <mutex>
+#include <cstdio>
+#include <cstdlib>
 #include <vector>
 
 #include "internal.h"
@@ -52,8 +58,12 @@ struct MeshTable {            // per triangle mesh, device arrays of length n_me
 struct BuildArrays {
     // per flat triangle
     float4 *v0, *v1, *v2;        // .w of v0 = mask bits
-    float4 *lo, *hi;             // padded AABB
+    float4 *lo, *hi;             // padded AABB of the triangle; lo.w = valid
+    uint32_t *cells, *cell_off;  // pre-split grid of the triangle (nx | ny << 8 | nz << 16) and its first candidate reference
     uint2* prim_ids;             // (geom_id, prim_id)
+    // per candidate reference (a triangle, or the part of a large triangle inside one cell of its split grid)
+    uint32_t* ref_prim;
+    float4 *rlo, *rhi;
     // sort
     unsigned long long *key_a, *key_b;
     uint32_t *idx_a, *idx_b;
@@ -65,7 +75,8 @@ struct BuildArrays {
     // BVH4
     uint32_t *is_root4, *id4;
     int *frontier_a, *frontier_b;
-    unsigned int* counters;      // [0] valid triangles, [1] next frontier size, [2] leaves, [8..13] bounds as ordered ints
+    unsigned int* counters;      // [0] valid triangles, [1] next frontier size, [2] leaves, [3] valid references,
+                                 // [4..5] sum of quantised triangle extents (u64), [8..13] bounds as ordered ints
 };
 
 __device__ __forceinline__ unsigned int f2ord(float f) {
@@ -81,6 +92,16 @@ __host__ __device__ inline float ord2f(unsigned int u) {
     memcpy(&f, &u, 4);
     return f;
 #endif
+}
+
+__device__ __forceinline__ unsigned long long spread21(unsigned long long x) {  // 21 bits -> every third bit
+    x &= 0x1FFFFFull;
+    x = (x | x << 32) & 0x1F00000000FFFFull;
+    x = (x | x << 16) & 0x1F0000FF0000FFull;
+    x = (x | x << 8) & 0x100F00F00F00F00Full;
+    x = (x | x << 4) & 0x10C30C30C30C30C3ull;
+    x = (x | x << 2) & 0x1249249249249249ull;
+    return x;
 }
 
 __global__ void __launch_bounds__(kB) tri_setup_kernel(uint32_t n, MeshTable mt, const float* __restrict__ verts, const uint32_t* __restrict__ idx, BuildArrays A) {
@@ -129,34 +150,131 @@ __global__ void __launch_bounds__(kB) tri_setup_kernel(uint32_t n, MeshTable mt,
     if (threadIdx.x == 0 && v) atomicAdd(A.counters + 0, v);
 }
 
-__device__ __forceinline__ unsigned long long spread21(unsigned long long x) {  // 21 bits -> every third bit
-    x &= 0x1FFFFFull;
-    x = (x | x << 32) & 0x1F00000000FFFFull;
-    x = (x | x << 16) & 0x1F0000FF0000FFull;
-    x = (x | x << 8) & 0x100F00F00F00F00Full;
-    x = (x | x << 4) & 0x10C30C30C30C30C3ull;
-    x = (x | x << 2) & 0x1249249249249249ull;
-    return x;
+// Mean triangle size, deterministically: longest AABB side of every valid triangle, quantised against the scene
+// extent (24 bits) and summed in integers.
+__global__ void __launch_bounds__(kB) extent_kernel(uint32_t n, float scene_extent, BuildArrays A) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long q = 0;
+    if (i < n) {
+        float4 lo = A.lo[i], hi = A.hi[i];
+        if (lo.w != 0.0f) q = (unsigned long long)(fminf(fmaxf(fmaxf(hi.x - lo.x, hi.y - lo.y), hi.z - lo.z) / scene_extent, 1.0f) * 16777216.0f);
+    }
+    typedef cub::BlockReduce<unsigned long long, kB> BR;
+    __shared__ typename BR::TempStorage tmp;
+    unsigned long long r = BR(tmp).Sum(q);
+    if (threadIdx.x == 0 && r) atomicAdd((unsigned long long*)(A.counters + 4), r);
 }
 
-__global__ void __launch_bounds__(kB) morton_kernel(uint32_t n, BuildArrays A) {
+// How many candidate references a triangle gets: triangles much larger than the typical one are cut along a
+// regular grid over their box (early split clipping), so one long shard or a ground plane does not inflate every
+// node above it. The reference reaches the same end with SBVH spatial splits (bvh.rs:974-1054).
+__global__ void __launch_bounds__(kB) count_kernel(uint32_t n, float cell, float split_above, BuildArrays A) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     float4 lo = A.lo[i], hi = A.hi[i];
-    unsigned long long key = ~0ull;  // invalid triangles go to the end
+    uint32_t dims = 0, count = 0;
     if (lo.w != 0.0f) {
+        float ex = hi.x - lo.x, ey = hi.y - lo.y, ez = hi.z - lo.z;
+        uint32_t nx = 1, ny = 1, nz = 1;
+        if (fmaxf(fmaxf(ex, ey), ez) > split_above) {
+            float c = cell;
+            for (int it = 0; it < 16; ++it) {  // coarsen until the grid has at most 4096 cells and 64 per axis
+                nx = (uint32_t)fminf(fmaxf(ceilf(ex / c), 1.0f), 64.0f);
+                ny = (uint32_t)fminf(fmaxf(ceilf(ey / c), 1.0f), 64.0f);
+                nz = (uint32_t)fminf(fmaxf(ceilf(ez / c), 1.0f), 64.0f);
+                if (nx * ny * nz <= 4096u) break;
+                c *= 1.5f;
+            }
+            if (nx * ny * nz > 4096u) nx = ny = nz = 1;
+        }
+        dims = nx | (ny << 8) | (nz << 16);
+        count = nx * ny * nz;
+    }
+    A.cells[i] = dims;
+    A.cell_off[i] = count;  // scanned in place afterwards
+}
+
+// Sutherland-Hodgman against one axis-aligned plane; keeps the side where sign * (p[axis] - value) >= 0.
+__device__ int clip_plane(float3* in, int n, float3* out, int axis, float value, float sign) {
+    int m = 0;
+    for (int k = 0; k < n; ++k) {
+        float3 a = in[k], b = in[(k + 1) % n];
+        float da = sign * ((axis == 0 ? a.x : axis == 1 ? a.y : a.z) - value), db = sign * ((axis == 0 ? b.x : axis == 1 ? b.y : b.z) - value);
+        if (da >= 0.0f) out[m++] = a;
+        if ((da > 0.0f && db < 0.0f) || (da < 0.0f && db > 0.0f)) {
+            float t = da / (da - db);
+            float3 p = make_float3(a.x + t * (b.x - a.x), a.y + t * (b.y - a.y), a.z + t * (b.z - a.z));
+            if (axis == 0) p.x = value; else if (axis == 1) p.y = value; else p.z = value;  // snap onto the plane
+            out[m++] = p;
+        }
+    }
+    return m;
+}
+
+__global__ void __launch_bounds__(kB) split_kernel(uint32_t n_tris, uint32_t n_cand, float eps, BuildArrays A) {
+    uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_cand) return;
+    // triangle of this candidate: last t with cell_off[t] <= r (cell_off is the exclusive scan of the counts)
+    uint32_t a = 0, b = n_tris;
+    while (b - a > 1) {
+        uint32_t m = (a + b) >> 1;
+        if (__ldg(A.cell_off + m) <= r) a = m; else b = m;
+    }
+    const uint32_t t = a, dims = A.cells[t], local = r - A.cell_off[t];
+    const uint32_t nx = dims & 0xFFu, ny = (dims >> 8) & 0xFFu, nz = dims >> 16;
+    float4 tlo = A.lo[t], thi = A.hi[t];
+    float3 lo = make_float3(tlo.x, tlo.y, tlo.z), hi = make_float3(thi.x, thi.y, thi.z);
+    bool valid = true;
+    if (nx * ny * nz > 1u) {
+        uint32_t ix = local % nx, iy = (local / nx) % ny, iz = local / (nx * ny);
+        float sx = (thi.x - tlo.x) / (float)nx, sy = (thi.y - tlo.y) / (float)ny, sz = (thi.z - tlo.z) / (float)nz;
+        // cell faces are computed the same way from both sides, so neighbouring cells share them exactly
+        float3 clo = make_float3(ix == 0 ? tlo.x : tlo.x + (float)ix * sx, iy == 0 ? tlo.y : tlo.y + (float)iy * sy, iz == 0 ? tlo.z : tlo.z + (float)iz * sz);
+        float3 chi = make_float3(ix + 1 == nx ? thi.x : tlo.x + (float)(ix + 1) * sx, iy + 1 == ny ? thi.y : tlo.y + (float)(iy + 1) * sy,
+                                 iz + 1 == nz ? thi.z : tlo.z + (float)(iz + 1) * sz);
+        float3 pa[10], pb[10];
+        float4 v0 = A.v0[t], v1 = A.v1[t], v2 = A.v2[t];
+        pa[0] = make_float3(v0.x, v0.y, v0.z), pa[1] = make_float3(v1.x, v1.y, v1.z), pa[2] = make_float3(v2.x, v2.y, v2.z);
+        int m = 3;
+        m = clip_plane(pa, m, pb, 0, clo.x, 1.0f);
+        if (m) m = clip_plane(pb, m, pa, 0, chi.x, -1.0f);
+        if (m) m = clip_plane(pa, m, pb, 1, clo.y, 1.0f);
+        if (m) m = clip_plane(pb, m, pa, 1, chi.y, -1.0f);
+        if (m) m = clip_plane(pa, m, pb, 2, clo.z, 1.0f);
+        if (m) m = clip_plane(pb, m, pa, 2, chi.z, -1.0f);
+        valid = m > 0;
+        if (valid) {
+            lo = pa[0], hi = pa[0];
+            for (int k = 1; k < m; ++k) {
+                lo = make_float3(fminf(lo.x, pa[k].x), fminf(lo.y, pa[k].y), fminf(lo.z, pa[k].z));
+                hi = make_float3(fmaxf(hi.x, pa[k].x), fmaxf(hi.y, pa[k].y), fmaxf(hi.z, pa[k].z));
+            }
+            // conservative: interpolated corners carry rounding error; never leave the triangle's own box
+            lo = make_float3(fmaxf(lo.x - eps, tlo.x), fmaxf(lo.y - eps, tlo.y), fmaxf(lo.z - eps, tlo.z));
+            hi = make_float3(fminf(hi.x + eps, thi.x), fminf(hi.y + eps, thi.y), fminf(hi.z + eps, thi.z));
+        }
+    }
+    unsigned long long key = ~0ull;
+    if (valid) {
         float3 smin = make_float3(ord2f(A.counters[8]), ord2f(A.counters[9]), ord2f(A.counters[10]));
         float3 smax = make_float3(ord2f(A.counters[11]), ord2f(A.counters[12]), ord2f(A.counters[13]));
+        // one scale for the three axes: cubic Morton cells (per-axis normalisation would cut flat scenes into pancakes)
+        float e = fmaxf(fmaxf(smax.x - smin.x, smax.y - smin.y), fmaxf(smax.z - smin.z, 1e-30f));
         float cx = 0.5f * (lo.x + hi.x), cy = 0.5f * (lo.y + hi.y), cz = 0.5f * (lo.z + hi.z);
-        float ex = fmaxf(smax.x - smin.x, 1e-30f), ey = fmaxf(smax.y - smin.y, 1e-30f), ez = fmaxf(smax.z - smin.z, 1e-30f);
-        unsigned long long qx = (unsigned long long)fminf(fmaxf((cx - smin.x) / ex * 2097152.0f, 0.0f), 2097151.0f);
-        unsigned long long qy = (unsigned long long)fminf(fmaxf((cy - smin.y) / ey * 2097152.0f, 0.0f), 2097151.0f);
-        unsigned long long qz = (unsigned long long)fminf(fmaxf((cz - smin.z) / ez * 2097152.0f, 0.0f), 2097151.0f);
+        unsigned long long qx = (unsigned long long)fminf(fmaxf((cx - smin.x) / e * 2097152.0f, 0.0f), 2097151.0f);
+        unsigned long long qy = (unsigned long long)fminf(fmaxf((cy - smin.y) / e * 2097152.0f, 0.0f), 2097151.0f);
+        unsigned long long qz = (unsigned long long)fminf(fmaxf((cz - smin.z) / e * 2097152.0f, 0.0f), 2097151.0f);
         key = (spread21(qx) << 2) | (spread21(qy) << 1) | spread21(qz);
     }
-    A.key_a[i] = key;
-    A.idx_a[i] = i;
+    A.ref_prim[r] = t;
+    A.rlo[r] = make_float4(lo.x, lo.y, lo.z, 0.0f);
+    A.rhi[r] = make_float4(hi.x, hi.y, hi.z, 0.0f);
+    A.key_a[r] = key;
+    A.idx_a[r] = r;
+    unsigned int v = __syncthreads_count(valid);
+    if (threadIdx.x == 0 && v) atomicAdd(A.counters + 3, v);
 }
+
 
 // Karras 2012. delta(i, j): common-prefix length of the keys at sorted positions i and j, positions breaking ties.
 __device__ __forceinline__ int delta(const unsigned long long* __restrict__ keys, int n, int i, int j) {
@@ -201,7 +319,7 @@ __global__ void __launch_bounds__(kB) refit_kernel(int n, const uint32_t* __rest
     if (j >= n) return;
     uint32_t t = sorted[j];
     int node = (n - 1) + j;
-    float4 lo = A.lo[t], hi = A.hi[t];
+    float4 lo = A.rlo[t], hi = A.rhi[t];
     A.nlo[node] = lo;
     A.nhi[node] = hi;
     if (n == 1) return;
@@ -259,7 +377,7 @@ __global__ void __launch_bounds__(kB) mark_kernel(int n, const int* __restrict__
 
 __device__ __forceinline__ void write_leaf_records(const BuildArrays& A, const uint32_t* __restrict__ sorted, float4* __restrict__ leafs, int first, int last) {
     for (int j = first; j <= last; ++j) {
-        uint32_t t = sorted[j];
+        uint32_t t = A.ref_prim[sorted[j]];
         float4 a = A.v0[t], b = A.v1[t], c = A.v2[t];
         int ti = j - first;
         uint32_t flags = REC_TRI | ((uint32_t)(ti & 3) << REC_LANE_SHIFT);
@@ -320,7 +438,7 @@ __global__ void tiny_kernel(int n, const uint32_t* __restrict__ sorted, DevNode*
     w.pad[0] = w.pad[1] = w.pad[2] = 0;
     float3 lo = make_float3(INFINITY, INFINITY, INFINITY), hi = make_float3(-INFINITY, -INFINITY, -INFINITY);
     for (int j = 0; j < n; ++j) {
-        float4 a = A.lo[sorted[j]], b = A.hi[sorted[j]];
+        float4 a = A.rlo[sorted[j]], b = A.rhi[sorted[j]];
         lo = make_float3(fminf(lo.x, a.x), fminf(lo.y, a.y), fminf(lo.z, a.z));
         hi = make_float3(fmaxf(hi.x, b.x), fmaxf(hi.y, b.y), fmaxf(hi.z, b.z));
     }
@@ -339,6 +457,29 @@ __global__ void pad_kernel(float4* leafs, size_t first) {  // kernels may over-r
 template <typename T>
 cudaError_t dmalloc(T** p, size_t count) { return cudaMalloc((void**)p, std::max<size_t>(count, 1) * sizeof(T)); }
 
+// Build scratch lives in one grow-only device arena and one pinned staging buffer kept for the life of the
+// process: cudaMalloc / cudaFree of a few dozen GB-scale buffers cost more than all the build kernels together.
+struct Arena {
+    std::mutex mu;
+    char* dev = nullptr;
+    size_t dev_cap = 0;
+    char* dev2 = nullptr;  // per-reference arrays (sized after the split count is known)
+    size_t dev2_cap = 0;
+    char* pinned = nullptr;
+    size_t pinned_cap = 0;
+} g_arena;
+struct Carver {
+    char* p;
+    char* end;
+    template <typename T>
+    T* take(size_t count) {
+        T* r = (T*)p;
+        p += (std::max<size_t>(count, 1) * sizeof(T) + 255) & ~(size_t)255;
+        return p <= end ? r : nullptr;
+    }
+};
+size_t padded(size_t count, size_t elem) { return (std::max<size_t>(count, 1) * elem + 255) & ~(size_t)255; }
+
 }  // namespace
 
 bool device_build_supported(const std::vector<Geom>& geoms) {
@@ -349,6 +490,15 @@ bool device_build_supported(const std::vector<Geom>& geoms) {
 
 int device_build(const std::vector<Geom>& geoms, crt_scene* s) {
     auto t0 = std::chrono::steady_clock::now();
+    const bool trace = getenv("CRT_DEVICE_BUILD_TRACE") != nullptr;  // per-phase wall times on stderr (synchronises)
+    const bool trace_sync = trace && atoi(getenv("CRT_DEVICE_BUILD_TRACE")) != 2;  // 2 = host-side times only, no extra synchronisation
+    auto lap = [&, last = t0](const char* what) mutable {
+        if (!trace) return;
+        if (trace_sync) cudaDeviceSynchronize();
+        auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[device_build] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(now - last).count());
+        last = now;
+    };
     // ---- concatenate the meshes (host) -------------------------------------------------------------------
     std::vector<uint32_t> tri_offset, vert_offset, n_verts, geom_id, mask;
     size_t n_tris = 0, n_v = 0;
@@ -376,41 +526,67 @@ int device_build(const std::vector<Geom>& geoms, crt_scene* s) {
         CKB(cudaMemcpy(s->d_desc, &d, sizeof d, cudaMemcpyHostToDevice));
         return CRT_OK;
     }
-    float* d_verts = nullptr;
-    uint32_t *d_idx = nullptr, *d_tab = nullptr;
-    CKB(dmalloc(&d_verts, 3 * n_v));
-    CKB(dmalloc(&d_idx, 3 * n_tris));
-    CKB(dmalloc(&d_tab, (size_t)5 * n_meshes + 1));
+    // ---- arena 1: the upload and everything that is per triangle; one pinned buffer for the upload --------------
+    const uint32_t N = (uint32_t)n_tris;
+    const size_t tab_words = (size_t)5 * n_meshes + 1;
+    size_t scan_tmp = 0;
+    CKB(cub::DeviceScan::ExclusiveSum(nullptr, scan_tmp, (uint32_t*)nullptr, (uint32_t*)nullptr, (int)N));
+    const size_t upload_bytes = padded(3 * n_v, 4) + padded(3 * n_tris, 4) + padded(tab_words, 4);
+    const size_t need1 = upload_bytes + 5 * padded(N, 16) + 2 * padded(N, 4) + padded(16, 4) + padded(scan_tmp, 1);
+    std::lock_guard<std::mutex> arena_lock(g_arena.mu);
+    auto grow = [](char*& p, size_t& cap, size_t need) -> cudaError_t {
+        if (need <= cap) return cudaSuccess;
+        cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        cudaError_t e = cudaMalloc((void**)&p, need);
+        if (e == cudaSuccess) cap = need;
+        return e;
+    };
+    CKB(grow(g_arena.dev, g_arena.dev_cap, need1));
+    if (upload_bytes > g_arena.pinned_cap) {
+        if (g_arena.pinned) cudaFreeHost(g_arena.pinned);
+        g_arena.pinned = nullptr;
+        g_arena.pinned_cap = 0;
+        CKB(cudaMallocHost((void**)&g_arena.pinned, upload_bytes));
+        g_arena.pinned_cap = upload_bytes;
+    }
+    Carver dc{g_arena.dev, g_arena.dev + g_arena.dev_cap};
+    float* d_verts = dc.take<float>(3 * n_v);
+    uint32_t* d_idx = dc.take<uint32_t>(3 * n_tris);
+    uint32_t* d_tab = dc.take<uint32_t>(tab_words);
     {
+        Carver hc{g_arena.pinned, g_arena.pinned + g_arena.pinned_cap};
+        float* h_verts = hc.take<float>(3 * n_v);
+        uint32_t* h_idx = hc.take<uint32_t>(3 * n_tris);
+        uint32_t* h_tab = hc.take<uint32_t>(tab_words);
         size_t vo = 0, io = 0;
         for (const Geom& G : geoms) {
             if (G.indices.empty()) continue;
-            CKB(cudaMemcpyAsync(d_verts + vo, G.verts.data(), G.verts.size() * 4, cudaMemcpyHostToDevice, 0));
-            CKB(cudaMemcpyAsync(d_idx + io, G.indices.data(), G.indices.size() * 4, cudaMemcpyHostToDevice, 0));
+            memcpy(h_verts + vo, G.verts.data(), G.verts.size() * 4);
+            memcpy(h_idx + io, G.indices.data(), G.indices.size() * 4);
             vo += G.verts.size();
             io += G.indices.size();
         }
-        std::vector<uint32_t> tab;
-        tab.insert(tab.end(), tri_offset.begin(), tri_offset.end());
-        tab.insert(tab.end(), vert_offset.begin(), vert_offset.end());
-        tab.insert(tab.end(), n_verts.begin(), n_verts.end());
-        tab.insert(tab.end(), geom_id.begin(), geom_id.end());
-        tab.insert(tab.end(), mask.begin(), mask.end());
-        CKB(cudaMemcpy(d_tab, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice));
+        uint32_t* t = h_tab;
+        for (auto* vec : {&tri_offset, &vert_offset, &n_verts, &geom_id, &mask}) {
+            memcpy(t, vec->data(), vec->size() * 4);
+            t += vec->size();
+        }
+        CKB(cudaMemcpyAsync(g_arena.dev, g_arena.pinned, upload_bytes, cudaMemcpyHostToDevice, 0));  // the three regions are laid out identically
     }
     MeshTable mt{d_tab, d_tab + n_meshes + 1, d_tab + 2 * (size_t)n_meshes + 1, d_tab + 3 * (size_t)n_meshes + 1, d_tab + 4 * (size_t)n_meshes + 1, n_meshes};
+    lap("concat + upload");
     auto t_up = std::chrono::steady_clock::now();
 
-    // ---- device arrays --------------------------------------------------------------------------------------
-    const uint32_t N = (uint32_t)n_tris;
     BuildArrays A{};
-    CKB(dmalloc(&A.v0, N)); CKB(dmalloc(&A.v1, N)); CKB(dmalloc(&A.v2, N));
-    CKB(dmalloc(&A.lo, N)); CKB(dmalloc(&A.hi, N));
-    uint2* d_prim_ids = nullptr;
+    A.v0 = dc.take<float4>(N), A.v1 = dc.take<float4>(N), A.v2 = dc.take<float4>(N), A.lo = dc.take<float4>(N), A.hi = dc.take<float4>(N);
+    A.cells = dc.take<uint32_t>(N), A.cell_off = dc.take<uint32_t>(N);
+    A.counters = dc.take<unsigned int>(16);
+    void* d_scan = dc.take<char>(scan_tmp);
+    uint2* d_prim_ids = nullptr;  // owned by the scene
     CKB(dmalloc(&d_prim_ids, N));
     A.prim_ids = d_prim_ids;
-    CKB(dmalloc(&A.key_a, N)); CKB(dmalloc(&A.key_b, N)); CKB(dmalloc(&A.idx_a, N)); CKB(dmalloc(&A.idx_b, N));
-    CKB(dmalloc(&A.counters, 16));
     {
         unsigned int init[16] = {0};
         for (int k = 8; k < 11; ++k) init[k] = 0xFFFFFFFFu;
@@ -418,80 +594,124 @@ int device_build(const std::vector<Geom>& geoms, crt_scene* s) {
     }
     const int grid_t = (int)((N + kB - 1) / kB);
     tri_setup_kernel<<<grid_t, kB>>>(N, mt, d_verts, d_idx, A);
-    morton_kernel<<<grid_t, kB>>>(N, A);
-    cub::DoubleBuffer<unsigned long long> keys(A.key_a, A.key_b);
-    cub::DoubleBuffer<uint32_t> vals(A.idx_a, A.idx_b);
-    size_t tmp_bytes = 0;
-    CKB(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys, vals, (int)N, 0, 64));
-    void* d_tmp = nullptr;
-    CKB(cudaMalloc(&d_tmp, tmp_bytes));
-    CKB(cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, keys, vals, (int)N, 0, 64));
     unsigned int h_counters[16];
     CKB(cudaMemcpy(h_counters, A.counters, sizeof h_counters, cudaMemcpyDeviceToHost));
-    const int n = (int)h_counters[0];  // valid triangles: the first n sorted positions
-    const unsigned long long* d_keys = keys.Current();
-    const uint32_t* d_sorted = vals.Current();
-    crt::count_launches(4);
-
-    s->n_prims = (uint64_t)n;
-    s->breakdown.triangles = (uint64_t)n;
-    s->non_empty = n > 0;
-    if (n > 0) s->root = Box{{ord2f(h_counters[8]), ord2f(h_counters[9]), ord2f(h_counters[10])}, {ord2f(h_counters[11]), ord2f(h_counters[12]), ord2f(h_counters[13])}};
+    const uint32_t n_valid = h_counters[0];
+    uint64_t launches = 1;
+    s->n_prims = (uint64_t)n_valid;
+    s->breakdown.triangles = (uint64_t)n_valid;
+    s->non_empty = n_valid > 0;
+    Box root{{ord2f(h_counters[8]), ord2f(h_counters[9]), ord2f(h_counters[10])}, {ord2f(h_counters[11]), ord2f(h_counters[12]), ord2f(h_counters[13])}};
+    if (n_valid > 0) s->root = root;
+    lap("tri_setup");
 
     DevNode* d_nodes = nullptr;
     float4* d_leafs = nullptr;
     uint32_t n4 = 0;
-    const size_t leaf_quads = 3 * (size_t)std::max(n, 0) + 4;
-    if (n > 0) {
+    int n = 0;             // references the tree is built over
+    size_t leaf_quads = 0;
+    if (n_valid > 0) {
+        // ---- early split clipping: how large is a typical triangle, which ones are much larger -----------------------
+        const float scene_extent = std::max(std::max(root.hi.x - root.lo.x, root.hi.y - root.lo.y), std::max(root.hi.z - root.lo.z, 1e-30f));
+        extent_kernel<<<grid_t, kB>>>(N, scene_extent, A);
+        unsigned long long ext_sum = 0;
+        CKB(cudaMemcpy(&ext_sum, A.counters + 4, 8, cudaMemcpyDeviceToHost));
+        const float mean_extent = (float)((double)ext_sum / 16777216.0 / (double)n_valid) * scene_extent;
+        const float cell = std::max(2.0f * mean_extent, scene_extent * (1.0f / 4096.0f));
+        count_kernel<<<grid_t, kB>>>(N, cell, 2.0f * cell, A);
+        uint32_t last_count = 0, last_off = 0;
+        CKB(cudaMemcpy(&last_count, A.cell_off + (N - 1), 4, cudaMemcpyDeviceToHost));
+        size_t scan_bytes = scan_tmp;
+        CKB(cub::DeviceScan::ExclusiveSum(d_scan, scan_bytes, A.cell_off, A.cell_off, (int)N));
+        CKB(cudaMemcpy(&last_off, A.cell_off + (N - 1), 4, cudaMemcpyDeviceToHost));
+        const uint64_t T64 = (uint64_t)last_off + last_count;
+        if (T64 > 0x3FFFFFFFull) return set_error(CRT_ERR_OOM, "device build: too many split references");
+        const uint32_t T = (uint32_t)T64;
+        launches += 3;
+        lap("extent + count + scan");
+
+        // ---- arena 2: everything per reference ------------------------------------------------------------------------
+        size_t sort_tmp = 0;
+        {
+            cub::DoubleBuffer<unsigned long long> k(nullptr, nullptr);
+            cub::DoubleBuffer<uint32_t> v(nullptr, nullptr);
+            CKB(cub::DeviceRadixSort::SortPairs(nullptr, sort_tmp, k, v, (int)T, 0, 64));
+        }
+        size_t scan_tmp2 = 0;
+        CKB(cub::DeviceScan::ExclusiveSum(nullptr, scan_tmp2, (uint32_t*)nullptr, (uint32_t*)nullptr, (int)T));
+        const size_t need2 = padded(T, 4) + 2 * padded(T, 16) + 2 * padded(T, 8) + 2 * padded(T, 4) + padded(sort_tmp, 1) + padded(scan_tmp2, 1)  //
+                             + 4 * padded(T, 4) + padded(2 * (size_t)T, 4) + 2 * padded(2 * (size_t)T, 16) + 3 * padded(T, 4) + 2 * padded(T, 4);
+        CKB(grow(g_arena.dev2, g_arena.dev2_cap, need2));
+        Carver rc{g_arena.dev2, g_arena.dev2 + g_arena.dev2_cap};
+        A.ref_prim = rc.take<uint32_t>(T), A.rlo = rc.take<float4>(T), A.rhi = rc.take<float4>(T);
+        A.key_a = rc.take<unsigned long long>(T), A.key_b = rc.take<unsigned long long>(T), A.idx_a = rc.take<uint32_t>(T), A.idx_b = rc.take<uint32_t>(T);
+        void* d_tmp = rc.take<char>(sort_tmp);
+        void* d_scan2 = rc.take<char>(scan_tmp2);
+        split_kernel<<<(int)((T + kB - 1) / kB), kB>>>(N, T, 1e-6f * scene_extent, A);
+        lap("split");
+        cub::DoubleBuffer<unsigned long long> keys(A.key_a, A.key_b);
+        cub::DoubleBuffer<uint32_t> vals(A.idx_a, A.idx_b);
+        size_t tmp_bytes = sort_tmp;
+        CKB(cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, keys, vals, (int)T, 0, 64));
+        CKB(cudaMemcpy(h_counters, A.counters, sizeof h_counters, cudaMemcpyDeviceToHost));
+        lap("radix sort");
+        n = (int)h_counters[3];  // valid references: the first n sorted positions
+        const unsigned long long* d_keys = keys.Current();
+        const uint32_t* d_sorted = vals.Current();
+        launches += 2;
+        leaf_quads = 3 * (size_t)n + 4;
         CKB(dmalloc(&d_leafs, leaf_quads));
         pad_kernel<<<1, 1>>>(d_leafs, 3 * (size_t)n);
         if (n <= (int)kLeafMax) {
             CKB(dmalloc(&d_nodes, 1));
             tiny_kernel<<<1, 1>>>(n, d_sorted, d_nodes, d_leafs, A);
             n4 = 1;
-            crt::count_launches(2);
+            launches += 2;
         } else {
             const int n_bin = 2 * n - 1;
-            CKB(dmalloc(&A.left, n)); CKB(dmalloc(&A.right, n)); CKB(dmalloc(&A.first, n)); CKB(dmalloc(&A.last, n));
-            CKB(dmalloc(&A.parent, n_bin)); CKB(dmalloc(&A.nlo, n_bin)); CKB(dmalloc(&A.nhi, n_bin));
-            CKB(dmalloc(&A.visits, n)); CKB(dmalloc(&A.is_root4, n)); CKB(dmalloc(&A.id4, n));
-            CKB(dmalloc(&A.frontier_a, n)); CKB(dmalloc(&A.frontier_b, n));
-            CKB(cudaMemset(A.visits, 0, (size_t)n * 4));
-            CKB(cudaMemset(A.is_root4, 0, (size_t)n * 4));
+            A.left = rc.take<int>(n), A.right = rc.take<int>(n), A.first = rc.take<int>(n), A.last = rc.take<int>(n);
+            A.parent = rc.take<int>(n_bin), A.nlo = rc.take<float4>(n_bin), A.nhi = rc.take<float4>(n_bin);
+            A.visits = rc.take<unsigned int>(n), A.is_root4 = rc.take<uint32_t>(n), A.id4 = rc.take<uint32_t>(n);
+            A.frontier_a = rc.take<int>(n), A.frontier_b = rc.take<int>(n);
+            if (!A.frontier_b) return set_error(CRT_ERR_OOM, "device build: scratch arena too small (internal sizing error)");
+            CKB(cudaMemsetAsync(A.visits, 0, (size_t)n * 4));
+            CKB(cudaMemsetAsync(A.is_root4, 0, (size_t)n * 4));
             const int grid_n = (n + kB - 1) / kB;
             karras_kernel<<<grid_n, kB>>>(n, d_keys, A);
             refit_kernel<<<grid_n, kB>>>(n, d_sorted, A);
+            lap("karras + refit");
             // level-synchronous marking of the binary nodes that become BVH4 nodes
             int zero = 0;
             CKB(cudaMemcpy(A.frontier_a, &zero, 4, cudaMemcpyHostToDevice));
             uint32_t count = 1;
             int *cur = A.frontier_a, *nxt = A.frontier_b;
-            uint64_t launches = 3;
+            uint64_t levels = 0;
             while (count > 0) {
-                CKB(cudaMemset(A.counters + 1, 0, 4));
+                CKB(cudaMemsetAsync(A.counters + 1, 0, 4));
                 mark_kernel<<<(int)((count + kB - 1) / kB), kB>>>(n, cur, count, nxt, A);
                 CKB(cudaMemcpy(&count, A.counters + 1, 4, cudaMemcpyDeviceToHost));
                 std::swap(cur, nxt);
-                ++launches;
+                ++levels;
             }
-            size_t scan_bytes = 0;
-            CKB(cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, A.is_root4, A.id4, n - 1));
-            void* d_scan = nullptr;
-            CKB(cudaMalloc(&d_scan, scan_bytes));
-            CKB(cub::DeviceScan::ExclusiveSum(d_scan, scan_bytes, A.is_root4, A.id4, n - 1));
+            if (trace) fprintf(stderr, "[device_build] %u triangles, %u candidate / %d valid references, cell %.4g, %llu mark levels\n", n_valid, T, n, cell,
+                               (unsigned long long)levels);
+            lap("mark (level loop)");
+            size_t scan_bytes2 = scan_tmp2;
+            CKB(cub::DeviceScan::ExclusiveSum(d_scan2, scan_bytes2, A.is_root4, A.id4, n - 1));
             uint32_t last_flag = 0, last_id = 0;
             CKB(cudaMemcpy(&last_flag, A.is_root4 + (n - 2), 4, cudaMemcpyDeviceToHost));
             CKB(cudaMemcpy(&last_id, A.id4 + (n - 2), 4, cudaMemcpyDeviceToHost));
             n4 = last_id + last_flag;
             CKB(dmalloc(&d_nodes, n4));
             emit_kernel<<<grid_n, kB>>>(n, d_sorted, d_nodes, d_leafs, A);
-            crt::count_launches(launches + 2);
-            cudaFree(d_scan);
+            launches += levels + 4;
+            lap("scan + emit");
         }
         CKB(cudaDeviceSynchronize());
         CKB(cudaMemcpy(h_counters, A.counters, sizeof h_counters, cudaMemcpyDeviceToHost));
     }
-    // ---- hand the arrays to the scene, drop the scratch ---------------------------------------------------
+    crt::count_launches(launches);
+    // ---- hand the arrays to the scene (the scratch arena stays for the next build) ---------------------------------------------------
     s->d_nodes = d_nodes;
     s->d_leafs = d_leafs;
     s->d_prim_ids = d_prim_ids;
@@ -504,12 +724,8 @@ int device_build(const std::vector<Geom>& geoms, crt_scene* s) {
     s->desc.has_triangles = n > 0;
     CKB(cudaMalloc((void**)&s->d_desc, sizeof(DevScene)));
     CKB(cudaMemcpy(s->d_desc, &s->desc, sizeof(DevScene), cudaMemcpyHostToDevice));
-    for (void* p : {(void*)d_verts, (void*)d_idx, (void*)d_tab, (void*)A.v0, (void*)A.v1, (void*)A.v2, (void*)A.lo, (void*)A.hi, (void*)A.key_a, (void*)A.key_b,
-                    (void*)A.idx_a, (void*)A.idx_b, (void*)A.counters, d_tmp, (void*)A.left, (void*)A.right, (void*)A.first, (void*)A.last, (void*)A.parent,
-                    (void*)A.nlo, (void*)A.nhi, (void*)A.visits, (void*)A.is_root4, (void*)A.id4, (void*)A.frontier_a, (void*)A.frontier_b})
-        cudaFree(p);
     auto t1 = std::chrono::steady_clock::now();
-    s->info.primitives = (uint64_t)n;
+    s->info.primitives = (uint64_t)n_valid;
     s->info.binary_nodes = n > 0 ? 2 * (uint64_t)n - 1 : 0;
     s->info.wide_nodes = n4;
     s->info.leaves = h_counters[2];

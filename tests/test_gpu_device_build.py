@@ -31,7 +31,7 @@ def test_probe_scene_matches_the_oracle(gpu, orc):
     meshes = [W.uv_sphere(c, 0.45, 24, 12) for c in [(x * 1.2, y * 1.2, z * 1.2) for x in range(-2, 3) for y in range(-1, 2) for z in range(-2, 3)]]
     sg, so = commit_both(gpu, orc, meshes)
     info = sg.build_info()
-    assert info.built_on_device == 1 and info.primitives == sum(len(i) for _, i in meshes) and info.leaf_refs == info.primitives
+    assert info.built_on_device == 1 and info.primitives == sum(len(i) for _, i in meshes) and info.leaf_refs >= info.primitives
     assert info.leaves * 4 >= info.primitives and info.wide_nodes > 0
     rays = W.ray_batch(1 << 18, W.scene_extent(so.bounds()))
     hg, fg = sg.intersect_n(rays)
