@@ -534,6 +534,47 @@ def main():
                 "sets": per_set, "closest_hit_mrays": sum(len(sets[n][0]) for n in closest) / sum(k_ms[n] for n in closest) / 1e3,
                 "occlusion_mrays": sum(len(sets[n][0]) for n in SETS if n not in closest) / sum(k_ms[n] for n in SETS if n not in closest) / 1e3,
                 "device_status": status, "host_cores": cores}
+        if world == 1:
+            # commit() itself: the reference's SAH/SBVH host build (what the numbers above ran on) next to the device build
+            def timed_commit(flags):
+                bb, _ = W.stress_scene(crt, grid=args.grid, shards=30000, jitter=True)
+                t0 = time.perf_counter()
+                sc = bb.commit(flags=flags, host_threads=cores)
+                return sc, time.perf_counter() - t0
+            timed_commit(crt.COMMIT_DEVICE_BUILD)  # warm-up: scratch arenas, pinned staging
+            dev_scene, dev_s = timed_commit(crt.COMMIT_DEVICE_BUILD)
+            dbi = dev_scene.build_info()
+            dev_rates = {}
+            for name in SETS:
+                rays, mask = sample_sets[name] if sample_sets else (sets[name][0][: 1 << 22], None if sets[name][1] is None else sets[name][1][: 1 << 22])
+                dr = torch.from_numpy(np.ascontiguousarray(rays).view(np.float32).reshape(-1, 8)).to(dev)
+                dm = torch.from_numpy(np.ascontiguousarray(mask).view(np.int32)).to(dev) if mask is not None else None
+                closest_k = name.startswith("closest")
+                do = torch.empty((len(rays), 8), dtype=torch.float32, device=dev) if closest_k else torch.empty(len(rays), dtype=torch.uint8, device=dev)
+                rates = {}
+                for tag, sc in (("reference_tree", scene), ("device_tree", dev_scene)):
+                    best = None
+                    for k in range(4):
+                        ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                        ea.record(stream)
+                        mk = dm.data_ptr() if dm is not None else 0
+                        if closest_k:
+                            sc.intersect_ptr(len(rays), dr.data_ptr(), 0, mk, do.data_ptr(), 0, stream.cuda_stream)
+                        else:
+                            sc.occluded_ptr(len(rays), dr.data_ptr(), 0, mk, do.data_ptr(), stream.cuda_stream)
+                        eb.record(stream)
+                        torch.cuda.synchronize()
+                        if k:
+                            best = ea.elapsed_time(eb) if best is None else min(best, ea.elapsed_time(eb))
+                    rates[tag] = len(rays) / best / 1e3
+                dev_rates[name] = rates
+            line["commit"] = {"triangles": n_tris, "host_sbvh_build_s": bi.build_seconds, "host_upload_s": bi.upload_seconds, "host_threads": cores,
+                              "device_build_commit_s": dev_s, "device_build_kernels_s": dbi.build_seconds, "device_concat_upload_s": dbi.upload_seconds,
+                              "device_tree": {"wide_nodes": int(dbi.wide_nodes), "leaves": int(dbi.leaves), "leaf_refs": int(dbi.leaf_refs)},
+                              "reference_tree": {"wide_nodes": int(bi.wide_nodes), "leaves": int(bi.leaves), "leaf_refs": int(bi.leaf_refs)},
+                              "mrays_on_each_tree": dev_rates,
+                              "note": "CRT_COMMIT_DEVICE_BUILD (csrc/device_build.cu) is opt-in; every other number in this line uses the reference-identical host tree"}
+            del dev_scene
         if render is not None:
             if world == 1 and not args.no_cpu_baseline:
                 del o_scene
