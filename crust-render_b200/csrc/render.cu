@@ -89,6 +89,7 @@ struct RenderParams {
     const uint32_t* geom_material;
     const Light* lights;
     const int32_t* geom_light;  // LightList::find_by_geom (light.rs:436-440) as a table
+    const EnvMap* envs;         // environment maps of dome lights, indexed by Light::env
     int n_lights;
     int motion;
     PathState ps;
@@ -270,7 +271,7 @@ __global__ void __launch_bounds__(kBlock, CRT_SHADE_MINBLOCKS) shade_kernel(cons
                     for (int l = 0; l < P.n_lights; ++l) {
                         V3 emitted;
                         float pdf;
-                        if (!light_escaped(P.lights[l], unit, emitted, pdf)) continue;
+                        if (!light_escaped(P.lights[l], unit, emitted, pdf, P.envs)) continue;
                         covered = true;
                         float w = 1.0f;
                         if (competing && strategy_samples_lights(P.st.sampling_strategy))
@@ -320,7 +321,7 @@ __global__ void __launch_bounds__(kBlock, CRT_SHADE_MINBLOCKS) shade_kernel(cons
                 draw_sample4(new_domain(v, K_NEE), nee_s);
                 int li = strategy_samples_lights(P.st.sampling_strategy) ? light_pick(P.n_lights, nee_s[0]) : -1;
                 LightSample ls;
-                if (li >= 0 && light_sample_li(P.lights[li], rec.p, nee_s[1], nee_s[2], ls)) {
+                if (li >= 0 && light_sample_li(P.lights[li], rec.p, nee_s[1], nee_s[2], ls, P.envs)) {
                     V3 contrib = splat(0.0f);
                     float cosine = fabsf(dot(rec.normal, ls.direction));
                     float light_pdf = fmaxf(ls.pdf / (float)P.n_lights, 1e-6f);
@@ -527,6 +528,9 @@ struct crt_world {
     uint32_t* d_geom_material = nullptr;
     Light* d_lights = nullptr;
     int32_t* d_geom_light = nullptr;
+    std::vector<float*> d_env_arrays;  // one block of device floats per environment map
+    std::vector<EnvMap> envs;          // device views
+    EnvMap* d_envs = nullptr;
     std::mutex mu;
     Scratch scratch;
     ~crt_world() {
@@ -534,6 +538,8 @@ struct crt_world {
         cudaFree(d_geom_material);
         cudaFree(d_lights);
         cudaFree(d_geom_light);
+        cudaFree(d_envs);
+        for (float* p : d_env_arrays) cudaFree(p);
         if (scene) crt_scene_release(scene);
     }
 };
@@ -584,6 +590,46 @@ int crt_world_new(crt_scene* scene, const crt_material* materials, size_t n_mate
 }
 
 void crt_world_release(crt_world* w) { delete w; }
+
+int crt_world_set_environment(crt_world* w, uint32_t light_index, uint32_t width, uint32_t height, const float* rgb, const float light_to_world[9]) {
+    if (!w || !rgb || !light_to_world) return crt::set_error(CRT_ERR_INVALID_ARG, "crt_world_set_environment: null argument");
+    if (light_index >= w->lights.size() || w->lights[light_index].kind != LIGHT_DOME)
+        return crt::set_error(CRT_ERR_INVALID_ARG, "crt_world_set_environment: light_index does not name a dome light");
+    EnvMapTables t;
+    if (width == 0 || height == 0 || width > 65536u || height > 65536u || !t.build((int32_t)width, (int32_t)height, rgb))
+        return crt::set_error(CRT_ERR_INVALID_ARG, "crt_world_set_environment: malformed map (environment.rs:118-120)");
+    std::lock_guard<std::mutex> lk(w->mu);
+    // one device block: pixels | marg_func | marg_cdf | cond_func | cond_cdf | cond_integral
+    const size_t np = t.pixels.size(), nmf = t.marg_func.size(), nmc = t.marg_cdf.size(), ncf = t.cond_func.size(), ncc = t.cond_cdf.size(), nci = t.cond_integral.size();
+    float* d = nullptr;
+    CKR(cudaMalloc((void**)&d, (np + nmf + nmc + ncf + ncc + nci) * sizeof(float)));
+    w->d_env_arrays.push_back(d);
+    size_t o = 0;
+    auto put = [&](const std::vector<float>& v) -> const float* {
+        cudaMemcpy(d + o, v.data(), v.size() * sizeof(float), cudaMemcpyHostToDevice);
+        const float* at = d + o;
+        o += v.size();
+        return at;
+    };
+    EnvMap m;
+    m.width = t.width, m.height = t.height;
+    m.pixels = put(t.pixels);
+    m.marg_func = put(t.marg_func);
+    m.marg_cdf = put(t.marg_cdf);
+    m.cond_func = put(t.cond_func);
+    m.cond_cdf = put(t.cond_cdf);
+    m.cond_integral = put(t.cond_integral);
+    m.marg_integral = t.marg_integral;
+    m.pad = 0;
+    w->envs.push_back(m);
+    cudaFree(w->d_envs);
+    w->d_envs = nullptr;
+    CKR(cudaMalloc((void**)&w->d_envs, w->envs.size() * sizeof(EnvMap)));
+    CKR(cudaMemcpy(w->d_envs, w->envs.data(), w->envs.size() * sizeof(EnvMap), cudaMemcpyHostToDevice));
+    light_set_environment(w->lights[light_index], (int32_t)w->envs.size() - 1, light_to_world);
+    CKR(cudaMemcpy(w->d_lights, w->lights.data(), w->lights.size() * sizeof(Light), cudaMemcpyHostToDevice));
+    return CRT_OK;
+}
 
 int crt_steal_cursor_create(crt_steal_cursor** out, unsigned char ipc_handle[64]) {
     if (!out) return crt::set_error(CRT_ERR_INVALID_ARG, "crt_steal_cursor_create: null argument");
@@ -776,6 +822,7 @@ int render_impl(crt_world* w, const crt_camera* camera, const crt_render_setting
     P.geom_material = w->d_geom_material;
     P.lights = w->d_lights;
     P.geom_light = w->d_geom_light;
+    P.envs = w->d_envs;
     P.n_lights = (int)w->lights.size();
     P.motion = motion ? 1 : 0;
     P.stats = sc.stats;

@@ -10,7 +10,7 @@ namespace shade {
 
 static_assert(offsetof(Material, pmf) == sizeof(crt_material), "crt_material must be the authored prefix of shade::Material");
 static_assert(sizeof(Light) == sizeof(crt_light), "crt_light layout");
-static_assert(sizeof(crt_material) == 236 && sizeof(crt_light) == 76, "documented sizes");
+static_assert(sizeof(crt_material) == 236 && sizeof(crt_light) == 116, "documented sizes");
 
 inline Material material_from_abi(const crt_material& m) {
     Material o{};
@@ -22,7 +22,24 @@ inline void material_to_abi(const Material& m, crt_material* out) { std::memcpy(
 inline Light light_from_abi(const crt_light& l) {
     Light o;
     std::memcpy(&o, &l, sizeof l);
+    o.env = -1;  // maps are attached through crt_world_set_environment only
     return o;
+}
+// 3x3 inverse by cofactors on column vectors (what glam's Mat3A::inverse computes)
+inline void mat3_inverse(V3 c0, V3 c1, V3 c2, V3& r0, V3& r1, V3& r2) {
+    V3 t0 = cross(c1, c2), t1 = cross(c2, c0), t2 = cross(c0, c1);
+    float inv_det = 1.0f / dot(c2, t2);
+    // inverse = transpose([t0 t1 t2]) * inv_det; columns of the inverse:
+    r0 = v3(t0.x, t1.x, t2.x) * inv_det;
+    r1 = v3(t0.y, t1.y, t2.y) * inv_det;
+    r2 = v3(t0.z, t1.z, t2.z) * inv_det;
+}
+inline void light_set_environment(Light& l, int32_t env, const float m[9]) {
+    l.a = v3(m[0], m[1], m[2]);
+    l.b = v3(m[3], m[4], m[5]);
+    l.c = v3(m[6], m[7], m[8]);
+    mat3_inverse(l.a, l.b, l.c, l.wa, l.wb, l.wc);
+    l.env = env;
 }
 inline Camera camera_from_abi(const crt_camera& c) {
     return camera_new(v3(c.lookfrom[0], c.lookfrom[1], c.lookfrom[2]), v3(c.lookat[0], c.lookat[1], c.lookat[2]), v3(c.vup[0], c.vup[1], c.vup[2]), c.vfov_deg,

@@ -6,6 +6,7 @@
 //   crates/crust-core/src/tracer.rs:62-105,639-661 (SamplingStrategy, RenderSettings)
 // Host + device. Environment-map domes (environment.rs) are a later row.
 #pragma once
+#include "envmap.h"
 #include "material.h"
 
 namespace shade {
@@ -22,7 +23,12 @@ struct Light {
     // distant: n = unit travel direction, r = cos(half angle), s = solid angle.
     V3 a, b, c, n;
     float r, s;
+    // dome with an environment map (light.rs:320-389): index into the world's EnvMap table (-1 = uniform dome),
+    // light_to_world in a, b, c (columns) and world_to_light in wa, wb, wc (columns)
+    int32_t env;
+    V3 wa, wb, wc;
 };
+CRT_HD V3 mat3_mul(V3 c0, V3 c1, V3 c2, V3 v) { return (c0 * v.x + c1 * v.y) + c2 * v.z; }  // glam Mat3A * Vec3A
 struct LightSample {  // light.rs:92-111
     V3 direction, radiance;
     float distance, pdf;
@@ -47,7 +53,7 @@ CRT_HD float light_solid_angle_pdf(const Light& l, V3 from, V3 light_point) {  /
     float cosine = fmaxf(dot(light_normal_at(l, light_point), -dir_to_light), 0.0f);
     return d2 / (cosine * light_area(l) + 1e-4f);
 }
-CRT_HD bool light_sample_li(const Light& l, V3 from, float u, float v, LightSample& out) {
+CRT_HD bool light_sample_li(const Light& l, V3 from, float u, float v, LightSample& out, const EnvMap* envs = nullptr) {
     if (l.kind <= LIGHT_RECT) {  // AreaLight::sample_li :202-215
         V3 lp = light_sample_point(l, u, v);
         V3 to_light = lp - from;
@@ -70,6 +76,16 @@ CRT_HD bool light_sample_li(const Light& l, V3 from, float u, float v, LightSamp
         out.pdf = 1.0f / fmaxf(l.s, 1e-12f);
         return true;
     }
+    if (l.env >= 0 && envs) {  // environment-mapped dome :352-363
+        V3 local, radiance;
+        float pdf;
+        if (!env_sample(envs[l.env], u, v, local, radiance, pdf)) return false;
+        out.direction = normalize(mat3_mul(l.a, l.b, l.c, local));
+        out.distance = INFINITY;
+        out.radiance = l.radiance * radiance;
+        out.pdf = pdf;
+        return pdf > 0.0f;
+    }
     // uniform dome :365-372
     float z = 1.0f - 2.0f * u;
     float rr = sqrtf(fmaxf(1.0f - z * z, 0.0f));
@@ -83,7 +99,7 @@ CRT_HD bool light_sample_li(const Light& l, V3 from, float u, float v, LightSamp
 CRT_HD float light_pdf_at_point(const Light& l, V3 from, V3 light_point) {  // :217-219, default 0
     return l.kind <= LIGHT_RECT ? light_solid_angle_pdf(l, from, light_point) : 0.0f;
 }
-CRT_HD bool light_escaped(const Light& l, V3 direction, V3& radiance, float& pdf) {  // :297-300, 384-387
+CRT_HD bool light_escaped(const Light& l, V3 direction, V3& radiance, float& pdf, const EnvMap* envs = nullptr) {  // :297-300, 384-387
     if (l.kind == LIGHT_DISTANT) {
         if (!(dot(direction, -l.n) >= l.r)) return false;
         radiance = l.radiance / fmaxf(l.s, 1e-12f);
@@ -91,6 +107,12 @@ CRT_HD bool light_escaped(const Light& l, V3 direction, V3& radiance, float& pdf
         return true;
     }
     if (l.kind == LIGHT_DOME) {
+        if (l.env >= 0 && envs) {  // radiance_toward / pdf_toward :334-347
+            V3 local = mat3_mul(l.wa, l.wb, l.wc, direction);
+            radiance = l.radiance * env_radiance(envs[l.env], local);
+            pdf = env_pdf(envs[l.env], local);
+            return true;
+        }
         radiance = l.radiance;
         pdf = 1.0f / (4.0f * PI_F);
         return true;

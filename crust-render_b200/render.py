@@ -47,6 +47,8 @@ class World:
         rt._ck(rt.lib().crt_world_new(scene._h, _p(materials), len(materials), _p(geom_material), len(geom_material), _p(self._lights),
                                       len(self._lights), C.byref(h)))
         self._h = h
+        for index, (px, cols) in lights.environments.items():
+            rt._ck(rt.lib().crt_world_set_environment(h, index, px.shape[1], px.shape[0], _p(px), _p(cols)))
 
     def __del__(self):
         L = getattr(rt, "_lib", None) if rt is not None else None  # module globals are gone at interpreter shutdown

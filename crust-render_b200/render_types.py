@@ -27,7 +27,7 @@ MATERIAL_DTYPE = np.dtype([
     ("geometry_thin_walled", "<u4"), ("emissive_color", *_V),
 ])
 LIGHT_DTYPE = np.dtype([("kind", "<u4"), ("geom_id", "<u4"), ("radiance", *_V), ("a", *_V), ("b", *_V), ("c", *_V), ("n", *_V),
-                        ("r", "<f4"), ("s", "<f4")])  # crt_light, 76 B
+                        ("r", "<f4"), ("s", "<f4"), ("env", "<i4"), ("w2l", "<f4", 9)])  # crt_light, 116 B
 CAMERA_DTYPE = np.dtype([("lookfrom", *_V), ("lookat", *_V), ("vup", *_V), ("vfov_deg", "<f4"), ("aspect", "<f4"),
                          ("aperture", "<f4"), ("focus_dist", "<f4")])  # crt_camera
 SETTINGS_DTYPE = np.dtype([("width", "<u4"), ("height", "<u4"), ("samples_per_pixel", "<u4"), ("max_depth", "<u4"),
@@ -37,7 +37,7 @@ SETTINGS_DTYPE = np.dtype([("width", "<u4"), ("height", "<u4"), ("samples_per_pi
                            ("steal_chunk_tiles", "<u4")])  # crt_render_settings
 STATS_DTYPE = np.dtype([(n, "<u8") for n in ("camera_rays", "closest_hit", "shadow_rays", "vertices", "rr_tested", "rr_killed",
                                               "ended_escaped", "ended_depth")])  # crt_ray_stats
-assert MATERIAL_DTYPE.itemsize == 236 and LIGHT_DTYPE.itemsize == 76 and CAMERA_DTYPE.itemsize == 52
+assert MATERIAL_DTYPE.itemsize == 236 and LIGHT_DTYPE.itemsize == 116 and CAMERA_DTYPE.itemsize == 52
 assert SETTINGS_DTYPE.itemsize == 64 and STATS_DTYPE.itemsize == 64
 
 MAT_OPENPBR, MAT_EMISSIVE = 0, 1
@@ -83,7 +83,7 @@ def _norm(v):
 def SphereLight(center, radius: float, radiance, geom_id: int) -> np.ndarray:
     """AreaLight over a SphereShape (light.rs:21-44, 150-160)."""
     l = np.zeros((), dtype=LIGHT_DTYPE)
-    l["kind"], l["geom_id"], l["radiance"], l["a"], l["r"] = LIGHT_SPHERE, geom_id, radiance, center, radius
+    l["kind"], l["geom_id"], l["radiance"], l["a"], l["r"], l["env"] = LIGHT_SPHERE, geom_id, radiance, center, radius, -1
     return l
 
 
@@ -91,7 +91,7 @@ def RectLight(origin, edge_u, edge_v, normal, radiance, geom_id: int) -> np.ndar
     """AreaLight over `RectShape::new` (light.rs:55-81); the normal is normalised like the constructor does."""
     l = np.zeros((), dtype=LIGHT_DTYPE)
     l["kind"], l["geom_id"], l["radiance"] = LIGHT_RECT, geom_id, radiance
-    l["a"], l["b"], l["c"], l["n"] = origin, edge_u, edge_v, _norm(normal)
+    l["a"], l["b"], l["c"], l["n"], l["env"] = origin, edge_u, edge_v, _norm(normal), -1
     return l
 
 
@@ -104,13 +104,15 @@ def DistantLight(direction, irradiance, angle_deg: float) -> np.ndarray:
     l["kind"], l["geom_id"], l["radiance"], l["n"] = LIGHT_DISTANT, NO_GEOM, irradiance, _norm(direction)
     l["r"] = cos_half
     l["s"] = np.float32(2.0) * np.float32(math.pi) * (np.float32(1.0) - cos_half)
+    l["env"] = -1
     return l
 
 
 def DomeLight(tint) -> np.ndarray:
-    """`DomeLight::new(tint, None, _)` — uniform dome (light.rs:320-389); environment maps are a later row."""
+    """`DomeLight::new(tint, None, _)` — uniform dome (light.rs:320-389). Give it an environment map with
+    `LightList.add(DomeLight(tint), environment=(pixels[h, w, 3], light_to_world 3x3))`."""
     l = np.zeros((), dtype=LIGHT_DTYPE)
-    l["kind"], l["geom_id"], l["radiance"] = LIGHT_DOME, NO_GEOM, tint
+    l["kind"], l["geom_id"], l["radiance"], l["env"] = LIGHT_DOME, NO_GEOM, tint, -1
     return l
 
 
@@ -229,8 +231,17 @@ class LightList:
 
     def __init__(self):
         self.lights: List[np.ndarray] = []
+        self.environments = {}  # light index -> (pixels f32 [h, w, 3], light_to_world f32 [9], glam column order)
 
-    def add(self, light: np.ndarray) -> None:
+    def add(self, light: np.ndarray, environment=None) -> None:
+        """`environment` = (lat-long pixels [h, w, 3], light_to_world 3x3 with columns = images of the axes) for a
+        DomeLight (light.rs:327-335)."""
+        if environment is not None:
+            px, m = environment
+            px = np.ascontiguousarray(np.asarray(px, np.float32))
+            assert int(light["kind"]) == LIGHT_DOME and px.ndim == 3 and px.shape[2] == 3
+            cols = np.ascontiguousarray(np.asarray(m, np.float32).reshape(3, 3).T.reshape(9))  # column-major
+            self.environments[len(self.lights)] = (px, cols)
         self.lights.append(light)
 
     def count(self) -> int:

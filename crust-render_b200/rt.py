@@ -131,6 +131,7 @@ def lib() -> C.CDLL:
         "crt_debug_tree_export": [vp, vp, u32p, u32p, u32p],
         # include/crt_render.h
         "crt_world_new": [vp, vp, sz, vp, sz, vp, sz, C.POINTER(vp)],
+        "crt_world_set_environment": [vp, u32, u32, u32, vp, vp],
         "crt_render": [vp, vp, vp, vp, vp, vp],
         "crt_render_host": [vp, vp, vp, vp, vp],
         "crt_render_last_info": [C.POINTER(u64), C.POINTER(C.c_double), C.POINTER(u64)],

@@ -270,6 +270,57 @@ def medcity(api, width: int = 640, height: int = 360, spp: int = 128, n_instance
 
 
 # ---------------------------------------------------------------------------------------------
+# samples/domelight.usda: lights at infinity
+# ---------------------------------------------------------------------------------------------
+def domelight(api, width: int = 480, height: int = 270, spp: int = 96, **settings_kw):
+    """A chrome and a clay sphere on a ground plane under a DomeLight carrying the lat-long HDRI sky_env.exr (rotated
+    20 degrees about Y, with a small very bright sun disc that importance sampling has to find) and a 1.5-degree
+    DistantLight; depth 8, min 32 spp, threshold 0.02. Replayed through the importer as a synthesised stage whose
+    texture asset is the decoded fixture tests/golden/sky_env_128x64.npy."""
+    from .usd.importer import import_stage
+    from .usd.usda import Attribute, Prim, Stage
+
+    def prim(ptype, name, parent, **attrs):
+        p = Prim("def", ptype, name, (parent.path if parent else "") + "/" + name, parent=parent)
+        for k, v in attrs.items():
+            p.attributes[k.replace("__", ":")] = Attribute(k.replace("__", ":"), "", v)
+        if parent is not None:
+            parent.children.append(p)
+        return p
+
+    world = prim("Xform", "World", None)
+    prim("Camera", "Cam", world, focalLength=28.0, horizontalAperture=20.955, xformOp__translate=(0.0, 2.3, 8.5), xformOp__rotateX=-8.0,
+         xformOpOrder=["xformOp:translate", "xformOp:rotateX"])
+    prim("DomeLight", "Sky", world, inputs__intensity=1.0, inputs__color=(1.0, 1.0, 1.0), inputs__texture__file="sky_env_128x64.npy",
+         inputs__texture__format="latlong", xformOp__rotateY=20.0, xformOpOrder=["xformOp:rotateY"])
+    prim("DistantLight", "Sun", world, inputs__intensity=2.2, inputs__angle=1.5, inputs__color=(1.0, 0.94, 0.82), xformOp__rotateY=40.0, xformOp__rotateX=-48.0,
+         xformOpOrder=["xformOp:rotateY", "xformOp:rotateX"])
+    looks = Prim("def", "Scope", "Looks", "/World/Looks", parent=world)
+
+    def material(name, **inputs):
+        m = prim("Material", name, looks)
+        sh = prim("Shader", "Shader", m, **{"info__id": "crust:openpbr", **{"inputs__" + k: v for k, v in inputs.items()}})
+        m.attributes["outputs:surface"] = Attribute("outputs:surface", "token", None, metadata={"connect": sh.path + ".outputs:surface"})
+        return m.path
+
+    metal = material("Metal", baseColor=(0.92, 0.9, 0.86), baseMetalness=1.0, specularRoughness=0.08)
+    clay = material("Clay", baseColor=(0.72, 0.36, 0.28), specularRoughness=0.65)
+    ground = material("Ground", baseColor=(0.48, 0.47, 0.45), specularRoughness=0.8)
+    for name, x, mat in (("Chrome", -1.6, metal), ("Matte", 1.6, clay)):
+        s = prim("Sphere", name, world, radius=1.0, xformOp__translate=(x, 1.0, 0.0), xformOpOrder=["xformOp:translate"])
+        s.relationships["material:binding"] = [mat]
+    floor = prim("Mesh", "Floor", world, faceVertexCounts=[4], faceVertexIndices=[0, 1, 2, 3], points=[(-40, 0, -40), (40, 0, -40), (40, 0, 40), (-40, 0, 40)])
+    floor.relationships["material:binding"] = [ground]
+    world.children.append(looks)
+    render = prim("Scope", "Render", None)
+    prim("RenderSettings", "settings", render, resolution=(480, 270), **{"crust__samplesPerPixel": 96, "crust__maxDepth": 8, "crust__minSamplesPerPixel": 32,
+                                                                          "crust__varianceThreshold": 0.02, "crust__frame": 0})
+    kw = dict(width=width, height=height, samples_per_pixel=spp)
+    kw.update(settings_kw)
+    return import_stage(api, Stage({"upAxis": "Y"}, [world, render]), os.path.join(GOLDEN, "domelight.usda"), **kw)
+
+
+# ---------------------------------------------------------------------------------------------
 # config 4 stand-in: a point-instanced city (two-level BVH)
 # ---------------------------------------------------------------------------------------------
 def _building(rng, floors: int, sides: int):

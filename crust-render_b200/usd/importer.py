@@ -10,14 +10,14 @@ What is reproduced, with the reference lines it follows:
     static => baked to world space, else instanced over a shared BLAS" (:1025-1089), mirrored
     placements swap indices 1 and 2 (:1109-1116), `crust:motion:translate` (:755-759), `crust:rayMask`;
   * spheres (:1235-1272), SphereLight / RectLight geometry + AreaLight sharing a geom_id with the
-    SHADOW|INDIRECT[|CAMERA] mask (:747-753, 2259-2349), DistantLight, uniform DomeLight;
+    SHADOW|INDIRECT[|CAMERA] mask (:747-753, 2259-2349), DistantLight, DomeLight (uniform, or a lat-long
+    environment map decoded by the host and importance-sampled, :2389-2460);
   * camera from focal length / apertures / fStop / focusDistance (:2174-2220);
   * materials: `crust:openpbr` decoded 1:1 (:2902-2975), `UsdPreviewSurface` mapped (:2661-2705),
     unbound => default grey OpenPBR; RenderSettings and the crust:* attributes (:3015-3100).
   * PointInstancer (:1674-1875): T * R * S placements, one Instance per prototype part, `invisibleIds`;
     binary crate files through usdc.py.
-Not reproduced yet: native instancing, nested instancers, BasisCurves, volumes, environment-map domes,
-Ptex, references/payloads/variants.
+Not reproduced yet: native instancing, nested instancers, BasisCurves, volumes, Ptex, references/payloads/variants.
 """
 from __future__ import annotations
 
@@ -286,8 +286,8 @@ def build_camera(prim: usda.Prim, world, settings: RenderSettings) -> Camera:  #
 
 
 class _Import:
-    def __init__(self, api, stage: usda.Stage):
-        self.api, self.stage = api, stage
+    def __init__(self, api, stage: usda.Stage, stage_path: str = "."):
+        self.api, self.stage, self.stage_path = api, stage, stage_path
         self.wb = api.WorldBuilder()
         self.lights = LightList()
         self.camera: Optional[Camera] = None
@@ -323,8 +323,8 @@ class _Import:
             elif t == "DistantLight":  # emit_distant_light (:2361-2380)
                 angle = prim.attr("inputs:angle")
                 self.lights.add(DistantLight(_vector(world, (0, 0, -1)), _lux_emission(prim), 0.53 if angle is None else float(angle)))
-            elif t == "DomeLight" and prim.attr("inputs:texture:file") is None:
-                self.lights.add(DomeLight(_lux_emission(prim)))
+            elif t == "DomeLight":
+                self.emit_dome_light(prim, world)
             for c in prim.children:
                 stack.append((c, world))
 
@@ -465,6 +465,38 @@ class _Import:
                     continue
                 self.wb.attach_masked(Geometry.Instance(scene, _affine(xf)), mat, mask)
 
+    def emit_dome_light(self, prim, world):  # :2389-2460
+        tint = _lux_emission(prim)
+        tex, fmt = prim.attr("inputs:texture:file"), prim.attr("inputs:texture:format")
+        env = None
+        if tex and fmt in (None, "latlong", "automatic"):
+            pixels = self.load_environment(tex)
+            if pixels is not None:
+                # the light's orientation only: columns of the world matrix, normalised (:2443-2448)
+                cols = [world[:3, k] for k in range(3)]
+                cols = [c / F(np.sqrt((c * c).sum(dtype=F))) if float((c * c).sum()) > 0 else np.eye(3, dtype=F)[k] for k, c in enumerate(cols)]
+                env = (pixels, np.stack(cols, axis=1))
+        self.lights.add(DomeLight(tint), environment=env)
+
+    def load_environment(self, asset: str):
+        """AssetLoader::load_environment (scene.rs:94-135): the host decodes the image; here OpenCV's EXR/HDR reader,
+        relative to the stage. Returns float32 [h, w, 3] RGB or None."""
+        import os
+        path = asset if os.path.isabs(asset) else os.path.join(os.path.dirname(os.path.abspath(self.stage_path)), asset)
+        if not os.path.exists(path):
+            return None
+        if path.endswith(".npy"):  # pre-decoded float32 [h, w, 3] (tests/golden fixtures)
+            return np.ascontiguousarray(np.load(path).astype(np.float32))
+        os.environ.setdefault("OPENCV_IO_ENABLE_OPENEXR", "1")
+        try:
+            import cv2
+            im = cv2.imread(path, cv2.IMREAD_UNCHANGED)
+        except Exception:
+            return None
+        if im is None or im.ndim != 3:
+            return None
+        return np.ascontiguousarray(im[:, :, 2::-1].astype(np.float32))
+
     def emit_sphere(self, prim, world):  # :1235-1272
         r = prim.attr("radius")
         radius = 1.0 if r is None else float(F(r))
@@ -503,7 +535,7 @@ def world_from_meshes(api, meshes, settings: RenderSettings):
     default material: applies the importer's dedup + bake-vs-instance rule (:769-798, 1025-1089). Used to
     rebuild a stage from a binary fixture (tests/golden/cornellbox_scene.npz)."""
     imp = _Import.__new__(_Import)
-    imp.api, imp.wb, imp.lights, imp.slots, imp.pending = api, api.WorldBuilder(), LightList(), {}, []
+    imp.api, imp.wb, imp.lights, imp.slots, imp.pending, imp.stage_path = api, api.WorldBuilder(), LightList(), {}, [], "."
     imp.settings = settings
     mat = OpenPBR()
     for pts, tris, l2w in meshes:
@@ -534,7 +566,7 @@ def load_scene(api, path: str, **overrides):
 
 def import_stage(api, stage: usda.Stage, path: str = "<stage>", **overrides):
     """The import proper, from an already parsed (or synthesised) Stage."""
-    imp = _Import(api, stage)
+    imp = _Import(api, stage, path)
     for k, v in overrides.items():
         setattr(imp.settings, k, v)
     # stream_roots (:67-115): import subtree by subtree when there are at least 4 of them

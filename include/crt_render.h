@@ -67,13 +67,15 @@ typedef struct crt_material {
 #define CRT_LIGHT_DOME 3u    /* light.rs:320-389, uniform (no environment map): radiance = tint */
 #define CRT_NO_GEOM 0xFFFFFFFFu
 
-/* 76 bytes */
+/* 116 bytes */
 typedef struct crt_light {
     uint32_t kind;
     uint32_t geom_id; /* world geom_id of the emissive geometry an area light shares (light.rs:150-160), else CRT_NO_GEOM */
     float radiance[3];
     float a[3], b[3], c[3], n[3];
     float r, s;
+    int32_t env;      /* set to -1; crt_world_set_environment fills it and the two matrices below */
+    float w2l[9];     /* dome with a map: world_to_light columns (light_to_world columns travel in a, b, c) */
 } crt_light;
 
 /* camera.rs:27-35 */
@@ -128,6 +130,11 @@ void crt_material_default(crt_material* out);
 int crt_world_new(crt_scene* scene, const crt_material* materials, size_t n_materials, const uint32_t* geom_material,
                   size_t n_geoms, const crt_light* lights, size_t n_lights, crt_world** out);
 void crt_world_release(crt_world* w);
+/* DomeLight::new(tint, Some(map), light_to_world) (light.rs:327-335, environment.rs:117-141): gives dome light
+ * `light_index` of the world a lat-long environment map (`rgb`: width * height * 3 floats, row 0 = the +Y pole,
+ * u = 0.5 looks down -Z) with luminance importance sampling. `light_to_world`: 9 floats, glam Mat3A column order. */
+int crt_world_set_environment(crt_world* w, uint32_t light_index, uint32_t width, uint32_t height, const float* rgb,
+                              const float light_to_world[9]);
 
 /* Renderer::render_with_stats (tracer.rs:194-212): one non-guided pass. `framebuffer` is a DEVICE
  * pointer to width*height float4 {r, g, b, samples taken}; row j is image row j counted from the

@@ -441,6 +441,66 @@ void* orc_world_new(void* scene, const crt_material* materials, size_t n_materia
     return h;
 }
 void orc_world_free(void* w) { delete (WorldHandle*)w; }
+int orc_world_set_environment(void* w, uint32_t light_index, uint32_t width, uint32_t height, const float* rgb, const float* l2w9) {
+    orcr::World& W = ((WorldHandle*)w)->world;
+    if (light_index >= W.lights.size() || W.lights[light_index].kind != shade::LIGHT_DOME) return 1;
+    W.env_tables.emplace_back();
+    if (!W.env_tables.back().build((int32_t)width, (int32_t)height, rgb)) {
+        W.env_tables.pop_back();
+        return 1;
+    }
+    shade::light_set_environment(W.lights[light_index], (int32_t)W.env_tables.size() - 1, l2w9);
+    W.envs.clear();
+    for (const auto& t : W.env_tables) W.envs.push_back(t.view());
+    return 0;
+}
+// A light of a world with its environment table (usd_scene.rs:873-922 probes lights through the scene).
+int orc_world_light_sample(void* w, uint32_t index, const float* from, float u, float v, float* out8) {
+    orcr::World& W = ((WorldHandle*)w)->world;
+    shade::LightSample ls;
+    if (index >= W.lights.size() || !shade::light_sample_li(W.lights[index], sv(from), u, v, ls, W.envs.data())) return 0;
+    put3(out8, ls.direction);
+    put3(out8 + 3, ls.radiance);
+    out8[6] = ls.distance;
+    out8[7] = ls.pdf;
+    return 1;
+}
+int orc_world_light_escaped(void* w, uint32_t index, const float* dir, float* radiance3, float* pdf) {
+    orcr::World& W = ((WorldHandle*)w)->world;
+    shade::V3 r;
+    if (index >= W.lights.size() || !shade::light_escaped(W.lights[index], sv(dir), r, *pdf, W.envs.data())) return 0;
+    put3(radiance3, r);
+    return 1;
+}
+// environment.rs hooks for tests/test_shade_kats.py: op 0 = sample(u1, u2) -> dir3, radiance3, pdf (returns 0 when
+// it declines), 1 = pdf(dir), 2 = radiance(dir), 3 = direction_to_uv, 4 = uv_to_direction (ops 3, 4 take a null map)
+void* orc_env_new(uint32_t width, uint32_t height, const float* rgb) {
+    auto* t = new shade::EnvMapTables();
+    if (!t->build((int32_t)width, (int32_t)height, rgb)) {
+        delete t;
+        return nullptr;
+    }
+    return t;
+}
+void orc_env_free(void* e) { delete (shade::EnvMapTables*)e; }
+int orc_env_call(void* e, int op, const float* a, float* out) {
+    if (op == 3) { shade::env_direction_to_uv(sv(a), out[0], out[1]); return 1; }
+    if (op == 4) { put3(out, shade::env_uv_to_direction(a[0], a[1])); return 1; }
+    if (!e) return -1;
+    shade::EnvMap m = ((shade::EnvMapTables*)e)->view();
+    if (op == 0) {
+        shade::V3 d, r;
+        float pdf;
+        if (!shade::env_sample(m, a[0], a[1], d, r, pdf)) return 0;
+        put3(out, d);
+        put3(out + 3, r);
+        out[6] = pdf;
+        return 1;
+    }
+    if (op == 1) { out[0] = shade::env_pdf(m, sv(a)); return 1; }
+    if (op == 2) { put3(out, shade::env_radiance(m, sv(a))); return 1; }
+    return -1;
+}
 // returns seconds
 double orc_render(void* w, const crt_camera* cam, const crt_render_settings* st, float* fb, double* var_map, uint64_t* stats8, int threads) {
     shade::Camera c = shade::camera_from_abi(*cam);

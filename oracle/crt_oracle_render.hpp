@@ -67,6 +67,8 @@ struct World {
     std::vector<shade::Material> materials;
     std::vector<uint32_t> geom_material;  // geom_id -> index into materials
     std::vector<shade::Light> lights;     // LightList, light.rs:404-446
+    std::vector<shade::EnvMapTables> env_tables;  // environment maps of dome lights (environment.rs)
+    std::vector<shade::EnvMap> envs;              // views into env_tables, indexed by Light::env
     const shade::Material& material(uint32_t geom_id) const { return materials[geom_material[geom_id]]; }
 };
 
@@ -142,7 +144,7 @@ inline V3 escaped_emission(const PrevBounce* prev, const World& w, V3 direction,
     for (const shade::Light& l : w.lights) {
         V3 emitted;
         float pdf;
-        if (!shade::light_escaped(l, direction, emitted, pdf)) continue;
+        if (!shade::light_escaped(l, direction, emitted, pdf, w.envs.data())) continue;
         covered = true;
         float weight = 1.0f;
         if (competing && shade::strategy_samples_lights(strategy)) weight = shade::strategy_bounce_weight(strategy, bounce_pdf, std::max(pdf / n_lights, 1e-6f));
@@ -278,7 +280,7 @@ inline V3 trace_path(const PathRay& r, const World& w, int depth, uint32_t strat
         draw_sample4(new_domain(v, K_NEE), nee_s);
         int li = strategy_samples_lights(strategy) ? light_pick((int)w.lights.size(), nee_s[0]) : -1;
         LightSample ls;
-        if (li >= 0 && light_sample_li(w.lights[li], rec.p, nee_s[1], nee_s[2], ls)) {
+        if (li >= 0 && light_sample_li(w.lights[li], rec.p, nee_s[1], nee_s[2], ls, w.envs.data())) {
             float n_lights = (float)w.lights.size();
             PathRay shadow_ray{rec.p, ls.direction, ray.time, MASK_SHADOW, -1};
             stats.shadow_rays++;

@@ -98,6 +98,13 @@ def lib() -> C.CDLL:
     L.orc_world_new.argtypes = [vp, vp, sz, vp, sz, vp, sz]
     L.orc_world_new.restype = vp
     L.orc_world_free.argtypes = [vp]
+    L.orc_world_set_environment.argtypes = [vp, u32, u32, u32, vp, vp]
+    L.orc_world_light_sample.argtypes = [vp, u32, vp, f, f, vp]
+    L.orc_world_light_escaped.argtypes = [vp, u32, vp, vp, vp]
+    L.orc_env_new.argtypes = [u32, u32, vp]
+    L.orc_env_new.restype = vp
+    L.orc_env_free.argtypes = [vp]
+    L.orc_env_call.argtypes = [vp, C.c_int, vp, vp]
     L.orc_render.argtypes = [vp, vp, vp, vp, vp, vp, C.c_int]
     L.orc_render.restype = C.c_double
     L.orc_material_default.argtypes = [vp]
@@ -361,6 +368,9 @@ class World:
         self._lights = lights.records()
         self._h = C.c_void_p(lib().orc_world_new(scene._h, _p(materials), len(materials), _p(geom_material), len(geom_material),
                                                  _p(self._lights), len(self._lights)))
+        for index, (px, cols) in lights.environments.items():
+            if lib().orc_world_set_environment(self._h, index, px.shape[1], px.shape[0], _p(px), _p(cols)):
+                raise ValueError("malformed environment map")
 
     def __del__(self):
         if getattr(self, "_h", None):
@@ -372,6 +382,19 @@ class World:
 
     def has_motion(self) -> bool:
         return self.scene.has_motion()
+
+    def light_sample_li(self, index: int, from_, u: float, v: float):
+        """Light::sample_li of light `index`, environment map included."""
+        out = np.zeros(8, np.float32)
+        if not lib().orc_world_light_sample(self._h, index, _p(_f3(from_)), u, v, _p(out)):
+            return None
+        return dict(direction=out[0:3].copy(), radiance=out[3:6].copy(), distance=float(out[6]), pdf=float(out[7]))
+
+    def light_escaped(self, index: int, direction):
+        r, pdf = np.zeros(3, np.float32), C.c_float()
+        if not lib().orc_world_light_escaped(self._h, index, _p(_f3(direction)), _p(r), C.byref(pdf)):
+            return None
+        return r, pdf.value
 
 
 class WorldBuilder(WorldBuilderBase):
@@ -505,3 +528,47 @@ def filter_sample_n(kind: int, radius: float, u: np.ndarray):
     off, w = np.zeros_like(u), np.zeros_like(u)
     lib().orc_filter_sample_n(kind, radius, len(u), _p(u), _p(off), _p(w))
     return off, w
+
+
+class EnvironmentMap:
+    """environment.rs EnvironmentMap over the oracle's tables (tests only)."""
+
+    def __init__(self, width: int, height: int, pixels):
+        px = np.ascontiguousarray(np.asarray(pixels, np.float32).reshape(-1))
+        self.valid = width > 0 and height > 0 and len(px) == 3 * width * height  # EnvironmentMap::new -> None otherwise
+        self._h = C.c_void_p(lib().orc_env_new(int(width), int(height), _p(px))) if self.valid else None
+
+    def __del__(self):
+        if getattr(self, "_h", None) and _lib is not None:
+            _lib.orc_env_free(self._h)
+            self._h = None
+
+    def _call(self, op, args, n_out):
+        a = np.ascontiguousarray(np.asarray(args, np.float32))
+        out = np.zeros(8, np.float32)
+        rc = lib().orc_env_call(self._h, op, _p(a), _p(out))
+        return rc, out[:n_out].copy()
+
+    def sample(self, u1, u2):
+        rc, o = self._call(0, [u1, u2], 7)
+        return None if rc <= 0 else (o[0:3], o[3:6], float(o[6]))
+
+    def pdf(self, d) -> float:
+        return float(self._call(1, d, 1)[1][0])
+
+    def radiance(self, d):
+        return self._call(2, d, 3)[1]
+
+    @staticmethod
+    def direction_to_uv(d):
+        a = np.ascontiguousarray(np.asarray(d, np.float32))
+        out = np.zeros(8, np.float32)
+        lib().orc_env_call(None, 3, _p(a), _p(out))
+        return float(out[0]), float(out[1])
+
+    @staticmethod
+    def uv_to_direction(u, v):
+        a = np.asarray([u, v], np.float32)
+        out = np.zeros(8, np.float32)
+        lib().orc_env_call(None, 4, _p(a), _p(out))
+        return out[:3].copy()

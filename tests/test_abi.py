@@ -30,7 +30,7 @@ def test_record_sizes(crt):
 
 def test_render_record_sizes_match_the_header(crt):
     from crust_render_b200 import render_types as T
-    assert T.MATERIAL_DTYPE.itemsize == 236 and T.LIGHT_DTYPE.itemsize == 76 and T.CAMERA_DTYPE.itemsize == 52
+    assert T.MATERIAL_DTYPE.itemsize == 236 and T.LIGHT_DTYPE.itemsize == 116 and T.CAMERA_DTYPE.itemsize == 52
     assert T.SETTINGS_DTYPE.itemsize == 64 and T.STATS_DTYPE.itemsize == 64
     rec = T.OpenPBR()
     out = rec.copy()

@@ -113,6 +113,15 @@ def test_config4_point_instanced_medcity(gpu, orc):
     assert sg.shadow_rays == 0 and sg.rr_tested > 0
 
 
+def test_dome_light_with_environment_map_and_distant_light(gpu, orc):
+    """samples/domelight.usda: an importance-sampled lat-long HDRI dome (rotated) plus a 1.5-degree
+    distant light; both are found by NEE and by escaping bounce rays with matching MIS densities."""
+    fg, sg, fo, so, _ = both(gpu, orc, scenes.domelight, width=160, height=90, spp=16, variance_threshold=0.0)
+    compare(fg, fo)
+    stats_close(sg, so)
+    assert sg.shadow_rays == sg.vertices and sg.ended_escaped > 0
+
+
 def test_synthetic_instanced_city(gpu, orc):
     """The scalable stand-in generator (any instance count) used for instancing stress runs."""
     fn = lambda api, **kw: scenes.point_instanced_city(api, **kw)  # noqa: E731

@@ -537,3 +537,65 @@ def test_camera_centre_ray_points_at_lookat(orc):  # camera.rs:27-84
     lens = Camera((0, 1, 5), (0, 1, 0), (0, 1, 0), 40.0, 1.0, 0.5, 5.0)
     o3, d3 = orc.camera_ray(lens, 0.5, 0.5, 0.9, 0.5)
     assert np.linalg.norm(o3 - np.asarray((0, 1, 5))) <= 0.25 + 1e-6 and np.allclose(o3 + d3, (0, 1, 0), atol=1e-5)  # in-focus point is fixed
+
+
+# ---- environment.rs:206-405 ----------------------------------------------------------------------------
+def spotty_map(orc, w, h, bx, by):
+    px = np.full((h, w, 3), 0.05, np.float32)
+    px[by, bx] = 500.0
+    return orc.EnvironmentMap(w, h, px)
+
+
+def test_env_direction_and_uv_round_trip_and_conventions(orc):
+    E = orc.EnvironmentMap
+    for d in ((0, 1, 0), (0, -1, 0), (1, 0, 0), (-1, 0, 0), (0, 0, 1), (0, 0, -1), n3((0.3, 0.5, -0.8)), n3((-0.6, -0.2, 0.7))):
+        u, v = E.direction_to_uv(d)
+        assert np.linalg.norm(E.uv_to_direction(u, v) - np.asarray(d, np.float32)) < 1e-4
+    u, v = E.direction_to_uv((0, 0, -1))
+    assert abs(u - 0.5) < 1e-5 and abs(v - 0.5) < 1e-5
+    assert E.direction_to_uv((0, 1, 0))[1] < 1e-5 and E.direction_to_uv((0, -1, 0))[1] > 1 - 1e-5
+
+
+def test_env_sample_and_pdf_agree(orc):
+    m = spotty_map(orc, 64, 32, 40, 8)
+    rng = np.random.default_rng(11)
+    for _ in range(3000):
+        s = m.sample(float(rng.random()), float(rng.random()))
+        if s is None:
+            continue
+        q = m.pdf(s[0])
+        assert abs(s[2] - q) <= 1e-3 * max(s[2], q)
+
+
+def test_env_pdf_is_normalized_and_concentrates_on_bright_texels(orc):
+    m = spotty_map(orc, 32, 16, 20, 6)
+    rng = np.random.default_rng(5)
+    total, n, hits, checked = 0.0, 200000, 0, 0
+    for k in range(n):
+        s = m.sample(float(rng.random()), float(rng.random()))
+        if s is not None and s[2] > 0:
+            total += 1.0 / s[2]
+            if k < 20000:
+                u, v = orc.EnvironmentMap.direction_to_uv(s[0])
+                hits += int(min(int(u * 32), 31) == 20 and min(int(v * 16), 15) == 6)
+                checked += 1
+    assert abs(total / n - 4 * PI) < 0.05 * 4 * PI
+    assert hits / checked > 0.5
+
+
+def test_env_uniform_map_has_uniform_solid_angle_pdf_and_poles_are_not_oversampled(orc):
+    w, h = 32, 16
+    m = orc.EnvironmentMap(w, h, np.ones((h, w, 3), np.float32))
+    for y in range(h):
+        d = orc.EnvironmentMap.uv_to_direction(0.5 / w, (y + 0.5) / h)
+        assert abs(m.pdf(d) - 1 / (4 * PI)) < 0.01 / (4 * PI)
+    m2 = orc.EnvironmentMap(64, 32, np.ones((32, 64, 3), np.float32))
+    at = lambda y: m2.pdf(orc.EnvironmentMap.uv_to_direction(0.5 / 64, (y + 0.5) / 32))  # noqa: E731
+    assert abs(at(0) - at(16)) < 0.02 * at(16)
+
+
+def test_env_black_map_declines_to_sample(orc):
+    m = orc.EnvironmentMap(8, 4, np.zeros((4, 8, 3), np.float32))
+    assert m.sample(0.5, 0.5) is None and m.pdf((0, 1, 0)) == 0.0
+    # rejects_malformed_buffers (:385-389)
+    assert not orc.EnvironmentMap(0, 4, []).valid and not orc.EnvironmentMap(4, 4, np.ones(9, np.float32)).valid

@@ -162,3 +162,29 @@ def test_crate_integer_coding_round_trip():
         cb[i // 4] |= c << (2 * (i % 4))
     out = decode_ints(struct.pack("<i", common) + bytes(cb) + payload, len(vals), 4, signed=True)
     assert np.array_equal(out, ((vals + 2**31) % 2**32) - 2**31)
+
+
+def test_loads_domelight_usda_and_infinite_lights_are_found_by_escaping_rays(orc):  # usd_scene.rs:815-922
+    world, cam, st = load_scene(orc, sample("domelight.usda"))
+    assert len(world._lights) == 2 and world.count() == 3
+    assert (st.width, st.height, st.samples_per_pixel, st.max_depth, st.min_samples_per_pixel) == (480, 270, 96, 8, 32) and abs(st.variance_threshold - 0.02) < 1e-7
+    dome_like = cone_like = 0
+    for li in range(2):
+        assert int(world._lights[li]["geom_id"]) == 0xFFFFFFFF
+        covered = sum(world.light_escaped(li, d) is not None for d in ((0, 1, 0), (0, -1, 0), (1, 0, 0), (0, 0, -1)))
+        dome_like += covered == 4
+        cone_like += covered != 4
+        s = world.light_sample_li(li, (0, 0, 0), 0.37, 0.62)
+        assert s is not None and np.isinf(s["distance"])
+        esc = world.light_escaped(li, s["direction"])
+        assert esc is not None and abs(esc[1] - s["pdf"]) <= 1e-3 * max(s["pdf"], esc[1])
+    assert dome_like == 1 and cone_like == 1
+    # the fixture-built scene (what the GPU box renders) equals the importer's output on the real files
+    wf, cf, sf = scenes.domelight(orc)
+    assert cf.record().tobytes() == cam.record().tobytes() and sf.record().tobytes() == st.record().tobytes()
+    assert wf._lights.tobytes() == world._lights.tobytes()
+    for s_ in (st, sf):
+        s_.width, s_.height, s_.samples_per_pixel, s_.variance_threshold = 64, 36, 4, 0.0
+    a, sa = orc.Renderer(cam, world, st).render_with_stats()
+    b, sb = orc.Renderer(cf, wf, sf).render_with_stats()
+    assert a.tobytes() == b.tobytes() and sa == sb
