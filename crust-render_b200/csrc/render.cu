@@ -19,7 +19,11 @@
 // hold (ray, path slot) so the traversal kernels read contiguous 32-byte ray records. Nothing in a
 // round synchronises with the host; the host reads one counter per adaptive round.
 //
-// Out of scope here: volume regions, path guiding, environment maps, Ptex.
+// Volume regions (volume.rs; tracer.rs:1166-1249 scatter vertex, :1040-1077 volume NEE, :1016-1035 shadow
+// transmittance) ride the same queues: the delta-tracking walk runs inside shade, a region scatter vertex feeds the
+// shadow and extend queues like a surface vertex, and nee_resolve ratio-tracks the unoccluded shadow rays. Those code
+// paths are compiled into separate kernel instances (<VOL = true>) launched only for worlds that have regions.
+// Out of scope here: path guiding, Ptex.
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -90,6 +94,8 @@ struct RenderParams {
     const Light* lights;
     const int32_t* geom_light;  // LightList::find_by_geom (light.rs:436-440) as a table
     const EnvMap* envs;         // environment maps of dome lights, indexed by Light::env
+    const VolumeRegion* volumes;  // Volumes (volume.rs:364-384), outside the BVH
+    int n_volumes;
     int n_lights;
     int motion;
     PathState ps;
@@ -169,7 +175,8 @@ __device__ __forceinline__ float bounce_emission_weight(const RenderParams& P, u
 }
 
 // ---- shade: one path vertex per queue entry (tracer.rs:1118-1535) --------------------------------
-__global__ void __launch_bounds__(kBlock, CRT_SHADE_MINBLOCKS) shade_kernel(const RenderParams P, int k, int cur) {
+template <bool VOL>
+__global__ void __launch_bounds__(kBlock, VOL ? 4 : CRT_SHADE_MINBLOCKS) shade_kernel(const RenderParams P, int k, int cur) {
     const int D = (int)P.st.max_depth;
     const uint32_t n = P.q.counts[k];
     uint32_t* next_count = P.q.counts + k + 1;
@@ -209,6 +216,10 @@ __global__ void __launch_bounds__(kBlock, CRT_SHADE_MINBLOCKS) shade_kernel(cons
                 V3 emitted = material_emitted_directional(mat, cos_o);
                 if (length_squared(emitted) > 0.0f) {
                     if (med) emitted *= medium_transmittance(*med, t_surf);
+                    if (VOL) {  // tracer.rs:1138-1141
+                        Rng rng = sampler_rng(new_domain(v, K_VOLUME));
+                        emitted *= volumes_transmittance(P.volumes, P.n_volumes, ro, rd, kTMin, t_surf, rng);
+                    }
                     float w = bounce_emission_weight(P, flags, prev_pdf, xyz(pp), geom_id, ro + t_surf * rd);
                     add = beta * (emitted * w);
                 }
@@ -225,8 +236,72 @@ __global__ void __launch_bounds__(kBlock, CRT_SHADE_MINBLOCKS) shade_kernel(cons
             float new_pdf = 0.0f;
             V3 new_prevp = splat(0.0f);
             uint32_t new_flags = 0;
+            // Volume-region interaction, clipped to whatever event would otherwise end the segment (tracer.rs:1166-1182).
+            V3 vol_tr = splat(1.0f);
+            bool vol_scatter = false;
+            if (VOL) {
+                Rng rng = sampler_rng(new_domain(v, K_VOLUME));
+                VolumeEvent ev;
+                volumes_sample_interaction(P.volumes, P.n_volumes, ro, rd, kTMin, fminf(t_surf, t_med), rng, ev);
+                add = beta * ev.emitted;  // segment_emit: already weighted by the walk, not attenuated again (:1552)
+                if (ev.scatter) {
+                    // Volume-region scatter vertex (tracer.rs:1184-1244): NEE with the phase function in place of brdf*cos
+                    // (volume_nee, :1040-1077), continuation factor ONE (the HG value and pdf cancel), prev = Phase.
+                    vol_scatter = true;
+                    const V3 wi = normalize(rd);
+                    float ps[4];
+                    draw_sample4(new_domain(v, K_PHASE), ps);
+                    V3 dir = phase_sample(ev.phase, wi, ps[0], ps[1], ps[2]);
+                    float phase_pdf_dir = fmaxf(phase_pdf(ev.phase, dot(wi, dir)), 1e-6f);
+                    beta *= ev.weight;
+                    if (strategy_samples_lights(P.st.sampling_strategy)) {
+                        float nee_s[4];
+                        draw_sample4(new_domain(v, K_NEE), nee_s);
+                        int li = light_pick(P.n_lights, nee_s[0]);
+                        LightSample ls;
+                        if (li >= 0 && light_sample_li(P.lights[li], ev.p, nee_s[1], nee_s[2], ls, P.envs)) {
+                            float light_pdf = fmaxf(ls.pdf / (float)P.n_lights, 1e-6f);
+                            float phase_val = phase_pdf(ev.phase, dot(wi, ls.direction));
+                            float weight = strategy_light_weight(P.st.sampling_strategy, light_pdf, phase_val);
+                            V3 contrib = beta * (ls.radiance * phase_val * weight / light_pdf);  // x shadow transmittance in nee_resolve
+                            cnt.x += 1u << CNT_SHADOW_SHIFT;
+                            uint32_t s = queue_push(sh_count);
+                            P.q.srays[2 * (size_t)s] = f4(ev.p, kTMin);
+                            P.q.srays[2 * (size_t)s + 1] = f4(ls.direction, ls.distance - 0.001f);
+                            if (P.q.stime) P.q.stime[s] = time;
+                            P.q.spath[s] = path;
+                            P.q.scontrib[s] = f4(contrib, 0.0f);
+                        }
+                    }
+                    bool survived = true;
+                    if (k >= RR_START_BOUNCE) {
+                        cnt.y += 1u << CNT_RR_TESTED_SHIFT;
+                        float p_survive = clampf(max_element(beta), RR_MIN_PROB, 1.0f);
+                        if (p_survive < 1.0f) {
+                            if (draw_rnd1(new_domain(v, K_RR)) >= p_survive) {
+                                survived = false;
+                                cnt.x |= CNT_RR_KILLED;
+                            } else {
+                                beta = beta / p_survive;
+                            }
+                        }
+                    }
+                    cnt.y += 1u;
+                    if (survived) {
+                        cont = true;
+                        no = ev.p;
+                        nd = dir;
+                        new_pdf = phase_pdf_dir;
+                        new_prevp = ev.p;
+                        new_flags = FLAG_HAS_PREV | ((uint32_t)(medium + 1) << 8);  // the carried medium is preserved (:1236-1240)
+                    }
+                } else {
+                    vol_tr = ev.weight;
+                }
+            }
 
-            if (t_med < t_surf) {
+            if (vol_scatter) {
+            } else if (t_med < t_surf) {
                 // Carried-medium scatter vertex (tracer.rs:1251-1318): no NEE, prev = None afterwards.
                 float sigma_bar = fmaxf(medium_sigma_t_max(*med), 1e-4f);
                 V3 pos = ro + t_med * rd;
@@ -235,7 +310,7 @@ __global__ void __launch_bounds__(kBlock, CRT_SHADE_MINBLOCKS) shade_kernel(cons
                 V3 dir = sample_henyey_greenstein(normalize(rd), med->g, ph[0], ph[1]);
                 V3 e = (splat(sigma_bar) - (med->sigma_a + med->sigma_s)) * t_med;
                 V3 factor = med->sigma_s / sigma_bar * v3(expf(e.x), expf(e.y), expf(e.z));
-                beta *= factor;
+                beta *= vol_tr * factor;
                 bool survived = true;
                 if (k >= RR_START_BOUNCE) {
                     cnt.y += 1u << CNT_RR_TESTED_SHIFT;
@@ -283,7 +358,7 @@ __global__ void __launch_bounds__(kBlock, CRT_SHADE_MINBLOCKS) shade_kernel(cons
                     float t = 0.5f * (unit.y + 1.0f);
                     background += (1.0f - t) * v3(1.0f, 1.0f, 1.0f) + t * v3(0.5f, 0.7f, 1.0f);
                 }
-                add = beta * background;
+                add += beta * (vol_tr * background);
             } else {
                 // Surface vertex.
                 const uint32_t mat_index = P.geom_material[geom_id];
@@ -304,16 +379,17 @@ __global__ void __launch_bounds__(kBlock, CRT_SHADE_MINBLOCKS) shade_kernel(cons
                         atten = medium_transmittance(*med, rec.t);
                     }
                 }
+                atten = vol_tr * atten;  // tracer.rs:1362
                 // emission ownership (tracer.rs:1369-1381)
                 float cos_o = fabsf(dot(normalize(rd), rec.normal));
                 V3 emitted = material_emitted_directional(mat, cos_o);
                 if (has_prev) {
                     if (length_squared(emitted) > 0.0f) {
                         float w = bounce_emission_weight(P, flags, prev_pdf, xyz(pp), geom_id, rec.p);
-                        add = beta * ((atten * emitted) * w);
+                        add += beta * ((atten * emitted) * w);
                     }
                 } else {
-                    add = beta * (atten * emitted);
+                    add += beta * (atten * emitted);
                 }
                 // 1. light sampling (tracer.rs:1394-1445): the shadow ray is queued with the contribution
                 //    it would deliver; every sampled light costs one occlusion query like the reference.
@@ -392,6 +468,7 @@ __global__ void __launch_bounds__(kBlock, CRT_SHADE_MINBLOCKS) shade_kernel(cons
 }
 
 // ---- NEE resolve: unoccluded contributions land on their path (tracer.rs:1416-1443) ---------------
+template <bool VOL>
 __global__ void __launch_bounds__(kBlock) nee_resolve_kernel(const RenderParams P, int k) {
     const int D = (int)P.st.max_depth;
     const uint32_t n = P.q.counts[(D + 2) + k];
@@ -400,6 +477,17 @@ __global__ void __launch_bounds__(kBlock) nee_resolve_kernel(const RenderParams 
         float4 c = P.q.scontrib[i];
         if (c.x == 0.0f && c.y == 0.0f && c.z == 0.0f) continue;
         uint32_t path = P.q.spath[i];
+        if (VOL) {
+            // shadow_transmittance (tracer.rs:1030-1034): the unoccluded segment pays the regions it crosses, walked with
+            // the vertex's K_NEE_SHADOW stream
+            const uint2 smp = P.ps.sampler[path];
+            Rng rng = sampler_rng(new_domain(new_domain(PathSampler{smp.x, smp.y}, k), K_NEE_SHADOW));
+            const float4 ra = P.q.srays[2 * (size_t)i], rb = P.q.srays[2 * (size_t)i + 1];
+            V3 tr = volumes_transmittance(P.volumes, P.n_volumes, xyz(ra), xyz(rb), kTMin, rb.w, rng);
+            c.x *= tr.x;
+            c.y *= tr.y;
+            c.z *= tr.z;
+        }
         float4 lw = P.ps.L_w[path];
         P.ps.L_w[path] = make_float4(lw.x + c.x, lw.y + c.y, lw.z + c.z, lw.w);
     }
@@ -531,6 +619,9 @@ struct crt_world {
     std::vector<float*> d_env_arrays;  // one block of device floats per environment map
     std::vector<EnvMap> envs;          // device views
     EnvMap* d_envs = nullptr;
+    std::vector<VolumeRegion> volumes;  // device views (grid data pointers are device addresses)
+    std::vector<float*> d_grids;
+    VolumeRegion* d_volumes = nullptr;
     std::mutex mu;
     Scratch scratch;
     ~crt_world() {
@@ -540,6 +631,8 @@ struct crt_world {
         cudaFree(d_geom_light);
         cudaFree(d_envs);
         for (float* p : d_env_arrays) cudaFree(p);
+        for (float* p : d_grids) cudaFree(p);
+        cudaFree(d_volumes);
         if (scene) crt_scene_release(scene);
     }
 };
@@ -628,6 +721,37 @@ int crt_world_set_environment(crt_world* w, uint32_t light_index, uint32_t width
     CKR(cudaMemcpy(w->d_envs, w->envs.data(), w->envs.size() * sizeof(EnvMap), cudaMemcpyHostToDevice));
     light_set_environment(w->lights[light_index], (int32_t)w->envs.size() - 1, light_to_world);
     CKR(cudaMemcpy(w->d_lights, w->lights.data(), w->lights.size() * sizeof(Light), cudaMemcpyHostToDevice));
+    return CRT_OK;
+}
+
+int crt_world_set_volumes(crt_world* w, const crt_volume* volumes, size_t n) {
+    if (!w || (n && !volumes)) return crt::set_error(CRT_ERR_INVALID_ARG, "crt_world_set_volumes: null argument");
+    if (n > CRT_MAX_VOLUMES) return crt::set_error(CRT_ERR_INVALID_ARG, "crt_world_set_volumes: at most CRT_MAX_VOLUMES regions");
+    for (size_t i = 0; i < n; ++i)
+        if (!volume_abi_valid(volumes[i])) return crt::set_error(CRT_ERR_INVALID_ARG, "crt_world_set_volumes: unknown field kind or malformed grid");
+    int rc = crt::require_device();
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(w->mu);
+    for (float* p : w->d_grids) cudaFree(p);
+    w->d_grids.clear();
+    w->volumes.clear();
+    cudaFree(w->d_volumes);
+    w->d_volumes = nullptr;
+    for (size_t i = 0; i < n; ++i) {
+        const crt_volume& v = volumes[i];
+        float* d = nullptr;
+        if (v.field == CRT_FIELD_GRID) {
+            size_t cells = (size_t)v.grid_dims[0] * v.grid_dims[1] * v.grid_dims[2];
+            CKR(cudaMalloc((void**)&d, cells * sizeof(float)));
+            w->d_grids.push_back(d);
+            CKR(cudaMemcpy(d, v.grid_data, cells * sizeof(float), cudaMemcpyHostToDevice));
+        }
+        w->volumes.push_back(volume_from_abi(v, v.grid_data, d));
+    }
+    if (n) {
+        CKR(cudaMalloc((void**)&w->d_volumes, n * sizeof(VolumeRegion)));
+        CKR(cudaMemcpy(w->d_volumes, w->volumes.data(), n * sizeof(VolumeRegion), cudaMemcpyHostToDevice));
+    }
     return CRT_OK;
 }
 
@@ -823,6 +947,8 @@ int render_impl(crt_world* w, const crt_camera* camera, const crt_render_setting
     P.lights = w->d_lights;
     P.geom_light = w->d_geom_light;
     P.envs = w->d_envs;
+    P.volumes = w->d_volumes;
+    P.n_volumes = (int)w->volumes.size();
     P.n_lights = (int)w->lights.size();
     P.motion = motion ? 1 : 0;
     P.stats = sc.stats;
@@ -878,7 +1004,10 @@ int render_impl(crt_world* w, const crt_camera* camera, const crt_render_setting
             qt.counter = sc.counts + 2 * (D + 2) + k;
             int r = crt::enqueue_queue_trace(w->scene, false, qt, stream);
             if (r) return r;
-            shade_kernel<<<grid_for(total), kBlock, 0, stream>>>(P, k, cur);
+            if (P.n_volumes > 0)
+                shade_kernel<true><<<grid_for(total), kBlock, 0, stream>>>(P, k, cur);
+            else
+                shade_kernel<false><<<grid_for(total), kBlock, 0, stream>>>(P, k, cur);
             launches += 2;
             ++trace_launches;
             if (k < D && P.n_lights > 0 && strategy_samples_lights(P.st.sampling_strategy)) {
@@ -893,7 +1022,10 @@ int render_impl(crt_world* w, const crt_camera* camera, const crt_render_setting
                 qs.counter = sc.counts + 3 * (D + 2) + k;
                 r = crt::enqueue_queue_trace(w->scene, true, qs, stream);
                 if (r) return r;
-                nee_resolve_kernel<<<grid_for(total), kBlock, 0, stream>>>(P, k);
+                if (P.n_volumes > 0)
+                    nee_resolve_kernel<true><<<grid_for(total), kBlock, 0, stream>>>(P, k);
+                else
+                    nee_resolve_kernel<false><<<grid_for(total), kBlock, 0, stream>>>(P, k);
                 launches += 2;
                 ++trace_launches;
             }

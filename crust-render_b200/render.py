@@ -14,6 +14,7 @@ from .render_types import (  # noqa: F401
     MATERIAL_DTYPE,
     STATS_DTYPE,
     Camera,
+    DensityField,
     DistantLight,
     DomeLight,
     Emissive,
@@ -26,11 +27,13 @@ from .render_types import (  # noqa: F401
     RenderSettings,
     SamplingStrategy,
     SphereLight,
+    VolumeRegion,
     WorldBuilderBase,
+    volume_records,
 )
 
 __all__ = ["World", "WorldBuilder", "Renderer", "StealCursor", "Camera", "RenderSettings", "SamplingStrategy", "PixelFilter", "PixelFilterKind",
-           "RayStats", "LightList", "OpenPBR", "Emissive", "SphereLight", "RectLight", "DistantLight", "DomeLight"]
+           "RayStats", "LightList", "OpenPBR", "Emissive", "SphereLight", "RectLight", "DistantLight", "DomeLight", "VolumeRegion", "DensityField"]
 
 
 def _p(a: Optional[np.ndarray]):
@@ -55,6 +58,13 @@ class World:
         if getattr(self, "_h", None) and L is not None:
             L.crt_world_release(self._h)
             self._h = None
+
+    def with_volumes(self, regions) -> "World":
+        """`Scene::with_volumes` (tracer.rs:167-170): free-standing participating media, outside the BVH."""
+        self._volumes = list(regions)  # keeps grid voxels alive during the call
+        recs = volume_records(self._volumes)
+        rt._ck(rt.lib().crt_world_set_volumes(self._h, _p(recs) if len(recs) else None, len(recs)))
+        return self
 
     def count(self) -> int:
         return self.scene.geometry_count()

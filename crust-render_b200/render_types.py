@@ -37,6 +37,12 @@ SETTINGS_DTYPE = np.dtype([("width", "<u4"), ("height", "<u4"), ("samples_per_pi
                            ("steal_chunk_tiles", "<u4")])  # crt_render_settings
 STATS_DTYPE = np.dtype([(n, "<u8") for n in ("camera_rays", "closest_hit", "shadow_rays", "vertices", "rr_tested", "rr_killed",
                                               "ended_escaped", "ended_depth")])  # crt_ray_stats
+# crt_volume (volume.rs:194-204 VolumeRegion::new arguments), 168 B with the grid pointer 8-aligned at 160
+VOLUME_DTYPE = np.dtype([("local_to_world", "<f4", 16), ("half_extent", *_V), ("sigma_s", *_V), ("sigma_a", *_V), ("g", "<f4"),
+                         ("emission", *_V), ("density_scale", "<f4"), ("field", "<u4"), ("noise_scale", "<f4"), ("noise_octaves", "<u4"),
+                         ("noise_gain", "<f4"), ("noise_lacunarity", "<f4"), ("noise_threshold", "<f4"), ("noise_seed", "<u4"),
+                         ("grid_dims", "<u4", 3), ("grid_data", "<u8")])
+assert VOLUME_DTYPE.itemsize == 168 and VOLUME_DTYPE.fields["grid_data"][1] == 160
 assert MATERIAL_DTYPE.itemsize == 236 and LIGHT_DTYPE.itemsize == 116 and CAMERA_DTYPE.itemsize == 52
 assert SETTINGS_DTYPE.itemsize == 64 and STATS_DTYPE.itemsize == 64
 
@@ -114,6 +120,62 @@ def DomeLight(tint) -> np.ndarray:
     l = np.zeros((), dtype=LIGHT_DTYPE)
     l["kind"], l["geom_id"], l["radiance"], l["env"] = LIGHT_DOME, NO_GEOM, tint, -1
     return l
+
+
+FIELD_HOMOGENEOUS, FIELD_NOISE, FIELD_GRID = 0, 1, 2
+MAX_VOLUMES = 16
+
+
+class DensityField:
+    """volume.rs:22-48. `Homogeneous()`, `Noise(scale, octaves, gain, lacunarity, threshold, seed)`, `Grid(nx, ny, nz, data)`."""
+
+    def __init__(self, kind: int, **kw):
+        self.kind, self.params = kind, kw
+
+    @staticmethod
+    def Homogeneous() -> "DensityField":
+        return DensityField(FIELD_HOMOGENEOUS)
+
+    @staticmethod
+    def Noise(scale=4.0, octaves=4, gain=0.5, lacunarity=2.0, threshold=0.3, seed=0) -> "DensityField":  # defaults: usd_import.rs:440-447
+        return DensityField(FIELD_NOISE, scale=scale, octaves=max(int(octaves), 1), gain=gain, lacunarity=lacunarity, threshold=threshold,
+                            seed=int(seed) & 0xFFFFFFFF)
+
+    @staticmethod
+    def Grid(nx: int, ny: int, nz: int, data) -> "DensityField":
+        data = np.ascontiguousarray(np.asarray(data, np.float32).reshape(-1))
+        assert nx >= 1 and ny >= 1 and nz >= 1 and data.size == nx * ny * nz
+        return DensityField(FIELD_GRID, dims=(nx, ny, nz), data=data)
+
+
+class VolumeRegion:
+    """`VolumeRegion::new(local_to_world, half_extent, sigma_s, sigma_a, g, emission, density_scale, field)`
+    (volume.rs:194-231). `local_to_world` is a 4x4 matrix in the column-vector convention (world = M @ local)."""
+
+    def __init__(self, local_to_world, half_extent, sigma_s, sigma_a, g: float, emission, density_scale: float, field: DensityField):
+        self.field = field
+        r = np.zeros((), dtype=VOLUME_DTYPE)
+        r["local_to_world"] = np.asarray(local_to_world, np.float32).reshape(4, 4).T.reshape(16)  # glam column-major
+        r["half_extent"], r["sigma_s"], r["sigma_a"], r["g"] = half_extent, sigma_s, sigma_a, g
+        r["emission"], r["density_scale"], r["field"] = emission, density_scale, field.kind
+        if field.kind == FIELD_NOISE:
+            q = field.params
+            r["noise_scale"], r["noise_octaves"], r["noise_gain"] = q["scale"], q["octaves"], q["gain"]
+            r["noise_lacunarity"], r["noise_threshold"], r["noise_seed"] = q["lacunarity"], q["threshold"], q["seed"]
+        elif field.kind == FIELD_GRID:
+            r["grid_dims"] = field.params["dims"]
+            r["grid_data"] = field.params["data"].ctypes.data  # kept alive by self.field
+        self.rec = r
+
+    def is_homogeneous(self) -> bool:  # volume.rs:274-276
+        return self.field.kind == FIELD_HOMOGENEOUS
+
+
+def volume_records(regions: Sequence["VolumeRegion"]) -> np.ndarray:
+    out = np.zeros(len(regions), dtype=VOLUME_DTYPE)
+    for i, v in enumerate(regions):
+        out[i] = v.rec
+    return out
 
 
 class SamplingStrategy(IntEnum):  # tracer.rs:62-75

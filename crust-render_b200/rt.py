@@ -132,6 +132,7 @@ def lib() -> C.CDLL:
         # include/crt_render.h
         "crt_world_new": [vp, vp, sz, vp, sz, vp, sz, C.POINTER(vp)],
         "crt_world_set_environment": [vp, u32, u32, u32, vp, vp],
+        "crt_world_set_volumes": [vp, vp, sz],
         "crt_render": [vp, vp, vp, vp, vp, vp],
         "crt_render_host": [vp, vp, vp, vp, vp],
         "crt_render_last_info": [C.POINTER(u64), C.POINTER(C.c_double), C.POINTER(u64)],

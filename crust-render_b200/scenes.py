@@ -22,6 +22,7 @@ import numpy as np
 
 from .render_types import (
     Camera,
+    DomeLight,
     Emissive,
     LightList,
     OpenPBR,
@@ -318,6 +319,118 @@ def domelight(api, width: int = 480, height: int = 270, spp: int = 96, **setting
     kw = dict(width=width, height=height, samples_per_pixel=spp)
     kw.update(settings_kw)
     return import_stage(api, Stage({"upAxis": "Y"}, [world, render]), os.path.join(GOLDEN, "domelight.usda"), **kw)
+
+
+# ---------------------------------------------------------------------------------------------
+# volume regions: the reference's samples/fog.usda and samples/smoke.usda, replayed through the
+# importer as synthesised stages (tests/test_usd_import.py proves them equal to the importer's output on the files)
+# ---------------------------------------------------------------------------------------------
+def _stage_prim(ptype, name, parent, **attrs):
+    from .usd.usda import Attribute, Prim
+
+    p = Prim("def", ptype, name, (parent.path if parent else "") + "/" + name, parent=parent)
+    for k, v in attrs.items():
+        p.attributes[k.replace("__", ":")] = Attribute(k.replace("__", ":"), "", v)
+    if parent is not None:
+        parent.children.append(p)
+    return p
+
+
+def _grey_room_stage(volume_prims, extra=None):
+    """The five-sided grey room under a 1.6 x 1.6 ceiling RectLight both samples share (fog.usda:11-27,49-60)."""
+    from .usd.usda import Stage
+
+    world = _stage_prim("Xform", "World", None)
+    _stage_prim("Camera", "Cam", world, focalLength=24.0, horizontalAperture=20.955, xformOp__translate=(0.0, 2.0, 8.5), xformOpOrder=["xformOp:translate"])
+    _stage_prim("Mesh", "Room", world, faceVertexCounts=[4] * 5, faceVertexIndices=list(range(20)),
+                points=[(-2, 0, -2), (2, 0, -2), (2, 0, 2), (-2, 0, 2), (-2, 4, -2), (2, 4, -2), (2, 4, 2), (-2, 4, 2), (-2, 0, -2), (2, 0, -2), (2, 4, -2),
+                        (-2, 4, -2), (-2, 0, -2), (-2, 0, 2), (-2, 4, 2), (-2, 4, -2), (2, 0, -2), (2, 0, 2), (2, 4, 2), (2, 4, -2)])
+    if extra:
+        extra(world)
+    for name, attrs in volume_prims:
+        _stage_prim("Cube", name, world, **attrs)
+    _stage_prim("RectLight", "CeilingLight", world, inputs__width=1.6, inputs__height=1.6, inputs__color=(10.0, 10.0, 10.0), inputs__intensity=1.0,
+                xformOp__rotateX=-90.0, xformOp__translate=(0.0, 3.98, 0.0), xformOpOrder=["xformOp:translate", "xformOp:rotateX"])
+    render = _stage_prim("Scope", "Render", None)
+    _stage_prim("RenderSettings", "settings", render, resolution=(320, 180), **{"crust__samplesPerPixel": 64, "crust__maxDepth": 16, "crust__minSamplesPerPixel": 16,
+                                                                                "crust__varianceThreshold": 0.05, "crust__frame": 0})
+    return Stage({"upAxis": "Y"}, [world, render])
+
+
+def fog(api, **settings_kw):
+    """samples/fog.usda: homogeneous fog filling a grey room, god rays around an occluding ball (volume NEE + the
+    analytic transmittance fast path). 320x180, 64 spp, depth 16, adaptive (min 16, threshold 0.05)."""
+    from .usd.importer import import_stage
+
+    ball = lambda w: _stage_prim("Sphere", "Ball", w, radius=0.6, xformOp__translate=(-0.7, 0.6, 0.3), xformOpOrder=["xformOp:translate"])  # noqa: E731
+    vols = [("Fog", dict(size=4.0, crust__volume__type="homogeneous", crust__volume__sigmaS=(0.15, 0.15, 0.15), crust__volume__sigmaA=(0.01, 0.015, 0.025),
+                         crust__volume__anisotropy=0.3, xformOp__translate=(0.0, 2.0, 0.0), xformOpOrder=["xformOp:translate"]))]
+    return import_stage(api, _grey_room_stage(vols, ball), "fog.usda", **settings_kw)
+
+
+# smoke.usda:66 — a 4x4x4 spherical blob
+_PUFF = [0.000, 0.092, 0.092, 0.000, 0.092, 0.309, 0.309, 0.092, 0.092, 0.309, 0.309, 0.092, 0.000, 0.092, 0.092, 0.000,
+         0.092, 0.309, 0.309, 0.092, 0.309, 0.639, 0.639, 0.309, 0.309, 0.639, 0.639, 0.309, 0.092, 0.309, 0.309, 0.092,
+         0.092, 0.309, 0.309, 0.092, 0.309, 0.639, 0.639, 0.309, 0.309, 0.639, 0.639, 0.309, 0.092, 0.309, 0.309, 0.092,
+         0.000, 0.092, 0.092, 0.000, 0.092, 0.309, 0.309, 0.092, 0.092, 0.309, 0.309, 0.092, 0.000, 0.092, 0.092, 0.000]
+
+
+def smoke(api, **settings_kw):
+    """samples/smoke.usda: a procedural fBm smoke plume, an emissive absorbing ember and a 4x4x4 density-grid puff in
+    the grey room (delta tracking, volume emission, ratio-tracked shadow rays, overlapping majorants)."""
+    from .usd.importer import import_stage
+
+    vols = [
+        ("Smoke", dict(size=2.0, crust__volume__type="smoke", crust__volume__densityScale=12.0, crust__volume__sigmaS=(0.8, 0.8, 0.8),
+                       crust__volume__sigmaA=(0.08, 0.08, 0.08), crust__volume__anisotropy=0.2, crust__volume__noiseScale=4.0, crust__volume__noiseOctaves=4,
+                       crust__volume__noiseGain=0.5, crust__volume__noiseLacunarity=2.0, crust__volume__noiseThreshold=0.25, crust__volume__noiseSeed=42,
+                       xformOp__scale=(0.9, 1.6, 0.9), xformOp__translate=(-0.4, 1.7, 0.0), xformOpOrder=["xformOp:translate", "xformOp:scale"])),
+        ("Ember", dict(size=0.5, crust__volume__type="homogeneous", crust__volume__densityScale=4.0, crust__volume__sigmaS=(0.05, 0.05, 0.05),
+                       crust__volume__sigmaA=(0.6, 0.35, 0.15), crust__volume__emission=(6.0, 2.2, 0.5), xformOp__translate=(0.9, 0.3, 0.4),
+                       xformOpOrder=["xformOp:translate"])),
+        ("GridPuff", dict(size=1.0, crust__volume__type="grid", crust__volume__densityScale=6.0, crust__volume__sigmaS=(0.7, 0.7, 0.7),
+                          crust__volume__sigmaA=(0.05, 0.05, 0.05), crust__volume__gridDims=[4, 4, 4], crust__volume__gridData=list(_PUFF),
+                          xformOp__translate=(1.1, 2.6, -0.8), xformOpOrder=["xformOp:translate"])),
+    ]
+    return import_stage(api, _grey_room_stage(vols), "smoke.usda", **settings_kw)
+
+
+def volume_slab(api, kind: str = "absorb", width: int = 32, height: int = 32, spp: int = 64, max_depth: int = 64, **settings_kw):
+    """Analytic probes of the volume integrator: a wide 1-unit-thick slab facing a 1-degree camera under a uniform
+    dome of radiance 1 (no geometry). `absorb`: gray sigma_a = 0.7 => pixel = e^-0.7. `emit`: the same slab emitting
+    Le => Le (1 - e^-0.7) + e^-0.7. `furnace` / `furnace_grid` / `furnace_noise`: albedo-1 scattering (g = 0.5)
+    => exactly 1 whatever the path does (volume NEE + phase-sampled escapes must MIS-sum to one). Gray on purpose: with
+    chromatic sigma_s the reference's tracker folds the weaker channels' null collisions into real scatters
+    (p_scatter = max-channel sigma_s / majorant, volume.rs:466-477), which loses energy in those channels — reproduced
+    here as is, so a chromatic furnace does not return 1."""
+    from .render_types import DensityField, VolumeRegion
+
+    wb = api.WorldBuilder()
+    lights = LightList()
+    lights.add(DomeLight((1.0, 1.0, 1.0)))
+    m = np.eye(4, dtype=np.float32)
+    half = (50.0, 50.0, 0.5)
+    le = (4.0, 1.5, 0.3)
+    if kind == "absorb":
+        regions = [VolumeRegion(m, half, (0,) * 3, (0.7,) * 3, 0.0, (0,) * 3, 1.0, DensityField.Homogeneous())]
+    elif kind == "emit":
+        regions = [VolumeRegion(m, half, (0,) * 3, (0.7,) * 3, 0.0, le, 1.0, DensityField.Homogeneous())]
+    elif kind == "furnace":
+        regions = [VolumeRegion(m, half, (1.2,) * 3, (0,) * 3, 0.5, (0,) * 3, 1.0, DensityField.Homogeneous())]
+    elif kind == "furnace_grid":
+        rng = np.random.default_rng(5)
+        regions = [VolumeRegion(m, half, (1.0,) * 3, (0,) * 3, 0.5, (0,) * 3, 2.0, DensityField.Grid(4, 4, 4, rng.random(64).astype(np.float32))),
+                   VolumeRegion(m, (50.0, 50.0, 0.25), (0.5,) * 3, (0,) * 3, -0.3, (0,) * 3, 1.0, DensityField.Homogeneous())]  # overlapping: mixed phase lobes
+    elif kind == "furnace_noise":
+        regions = [VolumeRegion(m, (2.0, 2.0, 0.5), (3.0,) * 3, (0,) * 3, 0.2, (0,) * 3, 1.0, DensityField.Noise(4.0, 3, 0.5, 2.0, 0.2, 7))]
+    else:
+        raise ValueError(kind)
+    world = wb.commit(lights).with_volumes(regions)
+    world.volumes = regions
+    cam = Camera((0.0, 0.0, 20.0), (0.0, 0.0, 0.0), (0.0, 1.0, 0.0), 1.0, width / height)
+    kw = dict(variance_threshold=0.0, min_samples_per_pixel=spp)
+    kw.update(settings_kw)
+    return world, cam, RenderSettings(spp, max_depth, width, height, **kw)
 
 
 # ---------------------------------------------------------------------------------------------

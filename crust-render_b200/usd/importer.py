@@ -16,8 +16,10 @@ What is reproduced, with the reference lines it follows:
   * materials: `crust:openpbr` decoded 1:1 (:2902-2975), `UsdPreviewSurface` mapped (:2661-2705),
     unbound => default grey OpenPBR; RenderSettings and the crust:* attributes (:3015-3100).
   * PointInstancer (:1674-1875): T * R * S placements, one Instance per prototype part, `invisibleIds`;
-    binary crate files through usdc.py.
-Not reproduced yet: native instancing, nested instancers, BasisCurves, volumes, Ptex, references/payloads/variants.
+    binary crate files through usdc.py;
+  * volumes: a prim carrying `crust:volume:type` (homogeneous | smoke | grid) imports as a VolumeRegion only, never
+    as geometry (:190-209, 427-503).
+Not reproduced yet: native instancing, nested instancers, BasisCurves, Ptex, references/payloads/variants.
 """
 from __future__ import annotations
 
@@ -28,6 +30,7 @@ import numpy as np
 
 from ..render_types import (
     Camera,
+    DensityField,
     DistantLight,
     DomeLight,
     Emissive,
@@ -39,6 +42,7 @@ from ..render_types import (
     RenderSettings,
     SamplingStrategy,
     SphereLight,
+    VolumeRegion,
 )
 from ..rt_types import MASK_ALL, MASK_CAMERA, MASK_INDIRECT, MASK_SHADOW, Affine3A, Geometry
 from . import usda
@@ -295,6 +299,7 @@ class _Import:
         self.materials = _Materials(stage)
         self.slots: Dict[tuple, dict] = {}      # MeshArena (:800-910)
         self.pending: List[dict] = []
+        self.volumes: List[VolumeRegion] = []
 
     # -- stage walk (:140-269) ------------------------------------------------------------------
     def traverse(self, roots: List[Tuple[usda.Prim, np.ndarray]]):
@@ -309,7 +314,9 @@ class _Import:
             if t == "PointInstancer":
                 self.emit_point_instancer(prim, world)
                 continue  # prototypes are drawn through the instancer, never on their own (:197-208)
-            if t == "Mesh":
+            if isinstance(prim.attr("crust:volume:type"), str):  # checked before every geometry schema (:190-209)
+                self.emit_volume(prim, world)
+            elif t == "Mesh":
                 self.emit_mesh(prim, world)
             elif t == "Sphere":
                 self.emit_sphere(prim, world)
@@ -465,6 +472,31 @@ class _Import:
                     continue
                 self.wb.attach_masked(Geometry.Instance(scene, _affine(xf)), mat, mask)
 
+    def emit_volume(self, prim, world):  # :435-503
+        ty = prim.attr("crust:volume:type")
+        g = lambda n, dv: dv if prim.attr(n) is None else prim.attr(n)  # noqa: E731
+        if ty == "homogeneous":
+            field = DensityField.Homogeneous()
+        elif ty == "smoke":
+            field = DensityField.Noise(float(g("crust:volume:noiseScale", 4.0)), max(int(g("crust:volume:noiseOctaves", 4)), 1), float(g("crust:volume:noiseGain", 0.5)),
+                                       float(g("crust:volume:noiseLacunarity", 2.0)), float(g("crust:volume:noiseThreshold", 0.3)), int(g("crust:volume:noiseSeed", 0)))
+        elif ty == "grid":
+            dims, data = prim.attr("crust:volume:gridDims"), prim.attr("crust:volume:gridData")
+            if dims is None or data is None or len(dims) != 3:
+                return
+            nx, ny, nz = (max(int(d), 1) for d in dims)
+            data = np.asarray(data, np.float64).astype(F).ravel()
+            if nx * ny * nz != data.size:
+                return
+            field = DensityField.Grid(nx, ny, nz, data)
+        else:
+            return  # unknown type: skipped with a warning in the reference
+        size = prim.attr("size")
+        half = F(0.5) if size is None else F(size) * F(0.5)
+        self.volumes.append(VolumeRegion(world, (half, half, half), g("crust:volume:sigmaS", (0.5, 0.5, 0.5)), g("crust:volume:sigmaA", (0.0, 0.0, 0.0)),
+                                         float(g("crust:volume:anisotropy", 0.0)), g("crust:volume:emission", (0.0, 0.0, 0.0)),
+                                         float(g("crust:volume:densityScale", 1.0)), field))
+
     def emit_dome_light(self, prim, world):  # :2389-2460
         tint = _lux_emission(prim)
         tex, fmt = prim.attr("inputs:texture:file"), prim.attr("inputs:texture:format")
@@ -588,6 +620,9 @@ def import_stage(api, stage: usda.Stage, path: str = "<stage>", **overrides):
         imp.traverse([(t, ident) for t in tops])
     imp.flush_meshes()
     world = imp.wb.commit(imp.lights)
+    world.volumes = imp.volumes
+    if imp.volumes:
+        world.with_volumes(imp.volumes)  # Scene::with_volumes (:421)
     if imp.camera is None:
         raise ValueError(f"{path}: no UsdGeomCamera on the stage")
     return world, imp.camera, imp.settings

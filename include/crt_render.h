@@ -13,6 +13,7 @@
  *   crt_camera     camera.rs:27-59       Camera::new arguments
  *   crt_render_settings tracer.rs:639-661 RenderSettings + filter.rs:28-60 PixelFilter
  *   crt_ray_stats  stats.rs:128-146      RayStats
+ *   crt_volume     volume.rs:168-231     VolumeRegion::new arguments (free-standing participating media)
  *   crt_render     tracer.rs:194-212     Renderer::render_with_stats (non-guided pass)
  *
  * No CPU fallback: crt_render fails with CRT_ERR_NO_DEVICE without a CUDA device.
@@ -135,6 +136,34 @@ void crt_world_release(crt_world* w);
  * u = 0.5 looks down -Z) with luminance importance sampling. `light_to_world`: 9 floats, glam Mat3A column order. */
 int crt_world_set_environment(crt_world* w, uint32_t light_index, uint32_t width, uint32_t height, const float* rgb,
                               const float light_to_world[9]);
+
+/* volume.rs:22-48 DensityField */
+#define CRT_FIELD_HOMOGENEOUS 0u /* density 1 inside the box */
+#define CRT_FIELD_NOISE 1u       /* hash-based value-noise fBm ("smoke") */
+#define CRT_FIELD_GRID 2u        /* voxel grid, x-fastest, trilinear, edge clamp */
+#define CRT_MAX_VOLUMES 16u
+
+/* VolumeRegion::new (volume.rs:194-231): an oriented box [-half, +half]^3 under `local_to_world` filled with a density
+ * field. sigma_s / sigma_a are per-channel coefficients at density 1 BEFORE density_scale is folded in. */
+typedef struct crt_volume {
+    float local_to_world[16]; /* glam Mat4, column-major; must be affine and invertible */
+    float half_extent[3];
+    float sigma_s[3], sigma_a[3];
+    float g; /* Henyey-Greenstein anisotropy, clamped to +-0.99 */
+    float emission[3];
+    float density_scale;
+    uint32_t field; /* CRT_FIELD_* */
+    float noise_scale;
+    uint32_t noise_octaves;
+    float noise_gain, noise_lacunarity, noise_threshold;
+    uint32_t noise_seed;
+    uint32_t grid_dims[3];
+    const float* grid_data; /* HOST pointer, grid_dims[0]*[1]*[2] floats (copied) */
+} crt_volume;
+/* Scene::with_volumes (tracer.rs:167-170): replaces the world's volume regions (n = 0 clears them). Regions live
+ * outside the BVH; the integrator delta-tracks through them on every segment and ratio-tracks shadow rays.
+ * At most CRT_MAX_VOLUMES regions (the reference has no cap; the device keeps a fixed span list per ray). */
+int crt_world_set_volumes(crt_world* w, const crt_volume* volumes, size_t n);
 
 /* Renderer::render_with_stats (tracer.rs:194-212): one non-guided pass. `framebuffer` is a DEVICE
  * pointer to width*height float4 {r, g, b, samples taken}; row j is image row j counted from the

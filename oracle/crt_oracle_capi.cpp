@@ -454,6 +454,104 @@ int orc_world_set_environment(void* w, uint32_t light_index, uint32_t width, uin
     for (const auto& t : W.env_tables) W.envs.push_back(t.view());
     return 0;
 }
+// Scene::with_volumes (tracer.rs:167-170)
+namespace {
+void set_volumes(std::vector<shade::VolumeRegion>& regions, std::vector<std::vector<float>>& grids, const crt_volume* v, size_t n) {
+    regions.clear();
+    grids.clear();
+    grids.reserve(n);
+    for (size_t i = 0; i < n; ++i) {
+        const float* data = nullptr;
+        if (v[i].field == CRT_FIELD_GRID) {
+            size_t cells = (size_t)v[i].grid_dims[0] * v[i].grid_dims[1] * v[i].grid_dims[2];
+            grids.emplace_back(v[i].grid_data, v[i].grid_data + cells);
+            data = grids.back().data();
+        }
+        regions.push_back(shade::volume_from_abi(v[i], data, data));
+    }
+}
+struct VolumesHandle {
+    std::vector<shade::VolumeRegion> regions;
+    std::vector<std::vector<float>> grids;
+};
+}  // namespace
+int orc_world_set_volumes(void* w, const crt_volume* v, size_t n) {
+    orcr::World& W = ((WorldHandle*)w)->world;
+    if (n > CRT_MAX_VOLUMES) return 1;
+    for (size_t i = 0; i < n; ++i)
+        if (!shade::volume_abi_valid(v[i])) return 1;
+    set_volumes(W.volumes, W.grids, v, n);
+    return 0;
+}
+// volume.rs unit-test surface: a bare Volumes aggregate and an Rng whose state the caller keeps between calls
+void* orc_volumes_new(const crt_volume* v, size_t n) {
+    auto* h = new VolumesHandle();
+    set_volumes(h->regions, h->grids, v, n);
+    return h;
+}
+void orc_volumes_free(void* h) { delete (VolumesHandle*)h; }
+uint32_t orc_rng_new(uint32_t seed) { return shade::rng_new(seed).state; }
+float orc_rng_next(uint32_t* state) {
+    shade::Rng r{*state};
+    float f = shade::rng_next_f32(r);
+    *state = r.state;
+    return f;
+}
+void orc_volumes_region_info(void* h, uint32_t i, float* out) {  // sigma_s3, sigma_a3, g, majorant, aabb6, homogeneous
+    const shade::VolumeRegion& r = ((VolumesHandle*)h)->regions[i];
+    put3(out, r.sigma_s);
+    put3(out + 3, r.sigma_a);
+    out[6] = r.g;
+    out[7] = r.majorant;
+    put3(out + 8, r.aabb_min);
+    put3(out + 11, r.aabb_max);
+    out[14] = r.field == shade::FIELD_HOMOGENEOUS ? 1.0f : 0.0f;
+}
+// n independent Volumes::transmittance calls on one ray, consuming one Rng stream (out: 3 floats each)
+void orc_volumes_transmittance_n(void* h, const float* o, const float* d, float t_eps, float t_max, uint32_t* state, size_t n, float* out) {
+    auto* H = (VolumesHandle*)h;
+    shade::Rng rng{*state};
+    for (size_t i = 0; i < n; ++i) put3(out + 3 * i, shade::volumes_transmittance(H->regions.data(), (int)H->regions.size(), sv(o), sv(d), t_eps, t_max, rng));
+    *state = rng.state;
+}
+// n Volumes::sample_interaction calls; out per call: scatter, t, p3, weight-or-transmittance3, emitted3, n_lobes, (w, g) of the first two lobes
+void orc_volumes_sample_n(void* h, const float* o, const float* d, float t_eps, float t_max, uint32_t* state, size_t n, float* out) {
+    auto* H = (VolumesHandle*)h;
+    shade::Rng rng{*state};
+    for (size_t i = 0; i < n; ++i) {
+        shade::VolumeEvent ev;
+        ev.t = 0.0f;
+        ev.p = shade::splat(0.0f);
+        shade::volumes_sample_interaction(H->regions.data(), (int)H->regions.size(), sv(o), sv(d), t_eps, t_max, rng, ev);
+        float* q = out + 16 * i;
+        q[0] = ev.scatter ? 1.0f : 0.0f;
+        q[1] = ev.t;
+        put3(q + 2, ev.p);
+        put3(q + 5, ev.weight);
+        put3(q + 8, ev.emitted);
+        q[11] = (float)ev.phase.n;
+        for (int k = 0; k < 2; ++k) {
+            q[12 + 2 * k] = k < ev.phase.n ? ev.phase.w[k] : 0.0f;
+            q[13 + 2 * k] = k < ev.phase.n ? ev.phase.g[k] : 0.0f;
+        }
+    }
+    *state = rng.state;
+}
+float orc_volumes_field_density(void* h, uint32_t i, const float* u) { return shade::field_density(((VolumesHandle*)h)->regions[i], sv(u)); }
+float orc_volumes_density(void* h, uint32_t i, const float* p_world) { return shade::region_density(((VolumesHandle*)h)->regions[i], sv(p_world)); }
+int orc_volumes_intersect(void* h, uint32_t i, const float* o, const float* d, float* out2) {
+    return shade::region_intersect(((VolumesHandle*)h)->regions[i], sv(o), sv(d), out2[0], out2[1]) ? 1 : 0;
+}
+float orc_vol_hash3(int32_t x, int32_t y, int32_t z, uint32_t seed) { return shade::vol_hash3(x, y, z, seed); }
+float orc_hg_phase(float cos_theta, float g) { return shade::hg_phase(cos_theta, g); }
+float orc_phase_single_pdf(float g, float cos_theta) {  // PhaseMix::single(g).pdf(cos_theta)
+    shade::PhaseMix m;
+    m.n = 1;
+    m.w[0] = 1.0f;
+    m.g[0] = g;
+    return shade::phase_pdf(m, cos_theta);
+}
+void orc_mat4_inverse(const float* m, float* out) { shade::mat4_inverse(m, out); }
 // A light of a world with its environment table (usd_scene.rs:873-922 probes lights through the scene).
 int orc_world_light_sample(void* w, uint32_t index, const float* from, float u, float v, float* out8) {
     orcr::World& W = ((WorldHandle*)w)->world;

@@ -12,12 +12,14 @@
 // for the host it is pinned by the reference's own unit-test properties (tests/test_shade_kats.py).
 // PARITY UNPINNED for sample values: the reference's sampler is the third-party crate
 // `openqmc-rs = "0.1"` (crates/crust-core/Cargo.toml:17), not vendored; see shade/base.h.
-// Volume regions (volume.rs), path guiding and environment-map domes are out of scope
-// (SURVEY §2 rows 23-25): `volumes.is_empty()` and `guiding == None` everywhere below.
+// Path guiding is out of scope: `guiding == None` everywhere below. Volume regions follow
+// tracer.rs:1016-1077 (shadow_transmittance, volume_nee) and :1166-1249 (the region scatter vertex) over
+// shade/volume.h's restatement of volume.rs.
 #pragma once
 #include <thread>
 
 #include "../crust-render_b200/csrc/shade/scene_desc.h"
+#include "../crust-render_b200/csrc/shade/volume.h"
 #include "crt_oracle.hpp"
 
 namespace orcr {
@@ -69,6 +71,8 @@ struct World {
     std::vector<shade::Light> lights;     // LightList, light.rs:404-446
     std::vector<shade::EnvMapTables> env_tables;  // environment maps of dome lights (environment.rs)
     std::vector<shade::EnvMap> envs;              // views into env_tables, indexed by Light::env
+    std::vector<shade::VolumeRegion> volumes;     // Volumes (volume.rs:364-384); grid voxels owned by `grids`
+    std::vector<std::vector<float>> grids;
     const shade::Material& material(uint32_t geom_id) const { return materials[geom_material[geom_id]]; }
 };
 
@@ -104,11 +108,13 @@ inline bool world_occluded(const World& w, const PathRay& r, float t_min, float 
     return w.scene->bvh.hit_any(kr, t_min, t_max, cx);
 }
 
-struct VertexRec {  // tracer.rs:832-863 (segment_emit is always zero without volume regions)
-    V3 atten, emit_here, nee, factor, next_emit;
+struct VertexRec {  // tracer.rs:832-863
+    V3 atten, segment_emit, emit_here, nee, factor, next_emit;
     float next_emit_weight;
 };
-struct PrevBounce {  // tracer.rs:898-905; `Phase` never arises without volume regions
+struct PrevBounce {  // PrevVertex, tracer.rs:898-920: Surface(PrevBounce) or Phase{pos, pdf}
+    bool phase = false;
+    V3 phase_pos{};
     PathRay ray;
     shade::SurfaceHit rec;
     const shade::Material* mat;
@@ -121,10 +127,14 @@ struct PrevBounce {  // tracer.rs:898-905; `Phase` never arises without volume r
 inline float bounce_emission_weight(const PrevBounce& p, const World& w, const WorldHit& hit, uint32_t strategy) {
     V3 value;
     float pdf;
-    if (p.delta || !shade::material_eval(*p.mat, p.ray.dir, p.rec, p.dir, value, pdf)) return 1.0f;
+    V3 from = p.phase_pos;
+    if (!p.phase) {
+        if (p.delta || !shade::material_eval(*p.mat, p.ray.dir, p.rec, p.dir, value, pdf)) return 1.0f;
+        from = p.rec.p;
+    }
     int li = shade::light_find_by_geom(w.lights.data(), (int)w.lights.size(), hit.geom_id);
     if (li < 0) return 1.0f;
-    float light_pdf = std::max(shade::light_pdf_at_point(w.lights[li], p.rec.p, hit.rec.p) / (float)w.lights.size(), 1e-6f);
+    float light_pdf = std::max(shade::light_pdf_at_point(w.lights[li], from, hit.rec.p) / (float)w.lights.size(), 1e-6f);
     return shade::strategy_bounce_weight(strategy, p.pdf, light_pdf);
 }
 // tracer.rs:966-1009
@@ -137,7 +147,7 @@ inline V3 escaped_emission(const PrevBounce* prev, const World& w, V3 direction,
     if (prev) {
         V3 value;
         float pdf;
-        competing = !prev->delta && shade::material_eval(*prev->mat, prev->ray.dir, prev->rec, prev->dir, value, pdf);
+        competing = prev->phase || (!prev->delta && shade::material_eval(*prev->mat, prev->ray.dir, prev->rec, prev->dir, value, pdf));
         bounce_pdf = prev->pdf;
     }
     float n_lights = (float)w.lights.size();
@@ -151,6 +161,33 @@ inline V3 escaped_emission(const PrevBounce* prev, const World& w, V3 direction,
         radiance += emitted * weight;
     }
     return radiance;
+}
+
+// tracer.rs:1016-1035: ZERO when a surface occludes the segment, else the transmittance through every region crossed
+inline V3 shadow_transmittance(const World& w, const PathRay& shadow_ray, float distance, PathSampler vertex, RayStats& stats, Ctx& cx) {
+    stats.shadow_rays++;
+    if (world_occluded(w, shadow_ray, 0.001f, distance - 0.001f, cx)) return splat(0.0f);
+    if (w.volumes.empty()) return splat(1.0f);
+    Rng rng = sampler_rng(new_domain(vertex, K_NEE_SHADOW));
+    return volumes_transmittance(w.volumes.data(), (int)w.volumes.size(), shadow_ray.origin, shadow_ray.dir, 0.001f, distance - 0.001f, rng);
+}
+// tracer.rs:1040-1077
+inline V3 volume_nee(V3 p, V3 wi, const PhaseMix& phase, const World& w, uint32_t strategy, PathSampler vertex, float time, RayStats& stats, Ctx& cx) {
+    if (!strategy_samples_lights(strategy)) return splat(0.0f);
+    float nee[4];
+    draw_sample4(new_domain(vertex, K_NEE), nee);
+    int li = light_pick((int)w.lights.size(), nee[0]);
+    if (li < 0) return splat(0.0f);
+    float n_lights = (float)w.lights.size();
+    LightSample s;
+    if (!light_sample_li(w.lights[li], p, nee[1], nee[2], s, w.envs.data())) return splat(0.0f);
+    PathRay shadow_ray{p, s.direction, time, MASK_SHADOW, -1};
+    V3 tr = shadow_transmittance(w, shadow_ray, s.distance, vertex, stats, cx);
+    if (is_zero(tr)) return splat(0.0f);
+    float light_pdf = fmaxf(s.pdf / n_lights, 1e-6f);
+    float phase_val = phase_pdf(phase, dot(wi, s.direction));
+    float weight = strategy_light_weight(strategy, light_pdf, phase_val);
+    return s.radiance * phase_val * tr * weight / light_pdf;
 }
 
 // tracer.rs:1086-1558
@@ -177,6 +214,10 @@ inline V3 trace_path(const PathRay& r, const World& w, int depth, uint32_t strat
                     V3 emitted = material_emitted_directional(*hit.mat, cos_o);
                     if (length_squared(emitted) > 0.0f) {
                         if (ray.medium >= 0) emitted *= medium_transmittance(w.materials[ray.medium].medium, hit.rec.t);
+                        if (!w.volumes.empty()) {
+                            Rng rng = sampler_rng(new_domain(v, K_VOLUME));
+                            emitted *= volumes_transmittance(w.volumes.data(), (int)w.volumes.size(), ray.origin, ray.dir, 0.001f, hit.rec.t, rng);
+                        }
                         records.back().next_emit = emitted;
                         records.back().next_emit_weight = bounce_emission_weight(prev, w, hit, strategy);
                     }
@@ -195,7 +236,53 @@ inline V3 trace_path(const PathRay& r, const World& w, int depth, uint32_t strat
             float sigma_t_max = fmaxf(medium_sigma_t_max(*med), 1e-4f);
             t_med = -logf(draw_rnd1(new_domain(v, K_MEDIUM))) / sigma_t_max;
         }
-        const V3 vol_tr = splat(1.0f);  // no volume regions: Passthrough{ONE, ZERO}
+        // volume-region interaction clipped to the event that would otherwise end the segment (:1166-1182)
+        V3 vol_tr = splat(1.0f), vol_emit = splat(0.0f);
+        if (!w.volumes.empty()) {
+            Rng rng = sampler_rng(new_domain(v, K_VOLUME));
+            VolumeEvent ev;
+            volumes_sample_interaction(w.volumes.data(), (int)w.volumes.size(), ray.origin, ray.dir, 0.001f, fminf(t_surf, t_med), rng, ev);
+            if (ev.scatter) {  // region scatter vertex (:1184-1244)
+                V3 wi = normalize(ray.dir);
+                float ps[4];
+                draw_sample4(new_domain(v, K_PHASE), ps);
+                V3 dir = phase_sample(ev.phase, wi, ps[0], ps[1], ps[2]);
+                float phase_pdf_dir = fmaxf(phase_pdf(ev.phase, dot(wi, dir)), 1e-6f);
+                V3 nee = volume_nee(ev.p, wi, ev.phase, w, strategy, v, ray.time, stats, cx);
+                VertexRec vrec{ev.weight, ev.emitted, splat(0.0f), nee, splat(1.0f), splat(0.0f), 1.0f};
+                beta *= ev.weight;
+                bool survived = true;
+                if ((int)records.size() >= RR_START_BOUNCE) {
+                    stats.rr_tested++;
+                    float p_survive = clampf(max_element(beta), RR_MIN_PROB, 1.0f);
+                    if (p_survive < 1.0f) {
+                        if (draw_rnd1(new_domain(v, K_RR)) >= p_survive) {
+                            survived = false;
+                            stats.rr_killed++;
+                            vrec.factor = splat(0.0f);
+                        } else {
+                            vrec.factor = vrec.factor / p_survive;
+                            beta = beta / p_survive;
+                        }
+                    }
+                }
+                stats.vertices++;
+                records.push_back(vrec);
+                if (!survived) break;
+                prev = PrevBounce{};
+                prev.phase = true;
+                prev.phase_pos = ev.p;
+                prev.pdf = phase_pdf_dir;
+                has_prev = true;
+                int m = ray.medium;
+                float time = ray.time;
+                ray = PathRay{ev.p, dir, time, MASK_INDIRECT, m};
+                remaining -= 1;
+                continue;
+            }
+            vol_tr = ev.weight;
+            vol_emit = ev.emitted;
+        }
 
         if (t_med < t_surf) {  // carried-medium scatter vertex (:1251-1318)
             float sigma_bar = fmaxf(medium_sigma_t_max(*med), 1e-4f);
@@ -205,7 +292,7 @@ inline V3 trace_path(const PathRay& r, const World& w, int depth, uint32_t strat
             V3 dir = sample_henyey_greenstein(normalize(ray.dir), med->g, ph[0], ph[1]);
             V3 e = (splat(sigma_bar) - (med->sigma_a + med->sigma_s)) * t_med;
             V3 factor = med->sigma_s / sigma_bar * v3(expf(e.x), expf(e.y), expf(e.z));
-            VertexRec vrec{vol_tr, splat(0), splat(0), factor, splat(0), 1.0f};
+            VertexRec vrec{vol_tr, vol_emit, splat(0), splat(0), factor, splat(0), 1.0f};
             beta *= vol_tr * factor;
             bool survived = true;
             if ((int)records.size() >= RR_START_BOUNCE) {
@@ -242,7 +329,7 @@ inline V3 trace_path(const PathRay& r, const World& w, int depth, uint32_t strat
                 float t = 0.5f * (unit_direction.y + 1.0f);
                 background += (1.0f - t) * v3(1.0f, 1.0f, 1.0f) + t * v3(0.5f, 0.7f, 1.0f);
             }
-            terminal = vol_tr * background;
+            terminal = vol_emit + vol_tr * background;
             break;
         }
         const SurfaceHit rec = hit.rec;
@@ -283,21 +370,20 @@ inline V3 trace_path(const PathRay& r, const World& w, int depth, uint32_t strat
         if (li >= 0 && light_sample_li(w.lights[li], rec.p, nee_s[1], nee_s[2], ls, w.envs.data())) {
             float n_lights = (float)w.lights.size();
             PathRay shadow_ray{rec.p, ls.direction, ray.time, MASK_SHADOW, -1};
-            stats.shadow_rays++;
-            bool occluded = world_occluded(w, shadow_ray, 0.001f, ls.distance - 0.001f, cx);  // shadow_transmittance :1016-1035
-            if (!occluded) {
+            V3 shadow_tr = shadow_transmittance(w, shadow_ray, ls.distance, v, stats, cx);
+            if (!is_zero(shadow_tr)) {
                 float cosine = fabsf(dot(rec.normal, ls.direction));
                 float light_pdf = fmaxf(ls.pdf / n_lights, 1e-6f);
                 V3 brdf_value;
                 float brdf_pdf;
                 if (material_eval(*mat, ray.dir, rec, ls.direction, brdf_value, brdf_pdf)) {
                     float weight = strategy_light_weight(strategy, light_pdf, brdf_pdf);
-                    nee += ls.radiance * brdf_value * cosine * splat(1.0f) * weight / light_pdf;
+                    nee += ls.radiance * brdf_value * cosine * shadow_tr * weight / light_pdf;
                 }
             }
         }
 
-        VertexRec vrec{atten, emit_here, nee, splat(0.0f), splat(0.0f), 1.0f};
+        VertexRec vrec{atten, vol_emit, emit_here, nee, splat(0.0f), splat(0.0f), 1.0f};
 
         // 2. BSDF sampling (:1459-1530)
         float bs[4];
@@ -324,7 +410,7 @@ inline V3 trace_path(const PathRay& r, const World& w, int depth, uint32_t strat
             }
             if (survived) {
                 vrec.factor = factor;
-                prev = PrevBounce{ray, rec, mat, dir, sample.pdf, sample.delta};
+                prev = PrevBounce{false, splat(0.0f), ray, rec, mat, dir, sample.pdf, sample.delta};
                 has_prev = true;
                 stats.vertices++;
                 records.push_back(vrec);
@@ -343,7 +429,7 @@ inline V3 trace_path(const PathRay& r, const World& w, int depth, uint32_t strat
     V3 radiance = terminal;
     for (size_t k = records.size(); k-- > 0;) {
         const VertexRec& vr = records[k];
-        radiance = vr.atten * (vr.emit_here + vr.nee + vr.factor * (vr.next_emit * vr.next_emit_weight + radiance));
+        radiance = vr.segment_emit + vr.atten * (vr.emit_here + vr.nee + vr.factor * (vr.next_emit * vr.next_emit_weight + radiance));
     }
     return radiance;
 }

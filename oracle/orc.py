@@ -99,6 +99,29 @@ def lib() -> C.CDLL:
     L.orc_world_new.restype = vp
     L.orc_world_free.argtypes = [vp]
     L.orc_world_set_environment.argtypes = [vp, u32, u32, u32, vp, vp]
+    L.orc_world_set_volumes.argtypes = [vp, vp, sz]
+    L.orc_volumes_new.argtypes = [vp, sz]
+    L.orc_volumes_new.restype = vp
+    L.orc_volumes_free.argtypes = [vp]
+    L.orc_rng_new.argtypes = [u32]
+    L.orc_rng_new.restype = u32
+    L.orc_rng_next.argtypes = [vp]
+    L.orc_rng_next.restype = f
+    L.orc_volumes_region_info.argtypes = [vp, u32, vp]
+    L.orc_volumes_transmittance_n.argtypes = [vp, vp, vp, f, f, vp, sz, vp]
+    L.orc_volumes_sample_n.argtypes = [vp, vp, vp, f, f, vp, sz, vp]
+    L.orc_volumes_field_density.argtypes = [vp, u32, vp]
+    L.orc_volumes_field_density.restype = f
+    L.orc_volumes_density.argtypes = [vp, u32, vp]
+    L.orc_volumes_density.restype = f
+    L.orc_volumes_intersect.argtypes = [vp, u32, vp, vp, vp]
+    L.orc_vol_hash3.argtypes = [C.c_int32, C.c_int32, C.c_int32, u32]
+    L.orc_vol_hash3.restype = f
+    L.orc_hg_phase.argtypes = [f, f]
+    L.orc_hg_phase.restype = f
+    L.orc_phase_single_pdf.argtypes = [f, f]
+    L.orc_phase_single_pdf.restype = f
+    L.orc_mat4_inverse.argtypes = [vp, vp]
     L.orc_world_light_sample.argtypes = [vp, u32, vp, f, f, vp]
     L.orc_world_light_escaped.argtypes = [vp, u32, vp, vp, vp]
     L.orc_env_new.argtypes = [u32, u32, vp]
@@ -359,6 +382,7 @@ from crust_render_b200.render_types import (  # noqa: E402  value types only
     RayStats,
     RenderSettings,
     WorldBuilderBase,
+    volume_records,
 )
 
 
@@ -376,6 +400,13 @@ class World:
         if getattr(self, "_h", None):
             lib().orc_world_free(self._h)
             self._h = None
+
+    def with_volumes(self, regions) -> "World":
+        self._volumes = list(regions)
+        recs = volume_records(self._volumes)
+        if lib().orc_world_set_volumes(self._h, _p(recs) if len(recs) else None, len(recs)):
+            raise ValueError("bad volume regions")
+        return self
 
     def count(self) -> int:
         return self.scene.geometry_count()
@@ -572,3 +603,79 @@ class EnvironmentMap:
         out = np.zeros(8, np.float32)
         lib().orc_env_call(None, 4, _p(a), _p(out))
         return out[:3].copy()
+
+
+class Rng:
+    """The walk stream (`openqmc::pcg::Rng` in the reference; shade/volume.h's PCG here)."""
+
+    def __init__(self, seed: int):
+        self.state = C.c_uint32(lib().orc_rng_new(seed & 0xFFFFFFFF))
+
+    def next_f32(self) -> float:
+        return float(lib().orc_rng_next(C.byref(self.state)))
+
+
+class Volumes:
+    """`Volumes::new(regions)` (volume.rs:364-384) over shade/volume.h, for the unit tests of volume.rs."""
+
+    def __init__(self, regions):
+        self._regions = list(regions)
+        recs = volume_records(self._regions)
+        self._h = C.c_void_p(lib().orc_volumes_new(_p(recs) if len(recs) else None, len(recs)))
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().orc_volumes_free(self._h)
+            self._h = None
+
+    def __len__(self):
+        return len(self._regions)
+
+    def region(self, i: int) -> dict:
+        o = np.zeros(15, np.float32)
+        lib().orc_volumes_region_info(self._h, i, _p(o))
+        return dict(sigma_s=o[0:3].copy(), sigma_a=o[3:6].copy(), g=float(o[6]), majorant=float(o[7]), aabb_min=o[8:11].copy(),
+                    aabb_max=o[11:14].copy(), homogeneous=bool(o[14]))
+
+    def transmittance(self, origin, direction, t_eps: float, t_max: float, rng: Rng, n: int = 1) -> np.ndarray:
+        out = np.zeros((n, 3), np.float32)
+        lib().orc_volumes_transmittance_n(self._h, _p(_f3(origin)), _p(_f3(direction)), t_eps, t_max, C.byref(rng.state), n, _p(out))
+        return out if n > 1 else out[0]
+
+    def sample_interaction(self, origin, direction, t_eps: float, t_max: float, rng: Rng, n: int = 1) -> np.ndarray:
+        """Rows: scatter, t, p[3], weight-or-transmittance[3], emitted[3], n_lobes, (w, g) x 2."""
+        out = np.zeros((n, 16), np.float32)
+        lib().orc_volumes_sample_n(self._h, _p(_f3(origin)), _p(_f3(direction)), t_eps, t_max, C.byref(rng.state), n, _p(out))
+        return out
+
+    def field_density(self, i: int, u) -> float:
+        return float(lib().orc_volumes_field_density(self._h, i, _p(_f3(u))))
+
+    def density(self, i: int, p_world) -> float:
+        return float(lib().orc_volumes_density(self._h, i, _p(_f3(p_world))))
+
+    def intersect(self, i: int, origin, direction):
+        out = np.zeros(2, np.float32)
+        if not lib().orc_volumes_intersect(self._h, i, _p(_f3(origin)), _p(_f3(direction)), _p(out)):
+            return None
+        return float(out[0]), float(out[1])
+
+
+def vol_hash3(x: int, y: int, z: int, seed: int) -> float:
+    return float(lib().orc_vol_hash3(x, y, z, seed))
+
+
+def hg_phase(cos_theta: float, g: float) -> float:
+    return float(lib().orc_hg_phase(cos_theta, g))
+
+
+def phase_single_pdf(g: float, cos_theta: float) -> float:
+    return float(lib().orc_phase_single_pdf(g, cos_theta))
+
+
+def mat4_inverse(m) -> np.ndarray:
+    """glam Mat4::inverse on a 4x4 (column-vector convention)."""
+    a = np.ascontiguousarray(np.asarray(m, np.float32).reshape(4, 4).T.reshape(16))
+    out = np.zeros(16, np.float32)
+    lib().orc_mat4_inverse(_p(a), _p(out))
+    return out.reshape(4, 4).T.copy()

@@ -122,6 +122,49 @@ def test_dome_light_with_environment_map_and_distant_light(gpu, orc):
     assert sg.shadow_rays == sg.vertices and sg.ended_escaped > 0
 
 
+# ---- volume regions: shade_kernel<VOL> / nee_resolve_kernel<VOL> against the oracle ----------------
+@pytest.mark.parametrize("kind", ["absorb", "emit", "furnace", "furnace_grid", "furnace_noise"])
+def test_volume_slab_probes(gpu, orc, kind):
+    fg, sg, fo, so, _ = both(gpu, orc, scenes.volume_slab, kind=kind, spp=16)
+    compare(fg, fo)
+    stats_close(sg, so)
+    if kind.startswith("furnace"):
+        assert abs(float(fg[..., :3].mean()) - 1.0) < 0.01  # the analytic answer, on the GPU itself
+    assert gpu.device_status() == 0
+
+
+def test_fog_sample_scene(gpu, orc):
+    """samples/fog.usda: homogeneous fog, volume NEE through the analytic transmittance fast path, adaptive rounds."""
+    fg, sg, fo, so, rg = both(gpu, orc, scenes.fog, variance_threshold=0.0, samples_per_pixel=32)
+    compare(fg, fo)
+    stats_close(sg, so)
+    fg, sg, fo, so, rg = both(gpu, orc, scenes.fog)  # as authored: adaptive
+    same = fg[..., 3] == fo[..., 3]
+    assert same.mean() >= 0.998 and rg.rounds > 1
+    compare(fg[same], fo[same])
+    stats_close(sg, so, tol=4e-3, adaptive=True)
+
+
+def test_smoke_sample_scene(gpu, orc):
+    """samples/smoke.usda: fBm smoke (delta + ratio tracking), an emissive ember, a voxel grid, overlapping majorants."""
+    fg, sg, fo, so, _ = both(gpu, orc, scenes.smoke, variance_threshold=0.0, samples_per_pixel=16)
+    compare(fg, fo)
+    stats_close(sg, so)
+
+
+def test_volumes_can_be_replaced_and_cleared(gpu, orc):
+    wg, cam, st = scenes.volume_slab(gpu, "furnace", spp=4)
+    a, _ = gpu.Renderer(cam, wg, st).render_with_stats()
+    wg.with_volumes([])
+    b, sb = gpu.Renderer(cam, wg, st).render_with_stats()
+    assert np.all(b[..., :3] == 1.0) and sb.vertices == 0  # the bare dome
+    wg.with_volumes(scenes.volume_slab(orc, "furnace", spp=4)[0].volumes)
+    c, _ = gpu.Renderer(cam, wg, st).render_with_stats()
+    assert a.tobytes() == c.tobytes()
+    with pytest.raises(gpu.CrtError):
+        wg.with_volumes(scenes.volume_slab(orc, "furnace", spp=4)[0].volumes * 17)  # CRT_MAX_VOLUMES
+
+
 def test_synthetic_instanced_city(gpu, orc):
     """The scalable stand-in generator (any instance count) used for instancing stress runs."""
     fn = lambda api, **kw: scenes.point_instanced_city(api, **kw)  # noqa: E731

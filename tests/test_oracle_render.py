@@ -147,3 +147,49 @@ def test_two_process_render_over_gloo_matches_single_process(orc, tmp_path):
     assert np.load(out).tobytes() == full.tobytes()
     line = [l for l in res.stdout.splitlines() if l.startswith("STATS")][0].split()
     assert [int(v) for v in line[1:]] == [sf.camera_rays, sf.closest_hit, sf.shadow_rays]
+
+
+# ---- volume regions (volume.rs, tracer.rs:1016-1077, 1166-1249): analytic probes of the oracle integrator ----------
+def _slab_mean(orc, kind, **kw):
+    w, c, s = scenes.volume_slab(orc, kind, **kw)
+    fb, st = orc.Renderer(c, w, s).render_with_stats()
+    return fb[..., :3].reshape(-1, 3).astype(np.float64).mean(axis=0), st
+
+
+def test_absorbing_slab_is_beer_lambert(orc):
+    mean, st = _slab_mean(orc, "absorb")
+    assert np.abs(mean - np.exp(-0.7)).max() < 0.008  # 65 536 Bernoulli(e^-0.7) samples: sigma = 0.002
+    assert st.vertices == 0 and st.shadow_rays == 0 and st.ended_escaped == st.camera_rays
+
+
+def test_emissive_slab_matches_the_analytic_source_term(orc):
+    mean, _ = _slab_mean(orc, "emit")
+    expect = np.array([4.0, 1.5, 0.3]) * (1.0 - np.exp(-0.7)) + np.exp(-0.7)
+    assert np.abs(mean / expect - 1.0).max() < 0.02
+
+
+@pytest.mark.parametrize("kind", ["furnace", "furnace_grid", "furnace_noise"])
+@pytest.mark.parametrize("strategy", [SamplingStrategy.PowerMis, SamplingStrategy.BalanceMis, SamplingStrategy.BsdfOnly])
+def test_white_furnace_in_a_scattering_volume(orc, kind, strategy):
+    """Albedo-1 medium under a uniform dome: volume NEE (phase value as the bsdf, tracer.rs:1040-1077) and the
+    phase-sampled escapes (PrevVertex::Phase in escaped_emission, :995) must sum to exactly the dome radiance."""
+    mean, st = _slab_mean(orc, kind, spp=16, sampling_strategy=strategy)
+    assert np.abs(mean - 1.0).max() < 0.01, mean
+    assert st.vertices > 0 and (st.shadow_rays == 0) == (strategy == SamplingStrategy.BsdfOnly)
+
+
+def test_fog_scene_renders_and_fog_dims_the_room(orc):
+    w, c, s = scenes.fog(orc, width=64, height=36, samples_per_pixel=16, variance_threshold=0.0)
+    fb, st = orc.Renderer(c, w, s).render_with_stats()
+    clear = scenes.fog(orc, width=64, height=36, samples_per_pixel=16, variance_threshold=0.0)[0].with_volumes([])
+    fc, sc = orc.Renderer(c, clear, s).render_with_stats()
+    assert np.isfinite(fb).all() and st.vertices > sc.vertices  # scatter vertices inside the fog add to the surface ones
+    # in-scattering brightens the dark open front of the room, extinction dims the lit back wall
+    assert fb[..., :3].mean() > 0.0 and abs(fb[..., :3].mean() / fc[..., :3].mean() - 1.0) > 0.02
+
+
+def test_smoke_scene_renders_deterministically(orc):
+    w, c, s = scenes.smoke(orc, width=48, height=27, samples_per_pixel=8, variance_threshold=0.0)
+    a, sa = orc.Renderer(c, w, s).render_with_stats(threads=1)
+    b, sb = orc.Renderer(c, w, s).render_with_stats(threads=4)
+    assert a.tobytes() == b.tobytes() and sa == sb and np.isfinite(a).all()

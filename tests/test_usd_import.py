@@ -69,6 +69,52 @@ def test_showcase_and_veach_importer_equals_the_transcription(orc):
         assert a.tobytes() == b.tobytes() and sa == sb
 
 
+def test_loads_fog_usda(orc):  # usd_scene.rs:192-224
+    world, _, st = load_scene(orc, sample("fog.usda"))
+    assert world.count() == 3 and len(world._lights) == 1 and len(world.volumes) == 1  # the Fog cube is a region, not geometry
+    vols = orc.Volumes(world.volumes)
+    fog = vols.region(0)
+    assert fog["homogeneous"] and abs(fog["g"] - 0.3) < 1e-6 and np.abs(fog["sigma_s"] - 0.15).max() < 1e-6
+    tr = vols.transmittance((0.0, 2.0, 10.0), (0.0, 0.0, -1.0), 1e-3, 100.0, orc.Rng(1))
+    assert abs(tr[0] - np.exp(-(0.15 + 0.01) * 4.0)) < 1e-4
+    assert (st.width, st.height, st.samples_per_pixel, st.max_depth, st.min_samples_per_pixel) == (320, 180, 64, 16, 16)
+
+
+def test_loads_smoke_usda(orc):  # usd_scene.rs:226-274
+    world, _, _ = load_scene(orc, sample("smoke.usda"))
+    assert world.count() == 2 and len(world._lights) == 1 and len(world.volumes) == 3
+    vols = orc.Volumes(world.volumes)
+    info = [vols.region(i) for i in range(3)]
+    smoke = next(i for i, v in enumerate(info) if not v["homogeneous"] and abs(v["g"] - 0.2) < 1e-6)
+    assert abs(info[smoke]["sigma_s"][0] - 9.6) < 1e-4  # densityScale folded in: 0.8 * 12
+    ember = next(i for i, v in enumerate(world.volumes) if max(v.rec["emission"]) > 0.0)
+    assert info[ember]["homogeneous"]
+    grid = next(i for i, v in enumerate(info) if not v["homogeneous"] and abs(v["g"]) < 1e-6)
+    assert vols.density(grid, (1.1, 2.6, -0.8)) > 0.3
+    assert vols.density(grid, (1.1 + 0.49, 2.6 + 0.49, -0.8 + 0.49)) < 1e-3
+
+
+def test_fog_and_smoke_importer_equals_the_transcription(orc):
+    for name, fn in (("fog.usda", scenes.fog), ("smoke.usda", scenes.smoke)):
+        wi, ci, si = load_scene(orc, sample(name))
+        wt, ct, st = fn(orc)
+        assert ci.record().tobytes() == ct.record().tobytes() and si.record().tobytes() == st.record().tobytes()
+        assert wi._lights.tobytes() == wt._lights.tobytes() and len(wi.volumes) == len(wt.volumes)
+        for a, b in zip(wi.volumes, wt.volumes):
+            ra, rb = a.rec.copy(), b.rec.copy()
+            ra["grid_data"] = rb["grid_data"] = 0  # addresses differ; the voxels are compared below
+            assert ra.tobytes() == rb.tobytes()
+            if a.field.kind == 2:
+                assert a.field.params["data"].tobytes() == b.field.params["data"].tobytes()
+        small = dict(width=48, height=27, samples_per_pixel=4, variance_threshold=0.0)
+        for k, v in small.items():
+            setattr(si, k, v)
+            setattr(st, k, v)
+        a, sa = orc.Renderer(ci, wi, si).render_with_stats()
+        b, sb = orc.Renderer(ct, wt, st).render_with_stats()
+        assert a.tobytes() == b.tobytes() and sa == sb
+
+
 def test_loads_veach_mis_and_rectlight_usda(orc):  # usd_scene.rs:106-156
     world, cam, st = load_scene(orc, sample("veach_mis.usda"))
     assert world.count() == 10 and len(world._lights) == 4 and (st.width, st.height) == (960, 540)
