@@ -45,6 +45,7 @@ class World:
 
     def __init__(self, scene: "rt.Scene", materials: np.ndarray, geom_material: np.ndarray, lights: LightList):
         self.scene = scene
+        self.materials, self.geom_material = materials, geom_material  # the geom_id-indexed table (rt_world.rs:142-160)
         self._lights = lights.records()
         h = C.c_void_p()
         rt._ck(rt.lib().crt_world_new(scene._h, _p(materials), len(materials), _p(geom_material), len(geom_material), _p(self._lights),

@@ -395,6 +395,20 @@ def smoke(api, **settings_kw):
     return import_stage(api, _grey_room_stage(vols), "smoke.usda", **settings_kw)
 
 
+def sample_stage(api, name: str, **settings_kw):
+    """samples/{instancing,nested_instancing,curves}.usda from their parsed-stage fixtures (tests/golden/*.stage.json,
+    made by tests/golden/make_stage_fixtures.py), through the importer: native instancing of class prototypes, a
+    PointInstancer nested inside a prototype, BasisCurves (linear + cubic bezier)."""
+    import json
+
+    from .usd.importer import import_stage
+    from .usd.usda import stage_from_json
+
+    with open(os.path.join(GOLDEN, name + ".stage.json")) as f:
+        stage = stage_from_json(json.load(f))
+    return import_stage(api, stage, os.path.join(GOLDEN, name + ".usda"), **settings_kw)
+
+
 def volume_slab(api, kind: str = "absorb", width: int = 32, height: int = 32, spp: int = 64, max_depth: int = 64, **settings_kw):
     """Analytic probes of the volume integrator: a wide 1-unit-thick slab facing a 1-degree camera under a uniform
     dome of radiance 1 (no geometry). `absorb`: gray sigma_a = 0.7 => pixel = e^-0.7. `emit`: the same slab emitting

@@ -16,10 +16,17 @@ What is reproduced, with the reference lines it follows:
   * materials: `crust:openpbr` decoded 1:1 (:2902-2975), `UsdPreviewSurface` mapped (:2661-2705),
     unbound => default grey OpenPBR; RenderSettings and the crust:* attributes (:3015-3100).
   * PointInstancer (:1674-1875): T * R * S placements, one Instance per prototype part, `invisibleIds`;
-    binary crate files through usdc.py;
+    binary crate files through usdc.py; a PointInstancer inside a prototype nests as sub-scenes instead of flattening
+    (`nested_instancer_parts`, :1549-1614);
+  * native instancing (:166-188, 1616-1635): an `instanceable` prim with an internal reference / inherit / specialize
+    arc places the shared prototype's parts and its own subtree is never walked; a native instance nested inside a
+    prototype is skipped exactly like the reference has to (:1418-1440);
+  * BasisCurves (:1936-2172): linear -> round cone segments, cubic bezier / bspline / catmullRom -> one Bezier-form span
+    per authored span, widths by vertex / curve / constant, as one Instance over its own committed scene;
   * volumes: a prim carrying `crust:volume:type` (homogeneous | smoke | grid) imports as a VolumeRegion only, never
     as geometry (:190-209, 427-503).
-Not reproduced yet: native instancing, nested instancers, BasisCurves, Ptex, references/payloads/variants.
+Not reproduced: Ptex, external-file references / payloads / variants (the stage is not composed: arcs resolve only to prims
+of the same layer, which covers every bundled sample).
 """
 from __future__ import annotations
 
@@ -44,13 +51,77 @@ from ..render_types import (
     SphereLight,
     VolumeRegion,
 )
-from ..rt_types import MASK_ALL, MASK_CAMERA, MASK_INDIRECT, MASK_SHADOW, Affine3A, Geometry
+from ..rt_types import MASK_ALL, MASK_CAMERA, MASK_INDIRECT, MASK_SHADOW, Affine3A, CubicCurveSegment, CurveSegment, Geometry
 from . import usda
 
 F = np.float32
 # usd_import.rs:46-52
 DEFAULTS = dict(width=640, height=360, spp=128, max_depth=32, min_spp=32, variance=0.05, frame=0)
 MIN_STREAM_CHUNKS = 4
+MAX_INSTANCE_NESTING = 8  # usd_import.rs:1277
+
+# cubic basis matrices, row-major [t^3 t^2 t 1] . M . [P0 P1 P2 P3]^T (:1912-1931)
+_BASES = {
+    "bezier": (np.asarray([[-1, 3, -3, 1], [3, -6, 3, 0], [-3, 3, 0, 0], [1, 0, 0, 0]], np.float32), 3),
+    "bspline": (np.asarray([[-1 / 6, 3 / 6, -3 / 6, 1 / 6], [3 / 6, -6 / 6, 3 / 6, 0], [-3 / 6, 0, 3 / 6, 0], [1 / 6, 4 / 6, 1 / 6, 0]], np.float32), 1),
+    "catmullRom": (np.asarray([[-0.5, 1.5, -1.5, 0.5], [1.0, -2.5, 2.0, -0.5], [-0.5, 0.0, 0.5, 0.0], [0.0, 1.0, 0.0, 0.0]], np.float32), 1),
+}
+
+
+def basis_to_bezier(m, cp):
+    """:1962-1977 — the Bernstein control points tracing the same cubic (f32, the reference's summation order)."""
+    cp = np.asarray(cp, np.float32)
+
+    def coeff(row):
+        acc = np.zeros(3, np.float32)
+        for c in range(4):
+            acc = acc + cp[c] * m[row][c]
+        return acc
+    a, b, c, d = coeff(0), coeff(1), coeff(2), coeff(3)
+    third = np.float32(3.0)
+    return np.stack([d, d + c / third, d + c * np.float32(2.0 / 3.0) + b / third, a + b + c + d]).astype(np.float32)
+
+
+def curve_segments(prim):
+    """:1993-2131 — (round segments, cubic spans) of a BasisCurves prim, or None."""
+    pts, counts = prim.attr("points"), prim.attr("curveVertexCounts")
+    if pts is None or counts is None:
+        return None
+    pts = np.asarray(pts, np.float64).reshape(-1, 3).astype(np.float32)
+    counts = [int(c) for c in np.asarray(counts).ravel()]
+    widths = prim.attr("widths")
+    widths = [1.0] if widths is None or len(widths) == 0 else [float(np.float32(w)) for w in np.asarray(widths, np.float64).ravel()]
+    ty = prim.attr("type") if isinstance(prim.attr("type"), str) else "cubic"
+    basis_name = prim.attr("basis") if isinstance(prim.attr("basis"), str) else "bezier"
+    if basis_name not in _BASES:
+        return None
+    basis, vstep = _BASES[basis_name]
+    n_points, n_curves = len(pts), len(counts)
+
+    def width_of(global_idx, curve_idx):
+        if len(widths) == n_points:
+            return widths[global_idx]
+        if len(widths) == n_curves:
+            return widths[curve_idx]
+        return widths[0]
+    segments, cubics = [], []
+    offset = 0
+    for curve_idx, cnt in enumerate(counts):
+        if cnt < 0 or offset + cnt > n_points:
+            break
+        cp = pts[offset:offset + cnt]
+        radius = lambda k: float(np.float32(0.5) * np.float32(max(width_of(offset + k, curve_idx), 1e-6)))  # noqa: E731
+        if ty == "linear":
+            for k in range(max(cnt - 1, 0)):
+                segments.append(CurveSegment(cp[k], cp[k + 1], radius(k), radius(k + 1)))
+        elif cnt >= 4:
+            for sp in range((cnt - 4) // vstep + 1):
+                base = sp * vstep
+                cubics.append(CubicCurveSegment(basis_to_bezier(basis, cp[base:base + 4]), radius(base), radius(base + 3)))
+        offset += cnt
+    if not segments and not cubics:
+        return None
+    return segments, cubics
 
 
 # ---- f32 4x4 matrices in glam's column-vector convention ---------------------------------------
@@ -308,9 +379,14 @@ class _Import:
             prim, parent_world = stack.pop()
             if prim.is_abstract() or not prim.is_active():
                 continue
-            local, resets = local_matrix(prim)
+            local, resets = self.local_matrix_at(prim)
             world = local if resets else _mul(parent_world, local)
-            t = prim.type
+            t = self.type_of(prim)
+            if self.is_instance(prim):  # native instancing (:166-188): place the prototype, never walk the proxy subtree
+                proto = self.prototype_of(prim)
+                if proto is not None:
+                    self.attach_proto_parts(self.prototype_parts(proto, 0), world)
+                    continue
             if t == "PointInstancer":
                 self.emit_point_instancer(prim, world)
                 continue  # prototypes are drawn through the instancer, never on their own (:197-208)
@@ -320,6 +396,8 @@ class _Import:
                 self.emit_mesh(prim, world)
             elif t == "Sphere":
                 self.emit_sphere(prim, world)
+            elif t == "BasisCurves":
+                self.emit_curves(prim, world)
             elif t == "Camera":
                 if self.camera is None:
                     self.camera = build_camera(prim, world, self.settings)
@@ -380,27 +458,78 @@ class _Import:
                     end = _affine(_mul(_translate(p["motion"]), l2w))
                 self.wb.set_geometry(p["geom_id"], Geometry.Instance(slot["scene"], _affine(l2w), end))
 
-    # -- PointInstancer (:1674-1875) ---------------------------------------------------------------
-    def proto_parts(self, root: usda.Prim):
-        """collect_proto_parts (:1379-1540): every mesh / sphere under a prototype root as (BLAS, local matrix,
-        material, mask). Nested instancers and curves inside prototypes are not expanded yet."""
-        key = root.path
+    # -- composition arcs, as far as one layer goes -----------------------------------------------------
+    def arc_target(self, prim):
+        """The prim an internal reference / inherit / specialize arc of `prim` names, or None."""
+        for key in ("references", "inherits", "specializes"):
+            v = prim.metadata.get(key)
+            if v is None:
+                continue
+            for item in (v if isinstance(v, (list, tuple)) else [v]):
+                if isinstance(item, str) and item.strip().startswith("</"):
+                    return self.stage.prim_at(item.strip().strip("<>"))
+        return None
+
+    def is_instance(self, prim) -> bool:  # Prim::is_instance: `instanceable = true` plus a composition arc
+        return str(prim.metadata.get("instanceable", "false")).lower() == "true" and self.arc_target(prim) is not None
+
+    def prototype_of(self, prim):
+        return self.arc_target(prim)
+
+    def type_of(self, prim) -> str:
+        """A typeless `def`/`over` with an arc takes the referenced prim's type (composition)."""
+        if prim.type:
+            return prim.type
+        target = self.arc_target(prim)
+        return target.type if target is not None else prim.type
+
+    def local_matrix_at(self, prim):
+        """The instance's own xformOps are the stronger opinion; without any, the referenced prim's apply."""
+        if prim.attr("xformOpOrder") is None:
+            target = self.arc_target(prim)
+            if target is not None:
+                return local_matrix(target)
+        return local_matrix(prim)
+
+    # -- prototypes (:1379-1700) -----------------------------------------------------------------------
+    def prototype_parts(self, root: usda.Prim, depth: int):  # :1808-1830, memoized by path
         cache = self.__dict__.setdefault("_protos", {})
-        if key in cache:
-            return cache[key]
+        if root.path not in cache:
+            cache[root.path] = self.collect_proto_parts(root, depth)
+        return cache[root.path]
+
+    def curve_scene(self, prim):
+        segs = curve_segments(prim)
+        if segs is None:
+            return None
+        sb = self.api.SceneBuilder()
+        if segs[0]:
+            sb.attach(Geometry.RoundCurves(segs[0]))
+        if segs[1]:
+            sb.attach(Geometry.CubicCurves(segs[1]))
+        return sb.commit()
+
+    def collect_proto_parts(self, root: usda.Prim, depth: int):
+        """:1379-1540 — every leaf geometry under a prototype root as (BLAS, root-relative matrix, material, mask).
+        Abstract prims are NOT skipped here: naming a class as a prototype is how instancing-only geometry is authored."""
         parts = []
+        if depth > MAX_INSTANCE_NESTING:
+            return parts
         stack = [(root, _ident())]
         while stack:
             prim, parent_local = stack.pop()
             if not prim.is_active():
                 continue
             if prim is root:
-                local = _ident()
+                local = _ident()  # the root's own transform is excluded: the instance supplies the placement
             else:
-                m, resets = local_matrix(prim)
+                m, resets = self.local_matrix_at(prim)
                 local = m if resets else _mul(parent_local, m)
             mask = _ray_mask(prim)
-            if prim.type == "Mesh":
+            if prim is not root and self.is_instance(prim):
+                continue  # nested native instance: unreadable with openusd 0.5, skipped with a warning (:1418-1440)
+            t = self.type_of(prim)
+            if t == "Mesh":
                 pts, counts, idx = prim.attr("points"), prim.attr("faceVertexCounts"), prim.attr("faceVertexIndices")
                 if pts is not None and counts is not None and idx is not None:
                     pts = np.asarray(pts, np.float64).reshape(-1, 3).astype(F)
@@ -413,30 +542,74 @@ class _Import:
                         tris = triangulate(counts, idx, len(pts))
                         slot = self.slots[skey] = dict(verts=pts, tris=tris, n_place=0, scene=None) if len(tris) else None
                     if slot is not None:
-                        if slot["scene"] is None:
+                        if slot["scene"] is None:  # committing also marks the slot ineligible for baking (:1446-1449)
                             sb = self.api.SceneBuilder()
                             sb.attach(Geometry.TriangleMesh(slot["verts"], slot["tris"]))
                             slot["scene"] = sb.commit()
                         parts.append((slot["scene"], local, mat, mask))
-            elif prim.type == "Sphere":
+            elif t == "Sphere":
                 r = prim.attr("radius")
                 sb = self.api.SceneBuilder()
                 sb.attach(Geometry.Sphere((0.0, 0.0, 0.0), 1.0 if r is None else float(F(r))))
                 parts.append((sb.commit(), local, self.materials.resolve(prim)[1], mask))
-            elif prim.type == "PointInstancer" and prim is not root:
-                continue
+            elif t == "BasisCurves":
+                scene = self.curve_scene(prim)
+                if scene is not None:
+                    parts.append((scene, local, self.materials.resolve(prim)[1], mask))
+            elif isinstance(prim.attr("crust:volume:type"), str):
+                pass  # volumes cannot be instanced (:1497-1506)
+            elif t == "PointInstancer":
+                parts.extend(self.nested_instancer_parts(prim, local, mask, depth + 1))
+                continue  # its prototypes are reached through it, never drawn directly
             for c in prim.children:
                 stack.append((c, local))
-        cache[key] = parts
         return parts
 
-    def emit_point_instancer(self, prim, world):
-        """read_instancer + emit_point_instancer (:1674-1875): placement = world * (T * R * S), one Instance per
-        prototype part; `orientationsf` wins over `orientations`; `invisibleIds` hides instances by id."""
+    def nested_instancer_parts(self, prim, local, mask, depth):
+        """:1549-1614 — one part per (prototype, part) of the nested instancer: a sub-scene holding that part once per
+        nested placement, so nesting nests instead of multiplying the outer instance count."""
+        layout = self.read_instancer(prim)
+        if layout is None:
+            return []
+        targets, placements = layout
+        out = []
+        for k, target in enumerate(targets):
+            for scene, part_local, mat, part_mask in (self.prototype_parts(target, depth) if target is not None else []):
+                sub = self.api.SceneBuilder()
+                placed = 0
+                for kk, xf in placements:
+                    if kk != k:
+                        continue
+                    placement = _mul(xf, part_local)
+                    if abs(float(np.linalg.det(placement.astype(np.float64)))) < 1e-12:
+                        continue
+                    sub.attach_masked(Geometry.Instance(scene, _affine(placement)), part_mask)
+                    placed += 1
+                if placed:
+                    out.append((sub.commit(), local, mat, mask))
+        return out
+
+    def attach_proto_parts(self, parts, placement) -> int:  # :1637-1671
+        attached = 0
+        for scene, local, mat, mask in parts:
+            xf = _mul(placement, local)
+            if abs(float(np.linalg.det(xf.astype(np.float64)))) < 1e-12:
+                continue
+            self.wb.attach_masked(Geometry.Instance(scene, _affine(xf)), mat, mask)
+            attached += 1
+        return attached
+
+    # -- PointInstancer (:1674-1875) ---------------------------------------------------------------
+    def proto_parts(self, root: usda.Prim):
+        return self.prototype_parts(root, 0)
+
+    def read_instancer(self, prim):
+        """:1702-1792 — (prototype root prims, [(target index, T * R * S)]) with `invisibleIds` already dropped;
+        `orientationsf` wins over `orientations`."""
         targets = prim.relationships.get("prototypes") or []
         proto_idx = prim.attr("protoIndices")
         if not targets or proto_idx is None:
-            return
+            return None
         proto_idx = np.asarray(proto_idx).astype(np.int64).ravel()
         positions = prim.attr("positions")
         positions = np.zeros((0, 3), F) if positions is None else np.asarray(positions, np.float64).reshape(-1, 3).astype(F)
@@ -448,10 +621,7 @@ class _Import:
         orient = None if orient is None or len(orient) == 0 else np.asarray(orient, np.float32).reshape(-1, 4)  # (w, x, y, z)
         ids = prim.attr("ids")
         invisible = set(int(v) for v in (prim.attr("invisibleIds") if prim.attr("invisibleIds") is not None else []))
-        protos = []
-        for t in targets:
-            root = self.stage.prim_at(t)
-            protos.append(self.proto_parts(root) if root is not None else [])
+        placements = []
         for i, k in enumerate(proto_idx):
             if i >= len(positions):
                 break
@@ -465,12 +635,23 @@ class _Import:
                 m = _mul(m, _quat(*orient[i]))
             if scales is not None and i < len(scales):
                 m = _mul(m, _scale(scales[i]))
-            placement = _mul(world, m)
-            for scene, local, mat, mask in protos[int(k)]:
-                xf = _mul(placement, local)
-                if abs(float(np.linalg.det(xf.astype(np.float64)))) < 1e-12:
-                    continue
-                self.wb.attach_masked(Geometry.Instance(scene, _affine(xf)), mat, mask)
+            placements.append((int(k), m))
+        return [self.stage.prim_at(t) for t in targets], placements
+
+    def emit_point_instancer(self, prim, world):  # :1832-1875
+        layout = self.read_instancer(prim)
+        if layout is None:
+            return
+        targets, placements = layout
+        protos = [self.prototype_parts(root, 0) if root is not None else [] for root in targets]
+        for k, xf in placements:
+            self.attach_proto_parts(protos[k], _mul(world, xf))
+
+    def emit_curves(self, prim, world):  # :2133-2168
+        scene = self.curve_scene(prim)
+        if scene is None or abs(float(np.linalg.det(world.astype(np.float64)))) < 1e-12:
+            return
+        self.wb.attach_masked(Geometry.Instance(scene, _affine(world)), self.materials.resolve(prim)[1], _ray_mask(prim))
 
     def emit_volume(self, prim, world):  # :435-503
         ty = prim.attr("crust:volume:type")

@@ -89,6 +89,52 @@ class Stage:
             yield from r.walk()
 
 
+# ---- a parsed stage as JSON (tests/golden/*.stage.json: what the GPU box imports, where the sample files are absent) ----
+def _enc(v):
+    if isinstance(v, np.ndarray):
+        return {"__nd__": str(v.dtype), "shape": list(v.shape), "data": v.ravel().tolist()}
+    if isinstance(v, np.generic):
+        return v.item()
+    if isinstance(v, tuple):
+        return {"__t__": [_enc(x) for x in v]}
+    if isinstance(v, list):
+        return [_enc(x) for x in v]
+    if isinstance(v, dict):
+        return {"__d__": [[_enc(k), _enc(x)] for k, x in v.items()]}
+    return v
+
+
+def _dec(v):
+    if isinstance(v, dict):
+        if "__nd__" in v:
+            return np.asarray(v["data"], dtype=v["__nd__"]).reshape(v["shape"])
+        if "__t__" in v:
+            return tuple(_dec(x) for x in v["__t__"])
+        return {_dec(k): _dec(x) for k, x in v["__d__"]}
+    if isinstance(v, list):
+        return [_dec(x) for x in v]
+    return v
+
+
+def stage_to_json(stage: Stage) -> dict:
+    def prim(p: Prim):
+        return {"specifier": p.specifier, "type": p.type, "name": p.name, "metadata": _enc(p.metadata),
+                "attributes": [[a.name, a.type, _enc(a.value), a.custom, a.uniform, _enc(a.time_samples), _enc(a.metadata)] for a in p.attributes.values()],
+                "relationships": _enc(p.relationships), "children": [prim(c) for c in p.children]}
+    return {"metadata": _enc(stage.metadata), "roots": [prim(r) for r in stage.roots]}
+
+
+def stage_from_json(doc: dict) -> Stage:
+    def prim(d, parent):
+        p = Prim(d["specifier"], d["type"], d["name"], (parent.path if parent else "") + "/" + d["name"], metadata=_dec(d["metadata"]), parent=parent)
+        for name, ty, value, custom, uniform, ts, meta in d["attributes"]:
+            p.attributes[name] = Attribute(name, ty, _dec(value), custom, uniform, _dec(ts), _dec(meta))
+        p.relationships = _dec(d["relationships"])
+        p.children = [prim(c, p) for c in d["children"]]
+        return p
+    return Stage(_dec(doc["metadata"]), [prim(r, None) for r in doc["roots"]])
+
+
 _TOKEN = re.compile(r'''
     (?P<ws>\s+|\#[^\n]*)                         |
     (?P<str3>"""(?:.|\n)*?"""|\'\'\'(?:.|\n)*?\'\'\') |

@@ -389,6 +389,7 @@ from crust_render_b200.render_types import (  # noqa: E402  value types only
 class World:
     def __init__(self, scene: "Scene", materials: np.ndarray, geom_material: np.ndarray, lights: LightList):
         self.scene = scene
+        self.materials, self.geom_material = materials, geom_material  # the geom_id-indexed table (rt_world.rs:142-160)
         self._lights = lights.records()
         self._h = C.c_void_p(lib().orc_world_new(scene._h, _p(materials), len(materials), _p(geom_material), len(geom_material),
                                                  _p(self._lights), len(self._lights)))

@@ -165,6 +165,16 @@ def test_volumes_can_be_replaced_and_cleared(gpu, orc):
         wg.with_volumes(scenes.volume_slab(orc, "furnace", spp=4)[0].volumes * 17)  # CRT_MAX_VOLUMES
 
 
+@pytest.mark.parametrize("name", ["instancing", "nested_instancing", "curves"])
+def test_instancing_and_curve_samples(gpu, orc, name):
+    """samples/instancing.usda (native instances of a two-material class prototype + a PointInstancer), nested_instancing.usda
+    (three-level descent: instancer -> nested instancer sub-scene -> leaf BLAS) and curves.usda (round cones + cubic Bezier spans)."""
+    fg, sg, fo, so, _ = both(gpu, orc, scenes.sample_stage, name=name, width=160, height=90, samples_per_pixel=16, variance_threshold=0.0)
+    compare(fg, fo)
+    stats_close(sg, so)
+    assert gpu.device_status() == 0
+
+
 def test_synthetic_instanced_city(gpu, orc):
     """The scalable stand-in generator (any instance count) used for instancing stress runs."""
     fn = lambda api, **kw: scenes.point_instanced_city(api, **kw)  # noqa: E731

@@ -115,6 +115,120 @@ def test_fog_and_smoke_importer_equals_the_transcription(orc):
         assert a.tobytes() == b.tobytes() and sa == sb
 
 
+def _shoot(world, origin, direction=(0.0, 0.0, -1.0), t_max=np.inf):
+    return world.scene.intersect(Ray(origin, direction), 0.001, t_max)
+
+
+def test_loads_curves_usda(orc):  # usd_scene.rs:326-365
+    world, _, st = load_scene(orc, sample("curves.usda"))
+    assert world.count() == 4  # 2 curve batches, floor, rect-light mesh
+    hit = _shoot(world, (1.6, 0.4, 5.0))
+    assert hit is not None and abs(hit.t - 5.4) < 0.1  # the linear Tripod strand's first segment, after the prim's translate
+    assert _shoot(world, (2.6, 0.4, 5.0), t_max=4.0) is None
+    up = np.asarray((2.6, 3.0, -8.0), np.float32) - np.asarray((2.6, 0.4, 5.0), np.float32)
+    assert _shoot(world, (2.6, 0.4, 5.0), up / np.linalg.norm(up)) is None
+    pb = world.scene.unique_primitive_breakdown()
+    assert pb.curve_segments == 3 and pb.cubic_curve_spans == 3  # 3 linear segments; one bezier span per 4-point strand
+    assert (st.width, st.height, st.samples_per_pixel, st.max_depth) == (64, 64, 8, 4)
+
+
+def test_basis_to_bezier(orc):  # usd_import.rs tests: bezier is the identity; bspline / catmullRom trace the same curve
+    from crust_render_b200.usd.importer import _BASES, basis_to_bezier
+    rng = np.random.default_rng(2)
+    cp = rng.normal(size=(4, 3)).astype(np.float32)
+    assert np.abs(basis_to_bezier(_BASES["bezier"][0], cp) - cp).max() < 1e-5
+    for name in ("bspline", "catmullRom"):
+        m = _BASES[name][0].astype(np.float64)
+        bz = basis_to_bezier(_BASES[name][0], cp).astype(np.float64)
+        for t in np.linspace(0, 1, 9):
+            direct = (np.array([t ** 3, t ** 2, t, 1.0]) @ m) @ cp.astype(np.float64)
+            bern = (1 - t) ** 3 * bz[0] + 3 * t * (1 - t) ** 2 * bz[1] + 3 * t * t * (1 - t) * bz[2] + t ** 3 * bz[3]
+            assert np.abs(direct - bern).max() < 1e-5
+    # catmullRom interpolates its inner control points
+    bz = basis_to_bezier(_BASES["catmullRom"][0], cp)
+    assert np.abs(bz[0] - cp[1]).max() < 1e-6 and np.abs(bz[3] - cp[2]).max() < 1e-6
+
+
+def test_loads_instancing_usda(orc):  # usd_scene.rs:465-588
+    world, _, _ = load_scene(orc, sample("instancing.usda"))
+    assert world.count() == 13  # 5 visible scatter instances + 3 towers x 2 prototype parts + floor + the light
+    assert world.scene.primitive_count() <= 16  # instanced, not baked
+    # the class prototype is never drawn at the origin
+    assert _shoot(world, (0.0, 1.0, 6.0), t_max=20.0) is None
+    at = lambda x, y: _shoot(world, (x, y, 6.0), t_max=20.0)  # noqa: E731
+    block, cap = at(-4.2, 1.0), at(-4.2, 2.2)
+    assert block is not None and cap is not None and block.geom_id != cap.geom_id  # both materials survive
+    assert at(-3.4, 1.0) is None
+    assert at(-0.4, 3.0) is not None and at(-4.2, 3.0) is None  # TowerC's non-uniform scale
+    # invisibleIds: id 13 (x = 5.4) hidden, every other gem stops a ray above the floor
+    def above(x, z):
+        h = world.scene.intersect(Ray((x, 4.0, z), (0.0, -1.0, 0.0)), 0.001, 10.0)
+        return h is not None and h.t < 3.9
+    assert above(1.6, 0.0) and above(2.9, -1.1) and above(4.2, 0.4) and above(2.2, 1.6) and above(3.8, 2.1)
+    assert not above(5.4, -0.6)
+    # materials bound inside the prototype ride the instances: copper block vs emerald cap
+    mats, gm = world_material_table(world)
+    assert mats[gm[block.geom_id]]["base_metalness"] == 1.0 and mats[gm[cap.geom_id]]["base_metalness"] == 0.0
+
+
+def world_material_table(world):
+    return world.materials, world.geom_material
+
+
+def test_loads_nested_instancing_usda(orc):  # usd_scene.rs:591-737
+    world, _, _ = load_scene(orc, sample("nested_instancing.usda"))
+    assert world.count() == 21  # 5 branches x 3 parts + 2 planters x 2 parts + floor + light
+    assert world.scene.primitive_count() <= 24  # nested, not flattened
+    at = lambda x, y: _shoot(world, (x, y, 10.0), t_max=40.0)  # noqa: E731
+    assert at(-5.95, 1.0) is not None and at(-5.95, 2.0) is None  # branch 0's first leaf
+    husk, tip = at(-6.4, 3.0), at(-6.4, 3.3)
+    assert husk is not None and tip is not None and husk.geom_id != tip.geom_id
+    assert at(-3.2, 3.75) is not None and at(-3.2, 4.125) is not None and at(-3.2, 3.3) is None  # outer scale x inner placement
+    for x in (-1.9, 1.9):  # a multi-part prototype placed by native instancing
+        post, orb = at(x, 0.6), at(x, 1.35)
+        assert post is not None and orb is not None and post.geom_id != orb.geom_id
+    assert at(0.0, 0.6) is None  # the class prototype is not drawn
+
+
+def test_nested_native_instance_degrades_gracefully(orc, tmp_path):  # usd_scene.rs:738-812
+    path = tmp_path / "nested_native.usda"
+    path.write_text('''#usda 1.0
+(defaultPrim = "W")
+def Xform "W" {
+    def Camera "c" {}
+    class Xform "_Inner" { def Sphere "s" { double radius = 0.5 } }
+    class Xform "_Outer" {
+        def Sphere "outer" { double radius = 0.4 }
+        def Xform "i" (instanceable = true; references = </W/_Inner>) {
+            double3 xformOp:translate = (3, 0, 0)
+            uniform token[] xformOpOrder = ["xformOp:translate"]
+        }
+    }
+    def Xform "A" (instanceable = true; references = </W/_Outer>) {}
+}
+''')
+    world, _, _ = load_scene(orc, str(path))
+    assert world.count() == 1  # the outer sphere only: the nested native instance is unreadable upstream and skipped
+    hit = lambda x: _shoot(world, (x, 0.0, 10.0), t_max=40.0) is not None  # noqa: E731
+    assert hit(0.0) and not hit(3.0)
+
+
+@pytest.mark.parametrize("name", ["instancing", "nested_instancing", "curves"])
+def test_stage_fixture_is_what_the_reader_parses(orc, name):
+    """tests/golden/<name>.stage.json (what the GPU box imports) against a fresh parse + import of the sample file."""
+    wi, ci, si = load_scene(orc, sample(name + ".usda"))
+    wf, cf, sf = scenes.sample_stage(orc, name)
+    assert ci.record().tobytes() == cf.record().tobytes() and si.record().tobytes() == sf.record().tobytes()
+    assert wi._lights.tobytes() == wf._lights.tobytes() and wi.count() == wf.count()
+    assert wi.materials.tobytes() == wf.materials.tobytes() and wi.geom_material.tobytes() == wf.geom_material.tobytes()
+    for k, v in dict(width=48, height=48, samples_per_pixel=2, variance_threshold=0.0).items():
+        setattr(si, k, v)
+        setattr(sf, k, v)
+    a, sa = orc.Renderer(ci, wi, si).render_with_stats()
+    b, sb = orc.Renderer(cf, wf, sf).render_with_stats()
+    assert a.tobytes() == b.tobytes() and sa == sb
+
+
 def test_loads_veach_mis_and_rectlight_usda(orc):  # usd_scene.rs:106-156
     world, cam, st = load_scene(orc, sample("veach_mis.usda"))
     assert world.count() == 10 and len(world._lights) == 4 and (st.width, st.height) == (960, 540)
