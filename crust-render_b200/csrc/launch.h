@@ -35,7 +35,7 @@ struct TraceParams {
 #endif
 #define CRT_LSTACK (128 - CRT_SSTACK)  // local-memory spill entries per thread
 #ifndef CRT_MINBLOCKS_CLOSEST
-#define CRT_MINBLOCKS_CLOSEST 8  // resident blocks per SM the closest-hit variants are compiled for (64 registers)
+#define CRT_MINBLOCKS_CLOSEST 7  // resident blocks per SM the closest-hit variants are compiled for: 72 registers without spills beat 64 with (measured 6/7/8 on B200, profiles/r01_tune_phase_balance.jsonl)
 #endif
 #ifndef CRT_MINBLOCKS_ANY
 #define CRT_MINBLOCKS_ANY 8
@@ -45,6 +45,25 @@ struct TraceParams {
 #endif
 #ifndef CRT_REFILL
 #define CRT_REFILL 16  // a warp refills its idle lanes when fewer than this many are active
+#endif
+
+// Phase balancing of the while-while loop: a phase ends early once fewer than NUM/DEN of the warp's running lanes are
+// still in it (0 = run every lane to the end of its phase).
+#ifndef CRT_NODE_EXIT_NUM
+#define CRT_NODE_EXIT_NUM 1  // node phase ends once fewer than 1/4 of the running lanes still search (measured 0, 1/8, 3/16, 1/4, 1/2, 3/4)
+#endif
+#ifndef CRT_NODE_EXIT_DEN
+#define CRT_NODE_EXIT_DEN 4
+#endif
+#ifndef CRT_LEAF_EXIT_NUM
+#define CRT_LEAF_EXIT_NUM 0
+#endif
+#ifndef CRT_LEAF_EXIT_DEN
+#define CRT_LEAF_EXIT_DEN 4
+#endif
+
+#ifndef CRT_SADDR
+#define CRT_SADDR 1  // shared-stack accesses through a register-held 32-bit shared address (inline PTX): -56 instructions in the closest-hit kernel
 #endif
 
 // Resident blocks per SM of the kernel variant a scene with `feat` uses.

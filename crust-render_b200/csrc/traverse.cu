@@ -66,9 +66,36 @@ __global__ void __launch_bounds__(CRT_BLOCK, (FEAT & FEAT_INSTANCE) ? CRT_MINBLO
     const float4* best_chain[INST ? CRT_MAX_INSTANCE_DEPTH : 1];
     F3 world_o = f3(0, 0, 0), world_d = f3(0, 0, 0);
 
+#if CRT_SADDR
+    // The thread's column of the shared stack as a 32-bit shared-window address held in a register: without it the
+    // compiler rebuilds the address (CTA window base + tid * 8) from special registers at every push and pop.
+    uint32_t sbase;
+    {
+        uint32_t a = (uint32_t)__cvta_generic_to_shared(&sstack[0][tid]);
+        asm volatile("mov.u32 %0, %1;" : "=r"(sbase) : "r"(a));
+    }
+    constexpr uint32_t kSlotBytes = CRT_BLOCK * sizeof(Entry);
+    auto sst = [&](int slot, Entry e) {
+        if constexpr (ANY_HIT)
+            asm volatile("st.shared.u32 [%0], %1;" ::"r"(sbase + (uint32_t)slot * kSlotBytes), "r"(e) : "memory");
+        else
+            asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(sbase + (uint32_t)slot * kSlotBytes), "r"(e.x), "r"(e.y) : "memory");
+    };
+    auto sld = [&](int slot) -> Entry {
+        Entry e;
+        if constexpr (ANY_HIT)
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(e) : "r"(sbase + (uint32_t)slot * kSlotBytes) : "memory");
+        else
+            asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(e.x), "=r"(e.y) : "r"(sbase + (uint32_t)slot * kSlotBytes) : "memory");
+        return e;
+    };
+#else
+    auto sst = [&](int slot, Entry e) { sstack[slot][tid] = e; };
+    auto sld = [&](int slot) -> Entry { return sstack[slot][tid]; };
+#endif
     auto push = [&](Entry e) {
         if (sp < CRT_SSTACK)
-            sstack[sp][tid] = e;
+            sst(sp, e);
         else if (sp < CRT_SSTACK + CRT_LSTACK)
             lstack[sp - CRT_SSTACK] = e;
         else
@@ -77,7 +104,7 @@ __global__ void __launch_bounds__(CRT_BLOCK, (FEAT & FEAT_INSTANCE) ? CRT_MINBLO
     };
     auto pop = [&]() -> Entry {
         --sp;
-        if (sp < CRT_SSTACK) return sstack[sp][tid];
+        if (sp < CRT_SSTACK) return sld(sp);
         if (sp < CRT_SSTACK + CRT_LSTACK) return lstack[sp - CRT_SSTACK];
         Entry e;
         if constexpr (ANY_HIT) e = 0u; else e = make_uint2(0u, 0x7f800000u);
@@ -232,7 +259,7 @@ __global__ void __launch_bounds__(CRT_BLOCK, (FEAT & FEAT_INSTANCE) ? CRT_MINBLO
                     const bool lf = (Lm >> l) & 1u;
                     const int rank = __popc(B[l] & (lf ? HL : HI));
                     const int slot = base + (lf ? n_int + n_leaf - 1 : n_int - 1) - rank;
-                    if (hit[l]) sstack[slot][tid] = make_entry(cw[l], tn[l]);
+                    if (hit[l]) sst(slot, make_entry(cw[l], tn[l]));
                 }
             } else {
 #pragma unroll
@@ -243,7 +270,7 @@ __global__ void __launch_bounds__(CRT_BLOCK, (FEAT & FEAT_INSTANCE) ? CRT_MINBLO
                     const int slot = base + (lf ? n_int + n_leaf - 1 : n_int - 1) - rank;
                     Entry e2 = make_entry(cw[l], tn[l]);
                     if (slot < CRT_SSTACK)
-                        sstack[slot][tid] = e2;
+                        sst(slot, e2);
                     else if (slot < CRT_SSTACK + CRT_LSTACK)
                         lstack[slot - CRT_SSTACK] = e2;
                     else
@@ -372,6 +399,7 @@ __global__ void __launch_bounds__(CRT_BLOCK, (FEAT & FEAT_INSTANCE) ? CRT_MINBLO
     for (;;) {
         // ---- warp-uniform housekeeping: write finished rays, refill idle lanes ----
         unsigned act = __ballot_sync(0xFFFFFFFFu, state == RUN);
+        [[maybe_unused]] const int n_run = __popc(act);
         if (__popc(act) < CRT_REFILL || exhausted) {
             if (!exhausted || act == 0u) {
                 if (state == DONE) {  // all finished lanes of the warp write their results together
@@ -453,9 +481,20 @@ __global__ void __launch_bounds__(CRT_BLOCK, (FEAT & FEAT_INSTANCE) ? CRT_MINBLO
                     if (__uint_as_float(e.y) > closest) continue;  // see traverse.cuh: same result as visiting
                 }
                 node_visit(child);
+#if CRT_NODE_EXIT_NUM > 0
+                // Phase balancing: when most running lanes already wait with a leaf, the stragglers stop searching and the
+                // warp moves on to the leaf phase (their search resumes in the next round with the lanes that finished a leaf).
+                // A scheduling heuristic only — every lane keeps its own stack and visiting order.
+                if (__popc(__activemask()) * CRT_NODE_EXIT_DEN < n_run * CRT_NODE_EXIT_NUM) break;
+#endif
             }
             // leaf phase
-            while (state == RUN && rec != nullptr) record_test();
+            while (state == RUN && rec != nullptr) {
+                record_test();
+#if CRT_LEAF_EXIT_NUM > 0
+                if (__popc(__activemask()) * CRT_LEAF_EXIT_DEN < n_run * CRT_LEAF_EXIT_NUM) break;
+#endif
+            }
         }
     }
     if (overflow) atomicOr(p.status, 1u);
