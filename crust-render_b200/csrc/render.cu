@@ -581,6 +581,8 @@ struct Scratch {  // grow-only device buffers reused across crt_render calls on 
     unsigned long long* stats = nullptr;
     uint32_t* active_count = nullptr;  // 2 words
     uint32_t* h_pinned = nullptr;      // pinned host mirror for small read-backs
+    void* host_fb = nullptr;           // crt_render_host: the device-side frame
+    size_t cap_host_fb = 0;
     // the static pixel list of the last frame stays on the device: same image size and tile deal => no host work
     uint64_t pixel_key = 0;
     uint32_t pixel_count = 0;
@@ -591,6 +593,7 @@ struct Scratch {  // grow-only device buffers reused across crt_render calls on 
         cudaFree(counts);
         cudaFree(stats);
         cudaFree(active_count);
+        cudaFree(host_fb);
         if (h_pinned) cudaFreeHost(h_pinned);
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
@@ -1175,15 +1178,31 @@ int crt_render_host(const crt_world* w, const crt_camera* camera, const crt_rend
     if (!settings || !framebuffer) return crt::set_error(CRT_ERR_INVALID_ARG, "crt_render_host: null argument");
     int rc = crt::require_device();
     if (rc) return rc;
+    if (!w) return crt::set_error(CRT_ERR_INVALID_ARG, "crt_render_host: null argument");
     size_t bytes = (size_t)settings->width * settings->height * 16;
+    crt_world* W = const_cast<crt_world*>(w);
     float* d = nullptr;
-    CKR(cudaMalloc(&d, bytes ? bytes : 16));
-    cudaError_t e = cudaMemcpy(d, framebuffer, bytes, cudaMemcpyHostToDevice);  // pixels of other ranks stay as given
+    {
+        // the device frame is kept with the world's scratch between calls (a 4K frame is 133 MB: allocating it per call
+        // costs more than copying it)
+        std::lock_guard<std::mutex> lk(W->mu);
+        if (bytes > W->scratch.cap_host_fb) {
+            cudaFree(W->scratch.host_fb);
+            W->scratch.host_fb = nullptr;
+            W->scratch.cap_host_fb = 0;
+            CKR(cudaMalloc(&W->scratch.host_fb, bytes ? bytes : 16));
+            W->scratch.cap_host_fb = bytes;
+        }
+        d = (float*)W->scratch.host_fb;
+    }
+    // Pixels of other ranks stay as given, so a tile split starts from the caller's frame; a whole-frame render overwrites
+    // every pixel and needs no upload.
+    cudaError_t e = cudaSuccess;
+    if (settings->tile_world > 1) e = cudaMemcpy(d, framebuffer, bytes, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) {
-        rc = render_impl(const_cast<crt_world*>(w), camera, settings, d, stats, nullptr, nullptr);
+        rc = render_impl(W, camera, settings, d, stats, nullptr, nullptr);
         if (rc == CRT_OK) e = cudaMemcpy(framebuffer, d, bytes, cudaMemcpyDeviceToHost);
     }
-    cudaFree(d);
     if (e != cudaSuccess) return crt::set_cuda_error(e, "crt_render_host copy");
     return rc;
 }
