@@ -4,7 +4,7 @@
 //   crates/crust-core/src/camera.rs:25-84   (thin-lens camera)
 //   crates/crust-core/src/filter.rs:28-260  (filter importance sampling)
 //   crates/crust-core/src/tracer.rs:62-105,639-661 (SamplingStrategy, RenderSettings)
-// Host + device. Environment-map domes (environment.rs) are a later row.
+// Host + device. Environment maps of dome lights: envmap.h.
 #pragma once
 #include "envmap.h"
 #include "material.h"
