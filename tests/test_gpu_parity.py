@@ -189,3 +189,45 @@ def test_device_pointer_entry_points(gpu, orc):
     assert np.array_equal(d_ff.cpu().numpy(), of)
     assert np.array_equal(d_occ.cpu().numpy(), o.occluded_n(rays, threads=0))
     assert gpu.device_status() == 0
+
+
+def test_full_size_k1_mesh_properties(gpu, orc):
+    """BASELINE's 10 M-triangle stress mesh (K1) at full size: the oracle checks a strided sample, and the
+    whole batch is checked through size-independent properties — bit determinism, invariance under a permutation of the
+    rays (persistent warps fetch rays dynamically, so this exercises the refill / phase-balancing scheduling),
+    hit_any == hit.is_some() (bvh.rs:1583-1607), a finite range equal to the open query's answer, and the hit point lying on
+    the reported triangle's plane."""
+    b_gpu, n_tris = workloads.stress_scene(gpu, grid=32, shards=30000, jitter=True)
+    assert n_tris > 10_000_000
+    p = b_gpu.commit()
+    ext = workloads.scene_extent(p.bounds())
+    n = 1 << 22
+    rays = workloads.ray_batch(n, ext, seed=0xC0FFEE)
+    h, ff = p.intersect_n(rays)
+    h2, ff2 = p.intersect_n(rays)
+    assert h.tobytes() == h2.tobytes() and ff.tobytes() == ff2.tobytes()
+    perm = np.random.default_rng(11).permutation(n)
+    hp, ffp = p.intersect_n(rays[perm])
+    assert hp.tobytes() == h[perm].tobytes() and ffp.tobytes() == ff[perm].tobytes()
+    hit = h["geom_id"] != 0xFFFFFFFF
+    assert 0.2 < hit.mean() < 0.99
+    occ = p.occluded_n(rays)
+    assert np.array_equal(occ.astype(bool), hit)
+    # a range that ends just beyond the found hit finds the same hit; one that ends just short of it finds nothing nearer
+    r2 = rays.copy()
+    r2["tmax"] = np.where(hit, h["t"] * np.float32(1.0 + 1e-6), np.float32(1.0))
+    hb, _ = p.intersect_n(r2)
+    same = hit & (hb["geom_id"] == h["geom_id"]) & (hb["prim_id"] == h["prim_id"]) & (hb["t"] == h["t"])
+    assert same.sum() == hit.sum()
+    r2["tmax"] = np.where(hit, h["t"] * np.float32(1.0 - 1e-5), np.float32(1.0))
+    hc, _ = p.intersect_n(r2)
+    assert not (hc["geom_id"][hit] != 0xFFFFFFFF).any() or (hc["t"][hit][hc["geom_id"][hit] != 0xFFFFFFFF] < h["t"][hit][hc["geom_id"][hit] != 0xFFFFFFFF]).all()
+    assert (hc["geom_id"][hit] != 0xFFFFFFFF).mean() < 1e-3  # closest means closest: (almost) nothing lies in front of it
+    # the oracle on a strided sample of the same batch
+    b_orc, _ = workloads.stress_scene(orc, grid=32, shards=30000, jitter=True)
+    o = b_orc.commit()
+    sub = rays[:: n // (1 << 16)]
+    oh, of = o.intersect_n(sub, threads=0)
+    ph = h[:: n // (1 << 16)]
+    assert ph.tobytes() == oh.tobytes() and np.array_equal(ff[:: n // (1 << 16)], of)
+    assert np.array_equal(occ[:: n // (1 << 16)], o.occluded_n(sub, threads=0))

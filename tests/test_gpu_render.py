@@ -303,3 +303,24 @@ def test_render_argument_errors(gpu):
     bad = rank_settings(st, 3, 2)
     with pytest.raises(gpu.CrtError):
         gpu.Renderer(cam, world, bad).render_with_stats()
+
+
+@pytest.mark.parametrize("name", ["furnace_room", "openpbr_showcase"])
+def test_converged_renders_agree_across_sampler_seeds(gpu, orc, name):
+    """BASELINE: "converged 4096-spp renders must match within 1e-3 relMSE". The sampler's values are unpinned against the
+    reference (openqmc-rs is not vendored), so convergence must not depend on them: the GPU at 4096 spp and seed 0 against
+    the ORACLE at 4096 spp and another seed (independent sample sets; the oracle against itself across these seeds measures
+    2e-4 / 6e-5) — and, at the same seed, the usual tight bound."""
+    fn = getattr(scenes, name)
+    kw = dict(width=48, height=32 if name == "furnace_room" else 27, spp=4096, variance_threshold=0.0)
+    wg, cam, st = fn(gpu, **kw)[:3]
+    fg, _ = gpu.Renderer(cam, wg, st).render_with_stats()
+    wo, _, st_o = fn(orc, **kw)[:3]
+    fo_same, _ = orc.Renderer(cam, wo, st_o).render_with_stats()
+    compare(fg, fo_same)
+    st_o.frame = 7
+    fo, _ = orc.Renderer(cam, wo, st_o).render_with_stats()
+    a, b = fg[..., :3].astype(np.float64), fo[..., :3].astype(np.float64)
+    relmse = float(((a - b) ** 2 / (b ** 2 + 1e-2)).mean())
+    assert relmse <= 1e-3, relmse
+    assert abs(a.mean() / b.mean() - 1.0) < 2e-3
