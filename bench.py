@@ -413,14 +413,17 @@ def main():
         renderer = crt.Renderer(r_cam, r_world, r_st)
         fb = torch.zeros((rh, rw, 4), dtype=torch.float32, device=dev)
         r_launches = 0
-        render_distributed(renderer, dist if world > 1 else None, fb=fb, stream=stream.cuda_stream)  # warm-up
+        # N > 1: peer-memory gather — every rank's film kernel stores its tiles into rank 0's IPC-mapped frame over NVLink
+        # (no frame collective); the RayStats reduce is the only collective in the step
+        r_gather = "peer" if world > 1 else "reduce"
+        render_distributed(renderer, dist if world > 1 else None, fb=fb, stream=stream.cuda_stream, gather=r_gather)  # warm-up
         barrier()
         r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         r_stats = []
         dev_ms = 0.0
         r0.record(stream)
         for _ in range(args.render_steps):
-            _, st_k = render_distributed(renderer, dist if world > 1 else None, fb=fb, stream=stream.cuda_stream)
+            r_frame, st_k = render_distributed(renderer, dist if world > 1 else None, fb=fb, stream=stream.cuda_stream, gather=r_gather)
             r_stats.append(st_k)
             r_launches += renderer.launches
             dev_ms += renderer.device_ms
@@ -430,7 +433,7 @@ def main():
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         r_ms = float(tt.item()) / args.render_steps
-        mean_rgb = [float(v) for v in fb[..., :3].mean(dim=(0, 1)).tolist()] if rank == 0 else None
+        mean_rgb = [float(v) for v in r_frame[..., :3].mean(dim=(0, 1)).tolist()] if rank == 0 else None
         # e2e: the same frame through crt_render_host (host framebuffer: the frame is copied back to host memory every step;
         # a tile split also uploads the caller's frame first, because pixels of other ranks stay as given)
         host_fb = np.empty((rh, rw, 4), dtype=np.float32)
@@ -454,7 +457,7 @@ def main():
             render = {"workload": f"config 5: stress mesh ({r_tris} triangles) + 12x12 RectLight, {rw}x{rh}, depth 6, {rspp} spp per step, power MIS, triangle filter",
                       "spp_per_s": rspp / (r_ms * 1e-3), "msamples_per_s": rw * rh * rspp / r_ms / 1e3, "mrays_per_s": st0.total_rays() / r_ms / 1e3,
                       "ms_per_step": r_ms, "steps": args.render_steps, "rays_per_sample": st0.total_rays() / max(1, st0.camera_rays), "n_gpus": world,
-                      "split": "whole frame" if world == 1 else f"32x32 tiles dealt round-robin over {world} ranks, NCCL sum-reduce to rank 0 inside the timed region",
+                      "split": "whole frame" if world == 1 else f"32x32 tiles dealt round-robin over {world} ranks; each rank's film kernel stores its tiles into rank 0's frame through CUDA-IPC peer memory (NVLink), RayStats reduced over NCCL, all inside the timed region",
                       "scaling": "strong", "gpu_launches_per_step_rank0": r_launches // args.render_steps, "device_ms_rank0_render_only": dev_ms / args.render_steps,
                       "e2e": {"spp_per_s": rspp / e2e_s, "unit": "spp/s", "d2h_bytes_per_step": rw * rh * 16, "h2d_bytes_per_step": rw * rh * 16 if world > 1 else 0,
                               "note": "crt_render_host: frame in/out of host memory, no cross-rank gather"},

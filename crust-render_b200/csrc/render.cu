@@ -815,6 +815,44 @@ void crt_steal_cursor_close(crt_steal_cursor* c) {
 int crt_render_steal(const crt_world* w, const crt_camera* camera, const crt_render_settings* settings, float* framebuffer, crt_ray_stats* stats, void* stream,
                      crt_steal_cursor* cursor);
 
+int crt_shared_frame_create(size_t bytes, void** device_ptr, unsigned char ipc_handle[64]) {
+    if (!device_ptr || !ipc_handle || bytes == 0) return crt::set_error(CRT_ERR_INVALID_ARG, "crt_shared_frame_create: null argument");
+    int rc = crt::require_device();
+    if (rc) return rc;
+    void* p = nullptr;
+    CKR(cudaMalloc(&p, bytes));  // a plain cudaMalloc block: the IPC handle then names exactly this frame (offset 0)
+    cudaError_t e = cudaMemset(p, 0, bytes);
+    cudaIpcMemHandle_t h;
+    if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) {
+        cudaFree(p);
+        return crt::set_cuda_error(e, "crt_shared_frame_create");
+    }
+    memcpy(ipc_handle, &h, 64);
+    *device_ptr = p;
+    return CRT_OK;
+}
+
+int crt_shared_frame_open(const unsigned char ipc_handle[64], void** device_ptr) {
+    if (!device_ptr || !ipc_handle) return crt::set_error(CRT_ERR_INVALID_ARG, "crt_shared_frame_open: null argument");
+    int rc = crt::require_device();
+    if (rc) return rc;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, ipc_handle, 64);
+    void* p = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) return crt::set_cuda_error(e, "cudaIpcOpenMemHandle (peer access between the two GPUs is required)");
+    *device_ptr = p;
+    return CRT_OK;
+}
+
+int crt_shared_frame_close(void* device_ptr, int owner) {
+    if (!device_ptr) return CRT_OK;
+    cudaError_t e = owner ? cudaFree(device_ptr) : cudaIpcCloseMemHandle(device_ptr);
+    if (e != cudaSuccess) return crt::set_cuda_error(e, "crt_shared_frame_close");
+    return CRT_OK;
+}
+
 int crt_render_last_info(uint64_t* launches, double* device_ms, uint64_t* rounds) {
     if (launches) *launches = t_last_launches;
     if (device_ms) *device_ms = t_last_ms;

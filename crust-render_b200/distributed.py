@@ -60,7 +60,36 @@ def shared_cursor(dist, device):
     return cur
 
 
-def render_distributed(renderer, dist=None, tile_size: int = 32, fb=None, stream: int = 0, steal: bool = False):
+_FRAMES = {}
+
+
+def shared_frame(dist, device, height: int, width: int):
+    """The peer-mapped final frame of this process group (render.SharedFrame): rank 0 owns it, the others map it through
+    its CUDA IPC handle. Returns (SharedFrame, torch view of it). Cached per (group, size)."""
+    import torch
+
+    from .render import SharedFrame
+
+    gkey = id(dist.group.WORLD) if dist is not None and dist.is_initialized() else None
+    key = (gkey, height, width)
+    if key in _FRAMES:
+        return _FRAMES[key]
+    world = dist.get_world_size() if gkey is not None else 1
+    rank = dist.get_rank() if world > 1 else 0
+    frame = SharedFrame(height, width) if rank == 0 else None
+    if world > 1:
+        t = torch.zeros(64, dtype=torch.uint8, device=device)
+        if rank == 0:
+            t.copy_(torch.frombuffer(bytearray(frame.handle), dtype=torch.uint8))
+        dist.broadcast(t, src=0)
+        if rank != 0:
+            frame = SharedFrame(height, width, bytes(t.cpu().numpy().tobytes()))
+    view = torch.as_tensor(frame, device=device)
+    _FRAMES[key] = (frame, view)
+    return _FRAMES[key]
+
+
+def render_distributed(renderer, dist=None, tile_size: int = 32, fb=None, stream: int = 0, steal: bool = False, gather: str = "reduce"):
     """Renders this rank's tiles and sum-reduces frame + RayStats to rank 0.
 
     steal=True (device framebuffer only): instead of the static round-robin deal, every rank pulls chunks of
@@ -70,6 +99,11 @@ def render_distributed(renderer, dist=None, tile_size: int = 32, fb=None, stream
     `renderer` is a Renderer (CUDA binding; the oracle's in CPU tests). With `fb` a CUDA torch tensor
     [h, w, 4] the render writes device memory and the reduce runs on it (NCCL); otherwise host
     buffers are used (gloo). Returns (frame, RayStats) — complete on rank 0, this rank's share elsewhere.
+
+    gather="peer" (device path): no per-rank frame and no frame collective at all — every rank's film kernel stores
+    its tiles directly into rank 0's frame, which the ranks map through CUDA IPC (NVLink / NVSwitch peer stores;
+    `shared_frame`). The frame is complete on rank 0 when the RayStats reduce (the only collective left) returns.
+    `fb` then only gives the device and the size; the returned frame is the shared one.
     """
     import torch
 
@@ -77,8 +111,24 @@ def render_distributed(renderer, dist=None, tile_size: int = 32, fb=None, stream
     rank = dist.get_rank() if world > 1 else 0
     base = renderer.settings
     renderer.settings = rank_settings(base, rank, world, tile_size)
+    peer = gather == "peer" and fb is not None and world > 1
+    if peer:
+        _, fb = shared_frame(dist, fb.device, base.height, base.width)
     try:
-        if fb is not None and steal:
+        if peer:
+            # tiles are disjoint and every pixel of the frame belongs to some rank: nothing to zero, nothing to reduce.
+            # The barrier keeps a fast rank from overwriting the previous frame while rank 0's consumer still reads it.
+            dist.barrier()
+            if steal:
+                cursor = shared_cursor(dist, fb.device)
+                if rank == 0:
+                    cursor.reset()
+                dist.barrier()
+                stats = renderer.render_steal(fb.data_ptr(), cursor, stream)
+            else:
+                stats = renderer.render_device(fb.data_ptr(), stream)
+            frame = fb
+        elif fb is not None and steal:
             cursor = shared_cursor(dist, fb.device)
             fb.zero_()
             if world > 1:
@@ -99,7 +149,8 @@ def render_distributed(renderer, dist=None, tile_size: int = 32, fb=None, stream
     finally:
         renderer.settings = base
     if world > 1:
-        dist.reduce(frame, dst=0, op=dist.ReduceOp.SUM)
+        if not peer:
+            dist.reduce(frame, dst=0, op=dist.ReduceOp.SUM)
         st = torch.tensor([getattr(stats, n) for n in STATS_DTYPE.names], dtype=torch.int64, device=frame.device)
         dist.reduce(st, dst=0, op=dist.ReduceOp.SUM)
         if rank == 0:

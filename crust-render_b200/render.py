@@ -32,7 +32,7 @@ from .render_types import (  # noqa: F401
     volume_records,
 )
 
-__all__ = ["World", "WorldBuilder", "Renderer", "StealCursor", "Camera", "RenderSettings", "SamplingStrategy", "PixelFilter", "PixelFilterKind",
+__all__ = ["World", "WorldBuilder", "Renderer", "StealCursor", "SharedFrame", "Camera", "RenderSettings", "SamplingStrategy", "PixelFilter", "PixelFilterKind",
            "RayStats", "LightList", "OpenPBR", "Emissive", "SphereLight", "RectLight", "DistantLight", "DomeLight", "VolumeRegion", "DensityField"]
 
 
@@ -113,6 +113,36 @@ class StealCursor:
         if getattr(self, "_h", None) and L is not None:
             L.crt_steal_cursor_close(self._h)
             self._h = None
+
+
+class SharedFrame:
+    """The final frame in the owning process's HBM, mapped by the peers through CUDA IPC (crt_shared_frame_*): every
+    process's film kernel stores its tiles straight into it over NVLink / NVSwitch peer access."""
+
+    def __init__(self, height: int, width: int, handle: Optional[bytes] = None):
+        self.height, self.width = height, width
+        self.nbytes = height * width * 16
+        p = C.c_void_p()
+        if handle is None:
+            buf = (C.c_ubyte * 64)()
+            rt._ck(rt.lib().crt_shared_frame_create(self.nbytes, C.byref(p), buf))
+            self.handle, self.owner = bytes(buf), True
+        else:
+            buf = (C.c_ubyte * 64).from_buffer_copy(handle)
+            rt._ck(rt.lib().crt_shared_frame_open(buf, C.byref(p)))
+            self.handle, self.owner = bytes(handle), False
+        self.ptr = p.value
+        # lets torch.as_tensor(frame, device="cuda") view the memory without copying
+        self.__cuda_array_interface__ = {"shape": (height, width, 4), "typestr": "<f4", "data": (self.ptr, False), "version": 3, "strides": None}
+
+    def close(self) -> None:
+        L = getattr(rt, "_lib", None) if rt is not None else None
+        if getattr(self, "ptr", None) and L is not None:
+            L.crt_shared_frame_close(C.c_void_p(self.ptr), int(self.owner))
+            self.ptr = None
+
+    def __del__(self):
+        self.close()
 
 
 class Renderer:

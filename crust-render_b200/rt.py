@@ -140,6 +140,9 @@ def lib() -> C.CDLL:
         "crt_steal_cursor_open": [vp, C.POINTER(vp)],
         "crt_steal_cursor_reset": [vp],
         "crt_render_steal": [vp, vp, vp, vp, vp, vp, vp],
+        "crt_shared_frame_create": [sz, C.POINTER(vp), vp],
+        "crt_shared_frame_open": [vp, C.POINTER(vp)],
+        "crt_shared_frame_close": [vp, C.c_int],
     }
     for name, args in sig.items():
         fn = getattr(L, name)

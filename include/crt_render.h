@@ -190,6 +190,16 @@ void crt_steal_cursor_close(crt_steal_cursor* c);
 int crt_render_steal(const crt_world* w, const crt_camera* camera, const crt_render_settings* settings, float* framebuffer,
                      crt_ray_stats* stats, void* stream, crt_steal_cursor* cursor);
 
+/* Peer-memory frame gather. The process that owns the final frame creates it here and hands the 64-byte CUDA
+ * IPC handle to the other per-GPU processes; they map it and pass the mapped pointer to crt_render / crt_render_steal as
+ * `framebuffer`, so the film kernel stores their tiles straight into the owner's HBM over NVLink / NVSwitch peer access.
+ * Pixel ownership is disjoint, so there is nothing to reduce and no per-process full frame to zero: the frame is complete
+ * on the owner once every process has returned from its render call (which synchronises its stream) and one barrier —
+ * e.g. the small RayStats reduce — has passed. */
+int crt_shared_frame_create(size_t bytes, void** device_ptr, unsigned char ipc_handle[64]);
+int crt_shared_frame_open(const unsigned char ipc_handle[64], void** device_ptr);
+int crt_shared_frame_close(void* device_ptr, int owner);
+
 /* Kernel launches issued by the last crt_render* call of this thread, and the device time it took
  * (CUDA events on the render stream), for bench.py. */
 int crt_render_last_info(uint64_t* launches, double* device_ms, uint64_t* rounds);

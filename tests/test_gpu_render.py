@@ -292,6 +292,28 @@ def test_work_stealing_cursor_single_process(gpu):
     assert r.render_steal(fb.data_ptr(), cur).camera_rays == sf.camera_rays
 
 
+def test_shared_frame_is_a_render_target(gpu):
+    """crt_shared_frame_create: the IPC-exportable frame the peer-memory gather renders into (the cross-process half runs
+    under torchrun: tools/steal_check.py). Here: it is zero-initialised device memory torch can view, a render into it
+    equals a render into a torch buffer, and tile-split renders of two 'ranks' into the one frame assemble the whole image."""
+    import torch
+    world, cam, st = scenes.furnace_room(gpu, width=96, height=64, spp=4, variance_threshold=0.0)
+    r = gpu.Renderer(cam, world, st)
+    ref, _ = r.render_with_stats()
+    frame = gpu.SharedFrame(64, 96)
+    view = torch.as_tensor(frame, device="cuda")
+    assert view.shape == (64, 96, 4) and float(view.abs().sum()) == 0.0 and len(frame.handle) == 64
+    r.render_device(frame.ptr)
+    assert np.array_equal(view.cpu().numpy(), ref)
+    view.zero_()
+    for rank in range(2):
+        r.settings = rank_settings(st, rank, 2)
+        r.render_device(frame.ptr)
+    assert np.array_equal(view.cpu().numpy(), ref)
+    del view
+    frame.close()
+
+
 def test_render_argument_errors(gpu):
     world, cam, st = scenes.furnace_room(gpu, width=16, height=16, spp=1)
     for field, value in (("width", 0), ("samples_per_pixel", 0), ("samples_per_pixel", 70000)):

@@ -1,8 +1,9 @@
 #!/usr/bin/env python
-"""Multi-GPU check of the work-stealing render path (run under torchrun, one rank per GPU):
-the adaptive openpbr_showcase frame rendered (a) with the static interleaved tile deal and (b) with the
-shared CUDA-IPC cursor must be bit-identical on rank 0, and identical to a single-rank render.
-Prints one JSON line with both timings (max over ranks)."""
+"""Multi-GPU check of the distributed render paths (run under torchrun, one rank per GPU): the adaptive
+openpbr_showcase frame rendered (a) with the static interleaved tile deal + NCCL sum-reduce, (b) with the shared CUDA-IPC
+work-stealing cursor + reduce, (c) with the static deal and the peer-memory gather (every rank's film kernel stores into
+rank 0's IPC-mapped frame, no frame collective) and (d) stealing + peer gather must be bit-identical on rank 0, and
+identical to a single-rank render. Prints one JSON line with the timings (max over ranks)."""
 import json
 import os
 import sys
@@ -34,8 +35,8 @@ stream = torch.cuda.current_stream().cuda_stream
 d = dist if world_size > 1 else None
 out = {}
 frames = {}
-for mode, steal in (("static", False), ("steal", True)):
-    render_distributed(r, d, fb=fb, stream=stream, steal=steal)  # warm-up
+for mode, steal, gather in (("static", False, "reduce"), ("steal", True, "reduce"), ("peer", False, "peer"), ("peer_steal", True, "peer")):
+    render_distributed(r, d, fb=fb, stream=stream, steal=steal, gather=gather)  # warm-up
     best = 1e9
     for _ in range(3):
         if d:
@@ -43,7 +44,7 @@ for mode, steal in (("static", False), ("steal", True)):
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        frame, stats = render_distributed(r, d, fb=fb, stream=stream, steal=steal)
+        frame, stats = render_distributed(r, d, fb=fb, stream=stream, steal=steal, gather=gather)
         e1.record()
         torch.cuda.synchronize()
         t = torch.tensor([e0.elapsed_time(e1)], device="cuda")
@@ -56,6 +57,8 @@ for mode, steal in (("static", False), ("steal", True)):
 if rank == 0:
     single, s1 = r.render_with_stats()
     out["static_equals_steal"] = bool(torch.equal(frames["static"], frames["steal"]))
+    out["static_equals_peer"] = bool(torch.equal(frames["static"], frames["peer"]))
+    out["static_equals_peer_steal"] = bool(torch.equal(frames["static"], frames["peer_steal"]))
     out["equals_single_rank"] = bool(np.array_equal(frames["steal"].cpu().numpy(), single))
     out.update(world=world_size, width=W, height=H, spp=SPP, mean_taken=float(single[..., 3].mean()))
     print(json.dumps(out), flush=True)
