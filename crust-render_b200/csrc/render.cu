@@ -1110,6 +1110,7 @@ int render_impl(crt_world* w, const crt_camera* camera, const crt_render_setting
         const uint32_t min_spp = std::max(s->min_samples_per_pixel, 2u);
         uint32_t n_active = n_pix, s_base = 0;
         int cur_list = 0;
+        double stop_rate = 1.0;  // fraction of the active pixels that stopped per 4-sample group in the last round
         while (n_active > 0 && s_base < spp) {
             uint32_t round_samples;
             if (!adaptive)
@@ -1120,6 +1121,10 @@ int render_impl(crt_world* w, const crt_camera* camera, const crt_render_setting
                 // later rounds: a multiple of 4 large enough to keep ~1 Mi paths in flight (samples a pixel turns out
                 // not to need are discarded by accumulate_kernel, so this only trades a little work for fewer rounds)
                 uint32_t groups = (uint32_t)std::min<size_t>(8, std::max<size_t>(1, ((size_t)1 << 20) / ((size_t)n_active * 4)));
+                // ... and longer rounds while few pixels are stopping: a round costs its launches whatever its length, a
+                // pixel that stops inside a G-group round wastes at most G - 1 groups of samples
+                const uint32_t by_rate = stop_rate > 0.10 ? 1u : (stop_rate > 0.03 ? 2u : (stop_rate > 0.01 ? 4u : 8u));
+                groups = std::max(groups, by_rate);
                 round_samples = std::min(spp - s_base, 4u * groups);
             }
             // split the round into wavefronts that fit the pool
@@ -1143,6 +1148,10 @@ int render_impl(crt_world* w, const crt_camera* camera, const crt_render_setting
             ++launches;
             CKR(cudaMemcpyAsync(sc.h_pinned, sc.active_count, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
             CKR(cudaStreamSynchronize(stream));
+            if (s_base > round_samples)  // not after the first round: its stop count covers min_spp samples, not one group
+                stop_rate = (double)(n_active - sc.h_pinned[0]) / (double)n_active / (double)(round_samples / 4u);
+            else
+                stop_rate = (double)(n_active - sc.h_pinned[0]) / (double)n_active;
             n_active = sc.h_pinned[0];
             cur_list ^= 1;
         }

@@ -20,7 +20,7 @@ struct StackT<true> {
 };
 
 struct LevelSave {  // what an instance descent must restore (prim.rs:345-365 returns into the caller's leaf loop)
-    F3 o, d;
+    LevelRay r;  // the caller's ray with its slab reciprocals and shear: restored, not recomputed (2 divisions + 4 reciprocals)
     const DevScene* scene;
     const float4* resume;  // next record of the instancing leaf, or nullptr
     const float4* inst;    // the instance record (for the hit chain)
@@ -361,8 +361,7 @@ __global__ void __launch_bounds__(CRT_BLOCK, (FEAT & FEAT_INSTANCE) ? CRT_MINBLO
                     Xf w2l = instance_w2l(owner, cur, time);
                     const DevScene* child = instance_child(cur);
                     LevelSave& s = saved[depth];
-                    s.o = r.o;
-                    s.d = r.d;
+                    s.r = r;
                     s.scene = cur_scene;
                     s.resume = resume;
                     s.inst = cur;
@@ -465,7 +464,7 @@ __global__ void __launch_bounds__(CRT_BLOCK, (FEAT & FEAT_INSTANCE) ? CRT_MINBLO
                         const DevScene& sc = cur_scene ? *cur_scene : p.scene;
                         nodes = sc.nodes;
                         leafs = (const float4*)sc.leafs;
-                        r.set(s.o, s.d, sc.has_triangles != 0);
+                        r = s.r;
                         rec = s.resume;
                         continue;
                     }
