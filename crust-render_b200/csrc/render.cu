@@ -1032,6 +1032,10 @@ int render_impl(crt_world* w, const crt_camera* camera, const crt_render_setting
             // max_depth 0: every path ends at `remaining <= 0` before tracing anything (tracer.rs:1123-1148)
             return CRT_OK;
         }
+        // Upper bound on the length of extend queue k (and of shadow queue k): a path yields at most one continuation and
+        // one shadow ray per vertex, so queue lengths only shrink with depth; refreshed whenever the host looks at a count.
+        // Sizes the grids of a thinning wavefront's launches (a full persistent grid costs ~10 us to start and drain).
+        uint32_t bound = total;
         for (int k = 0; k <= D; ++k) {
             const int cur = k & 1;
             crt::QueueTrace qt;
@@ -1041,14 +1045,14 @@ int render_impl(crt_world* w, const crt_camera* camera, const crt_render_setting
             qt.hits = P.q.hits;
             qt.flag = P.q.ff;
             qt.n_dev = sc.counts + k;
-            qt.capacity = total;
+            qt.capacity = bound;
             qt.counter = sc.counts + 2 * (D + 2) + k;
             int r = crt::enqueue_queue_trace(w->scene, false, qt, stream);
             if (r) return r;
             if (P.n_volumes > 0)
-                shade_kernel<true><<<grid_for(total), kBlock, 0, stream>>>(P, k, cur);
+                shade_kernel<true><<<grid_for(bound), kBlock, 0, stream>>>(P, k, cur);
             else
-                shade_kernel<false><<<grid_for(total), kBlock, 0, stream>>>(P, k, cur);
+                shade_kernel<false><<<grid_for(bound), kBlock, 0, stream>>>(P, k, cur);
             launches += 2;
             ++trace_launches;
             if (k < D && P.n_lights > 0 && strategy_samples_lights(P.st.sampling_strategy)) {
@@ -1059,14 +1063,14 @@ int render_impl(crt_world* w, const crt_camera* camera, const crt_render_setting
                 qs.hits = nullptr;
                 qs.flag = P.q.occ;
                 qs.n_dev = sc.counts + (D + 2) + k;
-                qs.capacity = total;
+                qs.capacity = bound;
                 qs.counter = sc.counts + 3 * (D + 2) + k;
                 r = crt::enqueue_queue_trace(w->scene, true, qs, stream);
                 if (r) return r;
                 if (P.n_volumes > 0)
-                    nee_resolve_kernel<true><<<grid_for(total), kBlock, 0, stream>>>(P, k);
+                    nee_resolve_kernel<true><<<grid_for(bound), kBlock, 0, stream>>>(P, k);
                 else
-                    nee_resolve_kernel<false><<<grid_for(total), kBlock, 0, stream>>>(P, k);
+                    nee_resolve_kernel<false><<<grid_for(bound), kBlock, 0, stream>>>(P, k);
                 launches += 2;
                 ++trace_launches;
             }
@@ -1075,6 +1079,7 @@ int render_impl(crt_world* w, const crt_camera* camera, const crt_render_setting
                 CKR(cudaMemcpyAsync(sc.h_pinned, sc.counts + k + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
                 CKR(cudaStreamSynchronize(stream));
                 if (sc.h_pinned[0] == 0) break;
+                bound = std::min(bound, sc.h_pinned[0]);
             }
         }
         return CRT_OK;
