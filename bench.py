@@ -416,6 +416,19 @@ def main():
         # N > 1: peer-memory gather — every rank's film kernel stores its tiles into rank 0's IPC-mapped frame over NVLink
         # (no frame collective); the RayStats reduce is the only collective in the step
         r_gather = "peer" if world > 1 else "reduce"
+        if world > 1:
+            # peer access needs every rank to see the owner's GPU; where it does not (e.g. one visible device per process)
+            # the frame is sum-reduced over NCCL instead, and `split` says which path ran
+            from crust_render_b200.distributed import shared_frame
+            ok = torch.ones(1, device=dev)
+            try:
+                shared_frame(dist, dev, rh, rw)
+            except Exception as e:  # noqa: BLE001
+                log(f"[bench] rank {rank}: peer-memory frame unavailable ({e}); using the NCCL reduce")
+                ok.zero_()
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if float(ok.item()) == 0.0:
+                r_gather = "reduce"
         render_distributed(renderer, dist if world > 1 else None, fb=fb, stream=stream.cuda_stream, gather=r_gather)  # warm-up
         barrier()
         r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -457,7 +470,8 @@ def main():
             render = {"workload": f"config 5: stress mesh ({r_tris} triangles) + 12x12 RectLight, {rw}x{rh}, depth 6, {rspp} spp per step, power MIS, triangle filter",
                       "spp_per_s": rspp / (r_ms * 1e-3), "msamples_per_s": rw * rh * rspp / r_ms / 1e3, "mrays_per_s": st0.total_rays() / r_ms / 1e3,
                       "ms_per_step": r_ms, "steps": args.render_steps, "rays_per_sample": st0.total_rays() / max(1, st0.camera_rays), "n_gpus": world,
-                      "split": "whole frame" if world == 1 else f"32x32 tiles dealt round-robin over {world} ranks; each rank's film kernel stores its tiles into rank 0's frame through CUDA-IPC peer memory (NVLink), RayStats reduced over NCCL, all inside the timed region",
+                      "split": "whole frame" if world == 1 else (f"32x32 tiles dealt round-robin over {world} ranks; each rank's film kernel stores its tiles into rank 0's frame through CUDA-IPC peer memory (NVLink), RayStats reduced over NCCL, all inside the timed region"
+                                if r_gather == "peer" else f"32x32 tiles dealt round-robin over {world} ranks, NCCL sum-reduce of the frame to rank 0 inside the timed region"),
                       "scaling": "strong", "gpu_launches_per_step_rank0": r_launches // args.render_steps, "device_ms_rank0_render_only": dev_ms / args.render_steps,
                       "e2e": {"spp_per_s": rspp / e2e_s, "unit": "spp/s", "d2h_bytes_per_step": rw * rh * 16, "h2d_bytes_per_step": rw * rh * 16 if world > 1 else 0,
                               "note": "crt_render_host: frame in/out of host memory, no cross-rank gather"},

@@ -76,14 +76,24 @@ def shared_frame(dist, device, height: int, width: int):
         return _FRAMES[key]
     world = dist.get_world_size() if gkey is not None else 1
     rank = dist.get_rank() if world > 1 else 0
-    frame = SharedFrame(height, width) if rank == 0 else None
+    frame, err = None, None
+    if rank == 0:
+        try:
+            frame = SharedFrame(height, width)
+        except Exception as e:  # noqa: BLE001  (the peers must still get their broadcast)
+            err = e
     if world > 1:
         t = torch.zeros(64, dtype=torch.uint8, device=device)
-        if rank == 0:
+        if frame is not None:
             t.copy_(torch.frombuffer(bytearray(frame.handle), dtype=torch.uint8))
         dist.broadcast(t, src=0)
+        handle = bytes(t.cpu().numpy().tobytes())
         if rank != 0:
-            frame = SharedFrame(height, width, bytes(t.cpu().numpy().tobytes()))
+            if not any(handle):
+                raise RuntimeError("the owning rank could not create the shared frame")
+            frame = SharedFrame(height, width, handle)
+    if err is not None:
+        raise err
     view = torch.as_tensor(frame, device=device)
     _FRAMES[key] = (frame, view)
     return _FRAMES[key]
