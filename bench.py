@@ -123,6 +123,59 @@ def time_sample_configs(crt, torch, stream):
     return out
 
 
+def time_other_scenes(crt, W, torch, stream, grid, with_cpu):
+    """SURVEY 8(d)'s other kernel inputs, timed resident like the main step (best of 3, CUDA events): K2 — the stress scene
+    with identical spheres, i.e. one 9 800-triangle BLAS x grid^2 instances over the flat shards/floor/slab (two-level
+    traversal); K3 — the reference's three throughput-probe scenes (ray_throughput.rs:50-100) with its LCG box rays
+    (:103-116). Beside each: the CPU restatement on one thread (the reference's own figure is per core) and on all, on a
+    2^18-ray sample, with hit agreement on that sample."""
+    import orc
+
+    def gpu_rate(scene, rays, closest):
+        n = len(rays)
+        d_r = torch.from_numpy(rays.view(np.float32).reshape(-1, 8).copy()).cuda()
+        d_o = torch.empty((n, 8), dtype=torch.float32, device="cuda") if closest else torch.empty(n, dtype=torch.uint8, device="cuda")
+        best = None
+        for k in range(4):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            if closest:
+                scene.intersect_ptr(n, d_r.data_ptr(), 0, 0, d_o.data_ptr(), 0, stream.cuda_stream)
+            else:
+                scene.occluded_ptr(n, d_r.data_ptr(), 0, 0, d_o.data_ptr(), stream.cuda_stream)
+            e1.record(stream)
+            torch.cuda.synchronize()
+            if k:
+                best = e0.elapsed_time(e1) if best is None else min(best, e0.elapsed_time(e1))
+        return n / best / 1e3, d_o.cpu().numpy()
+
+    out = {}
+    cases = [("K2 instanced stress", lambda api: W.stress_scene_instanced(api, grid=grid).commit(), 24),
+             ("K3 tri_spheres", lambda api: W.triangle_scene(api).commit(), 22),
+             ("K3 sphere_grid", lambda api: W.sphere_grid_scene(api).commit(), 22),
+             ("K3 instance_scene", lambda api: W.instance_scene(api).commit(), 22)]
+    for name, make, log2 in cases:
+        scene = make(crt)
+        rays = W.ray_batch(1 << log2, W.scene_extent(scene.bounds()))
+        pb = scene.primitive_breakdown()
+        rec = {"rays": len(rays), "top_level_primitives": scene.primitive_count(), "instances": pb.instances}
+        rec["closest_lcg_mrays"], hits = gpu_rate(scene, rays, True)
+        rec["occluded_lcg_mrays"], occ = gpu_rate(scene, rays, False)
+        if with_cpu:
+            o = make(orc)
+            sub = slice(0, None, len(rays) >> 18)
+            oh, _ = o.intersect_n(rays[sub], threads=0)
+            rec["cpu_all_threads_mrays"] = len(oh) / o.last_seconds / 1e6
+            o.intersect_n(rays[sub][: 1 << 16], threads=1)
+            rec["cpu_one_thread_mrays"] = (1 << 16) / o.last_seconds / 1e6
+            g = hits.view(np.uint32).reshape(-1, 8)[sub]
+            rec["oracle_agreement_on_sample"] = float(((g[:, 3] == oh["geom_id"]) & (g[:, 4] == oh["prim_id"]) & (g[:, 0].view(np.float32) == oh["t"])).mean())
+            rec["occlusion_agreement_on_sample"] = float((occ[sub] == o.occluded_n(rays[sub], threads=0)).mean())
+        out[name] = rec
+        del scene
+    return out
+
+
 # ---------------------------------------------------------------------------
 # workload
 # ---------------------------------------------------------------------------
@@ -397,6 +450,7 @@ def main():
 
     # ---- render: config 5 through the wavefront integrator, frame split over the ranks ----------
     render = None
+    other_scenes = None
     if not args.no_render:
         from crust_render_b200 import scenes
         from crust_render_b200.distributed import render_distributed
@@ -481,6 +535,7 @@ def main():
         # configs 1-4 of BASELINE.json at their own sizes (parity-test cases; timed here so every config has a number)
         if rank == 0 and world == 1:
             render["configs"] = time_sample_configs(crt, torch, stream)
+            other_scenes = time_other_scenes(crt, W, torch, stream, args.grid, not args.no_cpu_baseline)
     else:
         sample_sets = cpu_sample(sets, args.cpu_sample_log2) if (rank == 0 and world == 1 and not args.no_cpu_baseline) else None
         full_sets_sizes = {n: len(sets[n][0]) for n in SETS}
@@ -540,7 +595,7 @@ def main():
                 pass
             roofline = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic, "traffic_source": traffic_src,
                         "note": "algorithmic bytes are mostly served by L1/L2 (the 0.83 GB tree is hot in the 126 MB L2: lts hit 62-83 %); ncu shows the kernel "
-                                "issue-bound (smsp issue active 70-80 %, 9-19 of 32 lanes active per instruction), DRAM at 2-12 % of peak",
+                                "issue-bound (smsp issue active 63-79 %, 10.6-19.7 of 32 lanes active per instruction), DRAM at 1-11 % of peak",
                         "kernel": "trace_kernel<closest-hit, triangles>", "peak_source": peak_src,
                         "bytes_per_launch": tot_bytes / len(closest), "launch_ms": dur * 1e3 / len(closest)}
         for name in SETS:
@@ -555,6 +610,8 @@ def main():
                 "sets": per_set, "closest_hit_mrays": sum(len(sets[n][0]) for n in closest) / sum(k_ms[n] for n in closest) / 1e3,
                 "occlusion_mrays": sum(len(sets[n][0]) for n in SETS if n not in closest) / sum(k_ms[n] for n in SETS if n not in closest) / 1e3,
                 "device_status": status, "host_cores": cores}
+        if other_scenes is not None:
+            line["other_scenes"] = other_scenes
         if world == 1:
             # commit() itself: the reference's SAH/SBVH host build (what the numbers above ran on) next to the device build
             def timed_commit(flags):

@@ -230,6 +230,27 @@ def stress_scene(api, grid: int = 6, shards: int = 30000, jitter: bool = False):
     return b, n_tris
 
 
+def stress_scene_instanced(api, grid: int = 32, shards: int = 30000):
+    """K2: the stress scene as the importer hands it over when every sphere authors the same points
+    (no jitter) — content-hash dedup turns the grid*grid spheres into instances of ONE 9 800-triangle BLAS, each placed
+    by its translate (usd_import.rs:769-798, 1025-1089); shards, floor and slab are placed once and stay flat."""
+    from .rt_types import Affine3A
+
+    meshes = stress_meshes(1, shards, False)  # [sphere, shards, floor, slab]
+    base_pts, base_idx = _script_sphere(0.8)
+    blas = api.SceneBuilder()
+    blas.attach(api.Geometry.TriangleMesh(_round5(base_pts).astype(np.float32), base_idx))
+    blas = blas.commit()
+    b = api.SceneBuilder()
+    half = (grid - 1) * SPACING * 0.5
+    for i in range(grid):
+        for j in range(grid):
+            b.attach(api.Geometry.Instance(blas, Affine3A.from_translation((i * SPACING - half, 0.8, j * SPACING - half))))
+    for v, idx in meshes[1:]:
+        b.attach(api.Geometry.TriangleMesh(v, idx))
+    return b
+
+
 def scene_extent(bounds) -> float:
     """Half-diagonal of the scene bounds (the `extent` SURVEY §8(d) feeds ray_batch)."""
     d = np.asarray(bounds.maximum, np.float64) - np.asarray(bounds.minimum, np.float64)
