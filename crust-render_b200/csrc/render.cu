@@ -301,6 +301,8 @@ __global__ void __launch_bounds__(kBlock, VOL ? 4 : CRT_SHADE_MINBLOCKS) shade_k
             }
 
             if (vol_scatter) {
+                // the region scatter vertex above was this segment's event: it ends before the surface and the carried medium's
+                // free flight (the walk was clipped to both, tracer.rs:1172-1173)
             } else if (t_med < t_surf) {
                 // Carried-medium scatter vertex (tracer.rs:1251-1318): no NEE, prev = None afterwards.
                 float sigma_bar = fmaxf(medium_sigma_t_max(*med), 1e-4f);
