@@ -29,6 +29,7 @@ struct crt_scene {
     void *d_nodes = nullptr, *d_leafs = nullptr, *d_prim_ids = nullptr, *d_normals = nullptr, *d_motion = nullptr;
     DevScene desc{};
     DevScene* d_desc = nullptr;
+    size_t top_bytes = 0;  // leading bytes of d_nodes that hold the tree's top levels (L2 access-policy window), 0 = none
     crt_memory_footprint footprint{};
 
     ~crt_scene() {

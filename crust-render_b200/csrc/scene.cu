@@ -49,6 +49,8 @@ struct Device {
     unsigned int* status = nullptr;
     std::atomic<uint64_t> next_counter{0};
     std::atomic<uint64_t> launches{0};
+    size_t l2_persist_bytes = 0;  // L2 set aside for the top levels of the BVH (0 = feature off)
+    std::atomic<uint64_t> l2_applied{0}, l2_refused{0};
 } g_dev;
 constexpr int kCounterRing = 4096;
 
@@ -74,12 +76,84 @@ int ensure_device() {
         snprintf(buf, sizeof buf, "device is sm_%d%d; this library carries sm_100a code only", prop.major, prop.minor);
         return fail(CRT_ERR_NO_DEVICE, buf);
     }
+    {
+        // L2 persistence for the top levels of the tree (BASELINE north_star): a slice of the 126 MB L2 is set aside and
+        // every traversal launch carries an access-policy window over the leading, breadth-first-ordered nodes of its scene,
+        // so the lines every ray touches are not evicted by the streaming ray / hit / leaf-record traffic.
+        // CRT_L2_PERSIST_MB overrides the size (0 switches the feature off).
+        size_t want = (size_t)16 << 20;
+        if (const char* e = getenv("CRT_L2_PERSIST_MB")) want = (size_t)std::max(0L, atol(e)) << 20;
+        want = std::min(want, (size_t)prop.persistingL2CacheMaxSize);
+        if (want && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess)
+            g_dev.l2_persist_bytes = std::min(want, (size_t)prop.accessPolicyMaxWindowSize);
+        cudaGetLastError();
+    }
     CK(cudaMalloc(&g_dev.counters, sizeof(unsigned int) * (kCounterRing + 1)));
     CK(cudaMemset(g_dev.counters, 0, sizeof(unsigned int) * (kCounterRing + 1)));
     g_dev.status = g_dev.counters + kCounterRing;
     g_dev.ready = true;
     return CRT_OK;
 }
+
+// ---- L2 persistence of the top levels ------------------------------------------
+// The builder emits nodes in the reference's DFS pre-order, which scatters the top levels over the array. For the device
+// copy the first `budget` bytes' worth of nodes are re-ordered breadth-first from the root (the rest keep their DFS order
+// behind them) and child words are renumbered: same tree, same child lanes, same visiting order — only addresses change.
+// Returns the size of the breadth-first prefix in bytes (0 when the tree is smaller than two nodes or the feature is off).
+size_t top_levels_first(const std::vector<DevNode>& nodes, size_t budget, std::vector<DevNode>& out) {
+    const size_t n = nodes.size();
+    size_t n_top = std::min(n, budget / sizeof(DevNode));
+    if (n_top < 2) return 0;
+    if (n_top == n) return n * sizeof(DevNode);  // the whole tree fits the window: no need to move anything
+    std::vector<uint32_t> order;  // new index -> old index
+    order.reserve(n);
+    std::vector<uint32_t> new_of(n, 0xFFFFFFFFu);
+    order.push_back(0);
+    new_of[0] = 0;
+    for (size_t head = 0; head < order.size() && order.size() < n_top; ++head) {
+        const DevNode& nd = nodes[order[head]];
+        for (int k = 0; k < 4 && order.size() < n_top; ++k) {
+            uint32_t c = nd.child[k];
+            if (c == CRT_EMPTY_LANE || (c & CRT_LEAF_BIT) || new_of[c] != 0xFFFFFFFFu) continue;
+            new_of[c] = (uint32_t)order.size();
+            order.push_back(c);
+        }
+    }
+    n_top = order.size();
+    for (uint32_t old = 0; old < n; ++old)
+        if (new_of[old] == 0xFFFFFFFFu) {
+            new_of[old] = (uint32_t)order.size();
+            order.push_back(old);
+        }
+    out.resize(n);
+    for (size_t i = 0; i < n; ++i) {
+        DevNode nd = nodes[order[i]];
+        for (int k = 0; k < 4; ++k) {
+            uint32_t c = nd.child[k];
+            if (c != CRT_EMPTY_LANE && !(c & CRT_LEAF_BIT)) nd.child[k] = new_of[c];
+        }
+        out[i] = nd;
+    }
+    return n_top * sizeof(DevNode);
+}
+// Attaches the window to `stream` (a stream attribute: it applies to the launches that follow). Failure is not an error —
+// the hint is an optimisation only.
+void hint_top_levels(const crt_scene* s, cudaStream_t stream) {
+    if (!s->top_bytes || !g_dev.l2_persist_bytes) return;
+    cudaStreamAttrValue attr{};
+    attr.accessPolicyWindow.base_ptr = s->d_nodes;
+    attr.accessPolicyWindow.num_bytes = std::min(s->top_bytes, g_dev.l2_persist_bytes);
+    attr.accessPolicyWindow.hitRatio = 1.0f;
+    attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    attr.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
+    if (cudaStreamSetAttribute(stream, cudaStreamAttributeAccessPolicyWindow, &attr) != cudaSuccess) {
+        cudaGetLastError();
+        g_dev.l2_refused.fetch_add(1);
+    } else {
+        g_dev.l2_applied.fetch_add(1);
+    }
+}
+
 }  // namespace
 
 // ---------------------------------------------------------------------------
@@ -383,7 +457,10 @@ int crt_commit_ex(crt_builder* b, uint32_t flags, int host_threads, crt_scene** 
     if (!host_only) {
         auto t0 = std::chrono::steady_clock::now();
         int rc = CRT_OK;
-        if ((rc = upload(&s->d_nodes, t->nodes.data(), t->nodes.size())) ||
+        std::vector<DevNode> reordered;  // device copy only: the host tree keeps the reference's DFS order
+        s->top_bytes = top_levels_first(t->nodes, g_dev.l2_persist_bytes, reordered);
+        const DevNode* node_src = reordered.empty() ? t->nodes.data() : reordered.data();
+        if ((rc = upload(&s->d_nodes, node_src, t->nodes.size())) ||
             (rc = upload(&s->d_leafs, t->leafs.data(), t->leafs.size())) ||
             (rc = upload(&s->d_prim_ids, t->prim_ids.data(), t->prim_ids.size())) ||
             (rc = upload(&s->d_normals, t->normals.data(), t->normals.size())) ||
@@ -514,6 +591,7 @@ static int launch_query(const crt_scene* s, bool any_hit, size_t n, const crt_ra
     if (rc) return rc;
     const size_t kMaxPerLaunch = (size_t)1 << 30;  // 32-bit ray counter with head-room for overshoot
     int per_sm = trace_blocks_per_sm(any_hit, s->features);
+    hint_top_levels(s, stream);
     for (size_t off = 0; off < n; off += kMaxPerLaunch) {
         size_t cnt = std::min(kMaxPerLaunch, n - off);
         TraceParams p;
@@ -548,6 +626,12 @@ int crt_occluded_n(const crt_scene* s, size_t n, const crt_ray* rays, const floa
 }
 
 uint64_t crt_launch_count(void) { return g_dev.launches.load(); }
+int crt_l2_persist_info(uint64_t* set_aside_bytes, uint64_t* windows_applied, uint64_t* windows_refused) {
+    if (set_aside_bytes) *set_aside_bytes = g_dev.l2_persist_bytes;
+    if (windows_applied) *windows_applied = g_dev.l2_applied.load();
+    if (windows_refused) *windows_refused = g_dev.l2_refused.load();
+    return CRT_OK;
+}
 
 // Sticky device-side error bits (bit 0: a traversal stack overflowed and an
 // entry was dropped). Synchronises the device.
@@ -762,6 +846,7 @@ int enqueue_queue_trace(const crt_scene* s, bool any_hit, const QueueTrace& q, c
     p.n = q.capacity;
     p.n_dev = q.n_dev;
     int grid = g_dev.sm_count * trace_blocks_per_sm(any_hit, s->features);
+    hint_top_levels(s, stream);
     size_t need = ((size_t)q.capacity + CRT_BLOCK - 1) / CRT_BLOCK;
     if ((size_t)grid > need) grid = (int)(need ? need : 1);
     CK(launch_trace(any_hit, s->features, p, grid, stream));

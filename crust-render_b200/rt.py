@@ -37,7 +37,7 @@ __all__ = [
     "AABB", "Affine3A", "CrtError", "CubicCurveSegment", "CurveSegment", "Geometry", "HIT_DTYPE", "INVALID_ID",
     "MASK_ALL", "MASK_CAMERA", "MASK_INDIRECT", "MASK_SHADOW", "PrimitiveBreakdown", "RAY_DTYPE", "Ray", "RayHit",
     "Scene", "SceneBuilder", "MemoryFootprint", "BuildInfo", "lib", "lib_path", "make_rays", "init", "device_info",
-    "launch_count", "device_status", "COMMIT_KEEP_HOST_TREE", "COMMIT_HOST_ONLY", "COMMIT_DEVICE_BUILD",
+    "launch_count", "device_status", "l2_persist_info", "COMMIT_KEEP_HOST_TREE", "COMMIT_HOST_ONLY", "COMMIT_DEVICE_BUILD",
 ]
 
 COMMIT_KEEP_HOST_TREE = 0x1
@@ -94,6 +94,7 @@ def lib() -> C.CDLL:
     sig = {
         "crt_init": [C.c_int],
         "crt_device_info": [C.POINTER(C.c_int)] * 3 + [C.POINTER(u64)] * 2,
+        "crt_l2_persist_info": [C.POINTER(u64)] * 3,
         "crt_builder_new": [C.POINTER(vp)],
         "crt_builder_reserve": [vp, sz],
         "crt_builder_count": [vp, C.POINTER(sz)],
@@ -155,6 +156,16 @@ def lib() -> C.CDLL:
     _ = u8p
     _lib = L
     return L
+
+
+u64_ = C.c_uint64
+
+
+def l2_persist_info():
+    """(bytes of L2 set aside for the trees' top levels, launches that got the access-policy window, launches refused)."""
+    a, b, c = u64_(), u64_(), u64_()
+    _ck(lib().crt_l2_persist_info(C.byref(a), C.byref(b), C.byref(c)))
+    return a.value, b.value, c.value
 
 
 def _ck(rc: int) -> None:

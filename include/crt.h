@@ -100,6 +100,9 @@ const char* crt_last_error(void);
  * CRT_ERR_NO_DEVICE when there is none: this library has no host path. */
 int crt_init(int device);
 int crt_device_info(int* sm_count, int* cc_major, int* cc_minor, uint64_t* total_mem, uint64_t* l2_bytes);
+/* L2 persistence of the tree's top levels: bytes of L2 set aside at crt_init (CRT_L2_PERSIST_MB, default 16; 0 = off) and
+ * how many traversal launches had the access-policy window over their scene's leading nodes attached / refused. */
+int crt_l2_persist_info(uint64_t* set_aside_bytes, uint64_t* windows_applied, uint64_t* windows_refused);
 
 /* ---- SceneBuilder (scene.rs:151-342) -------------------------------------- */
 int crt_builder_new(crt_builder** out);                                   /* SceneBuilder::new */

@@ -231,3 +231,21 @@ def test_full_size_k1_mesh_properties(gpu, orc):
     ph = h[:: n // (1 << 16)]
     assert ph.tobytes() == oh.tobytes() and np.array_equal(ff[:: n // (1 << 16)], of)
     assert np.array_equal(occ[:: n // (1 << 16)], o.occluded_n(sub, threads=0))
+
+
+def test_l2_window_over_breadth_first_top_levels(gpu, orc):
+    """BASELINE north_star: "L2-persistence hints on top-level nodes". A tree larger than the L2 set-aside gets its top levels
+    re-ordered breadth-first at the head of the device node array (child words renumbered; the host tree keeps the reference's
+    DFS order) and every launch attaches an access-policy window over them: results stay bit-identical to the oracle."""
+    set_aside, applied0, _ = gpu.l2_persist_info()
+    assert set_aside > 0
+    # 383 k triangles: the whole 8 MB node array fits the window; the re-ordered case is the 215 MB tree of
+    # test_full_size_k1_mesh_properties
+    make = lambda api: workloads.stress_scene(api, grid=6, shards=30000)[0]  # noqa: E731
+    p, o = _pair(gpu, orc, make)
+    bi = p.build_info()
+    rays = workloads.ray_batch(1 << 18, workloads.scene_extent(p.bounds()), seed=5)
+    _compare_closest(p, o, rays)
+    _compare_occluded(p, o, rays)
+    _, applied1, refused = gpu.l2_persist_info()
+    assert applied1 > applied0 and refused == 0, (applied0, applied1, refused, bi.node_bytes)
