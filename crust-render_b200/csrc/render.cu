@@ -175,8 +175,17 @@ __device__ __forceinline__ float bounce_emission_weight(const RenderParams& P, u
 }
 
 // ---- shade: one path vertex per queue entry (tracer.rs:1118-1535) --------------------------------
-template <bool VOL>
+// PASS selects what one launch does with a vertex: SHADE_FUSED everything (worlds with volume regions); SHADE_VERTEX
+// everything except the BSDF sampling of a surface vertex; SHADE_SCATTER only that — BSDF sample, Russian roulette,
+// continuation ray (tracer.rs:1459-1530). The fused kernel is 230 KB of machine code and ncu attributes 44 % of its stalls to
+// instruction fetch (`stall_no_inst`): light sampling + material_eval and material_scatter are each a few thousand
+// instructions, and a warp walking both overruns the instruction caches. Two launches over the same queue, each with
+// half the code, cost a second read of the hit and path records and no arithmetic twice except the segment attenuation.
+enum : int { SHADE_FUSED = 0, SHADE_VERTEX = 1, SHADE_SCATTER = 2 };
+
+template <bool VOL, int PASS>
 __global__ void __launch_bounds__(kBlock, VOL ? 4 : CRT_SHADE_MINBLOCKS) shade_kernel(const RenderParams P, int k, int cur) {
+    static_assert(!VOL || PASS == SHADE_FUSED, "worlds with volume regions use the fused kernel");
     const int D = (int)P.st.max_depth;
     const uint32_t n = P.q.counts[k];
     uint32_t* next_count = P.q.counts + k + 1;
@@ -203,10 +212,11 @@ __global__ void __launch_bounds__(kBlock, VOL ? 4 : CRT_SHADE_MINBLOCKS) shade_k
         const float time = P.ps.time[path];
         V3 add = splat(0.0f);
         uint2 cnt = P.ps.counts[path];
-        cnt.x += 1u;  // this entry is one traced closest-hit query (stats.rs:133)
+        if (PASS != SHADE_SCATTER) cnt.x += 1u;  // this entry is one traced closest-hit query (stats.rs:133)
         const Medium* med = medium >= 0 ? &P.materials[medium].medium : nullptr;
 
         if (k >= D) {
+            if (PASS == SHADE_SCATTER) continue;
             // Depth exhausted (tracer.rs:1123-1148): the ray was traced for bounce-hit emission only.
             cnt.x |= CNT_DEPTH;
             if (have_hit) {
@@ -304,6 +314,7 @@ __global__ void __launch_bounds__(kBlock, VOL ? 4 : CRT_SHADE_MINBLOCKS) shade_k
                 // the region scatter vertex above was this segment's event: it ends before the surface and the carried medium's
                 // free flight (the walk was clipped to both, tracer.rs:1172-1173)
             } else if (t_med < t_surf) {
+                if (PASS == SHADE_SCATTER) continue;
                 // Carried-medium scatter vertex (tracer.rs:1251-1318): no NEE, prev = None afterwards.
                 float sigma_bar = fmaxf(medium_sigma_t_max(*med), 1e-4f);
                 V3 pos = ro + t_med * rd;
@@ -338,6 +349,7 @@ __global__ void __launch_bounds__(kBlock, VOL ? 4 : CRT_SHADE_MINBLOCKS) shade_k
                     }
                 }
             } else if (!have_hit) {
+                if (PASS == SHADE_SCATTER) continue;
                 // Background (tracer.rs:1321-1342) with escaped_emission (:966-1009).
                 cnt.x |= CNT_ESCAPED;
                 V3 unit = normalize(rd);
@@ -382,6 +394,7 @@ __global__ void __launch_bounds__(kBlock, VOL ? 4 : CRT_SHADE_MINBLOCKS) shade_k
                     }
                 }
                 atten = vol_tr * atten;  // tracer.rs:1362
+                if (PASS != SHADE_SCATTER) {
                 // emission ownership (tracer.rs:1369-1381)
                 float cos_o = fabsf(dot(normalize(rd), rec.normal));
                 V3 emitted = material_emitted_directional(mat, cos_o);
@@ -418,6 +431,9 @@ __global__ void __launch_bounds__(kBlock, VOL ? 4 : CRT_SHADE_MINBLOCKS) shade_k
                     P.q.spath[s] = path;
                     P.q.scontrib[s] = f4(contrib, 0.0f);
                 }
+                cnt.y += 1u;  // stats.vertices: counted whether or not the path goes on (:1531-1533)
+                }
+                if (PASS != SHADE_VERTEX) {
                 // 2. BSDF sampling + Russian roulette (tracer.rs:1459-1530)
                 float bs[4];
                 draw_sample4(new_domain(v, K_BSDF), bs);
@@ -449,7 +465,7 @@ __global__ void __launch_bounds__(kBlock, VOL ? 4 : CRT_SHADE_MINBLOCKS) shade_k
                         new_flags = FLAG_HAS_PREV | (sample.delta ? FLAG_PREV_DELTA : 0u) | (sample.enters_medium ? (mat_index + 1u) << 8 : 0u);
                     }
                 }
-                cnt.y += 1u;
+                }
             }
             if (cont) {
                 P.ps.beta_pdf[path] = f4(beta, new_pdf);
@@ -1024,6 +1040,10 @@ int render_impl(crt_world* w, const crt_camera* camera, const crt_render_setting
         return (int)std::max<size_t>(1, std::min<size_t>(blocks, (size_t)sms * 8));
     };
 
+    const bool split_shade = !getenv("CRT_SHADE_FUSED");  // development switch: the fused kernel for A/B timing
+    // without light sampling the vertex pass is nearly empty and the second launch costs more than it saves (measured on the
+    // sky-only cornellbox / MedCity scenes)
+    const bool PL_has_nee = P.n_lights > 0 && strategy_samples_lights(P.st.sampling_strategy);
     // ---- one wavefront: `nb` pixels (active[off .. off+nb)) x samples [s_base, s_base + s_count) ----
     auto wavefront = [&](const uint32_t* active, uint32_t nb, uint32_t s_base, uint32_t s_count) -> int {
         const uint32_t total = nb * s_count;
@@ -1051,10 +1071,17 @@ int render_impl(crt_world* w, const crt_camera* camera, const crt_render_setting
             qt.counter = sc.counts + 2 * (D + 2) + k;
             int r = crt::enqueue_queue_trace(w->scene, false, qt, stream);
             if (r) return r;
-            if (P.n_volumes > 0)
-                shade_kernel<true><<<grid_for(bound), kBlock, 0, stream>>>(P, k, cur);
-            else
-                shade_kernel<false><<<grid_for(bound), kBlock, 0, stream>>>(P, k, cur);
+            if (P.n_volumes > 0) {
+                shade_kernel<true, SHADE_FUSED><<<grid_for(bound), kBlock, 0, stream>>>(P, k, cur);
+            } else if (split_shade && PL_has_nee) {
+                shade_kernel<false, SHADE_VERTEX><<<grid_for(bound), kBlock, 0, stream>>>(P, k, cur);
+                if (k < D) {  // a depth-exhausted vertex has no continuation to sample
+                    shade_kernel<false, SHADE_SCATTER><<<grid_for(bound), kBlock, 0, stream>>>(P, k, cur);
+                    ++launches;
+                }
+            } else {
+                shade_kernel<false, SHADE_FUSED><<<grid_for(bound), kBlock, 0, stream>>>(P, k, cur);
+            }
             launches += 2;
             ++trace_launches;
             if (k < D && P.n_lights > 0 && strategy_samples_lights(P.st.sampling_strategy)) {

@@ -176,7 +176,7 @@ CRT_HD PathSampler new_domain(PathSampler s, int32_t key) {
 }
 // One 4-D Owen-scrambled Sobol point (all four dimensions are always computed, like the
 // reference's block, tracer.rs:549-551).
-CRT_HD void draw_sample4(PathSampler s, float out[4]) {
+CRT_HD_NOINLINE void draw_sample4(PathSampler s, float out[4]) {  // one copy per kernel: ~300 instructions, called at every event of a vertex
     uint32_t idx = owen_scramble(s.index, hash_combine(s.pattern, 0x51633E2Du));  // shuffle the sequence order
     idx &= 0xFFFFu;                                                                // 2^16 samples per pixel
 #if defined(__CUDA_ARCH__)
