@@ -47,6 +47,7 @@ namespace {
     } while (0)
 
 constexpr int kBlock = 128;
+constexpr int kShadeBins = 64;  // class 0 = miss, then one class per lobe signature of the world's materials (crt_world::mat_class)
 #ifndef CRT_SHADE_MINBLOCKS
 #define CRT_SHADE_MINBLOCKS 8  // resident blocks per SM shade_kernel is compiled for: 64 registers with spills beat 128 registers at half the occupancy (measured 4/5/6/8 on B200)
 #endif
@@ -75,6 +76,10 @@ struct Queues {
     uint32_t* spath;
     float4* scontrib;    // NEE contribution that lands if the shadow ray is unoccluded
     uint8_t* occ;
+    // shading order of the current extend queue: its entries grouped by class (miss, then one class per material), so a
+    // warp of shade threads runs one material's code; null = queue order
+    uint32_t* order;
+    uint32_t* bins;      // kShadeBins class counts, then kShadeBins scatter cursors
     // per wavefront, all zeroed by one memset: ext_count[D+2] | sh_count[D+2] | ext_fetch[D+2] | sh_fetch[D+2]
     uint32_t* counts;
 };
@@ -91,6 +96,7 @@ struct RenderParams {
     RenderSettings st;
     const Material* materials;
     const uint32_t* geom_material;
+    const uint8_t* mat_class;   // shading class of each material (1 .. kShadeBins - 1), see material_signature
     const Light* lights;
     const int32_t* geom_light;  // LightList::find_by_geom (light.rs:436-440) as a table
     const EnvMap* envs;         // environment maps of dome lights, indexed by Light::env
@@ -175,6 +181,45 @@ __device__ __forceinline__ float bounce_emission_weight(const RenderParams& P, u
 }
 
 // ---- shade: one path vertex per queue entry (tracer.rs:1118-1535) --------------------------------
+// ---- shading order: a counting sort of the extend queue by class ------------------------------------------------
+// Threads of a warp that shade different materials (or a miss next to a hit) execute each other's code paths one after the
+// other; OpenPBR's lobes are thousands of instructions each. Grouping the queue by class costs two light passes over the
+// hit records and makes most warps uniform. Only the ORDER in which entries are shaded changes — every entry is keyed by
+// its path slot, so images and RayStats are unaffected.
+__device__ __forceinline__ uint32_t shade_class(const RenderParams& P, uint32_t i) {
+    const uint32_t geom_id = __float_as_uint(P.q.hits[2 * (size_t)i].w);
+    if (geom_id == CRT_INVALID_ID) return 0u;
+    return P.mat_class[P.geom_material[geom_id]];
+}
+__global__ void __launch_bounds__(kBlock) classify_count_kernel(const RenderParams P, int k) {
+    const uint32_t n = P.q.counts[k];
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t c = shade_class(P, i);
+        const unsigned peers = __match_any_sync(__activemask(), c);
+        if ((threadIdx.x & 31u) == (unsigned)(__ffs(peers) - 1)) atomicAdd(P.q.bins + c, (uint32_t)__popc(peers));
+    }
+}
+__global__ void classify_scan_kernel(uint32_t* bins) {  // one thread: kShadeBins counts -> exclusive offsets in the cursor half
+    uint32_t run = 0;
+    for (int c = 0; c < kShadeBins; ++c) {
+        bins[kShadeBins + c] = run;
+        run += bins[c];
+    }
+}
+__global__ void __launch_bounds__(kBlock) classify_scatter_kernel(const RenderParams P, int k) {
+    const uint32_t n = P.q.counts[k];
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t c = shade_class(P, i);
+        const unsigned peers = __match_any_sync(__activemask(), c);
+        const unsigned lane = threadIdx.x & 31u;
+        const int leader = __ffs(peers) - 1;
+        uint32_t base = 0;
+        if ((int)lane == leader) base = atomicAdd(P.q.bins + kShadeBins + c, (uint32_t)__popc(peers));
+        base = __shfl_sync(peers, base, leader);
+        P.q.order[base + (uint32_t)__popc(peers & ((1u << lane) - 1u))] = i;
+    }
+}
+
 // PASS selects what one launch does with a vertex: SHADE_FUSED everything (worlds with volume regions); SHADE_VERTEX
 // everything except the BSDF sampling of a surface vertex; SHADE_SCATTER only that — BSDF sample, Russian roulette,
 // continuation ray (tracer.rs:1459-1530). The fused kernel is 230 KB of machine code and ncu attributes 44 % of its stalls to
@@ -184,7 +229,7 @@ __device__ __forceinline__ float bounce_emission_weight(const RenderParams& P, u
 enum : int { SHADE_FUSED = 0, SHADE_VERTEX = 1, SHADE_SCATTER = 2 };
 
 template <bool VOL, int PASS>
-__global__ void __launch_bounds__(kBlock, VOL ? 4 : CRT_SHADE_MINBLOCKS) shade_kernel(const RenderParams P, int k, int cur) {
+__global__ void __launch_bounds__(kBlock, VOL ? 4 : CRT_SHADE_MINBLOCKS) shade_kernel(const RenderParams P, int k, int cur, const uint32_t* __restrict__ order) {
     static_assert(!VOL || PASS == SHADE_FUSED, "worlds with volume regions use the fused kernel");
     const int D = (int)P.st.max_depth;
     const uint32_t n = P.q.counts[k];
@@ -192,7 +237,8 @@ __global__ void __launch_bounds__(kBlock, VOL ? 4 : CRT_SHADE_MINBLOCKS) shade_k
     uint32_t* sh_count = P.q.counts + (D + 2) + k;
     const int nxt = cur ^ 1;
 
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+        const uint32_t i = order ? order[j] : j;
         const uint32_t path = P.q.path[cur][i];
         const float4 ra = P.q.rays[cur][2 * (size_t)i], rb = P.q.rays[cur][2 * (size_t)i + 1];
         const V3 ro = xyz(ra), rd = xyz(rb);
@@ -637,6 +683,8 @@ struct crt_world {
     uint32_t* d_geom_material = nullptr;
     Light* d_lights = nullptr;
     int32_t* d_geom_light = nullptr;
+    uint8_t* d_mat_class = nullptr;
+    int n_signatures = 0;              // distinct lobe signatures among the materials
     std::vector<float*> d_env_arrays;  // one block of device floats per environment map
     std::vector<EnvMap> envs;          // device views
     EnvMap* d_envs = nullptr;
@@ -650,6 +698,7 @@ struct crt_world {
         cudaFree(d_geom_material);
         cudaFree(d_lights);
         cudaFree(d_geom_light);
+        cudaFree(d_mat_class);
         cudaFree(d_envs);
         for (float* p : d_env_arrays) cudaFree(p);
         for (float* p : d_grids) cudaFree(p);
@@ -684,6 +733,22 @@ int crt_world_new(crt_scene* scene, const crt_material* materials, size_t n_mate
     for (size_t i = 0; i < n_materials; ++i) w->materials.push_back(material_from_abi(materials[i]));
     w->geom_material.assign(geom_material, geom_material + n_geoms);
     for (size_t i = 0; i < n_lights; ++i) w->lights.push_back(light_from_abi(lights[i]));
+    // Shading classes: materials that take the same branches through the OpenPBR code (same set of active lobes) share one.
+    std::vector<uint8_t> mat_class(std::max<size_t>(n_materials, 1), 1);
+    {
+        std::vector<uint32_t> seen;
+        for (size_t i = 0; i < n_materials; ++i) {
+            const Material& m = w->materials[i];
+            uint32_t sig = m.kind == MAT_EMISSIVE ? 0x80000000u
+                                                  : (m.transmission_weight > 0.0f ? 1u : 0u) | (m.coat_weight > 0.0f ? 2u : 0u) | (m.fuzz_weight > 0.0f ? 4u : 0u) |
+                                                        (m.geometry_thin_walled ? 8u : 0u) | (m.base_metalness > 0.0f ? 16u : 0u) | (m.subsurface_weight > 0.0f ? 32u : 0u) |
+                                                        (m.thin_film_weight > 0.0f ? 64u : 0u) | (m.specular_weight > 0.0f ? 128u : 0u);
+            size_t c = std::find(seen.begin(), seen.end(), sig) - seen.begin();
+            if (c == seen.size()) seen.push_back(sig);
+            mat_class[i] = (uint8_t)std::min<size_t>(1 + c, kShadeBins - 1);
+        }
+        w->n_signatures = (int)seen.size();
+    }
     std::vector<int32_t> geom_light(n_geoms, -1);
     for (size_t g = 0; g < n_geoms; ++g) geom_light[g] = light_find_by_geom(w->lights.data(), (int)w->lights.size(), (uint32_t)g);
     auto up = [&](void** dst, const void* src, size_t bytes) -> cudaError_t {
@@ -695,7 +760,8 @@ int crt_world_new(crt_scene* scene, const crt_material* materials, size_t n_mate
     if ((e = up((void**)&w->d_materials, w->materials.data(), w->materials.size() * sizeof(Material))) != cudaSuccess ||
         (e = up((void**)&w->d_geom_material, w->geom_material.data(), n_geoms * sizeof(uint32_t))) != cudaSuccess ||
         (e = up((void**)&w->d_lights, w->lights.data(), w->lights.size() * sizeof(Light))) != cudaSuccess ||
-        (e = up((void**)&w->d_geom_light, geom_light.data(), n_geoms * sizeof(int32_t))) != cudaSuccess) {
+        (e = up((void**)&w->d_geom_light, geom_light.data(), n_geoms * sizeof(int32_t))) != cudaSuccess ||
+        (e = up((void**)&w->d_mat_class, mat_class.data(), mat_class.size())) != cudaSuccess) {
         delete w;
         return crt::set_cuda_error(e, "crt_world_new upload");
     }
@@ -971,7 +1037,8 @@ int render_impl(crt_world* w, const crt_camera* camera, const crt_render_setting
     {
         size_t need = 3 * carve_bytes(cap, 16) + 2 * carve_bytes(cap, 8) + carve_bytes(cap, 4)                       // path state
                       + 2 * (carve_bytes(2 * cap, 16) + 2 * carve_bytes(cap, 4)) + carve_bytes(2 * cap, 16) + carve_bytes(cap, 1)  // extend
-                      + carve_bytes(2 * cap, 16) + 2 * carve_bytes(cap, 4) + carve_bytes(cap, 16) + carve_bytes(cap, 1);          // shadow
+                      + carve_bytes(2 * cap, 16) + 2 * carve_bytes(cap, 4) + carve_bytes(cap, 16) + carve_bytes(cap, 1)           // shadow
+                      + carve_bytes(cap, 4) + carve_bytes(2 * kShadeBins, 4);                                                      // shading order
         if (need > sc.cap_paths) {
             cudaFree(sc.paths);
             sc.paths = nullptr;
@@ -1003,6 +1070,7 @@ int render_impl(crt_world* w, const crt_camera* camera, const crt_render_setting
     P.st = settings_from_abi(*s);
     P.materials = w->d_materials;
     P.geom_material = w->d_geom_material;
+    P.mat_class = w->d_mat_class;
     P.lights = w->d_lights;
     P.geom_light = w->d_geom_light;
     P.envs = w->d_envs;
@@ -1033,6 +1101,8 @@ int render_impl(crt_world* w, const crt_camera* camera, const crt_render_setting
         P.q.spath = carve<uint32_t>(p, cap);
         P.q.scontrib = carve<float4>(p, cap);
         P.q.occ = carve<uint8_t>(p, cap);
+        P.q.order = carve<uint32_t>(p, cap);
+        P.q.bins = carve<uint32_t>(p, 2 * kShadeBins);
         P.q.counts = sc.counts;
     }
     auto grid_for = [&](size_t n) {
@@ -1041,6 +1111,9 @@ int render_impl(crt_world* w, const crt_camera* camera, const crt_render_setting
     };
 
     const bool split_shade = !getenv("CRT_SHADE_FUSED");  // development switch: the fused kernel for A/B timing
+    // Worth it only where warps would otherwise mix several code paths (measured: openpbr_showcase, 7 signatures, -30 %;
+    // veach_mis, 3 signatures, +1.5 %; the two-signature stress scene +8 %: the sorted order costs the next queue's locality)
+    const bool sort_shade = !getenv("CRT_SHADE_UNSORTED") && (w->n_signatures >= 4 || getenv("CRT_SHADE_SORTED"));
     // without light sampling the vertex pass is nearly empty and the second launch costs more than it saves (measured on the
     // sky-only cornellbox / MedCity scenes)
     const bool PL_has_nee = P.n_lights > 0 && strategy_samples_lights(P.st.sampling_strategy);
@@ -1071,16 +1144,26 @@ int render_impl(crt_world* w, const crt_camera* camera, const crt_render_setting
             qt.counter = sc.counts + 2 * (D + 2) + k;
             int r = crt::enqueue_queue_trace(w->scene, false, qt, stream);
             if (r) return r;
+            // group the queue by class when it is long enough to pay for the three extra launches
+            const uint32_t* order = nullptr;
+            if (sort_shade && bound >= (1u << 17) && k < D) {
+                CKR(cudaMemsetAsync(P.q.bins, 0, 2 * kShadeBins * sizeof(uint32_t), stream));
+                classify_count_kernel<<<grid_for(bound), kBlock, 0, stream>>>(P, k);
+                classify_scan_kernel<<<1, 1, 0, stream>>>(P.q.bins);
+                classify_scatter_kernel<<<grid_for(bound), kBlock, 0, stream>>>(P, k);
+                launches += 3;
+                order = P.q.order;
+            }
             if (P.n_volumes > 0) {
-                shade_kernel<true, SHADE_FUSED><<<grid_for(bound), kBlock, 0, stream>>>(P, k, cur);
+                shade_kernel<true, SHADE_FUSED><<<grid_for(bound), kBlock, 0, stream>>>(P, k, cur, order);
             } else if (split_shade && PL_has_nee) {
-                shade_kernel<false, SHADE_VERTEX><<<grid_for(bound), kBlock, 0, stream>>>(P, k, cur);
+                shade_kernel<false, SHADE_VERTEX><<<grid_for(bound), kBlock, 0, stream>>>(P, k, cur, order);
                 if (k < D) {  // a depth-exhausted vertex has no continuation to sample
-                    shade_kernel<false, SHADE_SCATTER><<<grid_for(bound), kBlock, 0, stream>>>(P, k, cur);
+                    shade_kernel<false, SHADE_SCATTER><<<grid_for(bound), kBlock, 0, stream>>>(P, k, cur, order);
                     ++launches;
                 }
             } else {
-                shade_kernel<false, SHADE_FUSED><<<grid_for(bound), kBlock, 0, stream>>>(P, k, cur);
+                shade_kernel<false, SHADE_FUSED><<<grid_for(bound), kBlock, 0, stream>>>(P, k, cur, order);
             }
             launches += 2;
             ++trace_launches;
