@@ -79,7 +79,7 @@ struct Queues {
     // shading order of the current extend queue: its entries grouped by class (miss, then one class per material), so a
     // warp of shade threads runs one material's code; null = queue order
     uint32_t* order;
-    uint32_t* bins;      // kShadeBins class counts, then kShadeBins scatter cursors
+    uint32_t* bins;      // [class][sort block] counts, scanned in place into offsets
     // per wavefront, all zeroed by one memset: ext_count[D+2] | sh_count[D+2] | ext_fetch[D+2] | sh_fetch[D+2]
     uint32_t* counts;
 };
@@ -191,32 +191,86 @@ __device__ __forceinline__ uint32_t shade_class(const RenderParams& P, uint32_t 
     if (geom_id == CRT_INVALID_ID) return 0u;
     return P.mat_class[P.geom_material[geom_id]];
 }
-__global__ void __launch_bounds__(kBlock) classify_count_kernel(const RenderParams P, int k) {
-    const uint32_t n = P.q.counts[k];
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+// A STABLE counting sort: entries of one class keep their queue order, which is also the order in which their continuation
+// rays enter the next queue — neighbouring paths stay neighbours there, and the traversal kernel depends on that coherence
+// (an unstable scatter by atomics cost the stress scene 8 %). Each block owns one contiguous chunk of the queue.
+constexpr int kSortBlocks = 1024;
+__device__ __forceinline__ void sort_chunk(uint32_t n, uint32_t& begin, uint32_t& end) {
+    uint32_t per = (n + gridDim.x - 1) / gridDim.x;
+    per = (per + kBlock - 1) / kBlock * kBlock;
+    begin = min(n, blockIdx.x * per);
+    end = min(n, begin + per);
+}
+// pass 1: per-block class counts -> bins[class * gridDim + block]
+__global__ void __launch_bounds__(kBlock) classify_count_kernel(const RenderParams P, int k, int nc) {  // nc = classes in use
+    __shared__ uint32_t cnt[kShadeBins];
+    for (int c = threadIdx.x; c < nc; c += kBlock) cnt[c] = 0;
+    __syncthreads();
+    uint32_t begin, end;
+    sort_chunk(P.q.counts[k], begin, end);
+    for (uint32_t i = begin + threadIdx.x; i < end; i += kBlock) {
         const uint32_t c = shade_class(P, i);
         const unsigned peers = __match_any_sync(__activemask(), c);
-        if ((threadIdx.x & 31u) == (unsigned)(__ffs(peers) - 1)) atomicAdd(P.q.bins + c, (uint32_t)__popc(peers));
+        if ((threadIdx.x & 31u) == (unsigned)(__ffs(peers) - 1)) atomicAdd(&cnt[c], (uint32_t)__popc(peers));
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < nc; c += kBlock) P.q.bins[(size_t)c * gridDim.x + blockIdx.x] = cnt[c];
+}
+// pass 2: exclusive scan of the (class-major, block-minor) counts, in place; one block
+__global__ void __launch_bounds__(1024) classify_scan_kernel(uint32_t* bins, uint32_t total) {
+    __shared__ uint32_t part[1024];
+    const uint32_t per = (total + 1023u) / 1024u;
+    const uint32_t lo = min(total, threadIdx.x * per), hi = min(total, lo + per);
+    uint32_t sum = 0;
+    for (uint32_t i = lo; i < hi; ++i) sum += bins[i];
+    part[threadIdx.x] = sum;
+    __syncthreads();
+    for (int off = 1; off < 1024; off <<= 1) {  // Hillis-Steele inclusive scan of the 1024 partial sums
+        uint32_t v = threadIdx.x >= (unsigned)off ? part[threadIdx.x - off] : 0u;
+        __syncthreads();
+        part[threadIdx.x] += v;
+        __syncthreads();
+    }
+    uint32_t run = part[threadIdx.x] - sum;
+    for (uint32_t i = lo; i < hi; ++i) {
+        uint32_t v = bins[i];
+        bins[i] = run;
+        run += v;
     }
 }
-__global__ void classify_scan_kernel(uint32_t* bins) {  // one thread: kShadeBins counts -> exclusive offsets in the cursor half
-    uint32_t run = 0;
-    for (int c = 0; c < kShadeBins; ++c) {
-        bins[kShadeBins + c] = run;
-        run += bins[c];
-    }
-}
-__global__ void __launch_bounds__(kBlock) classify_scatter_kernel(const RenderParams P, int k) {
-    const uint32_t n = P.q.counts[k];
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const uint32_t c = shade_class(P, i);
-        const unsigned peers = __match_any_sync(__activemask(), c);
-        const unsigned lane = threadIdx.x & 31u;
-        const int leader = __ffs(peers) - 1;
-        uint32_t base = 0;
-        if ((int)lane == leader) base = atomicAdd(P.q.bins + kShadeBins + c, (uint32_t)__popc(peers));
-        base = __shfl_sync(peers, base, leader);
-        P.q.order[base + (uint32_t)__popc(peers & ((1u << lane) - 1u))] = i;
+// pass 3: every entry goes to (its block's offset for its class) + (its rank among the block's earlier entries of the class)
+__global__ void __launch_bounds__(kBlock) classify_scatter_kernel(const RenderParams P, int k, int nc) {
+    __shared__ uint32_t running[kShadeBins];            // entries of each class this block has placed so far
+    __shared__ uint32_t warp_cnt[kBlock / 32][kShadeBins];
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    for (int c = threadIdx.x; c < nc; c += kBlock) running[c] = P.q.bins[(size_t)c * gridDim.x + blockIdx.x];
+    uint32_t begin, end;
+    sort_chunk(P.q.counts[k], begin, end);
+    for (uint32_t base_i = begin; base_i < end; base_i += kBlock) {  // uniform trip count: the barriers below are safe
+        for (int c = threadIdx.x; c < (kBlock / 32) * nc; c += kBlock) warp_cnt[c / nc][c % nc] = 0;
+        __syncthreads();
+        const uint32_t i = base_i + threadIdx.x;
+        const bool live = i < end;
+        uint32_t c = 0, rank = 0;
+        if (live) {
+            c = shade_class(P, i);
+            const unsigned peers = __match_any_sync(__activemask(), c);
+            rank = (uint32_t)__popc(peers & ((1u << lane) - 1u));
+            if ((int)lane == __ffs(peers) - 1) warp_cnt[warp][c] = (uint32_t)__popc(peers);
+        }
+        __syncthreads();
+        if (live) {
+            uint32_t before = running[c];
+            for (unsigned w = 0; w < warp; ++w) before += warp_cnt[w][c];
+            P.q.order[before + rank] = i;
+        }
+        __syncthreads();
+        for (int cc = threadIdx.x; cc < nc; cc += kBlock) {
+            uint32_t add = 0;
+            for (int w = 0; w < kBlock / 32; ++w) add += warp_cnt[w][cc];
+            running[cc] += add;
+        }
+        __syncthreads();
     }
 }
 
@@ -1038,7 +1092,7 @@ int render_impl(crt_world* w, const crt_camera* camera, const crt_render_setting
         size_t need = 3 * carve_bytes(cap, 16) + 2 * carve_bytes(cap, 8) + carve_bytes(cap, 4)                       // path state
                       + 2 * (carve_bytes(2 * cap, 16) + 2 * carve_bytes(cap, 4)) + carve_bytes(2 * cap, 16) + carve_bytes(cap, 1)  // extend
                       + carve_bytes(2 * cap, 16) + 2 * carve_bytes(cap, 4) + carve_bytes(cap, 16) + carve_bytes(cap, 1)           // shadow
-                      + carve_bytes(cap, 4) + carve_bytes(2 * kShadeBins, 4);                                                      // shading order
+                      + carve_bytes(cap, 4) + carve_bytes((size_t)kShadeBins * kSortBlocks, 4);                                     // shading order
         if (need > sc.cap_paths) {
             cudaFree(sc.paths);
             sc.paths = nullptr;
@@ -1102,7 +1156,7 @@ int render_impl(crt_world* w, const crt_camera* camera, const crt_render_setting
         P.q.scontrib = carve<float4>(p, cap);
         P.q.occ = carve<uint8_t>(p, cap);
         P.q.order = carve<uint32_t>(p, cap);
-        P.q.bins = carve<uint32_t>(p, 2 * kShadeBins);
+        P.q.bins = carve<uint32_t>(p, (size_t)kShadeBins * kSortBlocks);
         P.q.counts = sc.counts;
     }
     auto grid_for = [&](size_t n) {
@@ -1113,7 +1167,7 @@ int render_impl(crt_world* w, const crt_camera* camera, const crt_render_setting
     const bool split_shade = !getenv("CRT_SHADE_FUSED");  // development switch: the fused kernel for A/B timing
     // Worth it only where warps would otherwise mix several code paths (measured: openpbr_showcase, 7 signatures, -30 %;
     // veach_mis, 3 signatures, +1.5 %; the two-signature stress scene +8 %: the sorted order costs the next queue's locality)
-    const bool sort_shade = !getenv("CRT_SHADE_UNSORTED") && (w->n_signatures >= 4 || getenv("CRT_SHADE_SORTED"));
+    const bool sort_shade = !getenv("CRT_SHADE_UNSORTED") && (w->n_signatures >= 3 || getenv("CRT_SHADE_SORTED"));
     // without light sampling the vertex pass is nearly empty and the second launch costs more than it saves (measured on the
     // sky-only cornellbox / MedCity scenes)
     const bool PL_has_nee = P.n_lights > 0 && strategy_samples_lights(P.st.sampling_strategy);
@@ -1147,10 +1201,11 @@ int render_impl(crt_world* w, const crt_camera* camera, const crt_render_setting
             // group the queue by class when it is long enough to pay for the three extra launches
             const uint32_t* order = nullptr;
             if (sort_shade && bound >= (1u << 17) && k < D) {
-                CKR(cudaMemsetAsync(P.q.bins, 0, 2 * kShadeBins * sizeof(uint32_t), stream));
-                classify_count_kernel<<<grid_for(bound), kBlock, 0, stream>>>(P, k);
-                classify_scan_kernel<<<1, 1, 0, stream>>>(P.q.bins);
-                classify_scatter_kernel<<<grid_for(bound), kBlock, 0, stream>>>(P, k);
+                const int sort_blocks = (int)std::min<size_t>(kSortBlocks, ((size_t)bound + 16 * kBlock - 1) / (16 * kBlock));
+                const int nc = std::min(kShadeBins, w->n_signatures + 1);  // miss + one class per signature
+                classify_count_kernel<<<sort_blocks, kBlock, 0, stream>>>(P, k, nc);
+                classify_scan_kernel<<<1, 1024, 0, stream>>>(P.q.bins, (uint32_t)(nc * sort_blocks));
+                classify_scatter_kernel<<<sort_blocks, kBlock, 0, stream>>>(P, k, nc);
                 launches += 3;
                 order = P.q.order;
             }
