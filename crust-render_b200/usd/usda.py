@@ -57,7 +57,8 @@ class Prim:
         return None if a is None else a.get()
 
     def is_active(self) -> bool:
-        return bool(self.metadata.get("active", True))
+        v = self.metadata.get("active", True)
+        return v.strip().lower() != "false" if isinstance(v, str) else bool(v)  # the text reader keeps `false` as a bare word
 
     def is_abstract(self) -> bool:
         return self.specifier == "class"
