@@ -173,12 +173,12 @@ CRT_HD float thin_film_reflectance_lambda(float cos_theta_1, float eta_1, float 
     float den = 1.0f + 2.0f * r_a * r_b * cos_phi + rab * rab;
     return clampf(num / fmaxf(den, 1e-8f), 0.0f, 1.0f);
 }
-CRT_HD V3 thin_film_fresnel(float cos_theta_1, float eta_1, float eta_film, float eta_2, float thickness_nm) {  // :381-394
+CRT_HD_NOINLINE V3 thin_film_fresnel(float cos_theta_1, float eta_1, float eta_film, float eta_2, float thickness_nm) {  // :381-394
     return {thin_film_reflectance_lambda(cos_theta_1, eta_1, eta_film, eta_2, thickness_nm, 615.0f),
             thin_film_reflectance_lambda(cos_theta_1, eta_1, eta_film, eta_2, thickness_nm, 545.0f),
             thin_film_reflectance_lambda(cos_theta_1, eta_1, eta_film, eta_2, thickness_nm, 465.0f)};
 }
-CRT_HD V3 thin_film_fresnel_metal(float cos_theta_1, float eta_1, float eta_film, V3 f0, float thickness_nm) {  // :396-412
+CRT_HD_NOINLINE V3 thin_film_fresnel_metal(float cos_theta_1, float eta_1, float eta_film, V3 f0, float thickness_nm) {  // :396-412
     float out[3];
     const float f0a[3] = {f0.x, f0.y, f0.z};
     for (int i = 0; i < 3; ++i) {

@@ -59,7 +59,7 @@ CRT_HD void env_texel(const EnvMap& m, V3 direction, int& x, int& y, float& v_ou
     y = y < m.height - 1 ? y : m.height - 1;
     v_out = v;
 }
-CRT_HD V3 env_radiance(const EnvMap& m, V3 direction) {  // :165-170
+CRT_HD_NOINLINE V3 env_radiance(const EnvMap& m, V3 direction) {  // :165-170
     int x, y;
     float v;
     env_texel(m, direction, x, y, v);
@@ -71,7 +71,7 @@ CRT_HD float env_solid_angle_pdf(float pdf_uv, float v) {  // :197-203
     if (sin_theta <= 0.0f) return 0.0f;
     return pdf_uv / (2.0f * PI_F * PI_F * sin_theta);
 }
-CRT_HD bool env_sample(const EnvMap& m, float u1, float u2, V3& direction, V3& radiance, float& pdf) {  // :174-184
+CRT_HD_NOINLINE bool env_sample(const EnvMap& m, float u1, float u2, V3& direction, V3& radiance, float& pdf) {  // :174-184
     if (m.marg_integral <= 0.0f) return false;
     float v, pdf_v, u, pdf_u;
     int row, col;
@@ -83,7 +83,7 @@ CRT_HD bool env_sample(const EnvMap& m, float u1, float u2, V3& direction, V3& r
     radiance = env_radiance(m, direction);
     return true;
 }
-CRT_HD float env_pdf(const EnvMap& m, V3 direction) {  // :188-195
+CRT_HD_NOINLINE float env_pdf(const EnvMap& m, V3 direction) {  // :188-195
     if (m.marg_integral <= 0.0f) return 0.0f;
     int x, y;
     float v;

@@ -48,7 +48,7 @@ CRT_HD Medium medium_blend(const Medium& a, float wa, const Medium& b, float wb)
     m.g = sa + sb > 1e-8f ? (a.g * sa + b.g * sb) / (sa + sb) : 0.0f;
     return m;
 }
-CRT_HD V3 sample_henyey_greenstein(V3 wi, float g, float u1, float u2) {  // :155-179
+CRT_HD_NOINLINE V3 sample_henyey_greenstein(V3 wi, float g, float u1, float u2) {  // :155-179
     float cos_theta;
     if (fabsf(g) < 1e-3f) {
         cos_theta = 1.0f - 2.0f * u1;
@@ -258,7 +258,7 @@ CRT_HD_NOINLINE V3 eval_specular(const Material& m, V3 v_local, V3 l_local, V3 h
     return (metal_term + diel_term) * brdf;
 }
 
-CRT_HD V3 eval_coat(const Material& m, V3 v_local, V3 l_local, V3 h_local, float ax, float ay) {  // openpbr.rs:553-576
+CRT_HD_NOINLINE V3 eval_coat(const Material& m, V3 v_local, V3 l_local, V3 h_local, float ax, float ay) {  // openpbr.rs:553-576
     float n_dot_v = fmaxf(v_local.z, 1e-4f), n_dot_l = fmaxf(l_local.z, 1e-4f), n_dot_h = fmaxf(h_local.z, 1e-4f);
     float v_dot_h = fmaxf(dot(v_local, h_local), 1e-4f);
     float d = ggx_d_aniso(n_dot_h, h_local.x, h_local.y, ax, ay);
@@ -267,7 +267,7 @@ CRT_HD V3 eval_coat(const Material& m, V3 v_local, V3 l_local, V3 h_local, float
     float brdf = d * g / (4.0f * n_dot_v * n_dot_l);
     return splat(m.coat_weight * f * brdf);
 }
-CRT_HD V3 coat_passage(const Material& m, float cos_theta) {  // openpbr.rs:587-603
+CRT_HD_NOINLINE V3 coat_passage(const Material& m, float cos_theta) {  // openpbr.rs:587-603
     float cos_i = clampf(cos_theta, 1e-4f, 1.0f);
     float eta = fmaxf(m.coat_ior, 1e-4f);
     float sin2_t = (1.0f - cos_i * cos_i) / (eta * eta);
@@ -283,7 +283,7 @@ CRT_HD V3 coat_attenuation(const Material& m, float cos_v, float cos_l) {  // op
     V3 dark = coat_darkening_factor(m.base_color, m.coat_ior, m.coat_darkening);
     return coat_passage(m, cos_v) * coat_passage(m, cos_l) * dark;
 }
-CRT_HD V3 eval_fuzz(const Material& m, V3 v_local, V3 l_local, V3 h_local) {  // openpbr.rs:622-627
+CRT_HD_NOINLINE V3 eval_fuzz(const Material& m, V3 v_local, V3 l_local, V3 h_local) {  // openpbr.rs:622-627
     float n_dot_v = fmaxf(v_local.z, 1e-4f), n_dot_l = fmaxf(l_local.z, 1e-4f), n_dot_h = fmaxf(h_local.z, 0.0f);
     return m.fuzz_color * m.fuzz_weight * sheen_charlie(n_dot_v, n_dot_l, n_dot_h, m.fuzz_roughness);
 }

@@ -53,18 +53,9 @@ CRT_HD float light_solid_angle_pdf(const Light& l, V3 from, V3 light_point) {  /
     float cosine = fmaxf(dot(light_normal_at(l, light_point), -dir_to_light), 0.0f);
     return d2 / (cosine * light_area(l) + 1e-4f);
 }
-CRT_HD bool light_sample_li(const Light& l, V3 from, float u, float v, LightSample& out, const EnvMap* envs = nullptr) {
-    if (l.kind <= LIGHT_RECT) {  // AreaLight::sample_li :202-215
-        V3 lp = light_sample_point(l, u, v);
-        V3 to_light = lp - from;
-        float distance = length(to_light);
-        if (distance < 1e-6f) return false;
-        out.direction = to_light / distance;
-        out.distance = distance;
-        out.radiance = l.radiance;
-        out.pdf = light_solid_angle_pdf(l, from, lp);
-        return true;
-    }
+// Lights at infinity, out of line: a shading kernel keeps only the area-light path inline (code that is compiled into
+// the hot instruction stream but never taken still costs instruction-cache lines).
+CRT_HD_NOINLINE bool light_sample_li_infinite(const Light& l, float u, float v, LightSample& out, const EnvMap* envs) {
     if (l.kind == LIGHT_DISTANT) {  // :281-295
         float cos_theta = 1.0f - u * (1.0f - l.r);
         float sin_theta = sqrtf(fmaxf(1.0f - cos_theta * cos_theta, 0.0f));
@@ -96,10 +87,24 @@ CRT_HD bool light_sample_li(const Light& l, V3 from, float u, float v, LightSamp
     out.pdf = 1.0f / (4.0f * PI_F);
     return true;
 }
+CRT_HD bool light_sample_li(const Light& l, V3 from, float u, float v, LightSample& out, const EnvMap* envs = nullptr) {
+    if (l.kind <= LIGHT_RECT) {  // AreaLight::sample_li :202-215
+        V3 lp = light_sample_point(l, u, v);
+        V3 to_light = lp - from;
+        float distance = length(to_light);
+        if (distance < 1e-6f) return false;
+        out.direction = to_light / distance;
+        out.distance = distance;
+        out.radiance = l.radiance;
+        out.pdf = light_solid_angle_pdf(l, from, lp);
+        return true;
+    }
+    return light_sample_li_infinite(l, u, v, out, envs);
+}
 CRT_HD float light_pdf_at_point(const Light& l, V3 from, V3 light_point) {  // :217-219, default 0
     return l.kind <= LIGHT_RECT ? light_solid_angle_pdf(l, from, light_point) : 0.0f;
 }
-CRT_HD bool light_escaped(const Light& l, V3 direction, V3& radiance, float& pdf, const EnvMap* envs = nullptr) {  // :297-300, 384-387
+CRT_HD_NOINLINE bool light_escaped(const Light& l, V3 direction, V3& radiance, float& pdf, const EnvMap* envs = nullptr) {  // :297-300, 384-387
     if (l.kind == LIGHT_DISTANT) {
         if (!(dot(direction, -l.n) >= l.r)) return false;
         radiance = l.radiance / fmaxf(l.s, 1e-12f);
