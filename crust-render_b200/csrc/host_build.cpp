@@ -5,6 +5,8 @@
 #include <algorithm>
 #include <chrono>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <future>
 #include <limits>
@@ -590,62 +592,126 @@ inline Vec3 v3at(const std::vector<float>& a, size_t i) { return V(a[3 * i], a[3
 bool build_host_tree(std::vector<Geom>& geoms, ChildInfoFn child_info, int threads, HostTree& out, const char** err) {
     auto t0 = std::chrono::steady_clock::now();
     PrimStore& ps = out.prims;
-    // scene.rs:237-238: size the primitive arrays once.
-    size_t total = 0;
-    for (const Geom& g : geoms)
-        total += g.type == G_MESH ? g.indices.size() / 3
-                                  : (g.type == G_CURVES ? g.segs.size() / 8 : (g.type == G_CUBICS ? g.segs.size() / 14 : 1));
-    ps.kind.reserve(total), ps.geom_id.reserve(total), ps.prim_id.reserve(total), ps.mask.reserve(total), ps.data.reserve(total);
-    auto push = [&](PrimKind k, uint32_t gid, uint32_t pid, uint32_t mask, uint32_t data) {
-        ps.kind.push_back(k), ps.geom_id.push_back(gid), ps.prim_id.push_back(pid), ps.mask.push_back(mask), ps.data.push_back(data);
+    if (threads <= 0) threads = (int)std::max(1u, std::thread::hardware_concurrency());
+    // Runs fn(k) for k in [0, count) on up to `threads` workers (static interleave). Every k writes its own slice of the
+    // output arrays, so the result does not depend on the thread count.
+    auto parallel_for = [&](size_t count, auto&& fn) {
+        const int nt = (int)std::min<size_t>((size_t)threads, count);
+        if (nt <= 1) {
+            for (size_t k = 0; k < count; ++k) fn(k);
+            return;
+        }
+        std::vector<std::thread> pool;
+        for (int w = 1; w < nt; ++w)
+            pool.emplace_back([&, w] {
+                for (size_t k = (size_t)w; k < count; k += (size_t)nt) fn(k);
+            });
+        for (size_t k = 0; k < count; k += (size_t)nt) fn(k);
+        for (auto& th : pool) th.join();
     };
-    for (size_t gi = 0; gi < geoms.size(); ++gi) {  // scene.rs:240-335
-        Geom& g = geoms[gi];
-        const uint32_t gid = (uint32_t)gi;
+
+    // scene.rs:240-335, in two passes so that meshes expand in parallel: (1) how many primitives / per-kind records each
+    // geometry contributes (a triangle with an out-of-range index is skipped but still consumes its prim_id, :251-253),
+    // (2) every geometry fills its own slices. Slot numbers are exactly those of a sequential expansion.
+    const size_t ng = geoms.size();
+    struct Slice {
+        size_t prims = 0, tris = 0, tri_normals = 0, spheres = 0, curves = 0, cubics = 0, insts = 0;
+    };
+    std::vector<Slice> cnt(ng), off(ng);
+    std::vector<ChildInfo> cinfo(ng);
+    for (size_t gi = 0; gi < ng; ++gi) {  // instances first (sequential: they may fail, and they are few)
+        const Geom& g = geoms[gi];
+        if (g.type != G_INSTANCE) continue;
+        ChildInfo ci = child_info(g.child);
+        cinfo[gi] = ci;
+        if (!ci.non_empty) continue;  // scene.rs:307-309
+        if (ci.instance_depth + 1 > CRT_MAX_INSTANCE_DEPTH) {
+            *err = "instance nesting deeper than CRT_MAX_INSTANCE_DEPTH";
+            return false;
+        }
+        cnt[gi].prims = cnt[gi].insts = 1;
+    }
+    parallel_for(ng, [&](size_t gi) {
+        const Geom& g = geoms[gi];
+        Slice& c = cnt[gi];
         switch (g.type) {
             case G_MESH: {
-                size_t nv = g.verts.size() / 3, nn = g.normals.size() / 3, nt = g.indices.size() / 3;
+                const size_t nv = g.verts.size() / 3, nn = g.normals.size() / 3, nt = g.indices.size() / 3;
                 for (size_t k = 0; k < nt; ++k) {
-                    size_t i0 = g.indices[3 * k], i1 = g.indices[3 * k + 1], i2 = g.indices[3 * k + 2];
-                    if (i0 >= nv || i1 >= nv || i2 >= nv) continue;  // scene.rs:251-253: id still consumed
-                    uint32_t slot = (uint32_t)(ps.tri.size() / 9);
-                    for (size_t i : {i0, i1, i2})
-                        for (int c = 0; c < 3; ++c) ps.tri.push_back(g.verts[3 * i + c]);
-                    if (g.has_normals && i0 < nn && i1 < nn && i2 < nn) {  // scene.rs:254-257
-                        ps.tri_normal_slot.push_back((uint32_t)(ps.tri_normals.size() / 9));
-                        for (size_t i : {i0, i1, i2})
-                            for (int c = 0; c < 3; ++c) ps.tri_normals.push_back(g.normals[3 * i + c]);
-                        ps.any_normals = true;
+                    const size_t i0 = g.indices[3 * k], i1 = g.indices[3 * k + 1], i2 = g.indices[3 * k + 2];
+                    if (i0 >= nv || i1 >= nv || i2 >= nv) continue;
+                    ++c.tris;
+                    if (g.has_normals && i0 < nn && i1 < nn && i2 < nn) ++c.tri_normals;
+                }
+                c.prims = c.tris;
+                break;
+            }
+            case G_SPHERE: c.prims = c.spheres = 1; break;
+            case G_CURVES: c.prims = c.curves = g.segs.size() / 8; break;
+            case G_CUBICS: c.prims = c.cubics = g.segs.size() / 14; break;
+            default: break;  // instances were counted above
+        }
+    });
+    Slice total;
+    for (size_t gi = 0; gi < ng; ++gi) {
+        off[gi] = total;
+        total.prims += cnt[gi].prims, total.tris += cnt[gi].tris, total.tri_normals += cnt[gi].tri_normals, total.spheres += cnt[gi].spheres;
+        total.curves += cnt[gi].curves, total.cubics += cnt[gi].cubics, total.insts += cnt[gi].insts;
+    }
+    ps.kind.resize(total.prims), ps.geom_id.resize(total.prims), ps.prim_id.resize(total.prims), ps.mask.resize(total.prims), ps.data.resize(total.prims);
+    ps.tri.resize(9 * total.tris), ps.tri_normal_slot.resize(total.tris), ps.tri_normals.resize(9 * total.tri_normals);
+    ps.sphere.resize(4 * total.spheres), ps.curve.resize(8 * total.curves), ps.cubic.resize(14 * total.cubics), ps.inst.resize(total.insts);
+    ps.any_normals = total.tri_normals != 0;
+    parallel_for(ng, [&](size_t gi) {
+        Geom& g = geoms[gi];
+        const uint32_t gid = (uint32_t)gi;
+        const Slice& o = off[gi];
+        size_t pi = o.prims;
+        auto push = [&](PrimKind k, uint32_t pid, uint32_t data) {
+            ps.kind[pi] = k, ps.geom_id[pi] = gid, ps.prim_id[pi] = pid, ps.mask[pi] = g.mask, ps.data[pi] = data;
+            ++pi;
+        };
+        switch (g.type) {
+            case G_MESH: {
+                const size_t nv = g.verts.size() / 3, nn = g.normals.size() / 3, nt = g.indices.size() / 3;
+                size_t slot = o.tris, nslot = o.tri_normals;
+                for (size_t k = 0; k < nt; ++k) {
+                    const size_t idx[3] = {g.indices[3 * k], g.indices[3 * k + 1], g.indices[3 * k + 2]};
+                    if (idx[0] >= nv || idx[1] >= nv || idx[2] >= nv) continue;  // scene.rs:251-253: id still consumed
+                    for (int v = 0; v < 3; ++v)
+                        for (int c = 0; c < 3; ++c) ps.tri[9 * slot + 3 * v + c] = g.verts[3 * idx[v] + c];
+                    if (g.has_normals && idx[0] < nn && idx[1] < nn && idx[2] < nn) {  // scene.rs:254-257
+                        ps.tri_normal_slot[slot] = (uint32_t)nslot;
+                        for (int v = 0; v < 3; ++v)
+                            for (int c = 0; c < 3; ++c) ps.tri_normals[9 * nslot + 3 * v + c] = g.normals[3 * idx[v] + c];
+                        ++nslot;
                     } else {
-                        ps.tri_normal_slot.push_back(0xFFFFFFFFu);
+                        ps.tri_normal_slot[slot] = 0xFFFFFFFFu;
                     }
-                    push(P_TRI, gid, (uint32_t)k, g.mask, slot);
+                    push(P_TRI, (uint32_t)k, (uint32_t)slot);
+                    ++slot;
                 }
                 break;
             }
             case G_SPHERE:
-                push(P_SPHERE, gid, 0, g.mask, (uint32_t)(ps.sphere.size() / 4));
-                ps.sphere.insert(ps.sphere.end(), g.sphere, g.sphere + 4);
+                std::memcpy(&ps.sphere[4 * o.spheres], g.sphere, 4 * sizeof(float));
+                push(P_SPHERE, 0, (uint32_t)o.spheres);
                 break;
             case G_CURVES:
                 for (size_t k = 0; k < g.segs.size() / 8; ++k) {
-                    push(P_CURVE, gid, (uint32_t)k, g.mask, (uint32_t)(ps.curve.size() / 8));
-                    ps.curve.insert(ps.curve.end(), g.segs.begin() + 8 * k, g.segs.begin() + 8 * k + 8);
+                    std::memcpy(&ps.curve[8 * (o.curves + k)], &g.segs[8 * k], 8 * sizeof(float));
+                    push(P_CURVE, (uint32_t)k, (uint32_t)(o.curves + k));
                 }
                 break;
             case G_CUBICS:
                 for (size_t k = 0; k < g.segs.size() / 14; ++k) {
-                    push(P_CUBIC, gid, (uint32_t)k, g.mask, (uint32_t)(ps.cubic.size() / 14));
-                    ps.cubic.insert(ps.cubic.end(), g.segs.begin() + 14 * k, g.segs.begin() + 14 * k + 14);
+                    std::memcpy(&ps.cubic[14 * (o.cubics + k)], &g.segs[14 * k], 14 * sizeof(float));
+                    push(P_CUBIC, (uint32_t)k, (uint32_t)(o.cubics + k));
                 }
                 break;
             case G_INSTANCE: {
-                ChildInfo ci = child_info(g.child);
-                if (!ci.non_empty) break;  // scene.rs:307-309
-                if (ci.instance_depth + 1 > CRT_MAX_INSTANCE_DEPTH) {
-                    *err = "instance nesting deeper than CRT_MAX_INSTANCE_DEPTH";
-                    return false;
-                }
+                if (!cnt[gi].insts) break;
+                const ChildInfo& ci = cinfo[gi];
                 InstancePrim I;
                 I.child = g.child;
                 I.l2w = g.l2w;
@@ -654,10 +720,8 @@ bool build_host_tree(std::vector<Geom>& geoms, ChildInfoFn child_info, int threa
                 I.l2w_end = g.has_end ? g.l2w_end : g.l2w;
                 I.bounds = g.has_end ? unite(transformed_box(ci.bounds, g.l2w), transformed_box(ci.bounds, g.l2w_end))
                                      : transformed_box(ci.bounds, g.l2w);
-                out.has_motion |= g.has_end || ci.has_motion;  // scene.rs:322
-                out.instance_depth = std::max(out.instance_depth, ci.instance_depth + 1);
-                push(P_INSTANCE, gid, 0, g.mask, (uint32_t)ps.inst.size());
-                ps.inst.push_back(I);
+                ps.inst[o.insts] = I;
+                push(P_INSTANCE, 0, (uint32_t)o.insts);
                 break;
             }
         }
@@ -666,14 +730,28 @@ bool build_host_tree(std::vector<Geom>& geoms, ChildInfoFn child_info, int threa
         std::vector<uint32_t>().swap(g.indices);
         std::vector<float>().swap(g.normals);
         std::vector<float>().swap(g.segs);
+    });
+    for (size_t gi = 0; gi < ng; ++gi) {  // scene.rs:322 and the nesting depth, over the instances that were kept
+        if (!cnt[gi].insts) continue;
+        out.has_motion |= geoms[gi].has_end || cinfo[gi].has_motion;
+        out.instance_depth = std::max(out.instance_depth, cinfo[gi].instance_depth + 1);
     }
 
+    const bool timing = getenv("CRT_BUILD_TIMING") != nullptr;
+    auto lap = [&](const char* what) {
+        if (timing) fprintf(stderr, "[host build] %-28s %.3f s\n", what, std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
+    };
+    lap("expand geometries");
     const size_t n = ps.size();
     out.prim_ids.resize(2 * n);
-    for (size_t i = 0; i < n; ++i) {
-        out.prim_ids[2 * i] = ps.geom_id[i];
-        out.prim_ids[2 * i + 1] = ps.prim_id[i];
-    }
+    const size_t kChunk = (size_t)1 << 16;
+    const size_t n_chunks = (n + kChunk - 1) / kChunk;
+    parallel_for(n_chunks, [&](size_t c) {
+        for (size_t i = c * kChunk, e = std::min(n, (c + 1) * kChunk); i < e; ++i) {
+            out.prim_ids[2 * i] = ps.geom_id[i];
+            out.prim_ids[2 * i + 1] = ps.prim_id[i];
+        }
+    });
     if (ps.any_normals) {
         out.normals.assign(9 * n, 0.0f);
         for (size_t i = 0; i < n; ++i)
@@ -690,19 +768,26 @@ bool build_host_tree(std::vector<Geom>& geoms, ChildInfoFn child_info, int threa
     }
 
     std::vector<Ref> refs(n);
+    std::vector<float> diag(n);
+    parallel_for(n_chunks, [&](size_t c) {  // boxes in parallel ...
+        for (size_t i = c * kChunk, e = std::min(n, (c + 1) * kChunk); i < e; ++i) {
+            refs[i] = Ref{prim_box(ps, (uint32_t)i), (uint32_t)i};
+            Vec3 ext = sub(refs[i].b.hi, refs[i].b.lo);
+            diag[i] = std::sqrt(dot3(ext, ext));
+        }
+    });
     Box root;
-    for (size_t i = 0; i < n; ++i) {
-        refs[i] = Ref{prim_box(ps, (uint32_t)i), (uint32_t)i};
+    for (size_t i = 0; i < n; ++i) {  // ... the reductions in input order (a float sum depends on it)
         root = i == 0 ? refs[0].b : unite(root, refs[i].b);
-        Vec3 e = sub(refs[i].b.hi, refs[i].b.lo);
-        float diag = std::sqrt(dot3(e, e));
-        out.extent_sum += diag;
-        out.extent_max = std::max(out.extent_max, diag);
+        out.extent_sum += diag[i];
+        out.extent_max = std::max(out.extent_max, diag[i]);
     }
-    if (threads <= 0) threads = (int)std::max(1u, std::thread::hardware_concurrency());
+    std::vector<float>().swap(diag);
+    lap("ids, normals, references");
     Builder bld{ps, area(root), {threads - 1}};
     Out bin;
     bld.build(bin, refs, 0);
+    lap("binary SAH/SBVH build");
     out.n_binary = bin.nodes.size();
     out.non_empty = true;
     out.root = root;
@@ -710,6 +795,7 @@ bool build_host_tree(std::vector<Geom>& geoms, ChildInfoFn child_info, int threa
     out.leafs.reserve(bin.indices.size() * 12 + 16);
     Flattener fl{ps, bin.nodes, bin.indices, out};
     fl.run();
+    lap("BVH4 collapse + leaf records");
     out.build_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     return true;
 }
