@@ -194,6 +194,26 @@ struct BinAcc {
     }
 };
 
+// Data-parallel passes over the references of one large node. [0, n) is cut into contiguous chunks, chunk k is processed by
+// fn(k, lo, hi), and callers merge the per-chunk partial results IN CHUNK ORDER: min / max (ties keep the earlier operand, like
+// the sequential fold), integer counts and order-preserving concatenation all come out exactly as one pass would produce
+// them, so the tree does not depend on the number of threads (bvh.rs:1621-1638).
+struct Par {
+    int threads = 1;
+    size_t min_refs = (size_t)1 << 19;
+    int chunks_for(size_t n) const { return (threads > 1 && n >= min_refs) ? threads : 1; }
+    template <class F>
+    void run(size_t n, int nc, F&& fn) const {
+        const size_t per = (n + (size_t)nc - 1) / (size_t)nc;
+        auto lo = [&](int k) { return std::min(n, (size_t)k * per); };
+        if (nc <= 1) return fn(0, (size_t)0, n);
+        std::vector<std::thread> pool;
+        for (int k = 1; k < nc; ++k) pool.emplace_back([&, k] { fn(k, lo(k), lo(k + 1)); });
+        fn(0, lo(0), lo(1));
+        for (auto& t : pool) t.join();
+    }
+};
+
 // Sweep shared by both split kinds: candidate plane after bin `s` costs
 // area(∪ bounds[0..=s]) * Σ lcount[0..=s] + area(∪ bounds[s+1..]) * Σ rcount[s+1..]
 // (bvh.rs:931-967, 1020-1052); strict `<` keeps the first best.
@@ -225,15 +245,33 @@ void sweep(const BinAcc* bins, const size_t* lcount, const size_t* rcount, Emit&
     }
 }
 
-bool object_split(const std::vector<Ref>& refs, ObjSplit& out) {  // bvh.rs:894-969
+bool object_split(const std::vector<Ref>& refs, ObjSplit& out, const Par& par) {  // bvh.rs:894-969
+    const int nc = par.chunks_for(refs.size());
     Vec3 cmin, cmax;
-    for (int a = 0; a < 3; ++a) cmin[a] = cmax[a] = centroid_axis(refs[0], a);
-    for (size_t i = 1; i < refs.size(); ++i)
-        for (int a = 0; a < 3; ++a) {
-            float c = centroid_axis(refs[i], a);
-            cmin[a] = std::min(cmin[a], c);
-            cmax[a] = std::max(cmax[a], c);
+    {
+        std::vector<Vec3> pmin(nc), pmax(nc);
+        par.run(refs.size(), nc, [&](int k, size_t lo, size_t hi) {
+            if (lo >= hi) return;
+            Vec3 mn, mx;
+            for (int a = 0; a < 3; ++a) mn[a] = mx[a] = centroid_axis(refs[lo], a);
+            for (size_t i = lo + 1; i < hi; ++i)
+                for (int a = 0; a < 3; ++a) {
+                    float c = centroid_axis(refs[i], a);
+                    mn[a] = std::min(mn[a], c);
+                    mx[a] = std::max(mx[a], c);
+                }
+            pmin[k] = mn, pmax[k] = mx;
+        });
+        cmin = pmin[0], cmax = pmax[0];
+        const size_t per = (refs.size() + (size_t)nc - 1) / (size_t)nc;
+        for (int k = 1; k < nc; ++k) {
+            if ((size_t)k * per >= refs.size()) break;  // empty trailing chunk
+            for (int a = 0; a < 3; ++a) {
+                cmin[a] = std::min(cmin[a], pmin[k][a]);
+                cmax[a] = std::max(cmax[a], pmax[k][a]);
+            }
         }
+    }
     Vec3 extent = sub(cmax, cmin);
     int axis = longest_axis(extent);
     if (extent[axis] <= 1e-6f) return false;
@@ -241,10 +279,26 @@ bool object_split(const std::vector<Ref>& refs, ObjSplit& out) {  // bvh.rs:894-
     float c0 = cmin[axis];
     BinAcc bins[kBins];
     size_t counts[kBins] = {};
-    for (const Ref& r : refs) {
-        size_t b = to_bin((centroid_axis(r, axis) - c0) * scale);
-        counts[b] += 1;
-        bins[b].grow(r.b);
+    {
+        struct Part {
+            BinAcc bins[kBins];
+            size_t counts[kBins] = {};
+        };
+        std::vector<Part> part(nc);
+        par.run(refs.size(), nc, [&](int k, size_t lo, size_t hi) {
+            Part& p = part[k];
+            for (size_t i = lo; i < hi; ++i) {
+                const Ref& r = refs[i];
+                size_t b = to_bin((centroid_axis(r, axis) - c0) * scale);
+                p.counts[b] += 1;
+                p.bins[b].grow(r.b);
+            }
+        });
+        for (int k = 0; k < nc; ++k)
+            for (size_t b = 0; b < kBins; ++b) {
+                counts[b] += part[k].counts[b];
+                if (part[k].bins[b].some) bins[b].grow(part[k].bins[b].b);
+            }
     }
     bool found = false;
     sweep(bins, counts, counts, [&](size_t s, float cost, const Box& lb, const Box& rb) {
@@ -260,7 +314,7 @@ struct SpatSplit {
     int axis;
     float pos, cost;
 };
-bool spatial_split(const PrimStore& ps, const std::vector<Ref>& refs, const Box& bbox, SpatSplit& out) {  // bvh.rs:974-1054
+bool spatial_split(const PrimStore& ps, const std::vector<Ref>& refs, const Box& bbox, SpatSplit& out, const Par& par) {  // bvh.rs:974-1054
     Vec3 extent = sub(bbox.hi, bbox.lo);
     int axis = longest_axis(extent);
     if (extent[axis] <= 1e-6f) return false;
@@ -268,18 +322,36 @@ bool spatial_split(const PrimStore& ps, const std::vector<Ref>& refs, const Box&
     float width = extent[axis] / (float)kBins;
     BinAcc bins[kBins];
     size_t entry[kBins] = {}, exit_[kBins] = {};
-    for (const Ref& r : refs) {
-        size_t b0 = to_bin((r.b.lo[axis] - lo) / width), b1 = to_bin((r.b.hi[axis] - lo) / width);
-        entry[b0] += 1;
-        exit_[b1] += 1;
-        if (b0 == b1) {
-            bins[b0].grow(r.b);
-            continue;
-        }
-        for (size_t b = b0; b <= b1; ++b) {
-            Box c;
-            if (clipped_ref_box(ps, r, axis, lo + (float)b * width, lo + (float)(b + 1) * width, c)) bins[b].grow(c);
-        }
+    {
+        struct Part {
+            BinAcc bins[kBins];
+            size_t entry[kBins] = {}, exit_[kBins] = {};
+        };
+        const int nc = par.chunks_for(refs.size());
+        std::vector<Part> part(nc);
+        par.run(refs.size(), nc, [&](int k, size_t from, size_t to) {
+            Part& p = part[k];
+            for (size_t i = from; i < to; ++i) {
+                const Ref& r = refs[i];
+                size_t b0 = to_bin((r.b.lo[axis] - lo) / width), b1 = to_bin((r.b.hi[axis] - lo) / width);
+                p.entry[b0] += 1;
+                p.exit_[b1] += 1;
+                if (b0 == b1) {
+                    p.bins[b0].grow(r.b);
+                    continue;
+                }
+                for (size_t b = b0; b <= b1; ++b) {
+                    Box c;
+                    if (clipped_ref_box(ps, r, axis, lo + (float)b * width, lo + (float)(b + 1) * width, c)) p.bins[b].grow(c);
+                }
+            }
+        });
+        for (int k = 0; k < nc; ++k)
+            for (size_t b = 0; b < kBins; ++b) {
+                entry[b] += part[k].entry[b];
+                exit_[b] += part[k].exit_[b];
+                if (part[k].bins[b].some) bins[b].grow(part[k].bins[b].b);
+            }
     }
     bool found = false;
     sweep(bins, entry, exit_, [&](size_t s, float cost, const Box&, const Box&) {
@@ -299,8 +371,23 @@ struct Builder {
     const PrimStore& ps;
     float root_area;
     std::atomic<int> spare_threads;
+    Par all;  // every thread of the build; a node at depth d uses threads >> d of them for its own passes
 
-    size_t min_leaf_for(const std::vector<Ref>& refs) const {  // bvh.rs:1201-1210
+    size_t min_leaf_for(const std::vector<Ref>& refs, const Par& par) const {  // bvh.rs:1201-1210
+        const int nc = par.chunks_for(refs.size());
+        if (nc > 1) {
+            std::vector<char> other(nc, 0);
+            par.run(refs.size(), nc, [&](int k, size_t lo, size_t hi) {
+                for (size_t i = lo; i < hi; ++i)
+                    if (ps.kind[refs[i].idx] != P_TRI) {
+                        other[k] = 1;
+                        break;
+                    }
+            });
+            for (char o : other)
+                if (o) return kMinLeaf;
+            return kMinLeafPacked;
+        }
         for (const Ref& r : refs)
             if (ps.kind[r.idx] != P_TRI) return kMinLeaf;
         return kMinLeafPacked;
@@ -309,13 +396,34 @@ struct Builder {
         out.nodes.push_back(BinNode{bbox, (uint32_t)out.indices.size(), (uint32_t)refs.size()});
         for (const Ref& r : refs) out.indices.push_back(r.idx);
     }
-    static void stable_split(std::vector<Ref>& refs, const ObjSplit& o, std::vector<Ref>& l, std::vector<Ref>& r) {  // bvh.rs:1224-1237
+    void stable_split(std::vector<Ref>& refs, const ObjSplit& o, std::vector<Ref>& l, std::vector<Ref>& r, const Par& par) const {  // bvh.rs:1224-1237
+        auto left = [&](const Ref& x) { return to_bin((centroid_axis(x, o.axis) - o.cmin) * o.scale) <= o.split_bin; };
+        const int nc = par.chunks_for(refs.size());
+        if (nc > 1) {  // per-chunk counts, offsets by prefix, every chunk writes its own slices: order preserved
+            std::vector<size_t> nl(nc + 1, 0), nr(nc + 1, 0);
+            par.run(refs.size(), nc, [&](int k, size_t lo, size_t hi) {
+                size_t c = 0;
+                for (size_t i = lo; i < hi; ++i) c += left(refs[i]);
+                nl[k + 1] = c;
+                nr[k + 1] = (hi - lo) - c;
+            });
+            for (int k = 0; k < nc; ++k) nl[k + 1] += nl[k], nr[k + 1] += nr[k];
+            l.resize(nl[nc]);
+            r.resize(nr[nc]);
+            par.run(refs.size(), nc, [&](int k, size_t lo, size_t hi) {
+                size_t a = nl[k], b = nr[k];
+                for (size_t i = lo; i < hi; ++i) {
+                    if (left(refs[i])) l[a++] = refs[i]; else r[b++] = refs[i];
+                }
+            });
+            std::vector<Ref>().swap(refs);
+            return;
+        }
         size_t nl = 0;
-        for (const Ref& x : refs) nl += to_bin((centroid_axis(x, o.axis) - o.cmin) * o.scale) <= o.split_bin;
+        for (const Ref& x : refs) nl += left(x);
         l.reserve(nl);
         r.reserve(refs.size() - nl);
-        for (const Ref& x : refs)
-            (to_bin((centroid_axis(x, o.axis) - o.cmin) * o.scale) <= o.split_bin ? l : r).push_back(x);
+        for (const Ref& x : refs) (left(x) ? l : r).push_back(x);
         std::vector<Ref>().swap(refs);
     }
     // Appends `sub` (built standalone) behind `out`, rebasing like bvh.rs:846-872.
@@ -352,41 +460,77 @@ struct Builder {
 
     // bvh.rs:1059-1169 — emits the subtree of `refs` in depth-first order.
     void build(Out& out, std::vector<Ref>& refs, size_t depth) {
+        // up to 2^depth sibling subtrees are being built at the same time: each large node takes its share of the threads
+        const Par par{std::max(1, all.threads >> (int)std::min<size_t>(depth, 20)), all.min_refs};
         Box bbox = refs[0].b;
-        for (size_t i = 1; i < refs.size(); ++i) bbox = unite(bbox, refs[i].b);
+        {
+            const int nc = par.chunks_for(refs.size());
+            if (nc > 1) {
+                std::vector<Box> part(nc);
+                std::vector<char> some(nc, 0);
+                par.run(refs.size(), nc, [&](int k, size_t lo, size_t hi) {
+                    if (lo >= hi) return;
+                    Box b = refs[lo].b;
+                    for (size_t i = lo + 1; i < hi; ++i) b = unite(b, refs[i].b);
+                    part[k] = b, some[k] = 1;
+                });
+                bbox = part[0];
+                for (int k = 1; k < nc; ++k)
+                    if (some[k]) bbox = unite(bbox, part[k]);
+            } else {
+                for (size_t i = 1; i < refs.size(); ++i) bbox = unite(bbox, refs[i].b);
+            }
+        }
         const size_t count = refs.size();
-        if (count <= min_leaf_for(refs) || depth >= kMaxDepth) return emit_leaf(out, bbox, refs);
+        if (count <= min_leaf_for(refs, par) || depth >= kMaxDepth) return emit_leaf(out, bbox, refs);
 
         ObjSplit obj{};
-        const bool have_obj = object_split(refs, obj);
+        const bool have_obj = object_split(refs, obj, par);
         SpatSplit spat{};
         bool have_spat = false;
         if (have_obj && depth < kSbvhMaxDepth) {
             Box ov;
             float overlap = overlap_box(obj.left, obj.right, ov) ? area(ov) : 0.0f;
-            if (overlap / root_area > kSbvhAlpha) have_spat = spatial_split(ps, refs, bbox, spat) && spat.cost < obj.cost;
+            if (overlap / root_area > kSbvhAlpha) have_spat = spatial_split(ps, refs, bbox, spat, par) && spat.cost < obj.cost;
         }
 
         std::vector<Ref> l, r;
         if (have_spat) {  // bvh.rs:1089-1135
-            for (const Ref& x : refs) {
-                if (x.b.hi[spat.axis] <= spat.pos)
-                    l.push_back(x);
-                else if (x.b.lo[spat.axis] >= spat.pos)
-                    r.push_back(x);
-                else {
-                    Box c;
-                    if (clipped_ref_box(ps, x, spat.axis, -kInf, spat.pos, c)) l.push_back(Ref{c, x.idx});
-                    if (clipped_ref_box(ps, x, spat.axis, spat.pos, kInf, c)) r.push_back(Ref{c, x.idx});
+            auto chop = [&](size_t lo, size_t hi, std::vector<Ref>& ll, std::vector<Ref>& rr) {
+                for (size_t i = lo; i < hi; ++i) {
+                    const Ref& x = refs[i];
+                    if (x.b.hi[spat.axis] <= spat.pos)
+                        ll.push_back(x);
+                    else if (x.b.lo[spat.axis] >= spat.pos)
+                        rr.push_back(x);
+                    else {
+                        Box c;
+                        if (clipped_ref_box(ps, x, spat.axis, -kInf, spat.pos, c)) ll.push_back(Ref{c, x.idx});
+                        if (clipped_ref_box(ps, x, spat.axis, spat.pos, kInf, c)) rr.push_back(Ref{c, x.idx});
+                    }
                 }
+            };
+            const int nc = par.chunks_for(refs.size());
+            if (nc > 1) {  // every chunk chops into its own pair of lists; concatenated in chunk order
+                std::vector<std::vector<Ref>> pl(nc), pr(nc);
+                par.run(refs.size(), nc, [&](int k, size_t lo, size_t hi) { chop(lo, hi, pl[k], pr[k]); });
+                size_t tl = 0, tr = 0;
+                for (int k = 0; k < nc; ++k) tl += pl[k].size(), tr += pr[k].size();
+                l.reserve(tl), r.reserve(tr);
+                for (int k = 0; k < nc; ++k) {
+                    l.insert(l.end(), pl[k].begin(), pl[k].end());
+                    r.insert(r.end(), pr[k].begin(), pr[k].end());
+                }
+            } else {
+                chop(0, refs.size(), l, r);
             }
             std::vector<Ref>().swap(refs);
             if (l.empty() || r.empty()) {  // degenerate chop: bvh.rs:1130-1134, 1173-1196
                 l.insert(l.end(), r.begin(), r.end());
                 std::vector<Ref>().swap(r);
-                if (have_obj && l.size() > min_leaf_for(l)) {
+                if (have_obj && l.size() > min_leaf_for(l, par)) {
                     std::vector<Ref> a, b;
-                    stable_split(l, obj, a, b);
+                    stable_split(l, obj, a, b, par);
                     if (a.empty() || b.empty()) {
                         a.insert(a.end(), b.begin(), b.end());
                         return emit_leaf(out, bbox, a);
@@ -402,7 +546,7 @@ struct Builder {
             }
         } else if (have_obj) {
             if (count <= kMaxLeaf && obj.cost >= area(bbox) * (float)count) return emit_leaf(out, bbox, refs);  // bvh.rs:1140
-            stable_split(refs, obj, l, r);
+            stable_split(refs, obj, l, r, par);
         } else {  // every centroid coincides: median by input order (bvh.rs:1148-1152)
             size_t mid = count / 2;
             r.assign(refs.begin() + mid, refs.end());
@@ -784,7 +928,7 @@ bool build_host_tree(std::vector<Geom>& geoms, ChildInfoFn child_info, int threa
     }
     std::vector<float>().swap(diag);
     lap("ids, normals, references");
-    Builder bld{ps, area(root), {threads - 1}};
+    Builder bld{ps, area(root), {threads - 1}, Par{threads, getenv("CRT_BUILD_PAR_MIN") ? (size_t)atoll(getenv("CRT_BUILD_PAR_MIN")) : ((size_t)1 << 19)}};
     Out bin;
     bld.build(bin, refs, 0);
     lap("binary SAH/SBVH build");

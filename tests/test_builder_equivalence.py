@@ -55,6 +55,18 @@ def test_parallel_build_is_thread_count_invariant(crt, orc):  # bvh.rs:1156-1168
     _assert_same_tree(p8, o1)
 
 
+@pytest.mark.parametrize("threads", [2, 3, 8])
+def test_data_parallel_node_passes_do_not_change_the_tree(crt, orc, threads, monkeypatch):
+    """Large nodes run their bounds / binning / spatial-split / partition passes over chunks of the references in parallel
+    (host_build.cpp `Par`, normally from 2^19 references up); CRT_BUILD_PAR_MIN=64 forces that path on small scenes. The tree
+    must still be the oracle's, whatever the chunking (odd thread counts give ragged chunks)."""
+    monkeypatch.setenv("CRT_BUILD_PAR_MIN", "64")
+    for make in (_mesh(*workloads.diagonal_shards(2000)), lambda api: workloads.stress_scene(api, grid=2, shards=3000)[0],
+                 lambda api: workloads.sphere_grid_prims(api, 6)):
+        p, o = _commit_pair(crt, orc, make, threads=threads)
+        _assert_same_tree(p, o)
+
+
 def test_stress_scene_small(crt, orc):  # scripts/gen_stress_scene.py at reduced size: spheres + shards + quads
     def make(api):
         return workloads.stress_scene(api, grid=2, shards=3000)[0]
