@@ -19,8 +19,9 @@
 //   sphere    32 B  q0 = c.xyz,  flags | q1 = radius, prim, mask, -
 //   curve     48 B  q0 = p0.xyz, flags | q1 = p1.xyz, prim  | q2 = r0, r1, mask, -
 //   cubic     96 B  q0..q3 = cp[k].xyz + {flags, prim, mask, -} | q4 = r0, r1, -, - | q5 pad
-//   instance  80 B  q0..q3 = w2l columns x,y,z,translation + {flags, prim, mask, motion}
-//                   q4 = child descriptor pointer (lo, hi), geom_id, -
+//   instance  96 B  q0..q3 = w2l columns x,y,z,translation + {flags, prim, mask, motion}
+//                   q4 = child descriptor pointer (lo, hi), geom_id, instance slot
+//                   q5 = child node array (lo, hi), child leaf-record array (lo, hi): the descent needs no descriptor read
 #pragma once
 #include <stdint.h>
 
@@ -40,6 +41,7 @@ enum : uint32_t {
     REC_PACKET_END = 1u << 6,   // 4th triangle of a reference packet, or the leaf's last triangle
     REC_MOTION = 1u << 7,       // instance with an end-of-shutter transform
     REC_LANE_SHIFT = 8,         // triangle: lane within its packet (0..3)
+    REC_CHILD_TRIS = 1u << 10,  // instance: the child scene holds triangles at its own level (its rays need the Woop shear)
 };
 
 // record sizes in 16-byte units
@@ -47,7 +49,7 @@ enum : uint32_t {
 #define REC_SPHERE_Q 2u
 #define REC_CURVE_Q 3u
 #define REC_CUBIC_Q 6u
-#define REC_INSTANCE_Q 5u
+#define REC_INSTANCE_Q 6u
 
 struct U4 {  // 16-byte unit of the leaf record stream (device code reads it as uint4 / float4)
     uint32_t x, y, z, w;

@@ -211,9 +211,8 @@ __device__ int clip_plane(float3* in, int n, float3* out, int axis, float value,
     return m;
 }
 
-__global__ void __launch_bounds__(kB) split_kernel(uint32_t n_tris, uint32_t n_cand, float eps, BuildArrays A) {
-    uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= n_cand) return;
+// One candidate reference (triangle x grid cell): clipped box + Morton key. Returns whether the cell holds any of the triangle.
+__device__ bool split_candidate(uint32_t r, uint32_t n_tris, float eps, const BuildArrays& A) {
     // triangle of this candidate: last t with cell_off[t] <= r (cell_off is the exclusive scan of the counts)
     uint32_t a = 0, b = n_tris;
     while (b - a > 1) {
@@ -271,6 +270,13 @@ __global__ void __launch_bounds__(kB) split_kernel(uint32_t n_tris, uint32_t n_c
     A.rhi[r] = make_float4(hi.x, hi.y, hi.z, 0.0f);
     A.key_a[r] = key;
     A.idx_a[r] = r;
+    return valid;
+}
+
+__global__ void __launch_bounds__(kB) split_kernel(uint32_t n_tris, uint32_t n_cand, float eps, BuildArrays A) {
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    // no early return: every thread of the (possibly partial) last block must reach the block-wide count
+    const bool valid = r < n_cand && split_candidate(r, n_tris, eps, A);
     unsigned int v = __syncthreads_count(valid);
     if (threadIdx.x == 0 && v) atomicAdd(A.counters + 3, v);
 }
@@ -586,6 +592,7 @@ int device_build(const std::vector<Geom>& geoms, crt_scene* s) {
     void* d_scan = dc.take<char>(scan_tmp);
     uint2* d_prim_ids = nullptr;  // owned by the scene
     CKB(dmalloc(&d_prim_ids, N));
+    s->d_prim_ids = d_prim_ids;  // from here on the scene owns it: every error return below frees it with the scene
     A.prim_ids = d_prim_ids;
     {
         unsigned int init[16] = {0};
@@ -625,7 +632,8 @@ int device_build(const std::vector<Geom>& geoms, crt_scene* s) {
         CKB(cub::DeviceScan::ExclusiveSum(d_scan, scan_bytes, A.cell_off, A.cell_off, (int)N));
         CKB(cudaMemcpy(&last_off, A.cell_off + (N - 1), 4, cudaMemcpyDeviceToHost));
         const uint64_t T64 = (uint64_t)last_off + last_count;
-        if (T64 > 0x3FFFFFFFull) return set_error(CRT_ERR_OOM, "device build: too many split references");
+        // a leaf word is CRT_LEAF_BIT | 3 * first_reference (16-byte units): 3 * T must stay below 2^31
+        if (T64 > 0x2AAAAAA0ull) return set_error(CRT_ERR_OOM, "device build: too many split references");
         const uint32_t T = (uint32_t)T64;
         launches += 3;
         lap("extent + count + scan");
@@ -661,9 +669,11 @@ int device_build(const std::vector<Geom>& geoms, crt_scene* s) {
         launches += 2;
         leaf_quads = 3 * (size_t)n + 4;
         CKB(dmalloc(&d_leafs, leaf_quads));
+        s->d_leafs = d_leafs;
         pad_kernel<<<1, 1>>>(d_leafs, 3 * (size_t)n);
         if (n <= (int)kLeafMax) {
             CKB(dmalloc(&d_nodes, 1));
+            s->d_nodes = d_nodes;
             tiny_kernel<<<1, 1>>>(n, d_sorted, d_nodes, d_leafs, A);
             n4 = 1;
             launches += 2;
@@ -703,6 +713,7 @@ int device_build(const std::vector<Geom>& geoms, crt_scene* s) {
             CKB(cudaMemcpy(&last_id, A.id4 + (n - 2), 4, cudaMemcpyDeviceToHost));
             n4 = last_id + last_flag;
             CKB(dmalloc(&d_nodes, n4));
+            s->d_nodes = d_nodes;
             emit_kernel<<<grid_n, kB>>>(n, d_sorted, d_nodes, d_leafs, A);
             launches += levels + 4;
             lap("scan + emit");
@@ -710,6 +721,7 @@ int device_build(const std::vector<Geom>& geoms, crt_scene* s) {
         CKB(cudaDeviceSynchronize());
         CKB(cudaMemcpy(h_counters, A.counters, sizeof h_counters, cudaMemcpyDeviceToHost));
     }
+    if (d_nodes) CKB(mark_empty_lanes(d_nodes, n4, 0));
     crt::count_launches(launches);
     // ---- hand the arrays to the scene (the scratch arena stays for the next build) ---------------------------------------------------
     s->d_nodes = d_nodes;

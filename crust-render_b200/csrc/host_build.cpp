@@ -656,6 +656,7 @@ struct Flattener {
                     qf(I.w2l.z.x, I.w2l.z.y, I.w2l.z.z, ps.mask[pi]);
                     qf(I.w2l.t.x, I.w2l.t.y, I.w2l.t.z, motion);
                     q(0, 0, ps.geom_id[pi], ps.data[pi]);  // words 0-1: child descriptor pointer, patched at upload
+                    q(0, 0, 0, 0);                         // child node / leaf-record arrays, patched at upload
                     break;
                 }
             }

@@ -32,7 +32,15 @@ struct crt_scene {
     size_t top_bytes = 0;  // leading bytes of d_nodes that hold the tree's top levels (L2 access-policy window), 0 = none
     crt_memory_footprint footprint{};
 
-    ~crt_scene() {
+    ~crt_scene();
+};
+
+namespace crt {
+void scene_device_memory_released(bool had_window);
+}
+
+inline crt_scene::~crt_scene() {
+    {
         delete host;
         cudaFree(d_nodes);
         cudaFree(d_leafs);
@@ -42,7 +50,8 @@ struct crt_scene {
         cudaFree(d_desc);
         for (crt_scene* c : children) crt_scene_release(c);
     }
-};
+    crt::scene_device_memory_released(top_bytes != 0);
+}
 
 namespace crt {
 
@@ -68,6 +77,11 @@ struct QueueTrace {
     unsigned int* counter;     // persistent-fetch ray counter
 };
 int enqueue_queue_trace(const crt_scene* s, bool any_hit, const QueueTrace& q, cudaStream_t stream);
+// L2 access-policy window over the top levels of `s` for the launches that follow on `stream`; the caller clears it when its
+// launches are enqueued (the stream belongs to the user). enqueue_queue_trace does not touch the attribute itself.
+bool hint_scene_top_levels(const crt_scene* s, cudaStream_t stream);
+void clear_scene_hint(cudaStream_t stream);
+void scene_device_memory_released(bool had_window);
 
 // device_build.cu
 bool device_build_supported(const std::vector<Geom>& geoms);

@@ -33,7 +33,6 @@ struct TraceParams {
 #ifndef CRT_SSTACK
 #define CRT_SSTACK 16  // shared-memory stack entries per thread
 #endif
-#define CRT_LSTACK (128 - CRT_SSTACK)  // local-memory spill entries per thread
 #ifndef CRT_MINBLOCKS_CLOSEST
 #define CRT_MINBLOCKS_CLOSEST 7  // resident blocks per SM the closest-hit variants are compiled for: 72 registers without spills beat 64 with (measured 6/7/8 on B200, profiles/r01_tune_phase_balance.jsonl)
 #endif
@@ -42,6 +41,9 @@ struct TraceParams {
 #endif
 #ifndef CRT_MINBLOCKS_INST
 #define CRT_MINBLOCKS_INST 5  // variants with instance descent carry more live state (level saves, hit chain): 96 registers without spills beat 64 with (measured 3/4/5/6/8 on B200)
+#endif
+#ifndef CRT_MINBLOCKS_INST1
+#define CRT_MINBLOCKS_INST1 6  // scenes whose instances nest one level deep: the parked top-level ray lives in shared memory
 #endif
 #ifndef CRT_REFILL
 #define CRT_REFILL 16  // a warp refills its idle lanes when fewer than this many are active
@@ -62,13 +64,20 @@ struct TraceParams {
 #define CRT_LEAF_EXIT_DEN 4
 #endif
 
+#ifndef CRT_SIGNSEL
+#define CRT_SIGNSEL 1  // slab test with the near / far planes picked by the ray's direction signs (by address) instead of min / max
+#endif
+
 #ifndef CRT_SADDR
 #define CRT_SADDR 1  // shared-stack accesses through a register-held 32-bit shared address (inline PTX): -56 instructions in the closest-hit kernel
 #endif
 
-// Resident blocks per SM of the kernel variant a scene with `feat` uses.
-int trace_blocks_per_sm(bool any_hit, uint32_t feat);
+// Resident blocks per SM of the kernel variant a scene with `feat` and instance nesting depth `instance_depth` uses.
+int trace_blocks_per_sm(bool any_hit, uint32_t feat, uint32_t instance_depth);
 // Enqueues one persistent launch of `grid` blocks x CRT_BLOCK threads.
-cudaError_t launch_trace(bool any_hit, uint32_t feat, const TraceParams& p, int grid, cudaStream_t stream);
+cudaError_t launch_trace(bool any_hit, uint32_t feat, uint32_t instance_depth, const TraceParams& p, int grid, cudaStream_t stream);
+// Rewrites the bounds of the empty lanes of `n` device nodes to lo = +inf, hi = -inf (what the sign-selected slab test needs
+// to reject them without looking at the child word); the host tree keeps the reference's +inf / +inf (bvh.rs:230-241).
+cudaError_t mark_empty_lanes(DevNode* nodes, size_t n, cudaStream_t stream);
 
 }  // namespace crt

@@ -701,8 +701,14 @@ struct Scratch {  // grow-only device buffers reused across crt_render calls on 
     uint32_t* h_pinned = nullptr;      // pinned host mirror for small read-backs
     void* host_fb = nullptr;           // crt_render_host: the device-side frame
     size_t cap_host_fb = 0;
-    // the static pixel list of the last frame stays on the device: same image size and tile deal => no host work
-    uint64_t pixel_key = 0;
+    // the static pixel list of the last frame stays on the device: same image size and tile deal => no host work.
+    // The deal is remembered as the real tuple (no hash: distinct deals must never alias).
+    struct PixelDeal {
+        uint32_t w = 0, h = 0, tile = 0, rank = 0, world = 0;
+        bool operator==(const PixelDeal& o) const { return w == o.w && h == o.h && tile == o.tile && rank == o.rank && world == o.world; }
+    };
+    PixelDeal pixel_deal;
+    bool pixel_deal_valid = false;
     uint32_t pixel_count = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     ~Scratch() {
@@ -1023,6 +1029,14 @@ int render_impl(crt_world* w, const crt_camera* camera, const crt_render_setting
     if (w->scene->host_only) return crt::set_error(CRT_ERR_NO_DEVICE, "scene was committed host-only: nothing to render with");
     std::lock_guard<std::mutex> lk(w->mu);
     Scratch& sc = w->scratch;
+    // L2 window over the tree's top levels for this call's traversal launches only (cleared on every exit path)
+    struct Hint {
+        bool on;
+        cudaStream_t st;
+        ~Hint() {
+            if (on) crt::clear_scene_hint(st);
+        }
+    } hint{crt::hint_scene_top_levels(w->scene, stream), stream};
     const int sms = crt::device_sm_count();
     const int D = (int)s->max_depth;
     uint64_t launches = 0, trace_launches = 0, rounds = 0, chunks_done = 0;
@@ -1039,8 +1053,10 @@ int render_impl(crt_world* w, const crt_camera* camera, const crt_render_setting
                     for (uint32_t x = bx; x < std::min({bx + 8, x0 + T, W}); ++x) out.push_back(y * W + x);
     };
     std::vector<uint32_t> pixels;
-    const uint64_t pixel_key = cursor ? 0 : (((uint64_t)W << 40) ^ ((uint64_t)H << 20) ^ ((uint64_t)(s->tile_world <= 1 ? 0 : T) << 52) ^ ((uint64_t)s->tile_rank << 8) ^ (uint64_t)s->tile_world) | 1ull;
-    const bool pixels_cached = !cursor && sc.pixel_key == pixel_key && sc.pixels != nullptr;
+    Scratch::PixelDeal deal;
+    deal.w = W, deal.h = H;
+    if (s->tile_world > 1) deal.tile = T, deal.rank = s->tile_rank, deal.world = s->tile_world;  // a whole-frame render ignores the tile fields
+    const bool pixels_cached = !cursor && sc.pixel_deal_valid && sc.pixel_deal == deal && sc.pixels != nullptr;
     // 0 = auto: about four chunks per participating process — coarse enough that each chunk's adaptive rounds still
     // fill the GPU (small chunks are launch-latency-bound), fine enough to absorb a slow or busy GPU
     const uint32_t auto_chunk = std::max(1u, n_tiles / (4u * std::max(1u, s->tile_world)));
@@ -1105,7 +1121,7 @@ int render_impl(crt_world* w, const crt_camera* camera, const crt_render_setting
             cudaFree(sc.pixels);
             sc.pixels = nullptr;
             sc.cap_pixels = 0;
-            sc.pixel_key = 0;
+            sc.pixel_deal_valid = false;
             CKR(cudaMalloc(&sc.pixels, need_px));
             sc.cap_pixels = need_px;
         }
@@ -1343,15 +1359,17 @@ int render_impl(crt_world* w, const crt_camera* camera, const crt_render_setting
             if (c >= n_chunks) break;
             pixels.clear();
             for (uint32_t t = c; t < n_tiles; t += n_chunks) append_tile(t, pixels);
-            sc.pixel_key = 0;  // the pixel scratch now holds a chunk's list
+            sc.pixel_deal_valid = false;  // the pixel scratch now holds a chunk's list
             int r = render_pixel_set(pixels, (uint32_t)pixels.size(), true);
             if (r) return r;
             ++chunks_done;
         }
     } else {
+        if (!pixels_cached) sc.pixel_deal_valid = false;  // the list is being replaced: not valid again until the set has rendered
         int r = render_pixel_set(pixels, pixels_cached ? sc.pixel_count : (uint32_t)pixels.size(), !pixels_cached);
         if (r) return r;
-        sc.pixel_key = pixel_key;
+        sc.pixel_deal = deal;
+        sc.pixel_deal_valid = true;
         sc.pixel_count = pixels_cached ? sc.pixel_count : (uint32_t)pixels.size();
     }
     CKR(cudaGetLastError());

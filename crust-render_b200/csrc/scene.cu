@@ -136,10 +136,12 @@ size_t top_levels_first(const std::vector<DevNode>& nodes, size_t budget, std::v
     }
     return n_top * sizeof(DevNode);
 }
-// Attaches the window to `stream` (a stream attribute: it applies to the launches that follow). Failure is not an error —
-// the hint is an optimisation only.
-void hint_top_levels(const crt_scene* s, cudaStream_t stream) {
-    if (!s->top_bytes || !g_dev.l2_persist_bytes) return;
+// Attaches the window to `stream` (a stream attribute: it applies to the launches that follow) and returns whether one was
+// set. Failure is not an error — the hint is an optimisation only. The caller clears it again with clear_top_levels_hint
+// once its launches are enqueued: the stream is the caller's (a user or torch stream) and must not keep a window over
+// memory this library may free, nor pass it on to the caller's own kernels.
+bool hint_top_levels(const crt_scene* s, cudaStream_t stream) {
+    if (!s->top_bytes || !g_dev.l2_persist_bytes) return false;
     cudaStreamAttrValue attr{};
     attr.accessPolicyWindow.base_ptr = s->d_nodes;
     attr.accessPolicyWindow.num_bytes = std::min(s->top_bytes, g_dev.l2_persist_bytes);
@@ -149,9 +151,16 @@ void hint_top_levels(const crt_scene* s, cudaStream_t stream) {
     if (cudaStreamSetAttribute(stream, cudaStreamAttributeAccessPolicyWindow, &attr) != cudaSuccess) {
         cudaGetLastError();
         g_dev.l2_refused.fetch_add(1);
-    } else {
-        g_dev.l2_applied.fetch_add(1);
+        return false;
     }
+    g_dev.l2_applied.fetch_add(1);
+    return true;
+}
+void clear_top_levels_hint(cudaStream_t stream) {
+    cudaStreamAttrValue attr{};  // num_bytes = 0 disables the window
+    attr.accessPolicyWindow.hitProp = cudaAccessPropertyNormal;
+    attr.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
+    if (cudaStreamSetAttribute(stream, cudaStreamAttributeAccessPolicyWindow, &attr) != cudaSuccess) cudaGetLastError();
 }
 
 }  // namespace
@@ -450,6 +459,12 @@ int crt_commit_ex(crt_builder* b, uint32_t flags, int host_threads, crt_scene** 
         uint64_t ptr = (uint64_t)(uintptr_t)child->d_desc;
         t->leafs[4 * (size_t)(q + 4) + 0] = (uint32_t)(ptr & 0xFFFFFFFFu);
         t->leafs[4 * (size_t)(q + 4) + 1] = (uint32_t)(ptr >> 32);
+        const uint64_t cn = (uint64_t)(uintptr_t)child->d_nodes, cl = (uint64_t)(uintptr_t)child->d_leafs;
+        t->leafs[4 * (size_t)(q + 5) + 0] = (uint32_t)(cn & 0xFFFFFFFFu);
+        t->leafs[4 * (size_t)(q + 5) + 1] = (uint32_t)(cn >> 32);
+        t->leafs[4 * (size_t)(q + 5) + 2] = (uint32_t)(cl & 0xFFFFFFFFu);
+        t->leafs[4 * (size_t)(q + 5) + 3] = (uint32_t)(cl >> 32);
+        if (child->desc.has_triangles) t->leafs[4 * (size_t)q + 3] |= REC_CHILD_TRIS;
     }
     // The builder's per-geometry references are no longer needed.
     crt_builder_free(b);
@@ -469,6 +484,7 @@ int crt_commit_ex(crt_builder* b, uint32_t flags, int host_threads, crt_scene** 
             crt_scene_release(s);
             return rc;
         }
+        if (s->d_nodes) CK(mark_empty_lanes((DevNode*)s->d_nodes, t->nodes.size(), 0));
         s->desc.nodes = (const DevNode*)s->d_nodes;
         s->desc.leafs = (const U4*)s->d_leafs;
         s->desc.prim_ids = (const U2*)s->d_prim_ids;
@@ -590,8 +606,15 @@ static int launch_query(const crt_scene* s, bool any_hit, size_t n, const crt_ra
     int rc = ensure_device();
     if (rc) return rc;
     const size_t kMaxPerLaunch = (size_t)1 << 30;  // 32-bit ray counter with head-room for overshoot
-    int per_sm = trace_blocks_per_sm(any_hit, s->features);
-    hint_top_levels(s, stream);
+    int per_sm = trace_blocks_per_sm(any_hit, s->features, s->instance_depth);
+    const bool hinted = hint_top_levels(s, stream);
+    struct Unhint {
+        bool on;
+        cudaStream_t st;
+        ~Unhint() {
+            if (on) clear_top_levels_hint(st);
+        }
+    } unhint{hinted, stream};
     for (size_t off = 0; off < n; off += kMaxPerLaunch) {
         size_t cnt = std::min(kMaxPerLaunch, n - off);
         TraceParams p;
@@ -610,7 +633,7 @@ static int launch_query(const crt_scene* s, bool any_hit, size_t n, const crt_ra
         size_t need = (cnt + CRT_BLOCK - 1) / CRT_BLOCK;
         if ((size_t)grid > need) grid = (int)need;
         CK(cudaMemsetAsync(p.counter, 0, sizeof(unsigned int), stream));
-        CK(launch_trace(any_hit, s->features, p, grid, stream));
+        CK(launch_trace(any_hit, s->features, s->instance_depth, p, grid, stream));
         g_dev.launches.fetch_add(1);
     }
     return CRT_OK;
@@ -831,6 +854,15 @@ int device_sm_count() { return g_dev.sm_count; }
 unsigned int* device_status_word() { return g_dev.status; }
 void count_launches(uint64_t n) { g_dev.launches.fetch_add(n); }
 
+bool hint_scene_top_levels(const crt_scene* s, cudaStream_t stream) { return s && !s->host_only && hint_top_levels(s, stream); }
+void clear_scene_hint(cudaStream_t stream) { clear_top_levels_hint(stream); }
+void scene_device_memory_released(bool had_window) {
+    // persisting lines of a freed tree must not outlive it
+    if (had_window && g_dev.ready && g_dev.l2_persist_bytes) {
+        if (cudaCtxResetPersistingL2Cache() != cudaSuccess) cudaGetLastError();
+    }
+}
+
 int enqueue_queue_trace(const crt_scene* s, bool any_hit, const QueueTrace& q, cudaStream_t stream) {
     if (!s || s->host_only) return fail(CRT_ERR_NO_DEVICE, "scene has no device data");
     TraceParams p;
@@ -845,11 +877,10 @@ int enqueue_queue_trace(const crt_scene* s, bool any_hit, const QueueTrace& q, c
     p.status = g_dev.status;
     p.n = q.capacity;
     p.n_dev = q.n_dev;
-    int grid = g_dev.sm_count * trace_blocks_per_sm(any_hit, s->features);
-    hint_top_levels(s, stream);
+    int grid = g_dev.sm_count * trace_blocks_per_sm(any_hit, s->features, s->instance_depth);
     size_t need = ((size_t)q.capacity + CRT_BLOCK - 1) / CRT_BLOCK;
     if ((size_t)grid > need) grid = (int)(need ? need : 1);
-    CK(launch_trace(any_hit, s->features, p, grid, stream));
+    CK(launch_trace(any_hit, s->features, s->instance_depth, p, grid, stream));
     g_dev.launches.fetch_add(1);
     return CRT_OK;
 }

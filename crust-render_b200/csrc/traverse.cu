@@ -9,6 +9,7 @@ namespace {
 // Stack entry: .x = child word (bit 31 = leaf record offset, else node index,
 // 0xFFFFFFFF = "return to the instancing level"), .y = entry distance bits.
 #define CRT_RETURN_MARK 0xFFFFFFFFu
+#define CRT_NO_REC 0xFFFFFFFFu
 
 template <bool ANY_HIT>
 struct StackT {
@@ -19,52 +20,75 @@ struct StackT<true> {
     typedef uint32_t type;
 };
 
-struct LevelSave {  // what an instance descent must restore (prim.rs:345-365 returns into the caller's leaf loop)
+// What an instance descent must restore (prim.rs:345-365 returns into the caller's leaf loop), generic nesting depth:
+// kept in local memory. Scenes whose instances nest one level deep (every bundled sample but nested_instancing) use the
+// MAXD == 1 variant instead, which parks the same words in shared memory and keeps the hit chain in one register.
+struct LevelSave {
     LevelRay r;  // the caller's ray with its slab reciprocals and shear: restored, not recomputed (2 divisions + 4 reciprocals)
-    const DevScene* scene;
-    const float4* resume;  // next record of the instancing leaf, or nullptr
-    const float4* inst;    // the instance record (for the hit chain)
+    const DevNode* nodes;
+    const float4* leafs;
+    const DevScene* scene;  // descriptor of the caller's level (nullptr = top level)
+    uint32_t resume;        // next record of the instancing leaf, or CRT_NO_REC
+    uint32_t inst;          // the instance record (offset in the caller's leafs), for the hit chain
 };
 
-template <bool ANY_HIT, uint32_t FEAT>
-__global__ void __launch_bounds__(CRT_BLOCK, (FEAT & FEAT_INSTANCE) ? CRT_MINBLOCKS_INST : (ANY_HIT ? CRT_MINBLOCKS_ANY : CRT_MINBLOCKS_CLOSEST)) trace_kernel(const TraceParams p) {
+// Capacity of the traversal stack per ray (entries). A stack never needs more than 3 entries per BVH4 level plus one, and
+// the builders bound the depth (bvh.rs:152 MAX_DEPTH = 60 binary levels on the host; Morton-code length on the device),
+// so these are upper bounds, not typical sizes (measured depth at 10 M triangles: 23): the first CRT_SSTACK entries
+// live in shared memory, the rest in local memory that only deep trees ever touch. The reference spills to the heap
+// (bvh.rs:711-755) and is unbounded; here an overflow beyond the bound sets a sticky status bit.
+template <int MAXD>
+struct StackCap {
+    static constexpr int value = MAXD == 0 ? 512 : (MAXD == 1 ? 1024 : 2048);
+};
+
+template <bool ANY_HIT, uint32_t FEAT, int MAXD>
+struct MinBlocks {
+    static constexpr int value = MAXD > 1 ? CRT_MINBLOCKS_INST : (MAXD == 1 ? CRT_MINBLOCKS_INST1 : (ANY_HIT ? CRT_MINBLOCKS_ANY : CRT_MINBLOCKS_CLOSEST));
+};
+
+template <bool ANY_HIT, uint32_t FEAT, int MAXD>
+__global__ void __launch_bounds__(CRT_BLOCK, MinBlocks<ANY_HIT, FEAT, MAXD>::value) trace_kernel(const TraceParams p) {
     typedef typename StackT<ANY_HIT>::type Entry;
+    constexpr bool INST = MAXD > 0;
+    static_assert(INST == ((FEAT & FEAT_INSTANCE) != 0), "MAXD > 0 exactly for the variants with instance descent");
+    constexpr int kLStack = StackCap<MAXD>::value - CRT_SSTACK;
     __shared__ Entry sstack[CRT_SSTACK][CRT_BLOCK];
-    Entry lstack[CRT_LSTACK];  // spill (local memory, touched only by deep trees)
+    // MAXD == 1: the top-level ray parked during an instance descent (o, d, inv, shear, packed axes, resume record)
+    __shared__ uint32_t ssave[MAXD == 1 ? 14 : 1][MAXD == 1 ? CRT_BLOCK : 1];
+    Entry lstack[kLStack];  // spill (local memory, touched only by deep trees)
 
     const unsigned lane = threadIdx.x & 31u;
     const unsigned tid = threadIdx.x;
     // wavefront queues pass their length by device pointer (written by the producing kernel)
     const uint32_t n_rays = p.n_dev ? min(__ldg(p.n_dev), p.n) : p.n;
-    constexpr bool INST = (FEAT & FEAT_INSTANCE) != 0;
 
     // ---- per-ray state -------------------------------------------------------
     enum : int { IDLE = 0, RUN = 1, DONE = 2 };  // DONE = traversal finished, result not yet written
     int state = IDLE;
     uint32_t ray_idx = 0;
-    LevelRay r;
+    LevelRay r;  // at depth 0 this is the ray as given (the world ray): finalize() relies on it
     float t_min = 0.0f, closest = 0.0f, time = 0.0f;
     uint32_t ray_mask = 0;
     const DevNode* nodes = nullptr;
     const float4* leafs = nullptr;
-    const DevScene* cur_scene = nullptr;  // nullptr = top level (p.scene)
     int sp = 0;
-    const float4* rec = nullptr;  // leaf mode: next record to test
+    uint32_t rec = CRT_NO_REC;  // leaf mode: next record to test (16-byte units from `leafs`)
     // packet state (bvh.rs:530-562)
     float pkt_tmax = 0.0f;
-    const float4* pkt_first = nullptr;
     uint32_t pkt_deferred = 0;
-    // best hit
-    const float4* best_rec = nullptr;
+    // best hit: record offset in the leafs of the level it was found at
+    uint32_t best_rec = CRT_NO_REC;
     F3 best_n = f3(0, 0, 0);
     bool any_found = false;
     bool overflow = false;  // a stack entry was dropped (reported once, at kernel exit)
     // instancing
     int depth = 0;
     int best_depth = 0;
-    LevelSave saved[INST ? CRT_MAX_INSTANCE_DEPTH : 1];
-    const float4* best_chain[INST ? CRT_MAX_INSTANCE_DEPTH : 1];
-    F3 world_o = f3(0, 0, 0), world_d = f3(0, 0, 0);
+    [[maybe_unused]] uint32_t cur_inst = CRT_NO_REC, best_inst = CRT_NO_REC;  // MAXD == 1: the instance record being traversed / of the best hit
+    [[maybe_unused]] const DevScene* cur_scene = nullptr;                    // MAXD > 1: descriptor of the current level (nullptr = top)
+    LevelSave saved[MAXD > 1 ? MAXD : 1];
+    uint32_t best_chain[MAXD > 1 ? MAXD : 1];
 
 #if CRT_SADDR
     // The thread's column of the shared stack as a 32-bit shared-window address held in a register: without it the
@@ -96,16 +120,16 @@ __global__ void __launch_bounds__(CRT_BLOCK, (FEAT & FEAT_INSTANCE) ? CRT_MINBLO
     auto push = [&](Entry e) {
         if (sp < CRT_SSTACK)
             sst(sp, e);
-        else if (sp < CRT_SSTACK + CRT_LSTACK)
+        else if (sp < CRT_SSTACK + kLStack)
             lstack[sp - CRT_SSTACK] = e;
         else
-            overflow = true;  // entry dropped; reported through crt_device_status()
+            overflow = true;  // beyond the depth bound of any tree the builders emit; reported through crt_device_status()
         ++sp;
     };
     auto pop = [&]() -> Entry {
         --sp;
         if (sp < CRT_SSTACK) return sld(sp);
-        if (sp < CRT_SSTACK + CRT_LSTACK) return lstack[sp - CRT_SSTACK];
+        if (sp < CRT_SSTACK + kLStack) return lstack[sp - CRT_SSTACK];
         Entry e;
         if constexpr (ANY_HIT) e = 0u; else e = make_uint2(0u, 0x7f800000u);
         return e;
@@ -113,49 +137,67 @@ __global__ void __launch_bounds__(CRT_BLOCK, (FEAT & FEAT_INSTANCE) ? CRT_MINBLO
     auto make_entry = [&](uint32_t child, float tn) -> Entry {
         if constexpr (ANY_HIT) return child; else return make_uint2(child, __float_as_uint(tn));
     };
-    auto accept = [&](const float4* at, float t) {
+    auto accept = [&](uint32_t at, float t) {
         closest = t;
         best_rec = at;
-        if constexpr (INST) {
+        if constexpr (MAXD == 1) best_inst = cur_inst;
+        if constexpr (MAXD > 1) {
             best_depth = depth;
             for (int k = 0; k < depth; ++k) best_chain[k] = saved[k].inst;
         }
     };
 
     // ---- result of a finished ray (runs for all DONE lanes of a warp together) ----
+    // A closest-hit ray is DONE only with an empty stack, i.e. back at depth 0: `r` holds the world ray again.
     auto finalize = [&]() {
         if constexpr (ANY_HIT) {
             p.flag[ray_idx] = any_found ? 1 : 0;
         } else {
             float4 h0, h1;
             uint8_t ff = 0;
-            if (best_rec == nullptr) {
+            if (best_rec == CRT_NO_REC) {
                 h0 = make_float4(__int_as_float(0x7f800000), 0.0f, 0.0f, __uint_as_float(CRT_INVALID_ID));
                 h1 = make_float4(__uint_as_float(CRT_INVALID_ID), 0.0f, 0.0f, 0.0f);
             } else {
                 // Re-derive the local ray at the hit level (same arithmetic as the descent).
                 LevelRay lr;
-                const DevScene* sc = nullptr;
-                F3 o = world_o, d = world_d;
-                Xf w2l[INST ? CRT_MAX_INSTANCE_DEPTH : 1];
-                if constexpr (INST) {
+                const F3 world_d = r.d;
+                F3 o = r.o, d = r.d;
+                const DevScene* sc = nullptr;  // descriptor of the hit level (nullptr = top)
+                const float4* hit_leafs = (const float4*)p.scene.leafs;
+                Xf w2l[INST ? MAXD : 1];
+                if constexpr (MAXD == 1) {
+                    if (best_inst != CRT_NO_REC) {
+                        const float4* ir = (const float4*)p.scene.leafs + best_inst;
+                        w2l[0] = instance_w2l(p.scene, ir, time);
+                        o = xf_point(w2l[0], o);
+                        d = xf_vec(w2l[0], d);
+                        sc = instance_child(ir);
+                        hit_leafs = instance_child_leafs(ir);
+                        best_depth = 1;
+                    }
+                }
+                if constexpr (MAXD > 1) {
                     for (int k = 0; k < best_depth; ++k) {
                         const DevScene& owner = sc ? *sc : p.scene;
-                        w2l[k] = instance_w2l(owner, best_chain[k], time);
+                        const float4* ir = (const float4*)owner.leafs + best_chain[k];
+                        w2l[k] = instance_w2l(owner, ir, time);
                         o = xf_point(w2l[k], o);
                         d = xf_vec(w2l[k], d);
-                        sc = instance_child(best_chain[k]);
+                        sc = instance_child(ir);
+                        hit_leafs = instance_child_leafs(ir);
                     }
                 }
                 const DevScene& hs = sc ? *sc : p.scene;
-                float4 q0 = __ldg(best_rec);
+                const float4* hit_rec = hit_leafs + best_rec;
+                float4 q0 = __ldg(hit_rec);
                 uint32_t flags = __float_as_uint(q0.w);
                 uint32_t kind = flags & REC_KIND_MASK;
                 float u = 0.0f, v = 0.0f, t = closest;
                 F3 n = best_n;
                 uint32_t prim;
                 if (kind == REC_TRI) {
-                    float4 q1 = __ldg(best_rec + 1), q2 = __ldg(best_rec + 2);
+                    float4 q1 = __ldg(hit_rec + 1), q2 = __ldg(hit_rec + 2);
                     prim = __float_as_uint(q1.w);
                     lr.set(o, d, true);
                     F3 v0 = xyz(q0), v1 = xyz(q1), v2 = xyz(q2);
@@ -172,18 +214,28 @@ __global__ void __launch_bounds__(CRT_BLOCK, (FEAT & FEAT_INSTANCE) ? CRT_MINBLO
                         n = normalize(cross(v1 - v0, v2 - v0));  // prim.rs:80-84
                     }
                 } else if (kind == REC_SPHERE) {
-                    prim = __float_as_uint(__ldg(best_rec + 1).y);
+                    prim = __float_as_uint(__ldg(hit_rec + 1).y);
                 } else {
-                    prim = __float_as_uint(__ldg(best_rec + 1).w);
+                    prim = __float_as_uint(__ldg(hit_rec + 1).w);
                 }
                 uint2 ids = __ldg((const uint2*)hs.prim_ids + prim);
                 uint32_t geom_id = ids.x;
                 if constexpr (INST) {
+                    const DevScene* oc = nullptr;
+                    uint32_t chain_geom[INST ? MAXD : 1];
+                    for (int k = 0; k < best_depth; ++k) {  // geom_id of every instance on the chain (outermost first)
+                        const DevScene& owner = oc ? *oc : p.scene;
+                        uint32_t at;
+                        if constexpr (MAXD == 1) at = best_inst; else at = best_chain[k];
+                        const float4* ir = (const float4*)owner.leafs + at;
+                        chain_geom[k] = __float_as_uint(__ldg(ir + 4).z);
+                        if (k + 1 < best_depth) oc = instance_child(ir);
+                    }
                     for (int k = best_depth - 1; k >= 0; --k) {  // prim.rs:359-363, innermost first
                         const Xf& m = w2l[k];                    // normal_mat = w2l.matrix3^T
                         F3 nx = f3(m.x.x, m.y.x, m.z.x), ny = f3(m.x.y, m.y.y, m.z.y), nz = f3(m.x.z, m.y.z, m.z.z);
                         n = normalize((nx * n.x + ny * n.y) + nz * n.z);
-                        geom_id = __float_as_uint(__ldg(best_chain[k] + 4).z);
+                        geom_id = chain_geom[k];
                     }
                 }
                 bool front = dot(world_d, n) < 0.0f;  // scene.rs:356-359
@@ -200,13 +252,41 @@ __global__ void __launch_bounds__(CRT_BLOCK, (FEAT & FEAT_INSTANCE) ? CRT_MINBLO
 
     // ---- node visit: 4-wide slab test (bvh.rs:790-808) + ordered push ------------
     auto node_visit = [&](uint32_t child) {
+        float tn[4];
+        bool hit[4];
+        uint32_t cw[4];
+#if CRT_SIGNSEL
+        // The near plane of an axis is the box's low face when the ray travels in +axis and the high face otherwise, so the
+        // planes are picked by address (three byte offsets per ray) instead of by 24 min / max. Bit-identical to
+        // min(t0, t1) / max(t0, t1): lo <= hi and rounded subtraction and multiplication are monotone, safe_inv keeps
+        // infinities and NaN out of `inv`, and the sign of a zero plays no part in the comparisons that follow
+        // (tests/test_slab_signselect.py). Empty lanes of the device copy carry lo = +inf, hi = -inf (scene.cu
+        // mark_empty_lanes), which fails `near <= far` for every ray, so the child word need not be looked at here.
+        const char* nb = (const char*)(nodes + child);
+        const float4 nx4 = __ldg((const float4*)(nb + r.near_x)), ny4 = __ldg((const float4*)(nb + r.near_y)),
+                     nz4 = __ldg((const float4*)(nb + r.near_z));
+        const float4 fx4 = __ldg((const float4*)(nb + (48u - r.near_x))), fy4 = __ldg((const float4*)(nb + (80u - r.near_y))),
+                     fz4 = __ldg((const float4*)(nb + (112u - r.near_z)));
+        const uint4 ch = __ldg((const uint4*)(nb + 96));
+        cw[0] = ch.x, cw[1] = ch.y, cw[2] = ch.z, cw[3] = ch.w;
+        const float nx[4] = {nx4.x, nx4.y, nx4.z, nx4.w}, ny[4] = {ny4.x, ny4.y, ny4.z, ny4.w}, nz[4] = {nz4.x, nz4.y, nz4.z, nz4.w};
+        const float fx[4] = {fx4.x, fx4.y, fx4.z, fx4.w}, fy[4] = {fy4.x, fy4.y, fy4.z, fy4.w}, fz[4] = {fz4.x, fz4.y, fz4.z, fz4.w};
+#pragma unroll
+        for (int l = 0; l < 4; ++l) {
+            float tnx = (nx[l] - r.o.x) * r.inv.x, tfx = (fx[l] - r.o.x) * r.inv.x;
+            float tny = (ny[l] - r.o.y) * r.inv.y, tfy = (fy[l] - r.o.y) * r.inv.y;
+            float tnz = (nz[l] - r.o.z) * r.inv.z, tfz = (fz[l] - r.o.z) * r.inv.z;
+            float near_ = fmaxf(fmaxf(fmaxf(tnx, tny), tnz), t_min);
+            float far_ = fminf(fminf(fminf(tfx, tfy), tfz), closest);
+            tn[l] = near_;
+            hit[l] = near_ <= far_;
+        }
+#else
         const float4* np = (const float4*)(nodes + child);
         float4 lox = __ldg(np), loy = __ldg(np + 1), loz = __ldg(np + 2);
         float4 hix = __ldg(np + 3), hiy = __ldg(np + 4), hiz = __ldg(np + 5);
         uint4 ch = __ldg((const uint4*)(np + 6));
-        float tn[4];
-        uint32_t cw[4] = {ch.x, ch.y, ch.z, ch.w};
-        bool hit[4];
+        cw[0] = ch.x, cw[1] = ch.y, cw[2] = ch.z, cw[3] = ch.w;
         const float lx[4] = {lox.x, lox.y, lox.z, lox.w}, ly[4] = {loy.x, loy.y, loy.z, loy.w},
                     lz[4] = {loz.x, loz.y, loz.z, loz.w};
         const float hx[4] = {hix.x, hix.y, hix.z, hix.w}, hy[4] = {hiy.x, hiy.y, hiy.z, hiy.w},
@@ -221,6 +301,7 @@ __global__ void __launch_bounds__(CRT_BLOCK, (FEAT & FEAT_INSTANCE) ? CRT_MINBLO
             tn[l] = near_;
             hit[l] = (near_ <= far_) & (cw[l] != CRT_EMPTY_LANE);
         }
+#endif
         if constexpr (ANY_HIT) {
             // bvh.rs:598-608 — no ordering needed for a boolean answer; queue internal
             // lanes first so leaf lanes (the cheap early exits) pop first.
@@ -271,7 +352,7 @@ __global__ void __launch_bounds__(CRT_BLOCK, (FEAT & FEAT_INSTANCE) ? CRT_MINBLO
                     Entry e2 = make_entry(cw[l], tn[l]);
                     if (slot < CRT_SSTACK)
                         sst(slot, e2);
-                    else if (slot < CRT_SSTACK + CRT_LSTACK)
+                    else if (slot < CRT_SSTACK + kLStack)
                         lstack[slot - CRT_SSTACK] = e2;
                     else
                         overflow = true;
@@ -283,12 +364,13 @@ __global__ void __launch_bounds__(CRT_BLOCK, (FEAT & FEAT_INSTANCE) ? CRT_MINBLO
 
     // ---- one leaf record (bvh.rs:514-572 / 617-653) -------------------------------
     auto record_test = [&]() {
-        const float4* cur = rec;
+        const uint32_t at = rec;
+        const float4* cur = leafs + at;
         float4 q0 = __ldg(cur), q1 = __ldg(cur + 1), q2 = __ldg(cur + 2);
         const uint32_t flags = __float_as_uint(q0.w);
         const uint32_t kind = flags & REC_KIND_MASK;
         if (kind == REC_TRI) {
-            rec = (flags & REC_LAST) ? nullptr : cur + REC_TRI_Q;
+            rec = (flags & REC_LAST) ? CRT_NO_REC : at + REC_TRI_Q;
             if (ray_mask & __float_as_uint(q2.w)) {  // triangle.rs:257-271 per-lane visibility
                 TriEval e = tri_eval(r, xyz(q0), xyz(q1), xyz(q2));
                 if (e.on_edge) {
@@ -298,23 +380,26 @@ __global__ void __launch_bounds__(CRT_BLOCK, (FEAT & FEAT_INSTANCE) ? CRT_MINBLO
                         if (in_range_packet(e, t_min, closest)) {
                             any_found = true;
                             state = DONE;
-                            rec = nullptr;
+                            rec = CRT_NO_REC;
                             return;
                         }
                     } else {
                         if (in_range_packet(e, t_min, pkt_tmax)) {
                             float t = e.t_scaled * (1.0f / e.det);
-                            if (!(t > closest) && !(flags & REC_DEGENERATE)) accept(cur, t);  // bvh.rs:542, prim.rs:80-83
+                            if (!(t > closest) && !(flags & REC_DEGENERATE)) accept(at, t);  // bvh.rs:542, prim.rs:80-83
                         }
                     }
                 }
             }
             if (flags & REC_PACKET_END) {
-                // Lanes sitting exactly on an edge: scalar f64 path (bvh.rs:551-561 / 636-643).
+                // Lanes sitting exactly on an edge: scalar f64 path (bvh.rs:551-561 / 636-643). The packet's first record is
+                // this one minus its lane number.
+                const uint32_t pkt_first = at - REC_TRI_Q * ((flags >> REC_LANE_SHIFT) & 3u);
                 while (pkt_deferred) {
                     int ln = __ffs(pkt_deferred) - 1;
                     pkt_deferred &= pkt_deferred - 1;
-                    const float4* fr = pkt_first + REC_TRI_Q * ln;
+                    const uint32_t fat = pkt_first + REC_TRI_Q * ln;
+                    const float4* fr = leafs + fat;
                     float4 f0 = __ldg(fr), f1 = __ldg(fr + 1), f2 = __ldg(fr + 2);
                     TriEval e = tri_eval_f64(r, xyz(f0), xyz(f1), xyz(f2));
                     if (mixed_signs(e) || e.det == 0.0f) continue;
@@ -322,16 +407,15 @@ __global__ void __launch_bounds__(CRT_BLOCK, (FEAT & FEAT_INSTANCE) ? CRT_MINBLO
                     if constexpr (ANY_HIT) {
                         any_found = true;
                         state = DONE;
-                        rec = nullptr;
+                        rec = CRT_NO_REC;
                         pkt_deferred = 0;
                         return;
                     } else {
                         if (__float_as_uint(f0.w) & REC_DEGENERATE) continue;
-                        accept(fr, e.t_scaled * (1.0f / e.det));
+                        accept(fat, e.t_scaled * (1.0f / e.det));
                     }
                 }
                 pkt_tmax = closest;
-                pkt_first = cur + REC_TRI_Q;
             }
             return;
         }
@@ -340,57 +424,81 @@ __global__ void __launch_bounds__(CRT_BLOCK, (FEAT & FEAT_INSTANCE) ? CRT_MINBLO
             float t = 0.0f;
             F3 n = f3(0, 0, 0);
             if (kind == REC_SPHERE) {
-                rec = (flags & REC_LAST) ? nullptr : cur + REC_SPHERE_Q;
+                rec = (flags & REC_LAST) ? CRT_NO_REC : at + REC_SPHERE_Q;
                 if (ray_mask & __float_as_uint(q1.z)) got = sphere_hit(r, xyz(q0), q1.x, t_min, closest, t, n);
             } else if ((FEAT & FEAT_CURVE) && kind == REC_CURVE) {
-                rec = (flags & REC_LAST) ? nullptr : cur + REC_CURVE_Q;
+                rec = (flags & REC_LAST) ? CRT_NO_REC : at + REC_CURVE_Q;
                 if (ray_mask & __float_as_uint(q2.z))
                     got = rounded_cone_hit(r.o, r.d, xyz(q0), xyz(q1), q2.x, q2.y, t_min, closest, t, n);
             } else if ((FEAT & FEAT_CURVE) && kind == REC_CUBIC) {
-                rec = (flags & REC_LAST) ? nullptr : cur + REC_CUBIC_Q;
+                rec = (flags & REC_LAST) ? CRT_NO_REC : at + REC_CUBIC_Q;
                 if (ray_mask & __float_as_uint(q2.w)) {
                     float4 q3 = __ldg(cur + 3), q4 = __ldg(cur + 4);
                     F3 cp[4] = {xyz(q0), xyz(q1), xyz(q2), xyz(q3)};
                     got = cubic_curve_hit(r.o, r.d, cp, q4.x, q4.y, t_min, closest, t, n);
                 }
             } else if (INST && kind == REC_INSTANCE) {
-                const float4* resume = (flags & REC_LAST) ? nullptr : cur + REC_INSTANCE_Q;
+                const uint32_t resume = (flags & REC_LAST) ? CRT_NO_REC : at + REC_INSTANCE_Q;
                 rec = resume;
-                if ((ray_mask & __float_as_uint(q2.w)) && depth < CRT_MAX_INSTANCE_DEPTH) {  // prim.rs:346-350
-                    const DevScene& owner = cur_scene ? *cur_scene : p.scene;
-                    Xf w2l = instance_w2l(owner, cur, time);
-                    const DevScene* child = instance_child(cur);
-                    LevelSave& s = saved[depth];
-                    s.r = r;
-                    s.scene = cur_scene;
-                    s.resume = resume;
-                    s.inst = cur;
+                if ((ray_mask & __float_as_uint(q2.w)) && depth < MAXD) {  // prim.rs:346-350 (commit refuses deeper nesting)
+                    // The record carries the child's node and record arrays, so the descent is one round of independent
+                    // loads (no dependent read of the child's descriptor).
+                    const float4 q3 = __ldg(cur + 3);
+                    const uint4 q5 = __ldg((const uint4*)(cur + 5));
+                    Xf w2l;
+                    if ((flags & REC_MOTION) && time > 0.0f) {
+                        if constexpr (MAXD == 1) {
+                            w2l = instance_w2l(p.scene, cur, time);
+                        } else {
+                            const DevScene& owner = cur_scene ? *cur_scene : p.scene;
+                            w2l = instance_w2l(owner, cur, time);
+                        }
+                    } else {
+                        w2l = Xf{xyz(q0), xyz(q1), xyz(q2), xyz(q3)};
+                    }
+                    if constexpr (MAXD == 1) {
+                        ssave[0][tid] = __float_as_uint(r.o.x), ssave[1][tid] = __float_as_uint(r.o.y), ssave[2][tid] = __float_as_uint(r.o.z);
+                        ssave[3][tid] = __float_as_uint(r.d.x), ssave[4][tid] = __float_as_uint(r.d.y), ssave[5][tid] = __float_as_uint(r.d.z);
+                        ssave[6][tid] = __float_as_uint(r.inv.x), ssave[7][tid] = __float_as_uint(r.inv.y), ssave[8][tid] = __float_as_uint(r.inv.z);
+                        ssave[9][tid] = __float_as_uint(r.sx), ssave[10][tid] = __float_as_uint(r.sy), ssave[11][tid] = __float_as_uint(r.sz);
+                        ssave[12][tid] = r.pack_axes();
+                        ssave[13][tid] = resume;
+                        cur_inst = at;
+                    } else {
+                        LevelSave& s = saved[depth];
+                        s.r = r;
+                        s.nodes = nodes;
+                        s.leafs = leafs;
+                        s.scene = cur_scene;
+                        s.resume = resume;
+                        s.inst = at;
+                        cur_scene = instance_child(cur);
+                    }
                     ++depth;
-                    cur_scene = child;
-                    nodes = child->nodes;
-                    leafs = (const float4*)child->leafs;
-                    r.set(xf_point(w2l, r.o), xf_vec(w2l, r.d), child->has_triangles != 0);  // prim.rs:333-341
-                    rec = nullptr;
+                    nodes = (const DevNode*)(((uint64_t)q5.y << 32) | (uint64_t)q5.x);
+                    leafs = (const float4*)(((uint64_t)q5.w << 32) | (uint64_t)q5.z);
+                    r.set(xf_point(w2l, r.o), xf_vec(w2l, r.d), (flags & REC_CHILD_TRIS) != 0);  // prim.rs:333-341
+                    rec = CRT_NO_REC;
                     push(make_entry(CRT_RETURN_MARK, 0.0f));
                     push(make_entry(0u, t_min));  // committed child scenes are never empty (scene.rs:307-309)
                 }
                 return;
             } else {
-                rec = nullptr;  // unreachable: a record kind this variant was not built for
+                rec = CRT_NO_REC;  // unreachable: a record kind this variant was not built for
                 return;
             }
             if (got) {
                 if constexpr (ANY_HIT) {
                     any_found = true;
                     state = DONE;
-                    rec = nullptr;
+                    rec = CRT_NO_REC;
                 } else {
-                    accept(cur, t);
+                    accept(at, t);
                     best_n = n;
                 }
             }
         } else {
-            rec = nullptr;  // unreachable: a record kind this variant was not built for
+            rec = CRT_NO_REC;  // unreachable: a record kind this variant was not built for
         }
     };
 
@@ -423,17 +531,17 @@ __global__ void __launch_bounds__(CRT_BLOCK, (FEAT & FEAT_INSTANCE) ? CRT_MINBLO
                         closest = b.w;
                         time = p.time ? __ldg(p.time + idx) : 0.0f;
                         ray_mask = p.mask ? __ldg(p.mask + idx) : p.mask_uniform;
-                        world_o = f3(a.x, a.y, a.z);
-                        world_d = f3(b.x, b.y, b.z);
-                        r.set(world_o, world_d, p.scene.has_triangles != 0);
+                        r.set(f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), p.scene.has_triangles != 0);
                         nodes = p.scene.nodes;
                         leafs = (const float4*)p.scene.leafs;
                         cur_scene = nullptr;
+                        cur_inst = CRT_NO_REC;
                         depth = 0;
-                        best_rec = nullptr;
+                        best_rec = CRT_NO_REC;
+                        best_inst = CRT_NO_REC;
                         best_depth = 0;
                         any_found = false;
-                        rec = nullptr;
+                        rec = CRT_NO_REC;
                         sp = 0;
                         state = RUN;
                         if (p.scene.n_nodes != 0) push(make_entry(0u, t_min));
@@ -448,7 +556,7 @@ __global__ void __launch_bounds__(CRT_BLOCK, (FEAT & FEAT_INSTANCE) ? CRT_MINBLO
         // reaches a leaf, then tests that leaf's records; lanes reconverge after each phase.
         if (state == RUN) {
             // node phase
-            while (rec == nullptr) {
+            while (rec == CRT_NO_REC) {
                 if (sp == 0) {
                     state = DONE;
                     break;
@@ -459,20 +567,31 @@ __global__ void __launch_bounds__(CRT_BLOCK, (FEAT & FEAT_INSTANCE) ? CRT_MINBLO
                 if constexpr (INST) {
                     if (child == CRT_RETURN_MARK) {  // back to the instancing level
                         --depth;
-                        const LevelSave& s = saved[depth];
-                        cur_scene = s.scene;
-                        const DevScene& sc = cur_scene ? *cur_scene : p.scene;
-                        nodes = sc.nodes;
-                        leafs = (const float4*)sc.leafs;
-                        r = s.r;
-                        rec = s.resume;
+                        if constexpr (MAXD == 1) {
+                            nodes = p.scene.nodes;
+                            leafs = (const float4*)p.scene.leafs;
+                            r.o = f3(__uint_as_float(ssave[0][tid]), __uint_as_float(ssave[1][tid]), __uint_as_float(ssave[2][tid]));
+                            r.d = f3(__uint_as_float(ssave[3][tid]), __uint_as_float(ssave[4][tid]), __uint_as_float(ssave[5][tid]));
+                            r.inv = f3(__uint_as_float(ssave[6][tid]), __uint_as_float(ssave[7][tid]), __uint_as_float(ssave[8][tid]));
+                            r.sx = __uint_as_float(ssave[9][tid]), r.sy = __uint_as_float(ssave[10][tid]), r.sz = __uint_as_float(ssave[11][tid]);
+                            r.unpack_axes(ssave[12][tid]);
+                            rec = ssave[13][tid];
+                            cur_inst = CRT_NO_REC;
+                        } else {
+                            const LevelSave& s = saved[depth];
+                            cur_scene = s.scene;
+                            nodes = s.nodes;
+                            leafs = s.leafs;
+                            r = s.r;
+                            rec = s.resume;
+                        }
+                        // the instancing leaf's packet state: instance records follow the leaf's triangles, so no packet is open
                         continue;
                     }
                 }
                 if (child & CRT_LEAF_BIT) {
-                    rec = leafs + (child & ~CRT_LEAF_BIT);
+                    rec = child & ~CRT_LEAF_BIT;
                     pkt_tmax = closest;
-                    pkt_first = rec;
                     pkt_deferred = 0;
                     break;
                 }
@@ -488,7 +607,7 @@ __global__ void __launch_bounds__(CRT_BLOCK, (FEAT & FEAT_INSTANCE) ? CRT_MINBLO
 #endif
             }
             // leaf phase
-            while (state == RUN && rec != nullptr) {
+            while (state == RUN && rec != CRT_NO_REC) {
                 record_test();
 #if CRT_LEAF_EXIT_NUM > 0
                 if (__popc(__activemask()) * CRT_LEAF_EXIT_DEN < n_run * CRT_LEAF_EXIT_NUM) break;
@@ -499,67 +618,102 @@ __global__ void __launch_bounds__(CRT_BLOCK, (FEAT & FEAT_INSTANCE) ? CRT_MINBLO
     if (overflow) atomicOr(p.status, 1u);
 }
 
-template <bool ANY_HIT, uint32_t FEAT>
+template <bool ANY_HIT, uint32_t FEAT, int MAXD>
 cudaError_t launch_variant(const TraceParams& p, int grid, cudaStream_t stream) {
-    trace_kernel<ANY_HIT, FEAT><<<grid, CRT_BLOCK, 0, stream>>>(p);
+    trace_kernel<ANY_HIT, FEAT, MAXD><<<grid, CRT_BLOCK, 0, stream>>>(p);
     return cudaGetLastError();
 }
 
-template <bool ANY_HIT, uint32_t FEAT>
+template <bool ANY_HIT, uint32_t FEAT, int MAXD>
 int blocks_per_sm_variant() {
     int n = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, trace_kernel<ANY_HIT, FEAT>, CRT_BLOCK, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, trace_kernel<ANY_HIT, FEAT, MAXD>, CRT_BLOCK, 0);
     return n > 0 ? n : 1;
 }
 
-// Feature sets actually instantiated; a scene uses the smallest superset.
+// Feature sets actually instantiated; a scene uses the smallest superset. Instanced scenes whose nesting depth is 1 (an
+// instance never contains another: every bundled sample but nested_instancing.usda) get their own variant.
 constexpr uint32_t V_TRI = 0;
 constexpr uint32_t V_SPH = FEAT_SPHERE | FEAT_NORMALS;
 constexpr uint32_t V_INST = FEAT_SPHERE | FEAT_NORMALS | FEAT_INSTANCE;
 constexpr uint32_t V_ALL = FEAT_SPHERE | FEAT_NORMALS | FEAT_INSTANCE | FEAT_CURVE;
+constexpr int kVariants = 5;
 
-int variant_of(uint32_t feat) {
+int variant_of(uint32_t feat, uint32_t instance_depth) {
     if ((feat & ~V_TRI) == 0) return 0;
     if ((feat & ~V_SPH) == 0) return 1;
-    if ((feat & ~V_INST) == 0) return 2;
-    return 3;
+    if ((feat & ~V_INST) == 0) return instance_depth <= 1 ? 2 : 3;
+    return 4;
+}
+
+// Calls f.template operator()<ANY_HIT, FEAT, MAXD>() for the variant (any_hit, v).
+template <class F>
+auto dispatch(bool any_hit, int v, F&& f) {
+    if (any_hit) {
+        switch (v) {
+            case 0: return f.template operator()<true, V_TRI, 0>();
+            case 1: return f.template operator()<true, V_SPH, 0>();
+            case 2: return f.template operator()<true, V_INST, 1>();
+            case 3: return f.template operator()<true, V_INST, CRT_MAX_INSTANCE_DEPTH>();
+            default: return f.template operator()<true, V_ALL, CRT_MAX_INSTANCE_DEPTH>();
+        }
+    }
+    switch (v) {
+        case 0: return f.template operator()<false, V_TRI, 0>();
+        case 1: return f.template operator()<false, V_SPH, 0>();
+        case 2: return f.template operator()<false, V_INST, 1>();
+        case 3: return f.template operator()<false, V_INST, CRT_MAX_INSTANCE_DEPTH>();
+        default: return f.template operator()<false, V_ALL, CRT_MAX_INSTANCE_DEPTH>();
+    }
+}
+
+struct BlocksFn {
+    template <bool A, uint32_t F, int D>
+    int operator()() const {
+        return blocks_per_sm_variant<A, F, D>();
+    }
+};
+struct LaunchFn {
+    const TraceParams& p;
+    int grid;
+    cudaStream_t stream;
+    template <bool A, uint32_t F, int D>
+    cudaError_t operator()() const {
+        return launch_variant<A, F, D>(p, grid, stream);
+    }
+};
+
+__global__ void mark_empty_lanes_kernel(DevNode* nodes, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    DevNode& nd = nodes[i];
+    const float ninf = __int_as_float(0xff800000), pinf = __int_as_float(0x7f800000);
+#pragma unroll
+    for (int l = 0; l < 4; ++l)
+        if (nd.child[l] == CRT_EMPTY_LANE) {
+            nd.bmin_x[l] = nd.bmin_y[l] = nd.bmin_z[l] = pinf;
+            nd.bmax_x[l] = nd.bmax_y[l] = nd.bmax_z[l] = ninf;
+        }
 }
 
 }  // namespace
 
-int trace_blocks_per_sm(bool any_hit, uint32_t feat) {
-    static int cache[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
-    int v = variant_of(feat);
+cudaError_t mark_empty_lanes(DevNode* nodes, size_t n, cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    mark_empty_lanes_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(nodes, n);
+    return cudaGetLastError();
+}
+
+int trace_blocks_per_sm(bool any_hit, uint32_t feat, uint32_t instance_depth) {
+    static int cache[2][kVariants] = {};
+    int v = variant_of(feat, instance_depth);
     int& c = cache[any_hit ? 1 : 0][v];
-    if (c == 0) {
-        if (any_hit)
-            c = v == 0 ? blocks_per_sm_variant<true, V_TRI>()
-                       : (v == 1 ? blocks_per_sm_variant<true, V_SPH>()
-                                 : (v == 2 ? blocks_per_sm_variant<true, V_INST>() : blocks_per_sm_variant<true, V_ALL>()));
-        else
-            c = v == 0 ? blocks_per_sm_variant<false, V_TRI>()
-                       : (v == 1 ? blocks_per_sm_variant<false, V_SPH>()
-                                 : (v == 2 ? blocks_per_sm_variant<false, V_INST>() : blocks_per_sm_variant<false, V_ALL>()));
-    }
+    if (c == 0) c = dispatch(any_hit, v, BlocksFn{});
     return c;
 }
 
-cudaError_t launch_trace(bool any_hit, uint32_t feat, const TraceParams& p, int grid, cudaStream_t stream) {
-    int v = variant_of(feat);
-    if (any_hit) {
-        switch (v) {
-            case 0: return launch_variant<true, V_TRI>(p, grid, stream);
-            case 1: return launch_variant<true, V_SPH>(p, grid, stream);
-            case 2: return launch_variant<true, V_INST>(p, grid, stream);
-            default: return launch_variant<true, V_ALL>(p, grid, stream);
-        }
-    }
-    switch (v) {
-        case 0: return launch_variant<false, V_TRI>(p, grid, stream);
-        case 1: return launch_variant<false, V_SPH>(p, grid, stream);
-        case 2: return launch_variant<false, V_INST>(p, grid, stream);
-        default: return launch_variant<false, V_ALL>(p, grid, stream);
-    }
+cudaError_t launch_trace(bool any_hit, uint32_t feat, uint32_t instance_depth, const TraceParams& p, int grid, cudaStream_t stream) {
+    return dispatch(any_hit, variant_of(feat, instance_depth), LaunchFn{p, grid, stream});
 }
 
 }  // namespace crt

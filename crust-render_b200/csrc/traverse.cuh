@@ -85,6 +85,11 @@ __device__ __forceinline__ const DevScene* instance_child(const float4* rec) {
     float4 q4 = __ldg(rec + 4);
     return (const DevScene*)(((uint64_t)__float_as_uint(q4.y) << 32) | (uint64_t)__float_as_uint(q4.x));
 }
+// The child's leaf-record array, carried by the instance record itself (q5.zw) next to its node array (q5.xy).
+__device__ __forceinline__ const float4* instance_child_leafs(const float4* rec) {
+    uint4 q5 = __ldg((const uint4*)(rec + 5));
+    return (const float4*)(((uint64_t)q5.w << 32) | (uint64_t)q5.z);
+}
 
 __device__ __forceinline__ float safe_inv(float d) {  // bvh.rs:662-668
     return fabsf(d) < 1e-20f ? copysignf(1e20f, d) : __frcp_rn(d);  // correctly rounded: same bits as 1.0f / d
@@ -96,10 +101,35 @@ struct LevelRay {
     F3 o, d, inv;
     float sx, sy, sz;
     int kx, ky, kz;
+#if CRT_SIGNSEL
+    // byte offsets, inside a 128-byte node, of the bounds vector holding each axis' near plane: the low faces (0, 16, 32)
+    // for a ray travelling in +axis, the high faces (48, 64, 80) otherwise; the far plane is the other one of the pair
+    uint32_t near_x, near_y, near_z;
+#endif
+    __device__ __forceinline__ uint32_t pack_axes() const {
+        uint32_t w = ((uint32_t)kx & 3u) | (((uint32_t)ky & 3u) << 2) | (((uint32_t)kz & 3u) << 4);  // the axes are unset (garbage) for a level without triangles
+#if CRT_SIGNSEL
+        w |= (near_x << 8) | (near_y << 16) | (near_z << 24);
+#endif
+        return w;
+    }
+    __device__ __forceinline__ void unpack_axes(uint32_t w) {
+        kx = (int)(w & 3u), ky = (int)((w >> 2) & 3u), kz = (int)((w >> 4) & 3u);
+#if CRT_SIGNSEL
+        near_x = (w >> 8) & 0xFFu, near_y = (w >> 16) & 0xFFu, near_z = w >> 24;
+#endif
+    }
     __device__ __forceinline__ void set(F3 org, F3 dir, bool want_shear) {
         o = org;
         d = dir;
         inv = {safe_inv(dir.x), safe_inv(dir.y), safe_inv(dir.z)};
+#if CRT_SIGNSEL
+        // the sign of `inv` (never zero, never NaN for a finite direction), not of `dir`: -0.0 travels "backwards" like the reference's
+        // copysign(1e20, d) (bvh.rs:662-668)
+        near_x = inv.x < 0.0f ? 48u : 0u;
+        near_y = inv.y < 0.0f ? 64u : 16u;
+        near_z = inv.z < 0.0f ? 80u : 32u;
+#endif
         if (want_shear) {
             float ax = fabsf(dir.x), ay = fabsf(dir.y), az = fabsf(dir.z);
             kz = ax > ay ? (ax > az ? 0 : 2) : (ay > az ? 1 : 2);

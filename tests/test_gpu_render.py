@@ -255,6 +255,20 @@ def test_bit_determinism_pool_size_and_tile_split(gpu):
     assert acc.tobytes() == full.tobytes() and rays == sf.total_rays()
 
 
+def test_cached_pixel_list_is_keyed_by_the_real_tile_deal(gpu):
+    """One World renders rank 0 of 2, then rank 0 of 3 (same image, same tile size), then rank 1 of 2 and the whole
+    frame: the device-resident pixel list of the previous call must never be reused for a different deal
+    (tile_world 2 and 3 once aliased in a hashed key)."""
+    world, cam, st = scenes.furnace_room(gpu, width=96, height=64, spp=4, variance_threshold=0.0)
+    full = gpu.Renderer(cam, world, st).render_with_stats()[0]
+    for rank, n in ((0, 2), (0, 3), (0, 3), (1, 2), (0, 4), (0, 5), (3, 4)):
+        part = gpu.Renderer(cam, world, rank_settings(st, rank, n, tile_size=16)).render_with_stats()[0]
+        m = owned_mask(96, 64, 16, rank, n)
+        assert np.all(part[~m] == 0) and np.array_equal(part[m], full[m]), (rank, n)
+    again = gpu.Renderer(cam, world, st).render_with_stats()[0]
+    assert again.tobytes() == full.tobytes()
+
+
 def test_device_framebuffer_entry_and_distributed_wrapper(gpu):
     import torch
     from crust_render_b200.distributed import render_distributed
