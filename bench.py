@@ -33,6 +33,13 @@ for _p in (ROOT, os.path.join(ROOT, "oracle")):
         sys.path.insert(0, _p)
 
 METRIC = "Mrays/s closest-hit+occlusion per GPU"
+
+
+def workload_config(n_tris, rays_log2, rays_per_step, info):
+    """The `config` object of the JSON line — identical in both arms (they run the same scene and the same ray sets)."""
+    return {"workload": f"K1 stress mesh ({n_tris} triangles, flat BVH4), ray sets (i)-(iv) of SURVEY 8(d)", "triangles": n_tris,
+            "rays_per_set": 1 << rays_log2, "rays_per_step_per_gpu": rays_per_step,
+            "l2": "inputs larger than L2 (rays+hits 2.7 GB, BVH 0.9 GB per step)", "scene": "replicated per GPU", **info}
 SETS = ["closest_lcg", "closest_camera", "closest_bounce", "occluded_lcg", "occluded_shadow"]
 
 
@@ -97,30 +104,113 @@ def cpu_render_sample(args, log_prefix):
             "sample": f"{w}x{h} x {spp} spp of the same scene/camera/settings, {r.seconds:.1f}s on {cores} threads (rows dealt to threads)"}
 
 
-def time_sample_configs(crt, torch, stream):
-    """BASELINE.json configs 1-4 through crt_render at the sizes the config list names (device framebuffer,
-    best of 3 after a warm-up): spp/s of the frame, Msamples/s, Mrays/s."""
+SAMPLE_CONFIGS = [
+    # (key, label, builder name, kwargs of the BASELINE size, kwargs of the scaled-up frame used for the multi-GPU curve)
+    ("1_cornellbox", "config 1 samples/cornellbox.usda (822 baked triangles + 2 instances, sky only, adaptive, depth 32)", "cornellbox",
+     dict(width=512, height=512, spp=64), dict(width=1920, height=1080, spp=64)),
+    ("2_veach_mis", "config 2 samples/veach_mis.usda (4 sphere lights, balance MIS, depth 8, adaptive off)", "veach_mis",
+     dict(width=960, height=540, spp=128), dict(width=1920, height=1080, spp=128)),
+    ("3_openpbr_showcase", "config 3 samples/openpbr_showcase.usda (all OpenPBR lobes, 2 sphere lights, adaptive)", "openpbr_showcase",
+     dict(width=640, height=360, spp=128), dict(width=1920, height=1080, spp=128)),
+    ("4_medcity", "config 4 samples/PointInstancedMedCity.usd (40 000 instances, two-level BVH, sky only, adaptive, depth 32)", "medcity",
+     dict(width=640, height=360, spp=128), dict(width=1920, height=1080, spp=128)),
+]
+
+
+def timed_render(renderer, dist, world, fb, stream, steps, gather, torch, dev):
+    """`steps` frames through render_distributed after one warm-up; device time by CUDA events on the launching stream,
+    max over ranks. Returns (ms per frame, RayStats of the last frame (whole job on rank 0), launches per frame on this rank)."""
+    from crust_render_b200.distributed import render_distributed
+
+    d = dist if world > 1 else None
+    render_distributed(renderer, d, fb=fb, stream=stream.cuda_stream, gather=gather)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches, stats = 0, None
+    e0.record(stream)
+    for _ in range(steps):
+        _, stats = render_distributed(renderer, d, fb=fb, stream=stream.cuda_stream, gather=gather)
+        launches += renderer.launches
+    e1.record(stream)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item()) / steps, stats, launches // steps
+
+
+def time_sample_configs(crt, torch, dist, world, rank, dev, stream, gather, with_cpu, steps=2):
+    """BASELINE.json configs 1-4 through crt_render on `world` GPUs (32x32 tiles dealt round-robin, frame gathered into rank
+    0's HBM inside the timed region): each at the size the config list names and on a 1920x1080 frame (9x to 16x the
+    pixels — the BASELINE frames are 0.23-0.52 Mpixel, i.e. 28-64 tiles per rank at 8 GPUs, too few to say anything about
+    scaling). spp/s of the frame, Msamples/s, Mrays/s. Beside each BASELINE-size number (rank 0, N = 1 only): the CPU
+    restatement of the integrator on all host threads at the same full settings."""
     from crust_render_b200 import scenes
 
     out = {}
-    cases = [("1 cornellbox 512x512 64spp (adaptive, depth 32, sky only)", lambda: scenes.cornellbox(crt)),
-             ("2 veach_mis 960x540 128spp (balance MIS, 4 sphere lights)", lambda: scenes.veach_mis(crt)),
-             ("3 openpbr_showcase 640x360 128spp (adaptive, all OpenPBR lobes)", lambda: scenes.openpbr_showcase(crt)),
-             ("4 PointInstancedMedCity 40000 instances 640x360 128spp (adaptive, two-level BVH, sky only)", lambda: scenes.medcity(crt))]
-    for name, build in cases:
-        world_k, cam_k, st_k = build()
-        r = crt.Renderer(cam_k, world_k, st_k)
-        fb = torch.zeros((st_k.height, st_k.width, 4), dtype=torch.float32, device="cuda")
-        best, stats = None, None
-        for k in range(4):
-            stats = r.render_device(fb.data_ptr(), stream.cuda_stream)
-            if k and (best is None or r.device_ms < best):
-                best = r.device_ms
-        taken = stats.camera_rays / (st_k.width * st_k.height)
-        out[name] = {"ms": best, "spp_per_s": taken / (best * 1e-3), "mean_spp_taken": taken, "msamples_per_s": stats.camera_rays / best / 1e3,
-                     "mrays_per_s": stats.total_rays() / best / 1e3, "launches": r.launches, "rounds": r.rounds}
-        del fb, r, world_k
+    for key, label, fn, base_kw, big_kw in SAMPLE_CONFIGS:
+        rec = {"workload": label}
+        for tag, kw in (("baseline_size", base_kw), ("frame_1920x1080", big_kw)):
+            world_k, cam_k, st_k = getattr(scenes, fn)(crt, **kw)
+            r = crt.Renderer(cam_k, world_k, st_k)
+            fb = torch.zeros((st_k.height, st_k.width, 4), dtype=torch.float32, device=dev)
+            ms, stats, launches = timed_render(r, dist, world, fb, stream, steps, gather, torch, dev)
+            if rank == 0:
+                taken = stats.camera_rays / (st_k.width * st_k.height)
+                rec[tag] = {"width": st_k.width, "height": st_k.height, "max_spp": st_k.samples_per_pixel, "ms": ms, "spp_per_s": taken / (ms * 1e-3),
+                            "mean_spp_taken": taken, "msamples_per_s": stats.camera_rays / ms / 1e3, "mrays_per_s": stats.total_rays() / ms / 1e3,
+                            "launches_rank0": launches, "n_gpus": world}
+            del fb, r, world_k
+        if with_cpu and rank == 0:
+            import orc
+            w_o, cam_o, st_o = getattr(scenes, fn)(orc, **base_kw)
+            ro = orc.Renderer(cam_o, w_o, st_o)
+            _, so = ro.render_with_stats(threads=0)
+            taken = so.camera_rays / (st_o.width * st_o.height)
+            rec["cpu_baseline"] = {"spp_per_s": taken / ro.seconds, "msamples_per_s": so.camera_rays / ro.seconds / 1e6, "mrays_per_s": so.total_rays() / ro.seconds / 1e6,
+                                   "seconds": ro.seconds, "cores": os.cpu_count() or 1, "kind": "port",
+                                   "sample": f"the whole frame at BASELINE size and full settings ({st_o.width}x{st_o.height}, up to {st_o.samples_per_pixel} spp), rows dealt to threads"}
+            rec["gpu_over_cpu_at_baseline_size"] = rec["baseline_size"]["spp_per_s"] / rec["cpu_baseline"]["spp_per_s"]
+            log(f"[bench] {key}: GPU {rec['baseline_size']['ms']:.1f} ms, CPU {ro.seconds:.1f} s on {os.cpu_count()} threads")
+        out[key] = rec
     return out
+
+
+def copy_ceiling(torch, dist, world, dev, mb=256, reps=6):
+    """What the box's PCIe / host-memory path can move: pinned H2D and D2H copies of `mb` MB running concurrently on two
+    streams, all ranks at once. GB/s per direction, whole job (summed over ranks)."""
+    n = mb << 20
+    h_in, h_out = torch.empty(n, dtype=torch.uint8).pin_memory(), torch.empty(n, dtype=torch.uint8).pin_memory()
+    d_in, d_out = torch.empty(n, dtype=torch.uint8, device=dev), torch.empty(n, dtype=torch.uint8, device=dev)
+    s_up, s_dn = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+
+    def run(up, down):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            if up:
+                with torch.cuda.stream(s_up):
+                    d_in.copy_(h_in, non_blocking=True)
+            if down:
+                with torch.cuda.stream(s_dn):
+                    h_out.copy_(d_out, non_blocking=True)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        t = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return world * reps * n / float(t.item()) / 1e9
+
+    run(True, True)
+    both = run(True, True)
+    return {"h2d_alone_gbs": run(True, False), "d2h_alone_gbs": run(False, True), "each_direction_concurrent_gbs": both,
+            "method": f"{mb} MB pinned buffers, {reps} copies per direction on two streams, all {world} rank(s) at once, wall clock, max over ranks"}
 
 
 def time_other_scenes(crt, W, torch, stream, grid, with_cpu):
@@ -304,8 +394,7 @@ def reference_arm(args):
     line = {"metric": METRIC, "value": v, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": secs / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "impl": "reference",
-            "config": {"workload": f"K1 stress mesh ({n_tris} triangles, flat BVH4), ray sets (i)-(iv) of SURVEY 8(d)", "triangles": n_tris,
-                       "rays_per_set": 1 << args.rays_log2, **info},
+            "config": workload_config(n_tris, args.rays_log2, sum(len(sets[n][0]) for n in SETS), info),
             "cpu_baseline": {"value": v, "unit": "Mrays/s", "cores": cores, "kind": "port", "sample": desc},
             "e2e": {"value": v, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -420,6 +509,11 @@ def main():
     value = rays_per_step * world / (ms_per_step * 1e-3) / 1e6
     k_ms = {name: float(np.mean([ev[k][j][0].elapsed_time(ev[k][j][1]) for k in range(args.steps)])) for j, name in enumerate(SETS)}
     status = crt.device_status()
+    # what the timed launches wrote, on the strided sample the CPU baseline runs: checked against the oracle below
+    timed_sample = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        m = 1 << args.cpu_sample_log2
+        timed_sample = {name: d_out[name][:: max(1, len(sets[name][0]) // m)][:m].cpu().numpy() for name in SETS}
 
     # ---- e2e: host buffers through the C ABI, copies inside the timed region ----
     e2e = None
@@ -447,17 +541,23 @@ def main():
         d2h = sum(len(sets[n][0]) * (32 if n.startswith("closest") else 1) for n in SETS)
         e2e = {"value": rays_per_step * world * args.steps / dt / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                "ms_per_step": dt / args.steps * 1e3}
+        # the ceiling of this box for that traffic: plain pinned copies in both directions at once, all ranks together
+        ceil = copy_ceiling(torch, dist, world, dev)
+        moved = world * h2d / (dt / args.steps) / 1e9  # H2D is the larger direction: 32 B per ray in, 32 B or 1 B out
+        e2e["copy_ceiling"] = ceil
+        e2e["h2d_gbs_achieved"] = moved
+        e2e["frac_of_copy_ceiling"] = moved / ceil["each_direction_concurrent_gbs"]
 
     # ---- render: config 5 through the wavefront integrator, frame split over the ranks ----------
     render = None
     other_scenes = None
+    sample_sets = cpu_sample(sets, args.cpu_sample_log2) if (rank == 0 and world == 1 and not args.no_cpu_baseline) else None
+    full_sets_sizes = {n: len(sets[n][0]) for n in SETS}
     if not args.no_render:
         from crust_render_b200 import scenes
-        from crust_render_b200.distributed import render_distributed
+        from crust_render_b200.distributed import rank_settings, shared_host_frame
 
-        sample_sets = cpu_sample(sets, args.cpu_sample_log2) if (rank == 0 and world == 1 and not args.no_cpu_baseline) else None
         del d_in, d_out, d_mask, h_in, h_out, h_mask
-        full_sets_sizes = {n: len(sets[n][0]) for n in SETS}
         torch.cuda.empty_cache()
         rw, rh, rspp = args.render_width, args.render_height, args.render_spp
         t0 = time.time()
@@ -466,7 +566,6 @@ def main():
             log(f"[bench] render world commit ({r_tris} triangles incl. the RectLight): {time.time() - t0:.1f}s")
         renderer = crt.Renderer(r_cam, r_world, r_st)
         fb = torch.zeros((rh, rw, 4), dtype=torch.float32, device=dev)
-        r_launches = 0
         # N > 1: peer-memory gather — every rank's film kernel stores its tiles into rank 0's IPC-mapped frame over NVLink
         # (no frame collective); the RayStats reduce is the only collective in the step
         r_gather = "peer" if world > 1 else "reduce"
@@ -483,31 +582,24 @@ def main():
             dist.all_reduce(ok, op=dist.ReduceOp.MIN)
             if float(ok.item()) == 0.0:
                 r_gather = "reduce"
-        render_distributed(renderer, dist if world > 1 else None, fb=fb, stream=stream.cuda_stream, gather=r_gather)  # warm-up
-        barrier()
-        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        r_stats = []
-        dev_ms = 0.0
-        r0.record(stream)
-        for _ in range(args.render_steps):
-            r_frame, st_k = render_distributed(renderer, dist if world > 1 else None, fb=fb, stream=stream.cuda_stream, gather=r_gather)
-            r_stats.append(st_k)
-            r_launches += renderer.launches
-            dev_ms += renderer.device_ms
-        r1.record(stream)
-        barrier()
-        tt = torch.tensor([r0.elapsed_time(r1)], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        r_ms = float(tt.item()) / args.render_steps
+        r_ms, st0, r_launches = timed_render(renderer, dist, world, fb, stream, args.render_steps, r_gather, torch, dev)
+        dev_ms = renderer.device_ms
+        if r_gather == "peer":
+            from crust_render_b200.distributed import shared_frame
+            r_frame = shared_frame(dist, dev, rh, rw)[1]
+        else:
+            r_frame = fb
         mean_rgb = [float(v) for v in r_frame[..., :3].mean(dim=(0, 1)).tolist()] if rank == 0 else None
-        # e2e: the same frame through crt_render_host (host framebuffer: the frame is copied back to host memory every step;
-        # a tile split also uploads the caller's frame first, because pixels of other ranks stay as given)
-        host_fb = np.empty((rh, rw, 4), dtype=np.float32)
-        host_fb.fill(0.0)
-        from crust_render_b200.distributed import rank_settings
+        # e2e: the same frame through crt_render_host into ONE host frame. N = 1: pinned caller memory, the resolved frame is
+        # copied straight into it. N > 1: the frame lives in POSIX shared memory mapped by every rank; each rank's
+        # crt_render_host downloads only the pixels it owns (packed D2H over its own PCIe link, host-side scatter), so the
+        # frame is complete in host memory when the last rank returns. Wall clock, barrier on both sides, max over ranks.
+        if world > 1:
+            host_fb = shared_host_frame(dist, rh, rw)
+        else:
+            host_fb = torch.empty((rh, rw, 4), dtype=torch.float32).pin_memory().numpy()
         renderer.settings = rank_settings(r_st, rank, world)
-        renderer.render_with_stats(out=host_fb)  # warm-up: device frame allocation, page faults of the host frame
+        renderer.render_with_stats(out=host_fb)  # warm-up: device frame / staging allocation, page faults of the host frame
         barrier()
         t0 = time.perf_counter()
         for _ in range(args.render_steps):
@@ -519,26 +611,27 @@ def main():
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         e2e_s = float(te.item())
         renderer.settings = r_st
+        host_mean = [float(v) for v in host_fb[..., :3].mean(axis=(0, 1))] if rank == 0 else None
         if rank == 0:
-            st0 = r_stats[-1]
             render = {"workload": f"config 5: stress mesh ({r_tris} triangles) + 12x12 RectLight, {rw}x{rh}, depth 6, {rspp} spp per step, power MIS, triangle filter",
                       "spp_per_s": rspp / (r_ms * 1e-3), "msamples_per_s": rw * rh * rspp / r_ms / 1e3, "mrays_per_s": st0.total_rays() / r_ms / 1e3,
                       "ms_per_step": r_ms, "steps": args.render_steps, "rays_per_sample": st0.total_rays() / max(1, st0.camera_rays), "n_gpus": world,
                       "split": "whole frame" if world == 1 else (f"32x32 tiles dealt round-robin over {world} ranks; each rank's film kernel stores its tiles into rank 0's frame through CUDA-IPC peer memory (NVLink), RayStats reduced over NCCL, all inside the timed region"
                                 if r_gather == "peer" else f"32x32 tiles dealt round-robin over {world} ranks, NCCL sum-reduce of the frame to rank 0 inside the timed region"),
-                      "scaling": "strong", "gpu_launches_per_step_rank0": r_launches // args.render_steps, "device_ms_rank0_render_only": dev_ms / args.render_steps,
-                      "e2e": {"spp_per_s": rspp / e2e_s, "unit": "spp/s", "d2h_bytes_per_step": rw * rh * 16, "h2d_bytes_per_step": rw * rh * 16 if world > 1 else 0,
-                              "note": "crt_render_host: frame in/out of host memory, no cross-rank gather"},
+                      "scaling": "strong", "gpu_launches_per_step_rank0": r_launches, "device_ms_rank0_render_only": dev_ms,
+                      "e2e": {"spp_per_s": rspp / e2e_s, "unit": "spp/s", "ms_per_step": e2e_s * 1e3, "frac_of_device_spp_per_s": (rspp / e2e_s) / (rspp / (r_ms * 1e-3)),
+                              "d2h_bytes_per_step": rw * rh * 16, "h2d_bytes_per_step": 0,
+                              "note": "crt_render_host: every rank downloads only the pixels it owns into one host frame (pinned memory at N = 1, a POSIX shared-memory frame mapped by all ranks at N > 1); the frame is complete in host memory inside the timed region",
+                              "mean_rgb_host_frame": host_mean},
                       "mean_rgb": mean_rgb, "ray_stats": st0.__dict__}
-        del fb, renderer, r_world
+        del fb, renderer, r_world, host_fb
         torch.cuda.empty_cache()
-        # configs 1-4 of BASELINE.json at their own sizes (parity-test cases; timed here so every config has a number)
-        if rank == 0 and world == 1:
-            render["configs"] = time_sample_configs(crt, torch, stream)
-            other_scenes = time_other_scenes(crt, W, torch, stream, args.grid, not args.no_cpu_baseline)
-    else:
-        sample_sets = cpu_sample(sets, args.cpu_sample_log2) if (rank == 0 and world == 1 and not args.no_cpu_baseline) else None
-        full_sets_sizes = {n: len(sets[n][0]) for n in SETS}
+        # configs 1-4 of BASELINE.json on the same N GPUs, each with the CPU restatement beside it (N = 1)
+        cfgs = time_sample_configs(crt, torch, dist, world, rank, dev, stream, r_gather, with_cpu=(world == 1 and not args.no_cpu_baseline), steps=args.render_steps)
+        if rank == 0:
+            render["configs"] = cfgs
+            if world == 1:
+                other_scenes = time_other_scenes(crt, W, torch, stream, args.grid, not args.no_cpu_baseline)
 
     # ---- CPU baseline + algorithmic bytes per ray (rank 0, N = 1 only) -----------
     cpu_baseline, roofline, per_set = None, None, {}
@@ -557,16 +650,18 @@ def main():
             o_scene = ob.commit(host_threads=0)
             log(f"[bench] oracle commit: {time.time() - t0:.1f}s")
             sample = sample_sets
-            # parity spot-check on the sample (checker role only)
+            # parity check of the TIMED buffers (checker role only): what the timed launches left in d_out, on the strided
+            # sample, against the oracle's answers for the same rays
             for name in SETS:
                 rays, mask = sample[name]
+                g = timed_sample[name]
                 if name.startswith("closest"):
-                    g = scene.intersect_n(rays, None, mask)[0]
                     c = o_scene.intersect_n(rays, None, mask, threads=0)[0]
-                    agree = float(((g["geom_id"] == c["geom_id"]) & (g["prim_id"] == c["prim_id"]) & (g["t"] == c["t"])).mean())
+                    gu = g.view(np.uint32).reshape(-1, 8)
+                    agree = float(((gu[:, 3] == c["geom_id"]) & (gu[:, 4] == c["prim_id"]) & (gu[:, 0].view(np.float32) == c["t"])).mean())
                 else:
-                    agree = float((scene.occluded_n(rays, None, mask) == o_scene.occluded_n(rays, None, mask, threads=0)).mean())
-                per_set.setdefault(name, {})["oracle_agreement_on_sample"] = agree
+                    agree = float((g == o_scene.occluded_n(rays, None, mask, threads=0)).mean())
+                per_set.setdefault(name, {})["oracle_agreement_of_timed_output"] = agree
             run_cpu(o_scene, sample, 0)
             r_all, s_all, _ = run_cpu(o_scene, sample, 0)
             r_1, s_1, _ = run_cpu(o_scene, {k: (v[0][: 1 << 17], None if v[1] is None else v[1][: 1 << 17]) for k, v in sample.items()}, 1)
@@ -588,14 +683,19 @@ def main():
             dur = sum(k_ms[n] for n in closest) * 1e-3
             ach = tot_bytes / dur / 1e9
             traffic, traffic_src = None, None
-            try:  # DRAM bytes per closest-hit launch from the committed `ncu --set full` capture of this command
+            try:  # DRAM bytes per closest-hit launch from the committed `ncu --set full` capture of this command — quoted only
+                # while the traversal sources are the ones it was captured on (tools/trace_traffic.py stamps their hash)
+                from tools.trace_traffic import source_sha
                 tj = json.load(open(os.path.join(ROOT, "profiles", "trace_traffic.json")))
-                traffic, traffic_src = float(tj["mean_traffic_per_closest_launch"]), tj["source"]
-            except (OSError, KeyError, ValueError):
+                if tj.get("source_sha") == source_sha():
+                    traffic, traffic_src = float(tj["mean_traffic_per_closest_launch"]), tj["source"]
+                else:
+                    traffic_src = "profiles/trace_traffic.json was captured on other traversal sources (hash mismatch): not quoted"
+            except (OSError, KeyError, ValueError, ImportError):
                 pass
             roofline = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic, "traffic_source": traffic_src,
-                        "note": "algorithmic bytes are mostly served by L1/L2 (the 0.83 GB tree is hot in the 126 MB L2: lts hit 62-83 %); ncu shows the kernel "
-                                "issue-bound (smsp issue active 63-79 %, 10.6-19.7 of 32 lanes active per instruction), DRAM at 1-11 % of peak",
+                        "note": "cache-oblivious figure (SURVEY 8(d)): the algorithmic bytes are mostly served by L1/L2 (the 0.83 GB tree is hot in the 126 MB L2); "
+                                "ncu (profiles/trace_traffic.json) shows the kernel issue- and divergence-bound, DRAM at a few percent of peak",
                         "kernel": "trace_kernel<closest-hit, triangles>", "peak_source": peak_src,
                         "bytes_per_launch": tot_bytes / len(closest), "launch_ms": dur * 1e3 / len(closest)}
         for name in SETS:
@@ -603,9 +703,7 @@ def main():
 
         line = {"metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": f"K1 stress mesh ({n_tris} triangles, flat BVH4), ray sets (i)-(iv) of SURVEY 8(d)", "triangles": n_tris,
-                           "rays_per_set": 1 << args.rays_log2, "rays_per_step_per_gpu": rays_per_step, "l2": "inputs larger than L2 (rays+hits 2.7 GB, BVH 0.9 GB per step)",
-                           "scene": "replicated per GPU", **info},
+                "config": workload_config(n_tris, args.rays_log2, rays_per_step, info),
                 "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
                 "sets": per_set, "closest_hit_mrays": sum(len(sets[n][0]) for n in closest) / sum(k_ms[n] for n in closest) / 1e3,
                 "occlusion_mrays": sum(len(sets[n][0]) for n in SETS if n not in closest) / sum(k_ms[n] for n in SETS if n not in closest) / 1e3,

@@ -43,7 +43,7 @@ struct TraceParams {
 #define CRT_MINBLOCKS_INST 5  // variants with instance descent carry more live state (level saves, hit chain): 96 registers without spills beat 64 with (measured 3/4/5/6/8 on B200)
 #endif
 #ifndef CRT_MINBLOCKS_INST1
-#define CRT_MINBLOCKS_INST1 6  // scenes whose instances nest one level deep: the parked top-level ray lives in shared memory
+#define CRT_MINBLOCKS_INST1 7  // scenes whose instances nest one level deep (the parked top-level ray lives in shared memory): 72 registers with a few spills beat 80 / 96 without (measured 5/6/7/8 on B200, profiles/r02_tune_signsel_d1.jsonl)
 #endif
 #ifndef CRT_REFILL
 #define CRT_REFILL 16  // a warp refills its idle lanes when fewer than this many are active
@@ -66,6 +66,10 @@ struct TraceParams {
 
 #ifndef CRT_SIGNSEL
 #define CRT_SIGNSEL 1  // slab test with the near / far planes picked by the ray's direction signs (by address) instead of min / max
+#endif
+
+#ifndef CRT_LEAF_PREFETCH
+#define CRT_LEAF_PREFETCH 0  // L1 prefetch of a popped leaf's first record(s) while the lane waits for the leaf phase (1: first 128-byte line, 2: two)
 #endif
 
 #ifndef CRT_SADDR

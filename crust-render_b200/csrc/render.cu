@@ -30,6 +30,7 @@
 #include <cmath>
 #include <cstring>
 #include <mutex>
+#include <thread>
 #include <vector>
 
 #include "crt_render.h"
@@ -678,12 +679,14 @@ __global__ void iota_kernel(uint32_t* __restrict__ out, uint32_t n) {
 }
 
 // ---- resolve the film (tracer.rs:627-634) ------------------------------------------------------------
-__global__ void __launch_bounds__(kBlock) film_kernel(const RenderParams P, uint32_t n, float4* __restrict__ fb) {
+// `packed`: pixel `pos` of this process' pixel list goes to fb[pos] (the host path downloads only the pixels it owns and
+// scatters them on the host); otherwise to its place in the full frame.
+__global__ void __launch_bounds__(kBlock) film_kernel(const RenderParams P, uint32_t n, float4* __restrict__ fb, int packed) {
     for (uint32_t pos = blockIdx.x * blockDim.x + threadIdx.x; pos < n; pos += gridDim.x * blockDim.x) {
         float4 sw = P.px.sum_w[pos];
         uint32_t taken = P.px.taken[pos] & ~PX_DONE;
         V3 mean = sw.w > 0.0f ? xyz(sw) / sw.w : xyz(sw) / (float)taken;
-        fb[P.px.pixels[pos]] = f4(mean, (float)taken);
+        fb[packed ? pos : P.px.pixels[pos]] = f4(mean, (float)taken);
     }
 }
 
@@ -699,16 +702,21 @@ struct Scratch {  // grow-only device buffers reused across crt_render calls on 
     unsigned long long* stats = nullptr;
     uint32_t* active_count = nullptr;  // 2 words
     uint32_t* h_pinned = nullptr;      // pinned host mirror for small read-backs
-    void* host_fb = nullptr;           // crt_render_host: the device-side frame
+    void* host_fb = nullptr;           // crt_render_host: the device-side frame (whole frame, or this process' pixels packed)
     size_t cap_host_fb = 0;
+    char* h_stage = nullptr;           // crt_render_host: pinned staging between the device frame and the caller's memory
+    size_t cap_stage = 0;
+    std::vector<uint32_t> h_pixels;    // crt_render_host with a tile split: host copy of the pixel list (scatter order)
+    cudaStream_t host_stream = nullptr;
+    cudaEvent_t stage_ev[2] = {nullptr, nullptr};
     // the static pixel list of the last frame stays on the device: same image size and tile deal => no host work.
     // The deal is remembered as the real tuple (no hash: distinct deals must never alias).
     struct PixelDeal {
         uint32_t w = 0, h = 0, tile = 0, rank = 0, world = 0;
         bool operator==(const PixelDeal& o) const { return w == o.w && h == o.h && tile == o.tile && rank == o.rank && world == o.world; }
     };
-    PixelDeal pixel_deal;
-    bool pixel_deal_valid = false;
+    PixelDeal pixel_deal, h_deal;  // of the device pixel list / of h_pixels
+    bool pixel_deal_valid = false, h_deal_valid = false;
     uint32_t pixel_count = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     ~Scratch() {
@@ -718,6 +726,10 @@ struct Scratch {  // grow-only device buffers reused across crt_render calls on 
         cudaFree(stats);
         cudaFree(active_count);
         cudaFree(host_fb);
+        if (h_stage) cudaFreeHost(h_stage);
+        if (host_stream) cudaStreamDestroy(host_stream);
+        for (cudaEvent_t e : stage_ev)
+            if (e) cudaEventDestroy(e);
         if (h_pinned) cudaFreeHost(h_pinned);
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
@@ -1016,9 +1028,37 @@ T* carve(char*& p, size_t count) {
 }
 size_t carve_bytes(size_t count, size_t elem) { return (count * elem + 255) & ~(size_t)255; }
 
+// Runs `fn(first, last)` over [0, n) on up to `threads` host threads (the calling thread takes the first slice).
+template <class F>
+void host_parallel_for(size_t n, unsigned threads, F&& fn) {
+    threads = (unsigned)std::max<size_t>(1, std::min<size_t>(threads, n));
+    std::vector<std::thread> pool;
+    const size_t per = (n + threads - 1) / threads;
+    for (unsigned t = 1; t < threads; ++t) {
+        size_t a = std::min(n, t * per), b = std::min(n, a + per);
+        if (a < b) pool.emplace_back([=, &fn] { fn(a, b); });
+    }
+    fn(0, std::min(n, per));
+    for (std::thread& t : pool) t.join();
+}
+
+bool host_pointer_is_pinned(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
+}
+
+// `host_fb` != nullptr (crt_render_host): the frame ends in host memory. The device frame is the world's own; with a tile
+// split only the pixels this process owns are resolved (packed, in pixel-list order), copied to pinned staging with one
+// asynchronous copy and scattered into the caller's frame on the host — the other ranks' pixels are neither uploaded nor
+// downloaded. A whole-frame render is copied straight into pinned caller memory, or through pinned staging and a
+// multi-threaded memcpy into pageable memory.
 int render_impl(crt_world* w, const crt_camera* camera, const crt_render_settings* s, float* d_fb, crt_ray_stats* stats_out, cudaStream_t stream,
-                crt_steal_cursor* cursor) {
-    if (!w || !camera || !s || !d_fb) return crt::set_error(CRT_ERR_INVALID_ARG, "crt_render: null argument");
+                crt_steal_cursor* cursor, float* host_fb = nullptr) {
+    if (!w || !camera || !s || (!d_fb && !host_fb)) return crt::set_error(CRT_ERR_INVALID_ARG, "crt_render: null argument");
     if (s->width == 0 || s->height == 0 || (uint64_t)s->width * s->height > 0x7FFFFFFFu) return crt::set_error(CRT_ERR_INVALID_ARG, "crt_render: bad image size");
     if (s->samples_per_pixel == 0 || s->samples_per_pixel > 65536u) return crt::set_error(CRT_ERR_INVALID_ARG, "crt_render: samples_per_pixel must be in 1..65536 (sampler index range)");
     if (s->max_depth > 4000u) return crt::set_error(CRT_ERR_INVALID_ARG, "crt_render: max_depth must be <= 4000 (12-bit per-sample ray counters)");
@@ -1078,6 +1118,30 @@ int render_impl(crt_world* w, const crt_camera* camera, const crt_render_setting
         // static deal: tile t belongs to rank t % world (interleaved, so adaptive cost is decorrelated from rank)
         for (uint32_t t = s->tile_rank; t < n_tiles; t += s->tile_world) append_tile(t, pixels);
         max_pixels = pixels.size();
+    }
+    const bool packed = host_fb != nullptr && s->tile_world > 1;
+    if (host_fb) {
+        const size_t need_fb = (packed ? max_pixels : (size_t)W * H) * 16;
+        if (need_fb > sc.cap_host_fb) {
+            cudaFree(sc.host_fb);
+            sc.host_fb = nullptr;
+            sc.cap_host_fb = 0;
+            CKR(cudaMalloc(&sc.host_fb, need_fb ? need_fb : 16));
+            sc.cap_host_fb = need_fb;
+        }
+        d_fb = (float*)sc.host_fb;
+        if (packed && !(sc.h_deal_valid && sc.h_deal == deal)) {
+            // host copy of the pixel list = the scatter order; kept per deal (a device-frame render of another deal in
+            // between leaves it alone, so it carries its own key)
+            if (!pixels_cached) {
+                sc.h_pixels = pixels;
+            } else {
+                sc.h_pixels.clear();
+                for (uint32_t t = s->tile_rank; t < n_tiles; t += s->tile_world) append_tile(t, sc.h_pixels);
+            }
+            sc.h_deal = deal;
+            sc.h_deal_valid = true;
+        }
     }
     if (!sc.ev0) {
         CKR(cudaEventCreate(&sc.ev0));
@@ -1343,7 +1407,7 @@ int render_impl(crt_world* w, const crt_camera* camera, const crt_render_setting
             n_active = sc.h_pinned[0];
             cur_list ^= 1;
         }
-        film_kernel<<<grid_for(n_pix), kBlock, 0, stream>>>(P, n_pix, (float4*)d_fb);
+        film_kernel<<<grid_for(n_pix), kBlock, 0, stream>>>(P, n_pix, (float4*)d_fb, packed ? 1 : 0);
         ++launches;
         return CRT_OK;
     };
@@ -1394,6 +1458,48 @@ int render_impl(crt_world* w, const crt_camera* camera, const crt_render_setting
     t_last_rounds = rounds;
     t_last_ms = (double)ms;
     t_last_chunks = chunks_done;
+    if (host_fb) {
+        const size_t n_out = packed ? (size_t)(pixels_cached ? sc.pixel_count : sc.h_pixels.size()) : (size_t)W * H;
+        const size_t bytes = n_out * 16;
+        if (!packed && host_pointer_is_pinned(host_fb)) {
+            CKR(cudaMemcpyAsync(host_fb, d_fb, bytes, cudaMemcpyDeviceToHost, stream));
+            CKR(cudaStreamSynchronize(stream));
+            return CRT_OK;
+        }
+        if (bytes > sc.cap_stage) {
+            if (sc.h_stage) cudaFreeHost(sc.h_stage);
+            sc.h_stage = nullptr;
+            sc.cap_stage = 0;
+            CKR(cudaMallocHost((void**)&sc.h_stage, bytes));
+            sc.cap_stage = bytes;
+        }
+        CKR(cudaMemcpyAsync(sc.h_stage, d_fb, bytes, cudaMemcpyDeviceToHost, stream));
+        CKR(cudaStreamSynchronize(stream));
+        const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+        const unsigned threads = std::min(8u, std::max(1u, hw / std::max(1u, s->tile_world)));
+        if (!packed) {
+            char* dst = (char*)host_fb;
+            const char* src = sc.h_stage;
+            host_parallel_for((bytes + ((size_t)1 << 20) - 1) >> 20, threads, [=](size_t a, size_t b) {
+                const size_t o0 = a << 20, o1 = std::min(bytes, b << 20);
+                memcpy(dst + o0, src + o0, o1 - o0);
+            });
+        } else {
+            // runs of consecutive pixel indices (8 pixels = 128 bytes in the 8x4-block order) are copied whole
+            const uint32_t* px = sc.h_pixels.data();
+            const float4* src = (const float4*)sc.h_stage;
+            float4* dst = (float4*)host_fb;
+            host_parallel_for((n_out + 4095) / 4096, threads, [=](size_t a, size_t b) {
+                const size_t i1 = std::min(n_out, b * 4096);
+                for (size_t i = a * 4096; i < i1;) {
+                    size_t j = i + 1;
+                    while (j < i1 && px[j] == px[j - 1] + 1) ++j;
+                    memcpy(dst + px[i], src + i, (j - i) * sizeof(float4));
+                    i = j;
+                }
+            });
+        }
+    }
     return CRT_OK;
 }
 
@@ -1412,36 +1518,11 @@ int crt_render_steal(const crt_world* w, const crt_camera* camera, const crt_ren
 }
 
 int crt_render_host(const crt_world* w, const crt_camera* camera, const crt_render_settings* settings, float* framebuffer, crt_ray_stats* stats) {
-    if (!settings || !framebuffer) return crt::set_error(CRT_ERR_INVALID_ARG, "crt_render_host: null argument");
+    if (!settings || !framebuffer || !w) return crt::set_error(CRT_ERR_INVALID_ARG, "crt_render_host: null argument");
     int rc = crt::require_device();
     if (rc) return rc;
-    if (!w) return crt::set_error(CRT_ERR_INVALID_ARG, "crt_render_host: null argument");
-    size_t bytes = (size_t)settings->width * settings->height * 16;
-    crt_world* W = const_cast<crt_world*>(w);
-    float* d = nullptr;
-    {
-        // the device frame is kept with the world's scratch between calls (a 4K frame is 133 MB: allocating it per call
-        // costs more than copying it)
-        std::lock_guard<std::mutex> lk(W->mu);
-        if (bytes > W->scratch.cap_host_fb) {
-            cudaFree(W->scratch.host_fb);
-            W->scratch.host_fb = nullptr;
-            W->scratch.cap_host_fb = 0;
-            CKR(cudaMalloc(&W->scratch.host_fb, bytes ? bytes : 16));
-            W->scratch.cap_host_fb = bytes;
-        }
-        d = (float*)W->scratch.host_fb;
-    }
-    // Pixels of other ranks stay as given, so a tile split starts from the caller's frame; a whole-frame render overwrites
-    // every pixel and needs no upload.
-    cudaError_t e = cudaSuccess;
-    if (settings->tile_world > 1) e = cudaMemcpy(d, framebuffer, bytes, cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) {
-        rc = render_impl(W, camera, settings, d, stats, nullptr, nullptr);
-        if (rc == CRT_OK) e = cudaMemcpy(framebuffer, d, bytes, cudaMemcpyDeviceToHost);
-    }
-    if (e != cudaSuccess) return crt::set_cuda_error(e, "crt_render_host copy");
-    return rc;
+    // Pixels of other ranks stay as given: with a tile split only this process' pixels are written.
+    return render_impl(const_cast<crt_world*>(w), camera, settings, nullptr, stats, nullptr, nullptr, framebuffer);
 }
 
 }  // extern "C"

@@ -39,7 +39,11 @@ struct LevelSave {
 // (bvh.rs:711-755) and is unbounded; here an overflow beyond the bound sets a sticky status bit.
 template <int MAXD>
 struct StackCap {
+#ifdef CRT_STACK_CAP_ALL  // test builds only: proves that tests/test_gpu_parity.py's deep-stack scene needs more than the old 128
+    static constexpr int value = CRT_STACK_CAP_ALL;
+#else
     static constexpr int value = MAXD == 0 ? 512 : (MAXD == 1 ? 1024 : 2048);
+#endif
 };
 
 template <bool ANY_HIT, uint32_t FEAT, int MAXD>
@@ -117,13 +121,25 @@ __global__ void __launch_bounds__(CRT_BLOCK, MinBlocks<ANY_HIT, FEAT, MAXD>::val
     auto sst = [&](int slot, Entry e) { sstack[slot][tid] = e; };
     auto sld = [&](int slot) -> Entry { return sstack[slot][tid]; };
 #endif
+    // Beyond the depth bound of any tree the builders emit. A dropped entry could be an instance-return marker, after which
+    // the walk is meaningless, so the ray is abandoned (it reports a miss) and the sticky bit of crt_device_status() is set.
+    auto abandon_ray = [&]() {
+        overflow = true;
+        sp = 0;
+        depth = 0;
+        rec = CRT_NO_REC;
+        best_rec = CRT_NO_REC;
+        best_inst = CRT_NO_REC;
+        best_depth = 0;
+        any_found = false;
+    };
     auto push = [&](Entry e) {
         if (sp < CRT_SSTACK)
             sst(sp, e);
         else if (sp < CRT_SSTACK + kLStack)
             lstack[sp - CRT_SSTACK] = e;
         else
-            overflow = true;  // beyond the depth bound of any tree the builders emit; reported through crt_device_status()
+            return abandon_ray();
         ++sp;
     };
     auto pop = [&]() -> Entry {
@@ -343,6 +359,7 @@ __global__ void __launch_bounds__(CRT_BLOCK, MinBlocks<ANY_HIT, FEAT, MAXD>::val
                     if (hit[l]) sst(slot, make_entry(cw[l], tn[l]));
                 }
             } else {
+                bool fits = true;
 #pragma unroll
                 for (int l = 0; l < 4; ++l) {
                     if (!hit[l]) continue;
@@ -355,8 +372,9 @@ __global__ void __launch_bounds__(CRT_BLOCK, MinBlocks<ANY_HIT, FEAT, MAXD>::val
                     else if (slot < CRT_SSTACK + kLStack)
                         lstack[slot - CRT_SSTACK] = e2;
                     else
-                        overflow = true;
+                        fits = false;
                 }
+                if (!fits) return abandon_ray();
             }
             sp = base + n_int + n_leaf;
         }
@@ -593,6 +611,13 @@ __global__ void __launch_bounds__(CRT_BLOCK, MinBlocks<ANY_HIT, FEAT, MAXD>::val
                     rec = child & ~CRT_LEAF_BIT;
                     pkt_tmax = closest;
                     pkt_deferred = 0;
+#if CRT_LEAF_PREFETCH
+                    // the lane now waits for the rest of the warp to finish the node phase: start fetching its leaf's records
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(leafs + rec));
+#if CRT_LEAF_PREFETCH > 1
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(leafs + rec + 6));
+#endif
+#endif
                     break;
                 }
                 if constexpr (!ANY_HIT) {

@@ -99,6 +99,48 @@ def shared_frame(dist, device, height: int, width: int):
     return _FRAMES[key]
 
 
+_HOST_FRAMES = {}
+
+
+def shared_host_frame(dist, height: int, width: int) -> np.ndarray:
+    """One [h, w, 4] float32 frame in POSIX shared memory mapped by every rank of the (single-node) process group: rank 0
+    creates it, the name is broadcast, the others attach. Each rank's crt_render_host then downloads the pixels it owns
+    straight into this frame (its own PCIe link, its own host threads), so the whole frame is assembled in host memory
+    without any cross-rank copy. Cached per (group, size); unlinked when the creating process exits."""
+    import atexit
+    from multiprocessing import shared_memory
+
+    world = dist.get_world_size() if dist is not None and dist.is_initialized() else 1
+    rank = dist.get_rank() if world > 1 else 0
+    key = (id(dist.group.WORLD) if world > 1 else None, height, width)
+    if key in _HOST_FRAMES:
+        return _HOST_FRAMES[key][1]
+    nbytes = height * width * 16
+    name = [None]
+    shm = None
+    if rank == 0:
+        shm = shared_memory.SharedMemory(create=True, size=nbytes)
+        name[0] = shm.name
+        atexit.register(lambda s=shm: (s.close(), s.unlink()))
+    if world > 1:
+        dist.broadcast_object_list(name, src=0)
+    if rank != 0:
+        shm = shared_memory.SharedMemory(name=name[0])
+        try:  # the creator unlinks; attaching processes must not (Python < 3.13 registers every attachment for cleanup)
+            from multiprocessing import resource_tracker
+            resource_tracker.unregister(shm._name, "shared_memory")
+        except Exception:  # noqa: BLE001
+            pass
+        atexit.register(shm.close)
+    frame = np.ndarray((height, width, 4), dtype=np.float32, buffer=shm.buf)
+    if rank == 0:
+        frame.fill(0.0)
+    if world > 1:
+        dist.barrier()
+    _HOST_FRAMES[key] = (shm, frame)
+    return frame
+
+
 def render_distributed(renderer, dist=None, tile_size: int = 32, fb=None, stream: int = 0, steal: bool = False, gather: str = "reduce"):
     """Renders this rank's tiles and sum-reduces frame + RayStats to rank 0.
 

@@ -152,6 +152,50 @@ def test_all_primitive_kinds_masks_motion_nesting(gpu, orc):
     _compare_occluded(p, o, rays, time, mask)
 
 
+def _deep_stack_scene(api, levels=8, quads=32768):
+    """Eight nested levels; each holds `quads` parallel quads stacked along +z (all crossed by a ray along the z axis) and,
+    squeezed in front of the first quad, an instance of the next level scaled down to the quad spacing — so the instance
+    sits at the bottom of its level's tree and every level leaves its ~3 far siblings per BVH4 level on the traversal
+    stack when the ray descends: about 8 x 25 = 200 live entries (a build with the capacity forced back to 128 fails this test: CRT_STACK_CAP_ALL), more than the 128 the first kernel kept."""
+    dz = np.float32(0.01)
+    k = np.arange(1, quads + 1, dtype=np.float32)
+    z = np.float32(10.0) + k * dz
+    corners = np.array([[-1, -2], [3, -2], [3, 2], [-1, 2]], np.float32)  # the z axis crosses the interior of the first triangle
+    v = np.zeros((quads, 4, 3), np.float32)
+    v[:, :, :2] = corners
+    v[:, :, 2] = z[:, None]
+    idx = (np.arange(quads, dtype=np.uint32)[:, None] * 4 + np.array([0, 1, 2, 0, 2, 3], np.uint32)).reshape(-1, 3)
+    s = np.float32(dz / (z[-1] - np.float32(10.0) + dz))  # the child's z extent -> one quad spacing
+    child = None
+    for _ in range(levels):
+        b = api.SceneBuilder()
+        b.attach(api.Geometry.TriangleMesh(v.reshape(-1, 3), idx))
+        if child is not None:
+            xf = Affine3A([s, 0, 0, 0, s, 0, 0, 0, s, 0, 0, float(np.float32(10.0) - np.float32(10.0) * s)])
+            b.attach(api.Geometry.Instance(child, xf))
+        child = b.commit()
+    return child
+
+
+def test_traversal_stack_deeper_than_128_entries(gpu, orc):
+    """crust-rt's traversal stack spills to the heap and never drops an entry (bvh.rs:711-755). The device stack is
+    bounded, but by more than any committed tree can need (traverse.cu StackCap): a scene built to keep ~150 entries
+    alive must give the oracle's hits bit for bit and leave the sticky overflow bit clear."""
+    p, o = _deep_stack_scene(gpu), _deep_stack_scene(orc)
+    n = 2048
+    rng = np.random.default_rng(5)
+    org = np.zeros((n, 3), np.float32)
+    org[:, 2] = -5.0
+    d = np.zeros((n, 3), np.float32)
+    d[:, 2] = 1.0
+    d[n // 2:, :2] = rng.normal(scale=0.02, size=(n - n // 2, 2)).astype(np.float32)  # half the batch leaves the axis
+    rays = make_rays(org, d, 0.001, INF)
+    hits = _compare_closest(p, o, rays)
+    assert hits == n
+    assert _compare_occluded(p, o, rays) == n
+    assert gpu.device_status() == 0
+
+
 def test_ragged_and_empty_batches(gpu, orc):
     p, o = _pair(gpu, orc, workloads.sphere_grid_scene)
     for n in (0, 1, 31, 33, 127, 129, 4097):

@@ -269,6 +269,31 @@ def test_cached_pixel_list_is_keyed_by_the_real_tile_deal(gpu):
     assert again.tobytes() == full.tobytes()
 
 
+def test_host_frame_tile_split_downloads_only_owned_pixels(gpu):
+    """crt_render_host with a tile split resolves, downloads and scatters only the pixels this rank owns: the other
+    ranks' pixels of the caller's frame stay as given (no upload, no whole-frame download), also when a device-frame
+    render of another deal ran on the same World in between (the host-side scatter order carries its own key)."""
+    import torch
+    world, cam, st = scenes.furnace_room(gpu, width=96, height=64, spp=4, variance_threshold=0.0)
+    full = gpu.Renderer(cam, world, st).render_with_stats()[0]
+    dev = torch.zeros((64, 96, 4), dtype=torch.float32, device="cuda")
+    frame = np.full((64, 96, 4), -7.0, dtype=np.float32)
+    for rank, n in ((0, 2), (1, 2)):
+        gpu.Renderer(cam, world, rank_settings(st, rank, n, tile_size=16)).render_with_stats(out=frame)
+        # a device-frame render of a different deal with the same pixel count on the same World
+        gpu.Renderer(cam, world, rank_settings(st, 1 - rank, n, tile_size=16)).render_device(dev.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        m = owned_mask(96, 64, 16, rank, n)
+        assert np.array_equal(frame[m], full[m])
+        if rank == 0:
+            assert np.all(frame[~m] == -7.0)
+        gpu.Renderer(cam, world, rank_settings(st, rank, n, tile_size=16)).render_with_stats(out=frame)  # cached deal, host copy must be this deal's
+        assert np.array_equal(frame[m], full[m])
+    assert frame.tobytes() == full.tobytes()
+    pinned = torch.empty((64, 96, 4), dtype=torch.float32).pin_memory()
+    out = gpu.Renderer(cam, world, st).render_with_stats(out=pinned.numpy())[0]  # whole frame straight into pinned caller memory
+    assert out.tobytes() == full.tobytes()
+
+
 def test_device_framebuffer_entry_and_distributed_wrapper(gpu):
     import torch
     from crust_render_b200.distributed import render_distributed

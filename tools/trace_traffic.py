@@ -1,0 +1,79 @@
+#!/usr/bin/env python
+"""Regenerates profiles/trace_traffic.json — DRAM bytes, L1/L2 behaviour and SIMT efficiency of the five timed traversal
+launches of one bench.py step — from an `ncu --set full` capture of the bench command:
+
+    ncu --set full --clock-control none --import-source on -k regex:trace_kernel --launch-skip <5*(warmup + set-up launches)> \
+        -c 5 -o gpurun_out/bench_trace python bench.py --steps 1 --warmup 1 --no-render --no-cpu-baseline --no-e2e
+    python tools/trace_traffic.py gpurun_out/bench_trace.ncu-rep [--last 5]
+
+The json is stamped with a hash of the traversal sources (`source_sha`); bench.py only quotes `roofline.traffic` from it
+when the hash matches the sources it is running, so the figure cannot silently go stale.
+"""
+import argparse
+import csv
+import hashlib
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SETS = ["closest_lcg", "closest_camera", "closest_bounce", "occluded_lcg", "occluded_shadow"]
+KERNEL_SOURCES = ["traverse.cu", "traverse.cuh", "launch.h", "crt_layout.h"]
+
+
+def source_sha() -> str:
+    h = hashlib.sha256()
+    for name in KERNEL_SOURCES:
+        h.update(open(os.path.join(ROOT, "crust-render_b200", "csrc", name), "rb").read())
+    return h.hexdigest()[:16]
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("report")
+    ap.add_argument("--last", type=int, default=5, help="use the last N trace_kernel launches of the report (one bench step)")
+    ap.add_argument("--out", default=os.path.join(ROOT, "profiles", "trace_traffic.json"))
+    ap.add_argument("--raw-out", default=None, help="also keep the raw csv page here")
+    a = ap.parse_args()
+    txt = subprocess.run(["ncu", "-i", a.report, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
+    if a.raw_out:
+        open(a.raw_out, "w").write(txt)
+    rows = list(csv.reader(txt.splitlines()))
+    hdr, data = rows[0], [r for r in rows[2:] if len(r) == len(rows[0])]
+    data = [r for r in data if "trace_kernel" in r[hdr.index("Kernel Name")]][-a.last:]
+    if len(data) != len(SETS):
+        sys.exit(f"expected {len(SETS)} trace_kernel launches, found {len(data)}")
+
+    def col(r, name):
+        return float(r[hdr.index(name)].replace(",", ""))
+
+    def in_bytes(r, name):
+        unit = rows[1][hdr.index(name)].lower()
+        scale = {"byte": 1.0, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}[unit]
+        return col(r, name) * scale
+
+    per = {}
+    for name, r in zip(SETS, data):
+        ms = col(r, "gpu__time_duration.sum")
+        unit = rows[1][hdr.index("gpu__time_duration.sum")]
+        ms *= {"ms": 1.0, "us": 1e-3, "ns": 1e-6, "s": 1e3}.get(unit, 1.0)
+        rd, wr = in_bytes(r, "dram__bytes_read.sum"), in_bytes(r, "dram__bytes_write.sum")
+        l2 = in_bytes(r, "lts__t_bytes.sum") if "lts__t_bytes.sum" in hdr else None
+        per[name] = {"kernel": r[hdr.index("Kernel Name")], "dram_read": rd, "dram_write": wr, "traffic": rd + wr, "kernel_ms": ms,
+                     "threads_per_inst": col(r, "smsp__thread_inst_executed_per_inst_executed.ratio"),
+                     "issue_active_pct": col(r, "smsp__issue_active.avg.pct_of_peak_sustained_active") if "smsp__issue_active.avg.pct_of_peak_sustained_active" in hdr else None,
+                     "l1_hit_pct": col(r, "l1tex__t_sector_hit_rate.pct"), "l2_hit_pct": col(r, "lts__t_sector_hit_rate.pct"),
+                     "warp_inst": col(r, "smsp__inst_executed.sum"), "registers": int(col(r, "launch__registers_per_thread")),
+                     "warps_active_pct": col(r, "sm__warps_active.avg.pct_of_peak_sustained_active"),
+                     "dram_gb_per_s": (rd + wr) / ms / 1e6, "l2_gb_per_s": None if l2 is None else l2 / ms / 1e6}
+    closest = [n for n in SETS if n.startswith("closest")]
+    out = {"source": f"{os.path.relpath(a.report, ROOT)} (ncu --set full --clock-control none, the five timed launches of one bench step); regenerate with tools/trace_traffic.py",
+           "source_sha": source_sha(), "kernel_sources": KERNEL_SOURCES, "per_launch": per,
+           "mean_traffic_per_closest_launch": sum(per[n]["traffic"] for n in closest) / len(closest)}
+    json.dump(out, open(a.out, "w"), indent=1)
+    print(json.dumps({k: (round(v["traffic"] / 1e9, 3), round(v["kernel_ms"], 3), v["threads_per_inst"]) for k, v in per.items()}))
+
+
+if __name__ == "__main__":
+    main()
