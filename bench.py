@@ -180,9 +180,10 @@ def time_sample_configs(crt, torch, dist, world, rank, dev, stream, gather, with
     return out
 
 
-def copy_ceiling(torch, dist, world, dev, mb=256, reps=6):
-    """What the box's PCIe / host-memory path can move: pinned H2D and D2H copies of `mb` MB running concurrently on two
-    streams, all ranks at once. GB/s per direction, whole job (summed over ranks)."""
+def copy_ceiling(torch, dist, world, dev, h2d_bytes, d2h_bytes, mb=256):
+    """What the box's PCIe / host-memory path needs for one step's traffic with no kernels at all: `h2d_bytes` up and
+    `d2h_bytes` down per rank as plain pinned copies (chunks of `mb` MB) running concurrently on two streams, all ranks at
+    once. Returns the wall time of that (max over ranks) and the rates it implies, whole job."""
     n = mb << 20
     h_in, h_out = torch.empty(n, dtype=torch.uint8).pin_memory(), torch.empty(n, dtype=torch.uint8).pin_memory()
     d_in, d_out = torch.empty(n, dtype=torch.uint8, device=dev), torch.empty(n, dtype=torch.uint8, device=dev)
@@ -193,77 +194,28 @@ def copy_ceiling(torch, dist, world, dev, mb=256, reps=6):
             dist.barrier()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        for _ in range(reps):
-            if up:
-                with torch.cuda.stream(s_up):
-                    d_in.copy_(h_in, non_blocking=True)
-            if down:
-                with torch.cuda.stream(s_dn):
-                    h_out.copy_(d_out, non_blocking=True)
+        with torch.cuda.stream(s_up):
+            for off in range(0, up, n):
+                c = min(n, up - off)
+                d_in[:c].copy_(h_in[:c], non_blocking=True)
+        with torch.cuda.stream(s_dn):
+            for off in range(0, down, n):
+                c = min(n, down - off)
+                h_out[:c].copy_(d_out[:c], non_blocking=True)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         t = torch.tensor([dt], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return world * reps * n / float(t.item()) / 1e9
+        return float(t.item())
 
-    run(True, True)
-    both = run(True, True)
-    return {"h2d_alone_gbs": run(True, False), "d2h_alone_gbs": run(False, True), "each_direction_concurrent_gbs": both,
-            "method": f"{mb} MB pinned buffers, {reps} copies per direction on two streams, all {world} rank(s) at once, wall clock, max over ranks"}
-
-
-def time_other_scenes(crt, W, torch, stream, grid, with_cpu):
-    """SURVEY 8(d)'s other kernel inputs, timed resident like the main step (best of 3, CUDA events): K2 — the stress scene
-    with identical spheres, i.e. one 9 800-triangle BLAS x grid^2 instances over the flat shards/floor/slab (two-level
-    traversal); K3 — the reference's three throughput-probe scenes (ray_throughput.rs:50-100) with its LCG box rays
-    (:103-116). Beside each: the CPU restatement on one thread (the reference's own figure is per core) and on all, on a
-    2^18-ray sample, with hit agreement on that sample."""
-    import orc
-
-    def gpu_rate(scene, rays, closest):
-        n = len(rays)
-        d_r = torch.from_numpy(rays.view(np.float32).reshape(-1, 8).copy()).cuda()
-        d_o = torch.empty((n, 8), dtype=torch.float32, device="cuda") if closest else torch.empty(n, dtype=torch.uint8, device="cuda")
-        best = None
-        for k in range(4):
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(stream)
-            if closest:
-                scene.intersect_ptr(n, d_r.data_ptr(), 0, 0, d_o.data_ptr(), 0, stream.cuda_stream)
-            else:
-                scene.occluded_ptr(n, d_r.data_ptr(), 0, 0, d_o.data_ptr(), stream.cuda_stream)
-            e1.record(stream)
-            torch.cuda.synchronize()
-            if k:
-                best = e0.elapsed_time(e1) if best is None else min(best, e0.elapsed_time(e1))
-        return n / best / 1e3, d_o.cpu().numpy()
-
-    out = {}
-    cases = [("K2 instanced stress", lambda api: W.stress_scene_instanced(api, grid=grid).commit(), 24),
-             ("K3 tri_spheres", lambda api: W.triangle_scene(api).commit(), 22),
-             ("K3 sphere_grid", lambda api: W.sphere_grid_scene(api).commit(), 22),
-             ("K3 instance_scene", lambda api: W.instance_scene(api).commit(), 22)]
-    for name, make, log2 in cases:
-        scene = make(crt)
-        rays = W.ray_batch(1 << log2, W.scene_extent(scene.bounds()))
-        pb = scene.primitive_breakdown()
-        rec = {"rays": len(rays), "top_level_primitives": scene.primitive_count(), "instances": pb.instances}
-        rec["closest_lcg_mrays"], hits = gpu_rate(scene, rays, True)
-        rec["occluded_lcg_mrays"], occ = gpu_rate(scene, rays, False)
-        if with_cpu:
-            o = make(orc)
-            sub = slice(0, None, len(rays) >> 18)
-            oh, _ = o.intersect_n(rays[sub], threads=0)
-            rec["cpu_all_threads_mrays"] = len(oh) / o.last_seconds / 1e6
-            o.intersect_n(rays[sub][: 1 << 16], threads=1)
-            rec["cpu_one_thread_mrays"] = (1 << 16) / o.last_seconds / 1e6
-            g = hits.view(np.uint32).reshape(-1, 8)[sub]
-            rec["oracle_agreement_on_sample"] = float(((g[:, 3] == oh["geom_id"]) & (g[:, 4] == oh["prim_id"]) & (g[:, 0].view(np.float32) == oh["t"])).mean())
-            rec["occlusion_agreement_on_sample"] = float((occ[sub] == o.occluded_n(rays[sub], threads=0)).mean())
-        out[name] = rec
-        del scene
-    return out
+    run(h2d_bytes, d2h_bytes)
+    both = min(run(h2d_bytes, d2h_bytes) for _ in range(3))
+    up = min(run(h2d_bytes, 0) for _ in range(2))
+    down = min(run(0, d2h_bytes) for _ in range(2))
+    return {"copy_only_ms_per_step": both * 1e3, "h2d_alone_gbs": world * h2d_bytes / up / 1e9, "d2h_alone_gbs": world * d2h_bytes / down / 1e9,
+            "h2d_gbs_with_d2h_running": world * h2d_bytes / both / 1e9,
+            "method": f"one step's bytes per rank as plain pinned copies in {mb} MB chunks, H2D and D2H on two streams, all {world} rank(s) at once, wall clock, max over ranks, best of 3"}
 
 
 # ---------------------------------------------------------------------------
@@ -542,11 +494,10 @@ def main():
         e2e = {"value": rays_per_step * world * args.steps / dt / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                "ms_per_step": dt / args.steps * 1e3}
         # the ceiling of this box for that traffic: plain pinned copies in both directions at once, all ranks together
-        ceil = copy_ceiling(torch, dist, world, dev)
-        moved = world * h2d / (dt / args.steps) / 1e9  # H2D is the larger direction: 32 B per ray in, 32 B or 1 B out
+        ceil = copy_ceiling(torch, dist, world, dev, h2d, d2h)
         e2e["copy_ceiling"] = ceil
-        e2e["h2d_gbs_achieved"] = moved
-        e2e["frac_of_copy_ceiling"] = moved / ceil["each_direction_concurrent_gbs"]
+        e2e["h2d_gbs_achieved"] = world * h2d / (dt / args.steps) / 1e9
+        e2e["frac_of_copy_ceiling"] = ceil["copy_only_ms_per_step"] / e2e["ms_per_step"]
 
     # ---- render: config 5 through the wavefront integrator, frame split over the ranks ----------
     render = None
@@ -589,7 +540,7 @@ def main():
             r_frame = shared_frame(dist, dev, rh, rw)[1]
         else:
             r_frame = fb
-        mean_rgb = [float(v) for v in r_frame[..., :3].mean(dim=(0, 1)).tolist()] if rank == 0 else None
+        mean_rgb = [float(v) for v in r_frame[..., :3].double().mean(dim=(0, 1)).tolist()] if rank == 0 else None
         # e2e: the same frame through crt_render_host into ONE host frame. N = 1: pinned caller memory, the resolved frame is
         # copied straight into it. N > 1: the frame lives in POSIX shared memory mapped by every rank; each rank's
         # crt_render_host downloads only the pixels it owns (packed D2H over its own PCIe link, host-side scatter), so the
@@ -611,7 +562,7 @@ def main():
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         e2e_s = float(te.item())
         renderer.settings = r_st
-        host_mean = [float(v) for v in host_fb[..., :3].mean(axis=(0, 1))] if rank == 0 else None
+        host_mean = [float(v) for v in host_fb[..., :3].mean(axis=(0, 1), dtype=np.float64)] if rank == 0 else None
         if rank == 0:
             render = {"workload": f"config 5: stress mesh ({r_tris} triangles) + 12x12 RectLight, {rw}x{rh}, depth 6, {rspp} spp per step, power MIS, triangle filter",
                       "spp_per_s": rspp / (r_ms * 1e-3), "msamples_per_s": rw * rh * rspp / r_ms / 1e3, "mrays_per_s": st0.total_rays() / r_ms / 1e3,

@@ -694,6 +694,34 @@ __global__ void __launch_bounds__(kBlock) film_kernel(const RenderParams P, uint
 // it with system-scope atomics (over NVLink / NVSwitch peer access).
 __global__ void fetch_chunk_kernel(unsigned int* cursor, uint32_t* out) { *out = atomicAdd_system(cursor, 1u); }
 
+// ---- test aid: one material's eval / scatter for n queries (crt_debug_material_*) ----------------------------------------
+__global__ void debug_material_kernel(Material m, uint32_t n, const float* __restrict__ ray_dir, const float* __restrict__ normal,
+                                      const uint8_t* __restrict__ front_face, const float* __restrict__ arg, float* __restrict__ out,
+                                      uint8_t* __restrict__ some, int scatter) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    SurfaceHit rec;
+    rec.p = v3(0.0f, 0.0f, 0.0f);
+    rec.normal = v3(normal[3 * i], normal[3 * i + 1], normal[3 * i + 2]);
+    rec.t = 1.0f;
+    rec.front_face = front_face[i] != 0;
+    const V3 rd = v3(ray_dir[3 * i], ray_dir[3 * i + 1], ray_dir[3 * i + 2]);
+    if (!scatter) {
+        V3 value = v3(0.0f, 0.0f, 0.0f);
+        float pdf = 0.0f;
+        bool ok = material_eval(m, rd, rec, v3(arg[3 * i], arg[3 * i + 1], arg[3 * i + 2]), value, pdf);
+        some[i] = ok ? 1 : 0;
+        out[4 * i] = value.x, out[4 * i + 1] = value.y, out[4 * i + 2] = value.z, out[4 * i + 3] = pdf;
+    } else {
+        const float s4[4] = {arg[4 * i], arg[4 * i + 1], arg[4 * i + 2], arg[4 * i + 3]};
+        ScatterSample ss{};
+        bool ok = material_scatter(m, rd, rec, s4, ss);
+        some[i] = ok ? 1 : 0;
+        float* o = out + 8 * (size_t)i;
+        o[0] = ss.dir.x, o[1] = ss.dir.y, o[2] = ss.dir.z, o[3] = ss.value.x, o[4] = ss.value.y, o[5] = ss.value.z, o[6] = ss.pdf, o[7] = ss.delta ? 1.0f : 0.0f;
+    }
+}
+
 struct Scratch {  // grow-only device buffers reused across crt_render calls on one world
     size_t cap_paths = 0, cap_pixels = 0, cap_counts = 0;
     void* paths = nullptr;   // everything sized by the path pool
@@ -1525,4 +1553,51 @@ int crt_render_host(const crt_world* w, const crt_camera* camera, const crt_rend
     return render_impl(const_cast<crt_world*>(w), camera, settings, nullptr, stats, nullptr, nullptr, framebuffer);
 }
 
+}  // extern "C"
+
+
+namespace {
+int debug_material(const crt_material* material, size_t n, const float* ray_dir, const float* normal, const uint8_t* front_face, const float* arg, size_t arg_w,
+                   float* out, size_t out_w, uint8_t* some, int scatter) {
+    if (!material || (n && (!ray_dir || !normal || !front_face || !arg || !out || !some))) return crt::set_error(CRT_ERR_INVALID_ARG, "crt_debug_material: null argument");
+    if (n > 0x7FFFFFFFu) return crt::set_error(CRT_ERR_INVALID_ARG, "crt_debug_material: too many queries");
+    int rc = crt::require_device();
+    if (rc) return rc;
+    if (n == 0) return CRT_OK;
+    const Material m = material_from_abi(*material);
+    float *d_rd = nullptr, *d_n = nullptr, *d_arg = nullptr, *d_out = nullptr;
+    uint8_t *d_ff = nullptr, *d_some = nullptr;
+    cudaError_t e = cudaSuccess;
+    auto up = [&](void** dst, const void* src, size_t bytes) {
+        if (e == cudaSuccess) e = cudaMalloc(dst, bytes);
+        if (e == cudaSuccess && src) e = cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice);
+    };
+    up((void**)&d_rd, ray_dir, 12 * n);
+    up((void**)&d_n, normal, 12 * n);
+    up((void**)&d_ff, front_face, n);
+    up((void**)&d_arg, arg, 4 * arg_w * n);
+    up((void**)&d_out, nullptr, 4 * out_w * n);
+    up((void**)&d_some, nullptr, n);
+    if (e == cudaSuccess) {
+        debug_material_kernel<<<(unsigned)((n + 127) / 128), 128>>>(m, (uint32_t)n, d_rd, d_n, d_ff, d_arg, d_out, d_some, scatter);
+        crt::count_launches(1);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(out, d_out, 4 * out_w * n, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(some, d_some, n, cudaMemcpyDeviceToHost);
+    cudaFree(d_rd), cudaFree(d_n), cudaFree(d_ff), cudaFree(d_arg), cudaFree(d_out), cudaFree(d_some);
+    if (e != cudaSuccess) return crt::set_cuda_error(e, "crt_debug_material");
+    return CRT_OK;
+}
+}  // namespace
+
+extern "C" {
+int crt_debug_material_eval(const crt_material* material, size_t n, const float* ray_dir, const float* normal, const uint8_t* front_face, const float* wi,
+                            float* value_pdf, uint8_t* some) {
+    return debug_material(material, n, ray_dir, normal, front_face, wi, 3, value_pdf, 4, some, 0);
+}
+int crt_debug_material_scatter(const crt_material* material, size_t n, const float* ray_dir, const float* normal, const uint8_t* front_face, const float* s4,
+                               float* out8, uint8_t* some) {
+    return debug_material(material, n, ray_dir, normal, front_face, s4, 4, out8, 8, some, 1);
+}
 }  // extern "C"

@@ -33,7 +33,7 @@ from .render_types import (  # noqa: F401
 )
 
 __all__ = ["World", "WorldBuilder", "Renderer", "StealCursor", "SharedFrame", "Camera", "RenderSettings", "SamplingStrategy", "PixelFilter", "PixelFilterKind",
-           "RayStats", "LightList", "OpenPBR", "Emissive", "SphereLight", "RectLight", "DistantLight", "DomeLight", "VolumeRegion", "DensityField"]
+           "RayStats", "LightList", "OpenPBR", "Emissive", "SphereLight", "RectLight", "DistantLight", "DomeLight", "VolumeRegion", "DensityField", "debug_material_eval", "debug_material_scatter"]
 
 
 def _p(a: Optional[np.ndarray]):
@@ -188,3 +188,28 @@ class Renderer:
         rt._ck(rt.lib().crt_render(self.world._h, _p(cam), _p(rec), C.c_void_p(fb_ptr), _p(stats), C.c_void_p(stream)))
         self._info()
         return RayStats.from_record(stats)
+
+
+def debug_material_eval(material: np.ndarray, ray_dir, normal, front_face, wi):
+    """crt_debug_material_eval: `Material::eval` of one crt_material record on the device for n queries.
+    Returns (value[n, 3] = brdf * |cos|, pdf[n], some[n] bool)."""
+    rd, nn, w = (np.ascontiguousarray(a, dtype=np.float32).reshape(-1, 3) for a in (ray_dir, normal, wi))
+    ff = np.ascontiguousarray(front_face, dtype=np.uint8).reshape(-1)
+    n = len(rd)
+    out, some = np.zeros((n, 4), np.float32), np.zeros(n, np.uint8)
+    mat = np.ascontiguousarray(material, dtype=MATERIAL_DTYPE).reshape(1)
+    rt._ck(rt.lib().crt_debug_material_eval(_p(mat), n, _p(rd), _p(nn), _p(ff), _p(w), _p(out), _p(some)))
+    return out[:, :3], out[:, 3], some.astype(bool)
+
+
+def debug_material_scatter(material: np.ndarray, ray_dir, normal, front_face, s4):
+    """crt_debug_material_scatter: `Material::scatter_importance` given the 4-D BSDF block of each query.
+    Returns (direction[n, 3], value[n, 3], pdf[n], delta[n] bool, some[n] bool)."""
+    rd, nn = (np.ascontiguousarray(a, dtype=np.float32).reshape(-1, 3) for a in (ray_dir, normal))
+    s = np.ascontiguousarray(s4, dtype=np.float32).reshape(-1, 4)
+    ff = np.ascontiguousarray(front_face, dtype=np.uint8).reshape(-1)
+    n = len(rd)
+    out, some = np.zeros((n, 8), np.float32), np.zeros(n, np.uint8)
+    mat = np.ascontiguousarray(material, dtype=MATERIAL_DTYPE).reshape(1)
+    rt._ck(rt.lib().crt_debug_material_scatter(_p(mat), n, _p(rd), _p(nn), _p(ff), _p(s), _p(out), _p(some)))
+    return out[:, :3], out[:, 3:6], out[:, 6], out[:, 7] != 0, some.astype(bool)

@@ -144,6 +144,8 @@ def lib() -> C.CDLL:
         "crt_shared_frame_create": [sz, C.POINTER(vp), vp],
         "crt_shared_frame_open": [vp, C.POINTER(vp)],
         "crt_shared_frame_close": [vp, C.c_int],
+        "crt_debug_material_eval": [vp, sz, vp, vp, vp, vp, vp, vp],
+        "crt_debug_material_scatter": [vp, sz, vp, vp, vp, vp, vp, vp],
     }
     for name, args in sig.items():
         fn = getattr(L, name)

@@ -204,6 +204,18 @@ int crt_shared_frame_close(void* device_ptr, int owner);
  * (CUDA events on the render stream), for bench.py. */
 int crt_render_last_info(uint64_t* launches, double* device_ms, uint64_t* rounds);
 
+/* Test aid: the Material trait surface of ONE material evaluated on the device for n independent queries (host buffers,
+ * copies inside), so the shading math can be checked against a witness that shares no source with it
+ * (oracle/openpbr_ref.py, tests/test_gpu_shade_independent.py).
+ *   crt_debug_material_eval    Material::eval (openpbr.rs:1138-1158): value_pdf[4i..] = brdf*|cos| (rgb), pdf; some[i] = Some?
+ *   crt_debug_material_scatter Material::scatter_importance given the 4-D BSDF block s (openpbr.rs:1026-1136):
+ *                              out[8i..] = direction (xyz), value (rgb), pdf, delta flag (0 / 1); some[i] = Some?
+ * ray_dir, normal, wi: 3 floats per query; front_face: 1 byte per query. */
+int crt_debug_material_eval(const crt_material* material, size_t n, const float* ray_dir, const float* normal, const uint8_t* front_face,
+                            const float* wi, float* value_pdf, uint8_t* some);
+int crt_debug_material_scatter(const crt_material* material, size_t n, const float* ray_dir, const float* normal, const uint8_t* front_face,
+                               const float* s4, float* out8, uint8_t* some);
+
 #ifdef __cplusplus
 }
 #endif

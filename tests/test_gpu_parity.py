@@ -275,6 +275,19 @@ def test_full_size_k1_mesh_properties(gpu, orc):
     ph = h[:: n // (1 << 16)]
     assert ph.tobytes() == oh.tobytes() and np.array_equal(ff[:: n // (1 << 16)], of)
     assert np.array_equal(occ[:: n // (1 << 16)], o.occluded_n(sub, threads=0))
+    # ... and the five ray sets of bench.py (LCG box rays, camera rays, cosine bounce rays, RectLight shadow rays)
+    # at 2^22 rays each, every ray against the oracle, bit for bit
+    import bench
+    sets, _ = bench.build_ray_sets(workloads, p.bounds(), 22, 0, lambda r: p.intersect_n(r)[0])
+    for name in bench.SETS:
+        set_rays, set_mask = sets[name]
+        assert len(set_rays) >= (1 << 22) * 0.9
+        if name.startswith("closest"):
+            gh, gf = p.intersect_n(set_rays, None, set_mask)
+            ch, cf = o.intersect_n(set_rays, None, set_mask, threads=0)
+            assert gh.tobytes() == ch.tobytes() and np.array_equal(gf, cf), name
+        else:
+            assert np.array_equal(p.occluded_n(set_rays, None, set_mask), o.occluded_n(set_rays, None, set_mask, threads=0)), name
 
 
 def test_l2_window_over_breadth_first_top_levels(gpu, orc):

@@ -113,6 +113,33 @@ def test_config4_point_instanced_medcity(gpu, orc):
     assert sg.shadow_rays == 0 and sg.rr_tested > 0
 
 
+# ---- BASELINE.json configs 1-3 at the sizes the config list names (the reduced-size tests above run first and fail faster) ----
+def test_config1_cornellbox_at_baseline_size(gpu, orc):
+    """512x512, 64 spp, adaptive (threshold 0.05, min 32), depth 32: the full config, every pixel against the oracle."""
+    fg, sg, fo, so, _ = both(gpu, orc, scenes.cornellbox, width=512, height=512, spp=64)
+    same = fg[..., 3] == fo[..., 3]
+    assert same.mean() >= 0.999
+    compare(fg[same], fo[same])
+    stats_close(sg, so, tol=2e-3, adaptive=True)
+
+
+def test_config2_veach_mis_at_baseline_size(gpu, orc):
+    """960x540, 128 spp, balance heuristic, depth 8, adaptive off (samples/veach_mis.usda:206-216)."""
+    fg, sg, fo, so, _ = both(gpu, orc, scenes.veach_mis, width=960, height=540, spp=128)
+    compare(fg, fo)
+    stats_close(sg, so)
+    assert np.array_equal(fg[..., 3], fo[..., 3])
+
+
+def test_config3_openpbr_showcase_at_baseline_size(gpu, orc):
+    """640x360, 128 spp, adaptive, depth 32: every OpenPBR lobe of the sample."""
+    fg, sg, fo, so, _ = both(gpu, orc, scenes.openpbr_showcase, width=640, height=360, spp=128)
+    same = fg[..., 3] == fo[..., 3]
+    assert same.mean() >= 0.999
+    compare(fg[same], fo[same])
+    stats_close(sg, so, tol=2e-3, adaptive=True)
+
+
 def test_dome_light_with_environment_map_and_distant_light(gpu, orc):
     """samples/domelight.usda: an importance-sampled lat-long HDRI dome (rotated) plus a 1.5-degree
     distant light; both are found by NEE and by escaping bounce rays with matching MIS densities."""
