@@ -24,6 +24,7 @@ struct TraceParams {
     uint32_t n;               // ray count, or the capacity bound when n_dev is set
     const uint32_t* n_dev;    // optional: ray count in device memory (read at kernel start)
     uint32_t mask_uniform;    // ray mask of every ray when `mask` is null
+    unsigned long long* stats;  // null, or 7 device counters the counting build of the kernel adds to (crt_trace_counters)
 };
 
 // Tunables (overridable with -D for the tuning harness, tools/tune_trace.py)

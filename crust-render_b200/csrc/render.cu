@@ -49,6 +49,12 @@ namespace {
 
 constexpr int kBlock = 128;
 constexpr int kShadeBins = 64;  // class 0 = miss, then one class per lobe signature of the world's materials (crt_world::mat_class)
+#ifndef CRT_SHADE_BLOCK
+#define CRT_SHADE_BLOCK 128  // threads per block of the shading kernels
+#endif
+#ifndef CRT_SHADE_SYNC
+#define CRT_SHADE_SYNC 0  // 1: the warps of a block start every queue entry together (block-wide barrier per grid-stride step), so warps that share an SM sub-partition fetch the same instruction lines at about the same time
+#endif
 #ifndef CRT_SHADE_MINBLOCKS
 #define CRT_SHADE_MINBLOCKS 8  // resident blocks per SM shade_kernel is compiled for: 64 registers with spills beat 128 registers at half the occupancy (measured 4/5/6/8 on B200)
 #endif
@@ -284,7 +290,7 @@ __global__ void __launch_bounds__(kBlock) classify_scatter_kernel(const RenderPa
 enum : int { SHADE_FUSED = 0, SHADE_VERTEX = 1, SHADE_SCATTER = 2 };
 
 template <bool VOL, int PASS>
-__global__ void __launch_bounds__(kBlock, VOL ? 4 : CRT_SHADE_MINBLOCKS) shade_kernel(const RenderParams P, int k, int cur, const uint32_t* __restrict__ order) {
+__global__ void __launch_bounds__(CRT_SHADE_BLOCK, (VOL ? 4 : CRT_SHADE_MINBLOCKS) * 128 / CRT_SHADE_BLOCK) shade_kernel(const RenderParams P, int k, int cur, const uint32_t* __restrict__ order) {
     static_assert(!VOL || PASS == SHADE_FUSED, "worlds with volume regions use the fused kernel");
     const int D = (int)P.st.max_depth;
     const uint32_t n = P.q.counts[k];
@@ -292,7 +298,14 @@ __global__ void __launch_bounds__(kBlock, VOL ? 4 : CRT_SHADE_MINBLOCKS) shade_k
     uint32_t* sh_count = P.q.counts + (D + 2) + k;
     const int nxt = cur ^ 1;
 
+#if CRT_SHADE_SYNC
+    for (uint32_t j0 = blockIdx.x * blockDim.x; j0 < n; j0 += gridDim.x * blockDim.x) {  // uniform trip count: the barrier is safe
+        __syncthreads();
+        const uint32_t j = j0 + threadIdx.x;
+        if (j >= n) continue;
+#else
     for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+#endif
         const uint32_t i = order ? order[j] : j;
         const uint32_t path = P.q.path[cur][i];
         const float4 ra = P.q.rays[cur][2 * (size_t)i], rb = P.q.rays[cur][2 * (size_t)i + 1];
@@ -1267,6 +1280,10 @@ int render_impl(crt_world* w, const crt_camera* camera, const crt_render_setting
         P.q.bins = carve<uint32_t>(p, (size_t)kShadeBins * kSortBlocks);
         P.q.counts = sc.counts;
     }
+    auto shade_grid = [&](size_t n) {
+        size_t blocks = (n + CRT_SHADE_BLOCK - 1) / CRT_SHADE_BLOCK;
+        return (int)std::max<size_t>(1, std::min<size_t>(blocks, (size_t)sms * (8 * 128 / CRT_SHADE_BLOCK)));
+    };
     auto grid_for = [&](size_t n) {
         size_t blocks = (n + kBlock - 1) / kBlock;
         return (int)std::max<size_t>(1, std::min<size_t>(blocks, (size_t)sms * 8));
@@ -1318,15 +1335,15 @@ int render_impl(crt_world* w, const crt_camera* camera, const crt_render_setting
                 order = P.q.order;
             }
             if (P.n_volumes > 0) {
-                shade_kernel<true, SHADE_FUSED><<<grid_for(bound), kBlock, 0, stream>>>(P, k, cur, order);
+                shade_kernel<true, SHADE_FUSED><<<shade_grid(bound), CRT_SHADE_BLOCK, 0, stream>>>(P, k, cur, order);
             } else if (split_shade && PL_has_nee) {
-                shade_kernel<false, SHADE_VERTEX><<<grid_for(bound), kBlock, 0, stream>>>(P, k, cur, order);
+                shade_kernel<false, SHADE_VERTEX><<<shade_grid(bound), CRT_SHADE_BLOCK, 0, stream>>>(P, k, cur, order);
                 if (k < D) {  // a depth-exhausted vertex has no continuation to sample
-                    shade_kernel<false, SHADE_SCATTER><<<grid_for(bound), kBlock, 0, stream>>>(P, k, cur, order);
+                    shade_kernel<false, SHADE_SCATTER><<<shade_grid(bound), CRT_SHADE_BLOCK, 0, stream>>>(P, k, cur, order);
                     ++launches;
                 }
             } else {
-                shade_kernel<false, SHADE_FUSED><<<grid_for(bound), kBlock, 0, stream>>>(P, k, cur, order);
+                shade_kernel<false, SHADE_FUSED><<<shade_grid(bound), CRT_SHADE_BLOCK, 0, stream>>>(P, k, cur, order);
             }
             launches += 2;
             ++trace_launches;

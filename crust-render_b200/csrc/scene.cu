@@ -49,6 +49,8 @@ struct Device {
     unsigned int* status = nullptr;
     std::atomic<uint64_t> next_counter{0};
     std::atomic<uint64_t> launches{0};
+    unsigned long long* trace_stats = nullptr;  // 7 counters of the counting traversal build
+    std::atomic<bool> count_traversal{false};
     size_t l2_persist_bytes = 0;  // L2 set aside for the top levels of the BVH (0 = feature off)
     std::atomic<uint64_t> l2_applied{0}, l2_refused{0};
 } g_dev;
@@ -91,6 +93,8 @@ int ensure_device() {
     CK(cudaMalloc(&g_dev.counters, sizeof(unsigned int) * (kCounterRing + 1)));
     CK(cudaMemset(g_dev.counters, 0, sizeof(unsigned int) * (kCounterRing + 1)));
     g_dev.status = g_dev.counters + kCounterRing;
+    CK(cudaMalloc(&g_dev.trace_stats, 8 * sizeof(unsigned long long)));
+    CK(cudaMemset(g_dev.trace_stats, 0, 8 * sizeof(unsigned long long)));
     g_dev.ready = true;
     return CRT_OK;
 }
@@ -629,6 +633,7 @@ static int launch_query(const crt_scene* s, bool any_hit, size_t n, const crt_ra
         p.n = (uint32_t)cnt;
         p.n_dev = nullptr;
         p.mask_uniform = CRT_MASK_ALL;
+        p.stats = g_dev.count_traversal.load() ? g_dev.trace_stats : nullptr;
         int grid = g_dev.sm_count * per_sm;
         size_t need = (cnt + CRT_BLOCK - 1) / CRT_BLOCK;
         if ((size_t)grid > need) grid = (int)need;
@@ -653,6 +658,27 @@ int crt_l2_persist_info(uint64_t* set_aside_bytes, uint64_t* windows_applied, ui
     if (set_aside_bytes) *set_aside_bytes = g_dev.l2_persist_bytes;
     if (windows_applied) *windows_applied = g_dev.l2_applied.load();
     if (windows_refused) *windows_refused = g_dev.l2_refused.load();
+    return CRT_OK;
+}
+
+// Counting traversal (bvh.rs:31-136 `stats`): while enabled, every traversal launch runs the counting
+// build of its kernel. crt_trace_counters_read synchronises the device and returns {rays, nodes fetched, popped entries
+// culled by entry distance, leaves entered, triangle records tested, other primitive records tested, instance descents}.
+int crt_trace_counters_enable(int on) {
+    int rc = ensure_device();
+    if (rc) return rc;
+    g_dev.count_traversal.store(on != 0);
+    return CRT_OK;
+}
+int crt_trace_counters_read(uint64_t out[7], int reset) {
+    int rc = ensure_device();
+    if (rc) return rc;
+    if (!out) return fail(CRT_ERR_INVALID_ARG, "null argument");
+    CK(cudaDeviceSynchronize());
+    unsigned long long v[8];
+    CK(cudaMemcpy(v, g_dev.trace_stats, sizeof v, cudaMemcpyDeviceToHost));
+    for (int k = 0; k < 7; ++k) out[k] = v[k];
+    if (reset) CK(cudaMemset(g_dev.trace_stats, 0, sizeof v));
     return CRT_OK;
 }
 
@@ -877,6 +903,7 @@ int enqueue_queue_trace(const crt_scene* s, bool any_hit, const QueueTrace& q, c
     p.status = g_dev.status;
     p.n = q.capacity;
     p.n_dev = q.n_dev;
+    p.stats = g_dev.count_traversal.load() ? g_dev.trace_stats : nullptr;
     int grid = g_dev.sm_count * trace_blocks_per_sm(any_hit, s->features, s->instance_depth);
     size_t need = ((size_t)q.capacity + CRT_BLOCK - 1) / CRT_BLOCK;
     if ((size_t)grid > need) grid = (int)(need ? need : 1);

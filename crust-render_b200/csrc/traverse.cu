@@ -51,7 +51,10 @@ struct MinBlocks {
     static constexpr int value = MAXD > 1 ? CRT_MINBLOCKS_INST : (MAXD == 1 ? CRT_MINBLOCKS_INST1 : (ANY_HIT ? CRT_MINBLOCKS_ANY : CRT_MINBLOCKS_CLOSEST));
 };
 
-template <bool ANY_HIT, uint32_t FEAT, int MAXD>
+// COUNT: the counting build of the same kernel (crt_trace_counters): what the traversal actually touches, summed over the
+// launch — nodes fetched, popped entries culled by their entry distance, leaves entered, triangle records tested, other
+// primitive records tested, instance descents — for the bytes-per-ray figure of bench.py. Never used by a timed launch.
+template <bool ANY_HIT, uint32_t FEAT, int MAXD, bool COUNT>
 __global__ void __launch_bounds__(CRT_BLOCK, MinBlocks<ANY_HIT, FEAT, MAXD>::value) trace_kernel(const TraceParams p) {
     typedef typename StackT<ANY_HIT>::type Entry;
     constexpr bool INST = MAXD > 0;
@@ -86,6 +89,7 @@ __global__ void __launch_bounds__(CRT_BLOCK, MinBlocks<ANY_HIT, FEAT, MAXD>::val
     F3 best_n = f3(0, 0, 0);
     bool any_found = false;
     bool overflow = false;  // a stack entry was dropped (reported once, at kernel exit)
+    [[maybe_unused]] uint32_t c_nodes = 0, c_culled = 0, c_leaves = 0, c_tris = 0, c_prims = 0, c_inst = 0, c_rays = 0;  // COUNT only
     // instancing
     int depth = 0;
     int best_depth = 0;
@@ -268,6 +272,7 @@ __global__ void __launch_bounds__(CRT_BLOCK, MinBlocks<ANY_HIT, FEAT, MAXD>::val
 
     // ---- node visit: 4-wide slab test (bvh.rs:790-808) + ordered push ------------
     auto node_visit = [&](uint32_t child) {
+        if constexpr (COUNT) ++c_nodes;
         float tn[4];
         bool hit[4];
         uint32_t cw[4];
@@ -389,6 +394,7 @@ __global__ void __launch_bounds__(CRT_BLOCK, MinBlocks<ANY_HIT, FEAT, MAXD>::val
         const uint32_t kind = flags & REC_KIND_MASK;
         if (kind == REC_TRI) {
             rec = (flags & REC_LAST) ? CRT_NO_REC : at + REC_TRI_Q;
+            if constexpr (COUNT) ++c_tris;
             if (ray_mask & __float_as_uint(q2.w)) {  // triangle.rs:257-271 per-lane visibility
                 TriEval e = tri_eval(r, xyz(q0), xyz(q1), xyz(q2));
                 if (e.on_edge) {
@@ -441,6 +447,9 @@ __global__ void __launch_bounds__(CRT_BLOCK, MinBlocks<ANY_HIT, FEAT, MAXD>::val
             bool got = false;
             float t = 0.0f;
             F3 n = f3(0, 0, 0);
+            if constexpr (COUNT) {
+                if (kind == REC_INSTANCE) ++c_inst; else ++c_prims;
+            }
             if (kind == REC_SPHERE) {
                 rec = (flags & REC_LAST) ? CRT_NO_REC : at + REC_SPHERE_Q;
                 if (ray_mask & __float_as_uint(q1.z)) got = sphere_hit(r, xyz(q0), q1.x, t_min, closest, t, n);
@@ -562,6 +571,7 @@ __global__ void __launch_bounds__(CRT_BLOCK, MinBlocks<ANY_HIT, FEAT, MAXD>::val
                         rec = CRT_NO_REC;
                         sp = 0;
                         state = RUN;
+                        if constexpr (COUNT) ++c_rays;
                         if (p.scene.n_nodes != 0) push(make_entry(0u, t_min));
                     }
                 }
@@ -608,6 +618,7 @@ __global__ void __launch_bounds__(CRT_BLOCK, MinBlocks<ANY_HIT, FEAT, MAXD>::val
                     }
                 }
                 if (child & CRT_LEAF_BIT) {
+                    if constexpr (COUNT) ++c_leaves;
                     rec = child & ~CRT_LEAF_BIT;
                     pkt_tmax = closest;
                     pkt_deferred = 0;
@@ -621,7 +632,10 @@ __global__ void __launch_bounds__(CRT_BLOCK, MinBlocks<ANY_HIT, FEAT, MAXD>::val
                     break;
                 }
                 if constexpr (!ANY_HIT) {
-                    if (__uint_as_float(e.y) > closest) continue;  // see traverse.cuh: same result as visiting
+                    if (__uint_as_float(e.y) > closest) {  // see traverse.cuh: same result as visiting
+                        if constexpr (COUNT) ++c_culled;
+                        continue;
+                    }
                 }
                 node_visit(child);
 #if CRT_NODE_EXIT_NUM > 0
@@ -641,18 +655,30 @@ __global__ void __launch_bounds__(CRT_BLOCK, MinBlocks<ANY_HIT, FEAT, MAXD>::val
         }
     }
     if (overflow) atomicOr(p.status, 1u);
+    if constexpr (COUNT) {
+        const uint32_t c[7] = {c_rays, c_nodes, c_culled, c_leaves, c_tris, c_prims, c_inst};
+#pragma unroll
+        for (int k = 0; k < 7; ++k) {
+            uint32_t v = c[k];
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+            if (lane == 0 && v) atomicAdd(p.stats + k, (unsigned long long)v);
+        }
+    }
 }
 
 template <bool ANY_HIT, uint32_t FEAT, int MAXD>
 cudaError_t launch_variant(const TraceParams& p, int grid, cudaStream_t stream) {
-    trace_kernel<ANY_HIT, FEAT, MAXD><<<grid, CRT_BLOCK, 0, stream>>>(p);
+    if (p.stats)
+        trace_kernel<ANY_HIT, FEAT, MAXD, true><<<grid, CRT_BLOCK, 0, stream>>>(p);
+    else
+        trace_kernel<ANY_HIT, FEAT, MAXD, false><<<grid, CRT_BLOCK, 0, stream>>>(p);
     return cudaGetLastError();
 }
 
 template <bool ANY_HIT, uint32_t FEAT, int MAXD>
 int blocks_per_sm_variant() {
     int n = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, trace_kernel<ANY_HIT, FEAT, MAXD>, CRT_BLOCK, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, trace_kernel<ANY_HIT, FEAT, MAXD, false>, CRT_BLOCK, 0);
     return n > 0 ? n : 1;
 }
 

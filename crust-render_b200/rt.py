@@ -37,7 +37,7 @@ __all__ = [
     "AABB", "Affine3A", "CrtError", "CubicCurveSegment", "CurveSegment", "Geometry", "HIT_DTYPE", "INVALID_ID",
     "MASK_ALL", "MASK_CAMERA", "MASK_INDIRECT", "MASK_SHADOW", "PrimitiveBreakdown", "RAY_DTYPE", "Ray", "RayHit",
     "Scene", "SceneBuilder", "MemoryFootprint", "BuildInfo", "lib", "lib_path", "make_rays", "init", "device_info",
-    "launch_count", "device_status", "l2_persist_info", "COMMIT_KEEP_HOST_TREE", "COMMIT_HOST_ONLY", "COMMIT_DEVICE_BUILD",
+    "launch_count", "device_status", "trace_counters_enable", "trace_counters_read", "TRACE_COUNTER_NAMES", "l2_persist_info", "COMMIT_KEEP_HOST_TREE", "COMMIT_HOST_ONLY", "COMMIT_DEVICE_BUILD",
 ]
 
 COMMIT_KEEP_HOST_TREE = 0x1
@@ -128,6 +128,8 @@ def lib() -> C.CDLL:
         "crt_intersect1": [vp, vp, C.c_float, u32, vp, C.POINTER(C.c_int), C.POINTER(C.c_int)],
         "crt_occluded1": [vp, vp, C.c_float, u32, C.POINTER(C.c_int)],
         "crt_device_status": [u32p],
+        "crt_trace_counters_enable": [C.c_int],
+        "crt_trace_counters_read": [C.POINTER(u64), C.c_int],
         "crt_debug_tree_sizes": [vp, C.POINTER(u64)],
         "crt_debug_tree_export": [vp, vp, u32p, u32p, u32p],
         # include/crt_render.h
@@ -188,6 +190,20 @@ def device_info() -> dict:
 
 def launch_count() -> int:
     return int(lib().crt_launch_count())
+
+
+TRACE_COUNTER_NAMES = ("rays", "nodes_fetched", "entries_culled_on_pop", "leaves_entered", "triangle_records", "other_records", "instance_descents")
+
+
+def trace_counters_enable(on: bool = True) -> None:
+    """crt_trace_counters_enable: traversal launches run the counting build of their kernel while enabled."""
+    _ck(lib().crt_trace_counters_enable(1 if on else 0))
+
+
+def trace_counters_read(reset: bool = True) -> dict:
+    out = (C.c_uint64 * 7)()
+    _ck(lib().crt_trace_counters_read(out, 1 if reset else 0))
+    return dict(zip(TRACE_COUNTER_NAMES, (int(v) for v in out)))
 
 
 def device_status() -> int:

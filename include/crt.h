@@ -179,8 +179,14 @@ int crt_intersect_host_n(const crt_scene* s, size_t n, const crt_ray* rays, cons
                          crt_hit* hits, uint8_t* front_face);
 int crt_occluded_host_n(const crt_scene* s, size_t n, const crt_ray* rays, const float* time, const uint32_t* mask,
                         uint8_t* occluded);
-/* One ray, reference call shape (Scene::intersect / Scene::occluded). Runs the
- * same device kernel on a batch of one. `*hit` = 1 when something was hit. */
+/* One ray, reference call shape (Scene::intersect / Scene::occluded, scene.rs:354-372). Runs the
+ * same device kernel on a batch of one; `*hit` = 1 when something was hit.
+ * This is the reference's SEMANTICS on one ray, for tests and spot checks — not its calling pattern: the reference's
+ * queries are `&self` and are called once per ray from every rayon worker concurrently, whereas each call here is one
+ * kernel launch plus two copies (tens of microseconds) and calls from several host threads are serialised by the
+ * host-buffer pipeline's lock. A host integrator must batch its rays and use crt_*_n / crt_*_host_n (any number of host
+ * threads may call those concurrently; the _host_n entries share one staging pipeline), or run on the device through
+ * crt_render (include/crt_render.h). */
 int crt_intersect1(const crt_scene* s, const crt_ray* ray, float time, uint32_t mask, crt_hit* out, int* front_face,
                    int* hit);
 int crt_occluded1(const crt_scene* s, const crt_ray* ray, float time, uint32_t mask, int* occluded);
@@ -190,6 +196,13 @@ uint64_t crt_launch_count(void);
 /* Sticky device-side error bits; bit 0 = a traversal stack overflowed (an
  * entry was dropped, results of that launch are not trustworthy).
  * Synchronises the device. */
+/* Device-side traversal counters (the reference's `stats` module, bvh.rs:31-136, counts on the CPU): while enabled, every
+ * traversal launch runs the counting build of its kernel (slower; never enable it around a timed region).
+ * crt_trace_counters_read synchronises the device; out = {rays, BVH4 nodes fetched, popped entries culled by their entry
+ * distance without a fetch, leaves entered, triangle records tested, other primitive records tested, instance descents}. */
+int crt_trace_counters_enable(int on);
+int crt_trace_counters_read(uint64_t out[7], int reset);
+
 int crt_device_status(uint32_t* bits);
 
 /* ---- debug / test support (needs CRT_COMMIT_KEEP_HOST_TREE) ---------------

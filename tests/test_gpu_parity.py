@@ -306,3 +306,33 @@ def test_l2_window_over_breadth_first_top_levels(gpu, orc):
     _compare_occluded(p, o, rays)
     _, applied1, refused = gpu.l2_persist_info()
     assert applied1 > applied0 and refused == 0, (applied0, applied1, refused, bi.node_bytes)
+
+
+def test_device_traversal_counters_match_the_reference_counters(gpu, orc):
+    """The counting build of the kernels (crt_trace_counters_*) against the oracle's restatement of the reference's `stats`
+    counters (bvh.rs:31-136) on the same batch. The device culls a popped entry whose stored entry distance already exceeds
+    `closest` without fetching the node; the reference fetches it and finds nothing — so nodes fetched + entries culled
+    equals the reference's nodes popped, and leaves / triangle lanes / instance descents are equal one to one."""
+    for make, extent in ((workloads.triangle_scene, 6.0), (workloads.instance_scene, 7.0)):
+        p, o = _pair(gpu, orc, make)
+        rays = workloads.ray_batch(1 << 16, extent, seed=99)
+        _, _, st = o.intersect_n(rays, threads=0, stats=True)
+        gpu.trace_counters_read(reset=True)
+        gpu.trace_counters_enable(True)
+        try:
+            hits, _ = p.intersect_n(rays)
+            c = gpu.trace_counters_read(reset=True)
+            occ = p.occluded_n(rays)
+            ca = gpu.trace_counters_read(reset=True)
+        finally:
+            gpu.trace_counters_enable(False)
+        assert c["rays"] == len(rays) and ca["rays"] == len(rays)
+        assert c["nodes_fetched"] + c["entries_culled_on_pop"] == st["nodes_top"] + st["nodes_inst"]
+        assert c["nodes_fetched"] < st["nodes_top"] + st["nodes_inst"]  # culling on pop does save fetches
+        assert c["leaves_entered"] == st["leaves_top"] + st["leaves_inst"]
+        assert c["triangle_records"] == st["tri_lanes"]
+        assert c["instance_descents"] <= st["instance_tests"] and c["instance_descents"] + c["other_records"] >= st["instance_tests"]
+        assert 0 < ca["nodes_fetched"] <= c["nodes_fetched"] + c["entries_culled_on_pop"]  # any-hit stops at the first hit
+        # counting launches give the same answers as the plain ones
+        h2, _ = p.intersect_n(rays)
+        assert h2.tobytes() == hits.tobytes() and np.array_equal(p.occluded_n(rays), occ)
