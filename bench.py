@@ -382,14 +382,24 @@ def main():
     dev = torch.device("cuda", local)
     cores = os.cpu_count() or 1
 
-    # ---- scene: replicated on every GPU -------------------------
+    # ---- scene: replicated on every GPU; built once by rank 0 on all host cores and broadcast over NCCL ----
+    from crust_render_b200.distributed import shared_commits
+    share = shared_commits(dist if world > 1 else None, dev)
+    share.__enter__()  # stays on for every commit of this process (scene, render worlds, sample configs)
     t0 = time.time()
     b, n_tris = W.stress_scene(crt, grid=args.grid, shards=30000, jitter=True)
-    scene = b.commit(host_threads=max(1, cores // world))
+    t_gen = time.time() - t0
+    scene = b.commit(host_threads=cores)
+    commit_s = time.time() - t0 - t_gen
     bi = scene.build_info()
+    tc = torch.tensor([commit_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tc, op=dist.ReduceOp.MAX)
+    commit_s_max = float(tc.item())
     if rank == 0:
-        log(f"[bench] commit of {n_tris} triangles: {time.time() - t0:.1f}s (host build {bi.build_seconds:.1f}s, upload {bi.upload_seconds:.2f}s), "
-            f"{bi.wide_nodes} BVH4 nodes ({bi.node_bytes / 1e6:.0f} MB), {bi.leaf_refs} leaf refs ({bi.leaf_bytes / 1e6:.0f} MB)")
+        log(f"[bench] commit of {n_tris} triangles: {commit_s_max:.1f}s on the slowest rank (mesh generation {t_gen:.1f}s before it; host build {bi.build_seconds:.1f}s on rank 0 with {cores} threads, "
+            f"upload {bi.upload_seconds:.2f}s" + (f", then one NCCL broadcast of {share.bytes / 1e6:.0f} MB to {world - 1} ranks" if world > 1 else "") +
+            f"), {bi.wide_nodes} BVH4 nodes ({bi.node_bytes / 1e6:.0f} MB), {bi.leaf_refs} leaf refs ({bi.leaf_bytes / 1e6:.0f} MB)")
 
     t0 = time.time()
     sets, info = build_ray_sets(W, scene.bounds(), args.rays_log2, rank, lambda r: scene.intersect_n(r)[0])
@@ -684,7 +694,9 @@ def main():
                 "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
                 "sets": per_set, "closest_hit_mrays": sum(len(sets[n][0]) for n in closest) / sum(k_ms[n] for n in closest) / 1e3,
                 "occlusion_mrays": sum(len(sets[n][0]) for n in SETS if n not in closest) / sum(k_ms[n] for n in SETS if n not in closest) / 1e3,
-                "device_status": status, "host_cores": cores}
+                "device_status": status, "host_cores": cores,
+                "commit_seconds_slowest_rank": commit_s_max,
+                "commit_sharing": ("one process" if world == 1 else f"rank 0 builds with {cores} host threads, crt_scene_export -> NCCL broadcast -> crt_scene_import on the other {world - 1} ranks")}
         if other_scenes is not None:
             line["other_scenes"] = other_scenes
         if world == 1:

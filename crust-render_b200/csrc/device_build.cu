@@ -734,6 +734,7 @@ int device_build(const std::vector<Geom>& geoms, crt_scene* s) {
     s->desc.motion = nullptr;
     s->desc.n_nodes = n4;
     s->desc.has_triangles = n > 0;
+    s->n_nodes = n4, s->n_leaf_quads = n > 0 ? leaf_quads : 0, s->n_prim_ids = N, s->n_normal_floats = 0, s->n_motion = 0;
     CKB(cudaMalloc((void**)&s->d_desc, sizeof(DevScene)));
     CKB(cudaMemcpy(s->d_desc, &s->desc, sizeof(DevScene), cudaMemcpyHostToDevice));
     auto t1 = std::chrono::steady_clock::now();

@@ -30,6 +30,10 @@ struct crt_scene {
     DevScene desc{};
     DevScene* d_desc = nullptr;
     size_t top_bytes = 0;  // leading bytes of d_nodes that hold the tree's top levels (L2 access-policy window), 0 = none
+    // element counts of the device arrays and where the instance records sit (crt_scene_export / crt_scene_import)
+    uint64_t n_nodes = 0, n_leaf_quads = 0, n_prim_ids = 0, n_normal_floats = 0, n_motion = 0;
+    std::vector<uint32_t> inst_q;      // offset (16-byte units) of every instance record in d_leafs
+    std::vector<uint32_t> inst_child;  // index into `children` of the scene that record instances
     crt_memory_footprint footprint{};
 
     ~crt_scene();

@@ -2,6 +2,7 @@
 // queries and the batched / host-buffer query entry points.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <atomic>
 #include <chrono>
 #include <cstdio>
@@ -456,10 +457,17 @@ int crt_commit_ex(crt_builder* b, uint32_t flags, int host_threads, crt_scene** 
     s->info.build_seconds = t->build_seconds;
     s->info.instance_depth = t->instance_depth;
 
+    s->n_nodes = t->nodes.size();
+    s->n_leaf_quads = t->leafs.size() / 4;
+    s->n_prim_ids = t->prim_ids.size() / 2;
+    s->n_normal_floats = t->normals.size();
+    s->n_motion = t->motion.size();
     // Patch child descriptor pointers into the instance records.
     for (uint32_t q : t->instance_record_q) {
         uint32_t slot = t->leafs[4 * (size_t)(q + 4) + 3];
         crt_scene* child = t->prims.inst[slot].child;
+        s->inst_q.push_back(q);
+        s->inst_child.push_back((uint32_t)(std::find(s->children.begin(), s->children.end(), child) - s->children.begin()));
         uint64_t ptr = (uint64_t)(uintptr_t)child->d_desc;
         t->leafs[4 * (size_t)(q + 4) + 0] = (uint32_t)(ptr & 0xFFFFFFFFu);
         t->leafs[4 * (size_t)(q + 4) + 1] = (uint32_t)(ptr >> 32);
@@ -597,6 +605,191 @@ int crt_memory_footprint_of(const crt_scene* s, crt_memory_footprint* out) {
 int crt_build_info_of(const crt_scene* s, crt_build_info* out) {
     if (!s || !out) return fail(CRT_ERR_INVALID_ARG, "null argument");
     *out = s->info;
+    return CRT_OK;
+}
+
+// ---- replicating a commit (multi-GPU: build once, share) --------------------
+// A committed scene as one flat blob: header (host-side metadata + array sizes) | nodes | leaf records | prim ids | normals
+// | motion | instance-record offsets | instance-record child indices. Instanced scenes are referenced by their index in the
+// scene's list of distinct children (first-appearance order over the attached geometries — the same on every process that
+// attaches the same geometries), so each scene of an instancing hierarchy travels on its own and the importer hands in the
+// handles of the children it imported before. The blob lives in host or device memory; a device blob goes straight through
+// an NCCL broadcast and is unpacked with device-to-device copies.
+namespace {
+struct BlobHeader {
+    uint32_t magic, version;
+    uint64_t total_bytes;
+    uint64_t n_nodes, n_leaf_quads, n_prim_ids, n_normal_floats, n_motion, n_children, n_inst;
+    uint64_t top_bytes;
+    // host-side metadata of crt_scene
+    uint32_t non_empty, has_motion, n_geoms, instance_depth, features, has_triangles;
+    uint64_t n_prims;
+    float root[6];
+    float extent_sum, extent_max;
+    crt_primitive_breakdown breakdown;
+    crt_build_info info;
+    crt_memory_footprint footprint;
+};
+constexpr uint32_t kBlobMagic = 0x42545243u;  // "CRTB"
+constexpr uint32_t kBlobVersion = 1;
+size_t pad16(size_t b) { return (b + 15) & ~(size_t)15; }
+struct BlobLayout {
+    size_t nodes, leafs, prim_ids, normals, motion, inst_q, inst_child, total;
+    explicit BlobLayout(const BlobHeader& h) {
+        size_t o = pad16(sizeof(BlobHeader));
+        nodes = o, o += pad16(h.n_nodes * sizeof(DevNode));
+        // nodes are 128-byte records; keep them 128-byte aligned inside the blob as well (cheap, and lets a consumer map them)
+        leafs = o, o += pad16(h.n_leaf_quads * 16);
+        prim_ids = o, o += pad16(h.n_prim_ids * 8);
+        normals = o, o += pad16(h.n_normal_floats * 4);
+        motion = o, o += pad16(h.n_motion * sizeof(MotionXform));
+        inst_q = o, o += pad16(h.n_inst * 4);
+        inst_child = o, o += pad16(h.n_inst * 4);
+        total = o;
+    }
+};
+BlobHeader header_of(const crt_scene* s) {
+    BlobHeader h{};
+    h.magic = kBlobMagic, h.version = kBlobVersion;
+    h.n_nodes = s->n_nodes, h.n_leaf_quads = s->n_leaf_quads, h.n_prim_ids = s->n_prim_ids, h.n_normal_floats = s->n_normal_floats;
+    h.n_motion = s->n_motion, h.n_children = s->children.size(), h.n_inst = s->inst_q.size(), h.top_bytes = s->top_bytes;
+    h.non_empty = s->non_empty, h.has_motion = s->has_motion, h.n_geoms = s->n_geoms, h.instance_depth = s->instance_depth;
+    h.features = s->features, h.has_triangles = s->desc.has_triangles, h.n_prims = s->n_prims;
+    h.root[0] = s->root.lo.x, h.root[1] = s->root.lo.y, h.root[2] = s->root.lo.z, h.root[3] = s->root.hi.x, h.root[4] = s->root.hi.y, h.root[5] = s->root.hi.z;
+    h.extent_sum = s->extent_sum, h.extent_max = s->extent_max;
+    h.breakdown = s->breakdown, h.info = s->info, h.footprint = s->footprint;
+    h.total_bytes = BlobLayout(h).total;
+    return h;
+}
+__global__ void patch_instances_kernel(U4* leafs, const uint32_t* __restrict__ q, const uint32_t* __restrict__ child, const uint64_t* __restrict__ ptrs,
+                                       uint32_t n) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint64_t* c = ptrs + 3 * (size_t)child[i];  // descriptor, nodes, leafs of the child in THIS process
+    U4& q4 = leafs[q[i] + 4];
+    q4.x = (uint32_t)(c[0] & 0xFFFFFFFFu), q4.y = (uint32_t)(c[0] >> 32);
+    U4& q5 = leafs[q[i] + 5];
+    q5.x = (uint32_t)(c[1] & 0xFFFFFFFFu), q5.y = (uint32_t)(c[1] >> 32), q5.z = (uint32_t)(c[2] & 0xFFFFFFFFu), q5.w = (uint32_t)(c[2] >> 32);
+}
+}  // namespace
+
+int crt_scene_export_size(const crt_scene* s, size_t* bytes) {
+    if (!s || !bytes) return fail(CRT_ERR_INVALID_ARG, "null argument");
+    if (s->host_only) return fail(CRT_ERR_NO_DEVICE, "scene was committed host-only: nothing to export");
+    *bytes = header_of(s).total_bytes;
+    return CRT_OK;
+}
+
+int crt_scene_export(const crt_scene* s, void* dst, size_t bytes, int dst_on_device, void* stream_) {
+    if (!s || !dst) return fail(CRT_ERR_INVALID_ARG, "null argument");
+    if (s->host_only) return fail(CRT_ERR_NO_DEVICE, "scene was committed host-only: nothing to export");
+    const BlobHeader h = header_of(s);
+    if (bytes < h.total_bytes) return fail(CRT_ERR_INVALID_ARG, "crt_scene_export: buffer smaller than crt_scene_export_size");
+    const BlobLayout L(h);
+    cudaStream_t st = (cudaStream_t)stream_;
+    const cudaMemcpyKind from_dev = dst_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+    const cudaMemcpyKind from_host = dst_on_device ? cudaMemcpyHostToDevice : cudaMemcpyHostToHost;
+    char* d = (char*)dst;
+    CK(cudaMemcpyAsync(d, &h, sizeof h, from_host, st));
+    if (h.n_nodes) CK(cudaMemcpyAsync(d + L.nodes, s->d_nodes, h.n_nodes * sizeof(DevNode), from_dev, st));
+    if (h.n_leaf_quads) CK(cudaMemcpyAsync(d + L.leafs, s->d_leafs, h.n_leaf_quads * 16, from_dev, st));
+    if (h.n_prim_ids) CK(cudaMemcpyAsync(d + L.prim_ids, s->d_prim_ids, h.n_prim_ids * 8, from_dev, st));
+    if (h.n_normal_floats) CK(cudaMemcpyAsync(d + L.normals, s->d_normals, h.n_normal_floats * 4, from_dev, st));
+    if (h.n_motion) CK(cudaMemcpyAsync(d + L.motion, s->d_motion, h.n_motion * sizeof(MotionXform), from_dev, st));
+    if (h.n_inst) {
+        CK(cudaMemcpyAsync(d + L.inst_q, s->inst_q.data(), h.n_inst * 4, from_host, st));
+        CK(cudaMemcpyAsync(d + L.inst_child, s->inst_child.data(), h.n_inst * 4, from_host, st));
+    }
+    CK(cudaStreamSynchronize(st));  // the header and the two index lists are read from this call's stack / the scene's vectors
+    return CRT_OK;
+}
+
+int crt_scene_import(const void* src, size_t bytes, int src_on_device, crt_scene* const* children, size_t n_children, crt_scene** out) {
+    if (!src || !out || (n_children && !children)) return fail(CRT_ERR_INVALID_ARG, "null argument");
+    *out = nullptr;
+    int rc = ensure_device();
+    if (rc) return rc;
+    if (bytes < sizeof(BlobHeader)) return fail(CRT_ERR_INVALID_ARG, "crt_scene_import: truncated blob");
+    BlobHeader h;
+    CK(cudaMemcpy(&h, src, sizeof h, src_on_device ? cudaMemcpyDeviceToHost : cudaMemcpyHostToHost));
+    if (h.magic != kBlobMagic || h.version != kBlobVersion) return fail(CRT_ERR_INVALID_ARG, "crt_scene_import: not a scene blob of this library version");
+    const BlobLayout L(h);
+    if (h.total_bytes != L.total || bytes < L.total) return fail(CRT_ERR_INVALID_ARG, "crt_scene_import: truncated blob");
+    if (h.n_children != n_children) return fail(CRT_ERR_INVALID_ARG, "crt_scene_import: the blob instances a different number of distinct scenes than were handed in");
+    for (size_t c = 0; c < n_children; ++c)
+        if (!children[c] || children[c]->host_only) return fail(CRT_ERR_INVALID_ARG, "crt_scene_import: child scene missing or host-only");
+    const char* b = (const char*)src;
+    const cudaMemcpyKind to_dev = src_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    crt_scene* s = new crt_scene();
+    for (size_t c = 0; c < n_children; ++c) {
+        crt_scene_retain(children[c]);
+        s->children.push_back(children[c]);
+    }
+    s->non_empty = h.non_empty != 0, s->has_motion = h.has_motion != 0, s->n_geoms = h.n_geoms, s->instance_depth = h.instance_depth;
+    s->features = h.features, s->n_prims = h.n_prims, s->top_bytes = (size_t)h.top_bytes;
+    s->root.lo.x = h.root[0], s->root.lo.y = h.root[1], s->root.lo.z = h.root[2], s->root.hi.x = h.root[3], s->root.hi.y = h.root[4], s->root.hi.z = h.root[5];
+    s->extent_sum = h.extent_sum, s->extent_max = h.extent_max;
+    s->breakdown = h.breakdown, s->info = h.info, s->footprint = h.footprint;
+    s->n_nodes = h.n_nodes, s->n_leaf_quads = h.n_leaf_quads, s->n_prim_ids = h.n_prim_ids, s->n_normal_floats = h.n_normal_floats, s->n_motion = h.n_motion;
+    auto fail_free = [&](int code) {
+        crt_scene_release(s);
+        return code;
+    };
+    auto take = [&](void** dst, size_t off, size_t nbytes) -> int {
+        *dst = nullptr;
+        if (!nbytes) return CRT_OK;
+        cudaError_t e = cudaMalloc(dst, nbytes);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            return fail(e == cudaErrorMemoryAllocation ? CRT_ERR_OOM : CRT_ERR_CUDA, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+        }
+        e = cudaMemcpy(*dst, b + off, nbytes, to_dev);
+        return e == cudaSuccess ? CRT_OK : fail_cuda(e, "crt_scene_import copy");
+    };
+    if ((rc = take(&s->d_nodes, L.nodes, h.n_nodes * sizeof(DevNode))) || (rc = take(&s->d_leafs, L.leafs, h.n_leaf_quads * 16)) ||
+        (rc = take(&s->d_prim_ids, L.prim_ids, h.n_prim_ids * 8)) || (rc = take(&s->d_normals, L.normals, h.n_normal_floats * 4)) ||
+        (rc = take(&s->d_motion, L.motion, h.n_motion * sizeof(MotionXform))))
+        return fail_free(rc);
+    if (h.n_inst) {
+        s->inst_q.resize(h.n_inst);
+        s->inst_child.resize(h.n_inst);
+        const cudaMemcpyKind to_host = src_on_device ? cudaMemcpyDeviceToHost : cudaMemcpyHostToHost;
+        cudaError_t e = cudaMemcpy(s->inst_q.data(), b + L.inst_q, h.n_inst * 4, to_host);
+        if (e == cudaSuccess) e = cudaMemcpy(s->inst_child.data(), b + L.inst_child, h.n_inst * 4, to_host);
+        if (e != cudaSuccess) return fail_free(fail_cuda(e, "crt_scene_import copy"));
+        for (uint32_t c : s->inst_child)
+            if (c >= n_children) return fail_free(fail(CRT_ERR_INVALID_ARG, "crt_scene_import: corrupt child index"));
+        // the instance records carry addresses of the exporting process: rewrite them with this process' children
+        std::vector<uint64_t> ptrs(3 * n_children);
+        for (size_t c = 0; c < n_children; ++c) {
+            ptrs[3 * c] = (uint64_t)(uintptr_t)children[c]->d_desc;
+            ptrs[3 * c + 1] = (uint64_t)(uintptr_t)children[c]->d_nodes;
+            ptrs[3 * c + 2] = (uint64_t)(uintptr_t)children[c]->d_leafs;
+        }
+        uint32_t *d_q = nullptr, *d_c = nullptr;
+        uint64_t* d_p = nullptr;
+        e = cudaMalloc(&d_q, h.n_inst * 4);
+        if (e == cudaSuccess) e = cudaMalloc(&d_c, h.n_inst * 4);
+        if (e == cudaSuccess) e = cudaMalloc(&d_p, ptrs.size() * 8);
+        if (e == cudaSuccess) e = cudaMemcpy(d_q, s->inst_q.data(), h.n_inst * 4, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMemcpy(d_c, s->inst_child.data(), h.n_inst * 4, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMemcpy(d_p, ptrs.data(), ptrs.size() * 8, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) {
+            patch_instances_kernel<<<(unsigned)((h.n_inst + 255) / 256), 256>>>((U4*)s->d_leafs, d_q, d_c, d_p, (uint32_t)h.n_inst);
+            e = cudaDeviceSynchronize();
+        }
+        cudaFree(d_q), cudaFree(d_c), cudaFree(d_p);
+        if (e != cudaSuccess) return fail_free(fail_cuda(e, "crt_scene_import patch"));
+    }
+    s->desc.nodes = (const DevNode*)s->d_nodes;
+    s->desc.leafs = (const U4*)s->d_leafs;
+    s->desc.prim_ids = (const U2*)s->d_prim_ids;
+    s->desc.normals = (const float*)s->d_normals;
+    s->desc.motion = (const MotionXform*)s->d_motion;
+    s->desc.n_nodes = (uint32_t)h.n_nodes;
+    s->desc.has_triangles = h.has_triangles;
+    if ((rc = upload((void**)&s->d_desc, &s->desc, 1))) return fail_free(rc);
+    *out = s;
     return CRT_OK;
 }
 

@@ -99,6 +99,62 @@ def shared_frame(dist, device, height: int, width: int):
     return _FRAMES[key]
 
 
+class shared_commits:
+    """Build once, share: inside this context every `SceneBuilder.commit()` of the product binding is performed by rank 0
+    alone — with all the host's cores instead of cores / world — and the committed scene (flattened BVH4 nodes, leaf
+    records, id table; crt_scene_export) is broadcast to the other ranks over NCCL as one device buffer and unpacked there
+    with device-to-device copies (crt_scene_import). The other ranks discard their builders without building. All ranks must
+    commit the same scenes in the same order (SPMD), which scenes.py / the importer do. The reference builds once per
+    process (scene.rs:226); one process per GPU would otherwise repeat the SAH/SBVH build N times on 1/N of the cores."""
+
+    def __init__(self, dist, device):
+        self.dist, self.device = dist, device
+        self.world = dist.get_world_size() if dist is not None and dist.is_initialized() else 1
+        self.rank = dist.get_rank() if self.world > 1 else 0
+        self.commits, self.bytes = 0, 0
+
+    def _commit(self, builder, flags, host_threads):
+        import os
+
+        import torch
+
+        from . import rt
+
+        if self.world <= 1 or (flags & rt.COMMIT_HOST_ONLY):
+            return builder.commit_local(flags, host_threads)
+        children = builder.distinct_children()
+        n = torch.zeros(1, dtype=torch.int64, device=self.device)
+        scene = None
+        if self.rank == 0:
+            scene = builder.commit_local(flags, os.cpu_count() or 1)
+            n[0] = scene.export_size()
+        else:
+            builder.discard()
+        self.dist.broadcast(n, src=0)
+        nbytes = int(n.item())
+        blob = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        if self.rank == 0:
+            scene.export_to(blob.data_ptr(), nbytes, True, torch.cuda.current_stream().cuda_stream)
+        self.dist.broadcast(blob, src=0)
+        if self.rank != 0:
+            torch.cuda.current_stream().synchronize()
+            scene = rt.Scene.import_from(blob.data_ptr(), nbytes, True, children)
+        self.commits += 1
+        self.bytes += nbytes
+        return scene
+
+    def __enter__(self):
+        from . import rt
+        self._prev = rt._commit_override
+        rt._commit_override = self._commit
+        return self
+
+    def __exit__(self, *exc):
+        from . import rt
+        rt._commit_override = self._prev
+        return False
+
+
 _HOST_FRAMES = {}
 
 

@@ -128,6 +128,9 @@ def lib() -> C.CDLL:
         "crt_intersect1": [vp, vp, C.c_float, u32, vp, C.POINTER(C.c_int), C.POINTER(C.c_int)],
         "crt_occluded1": [vp, vp, C.c_float, u32, C.POINTER(C.c_int)],
         "crt_device_status": [u32p],
+        "crt_scene_export_size": [vp, C.POINTER(sz)],
+        "crt_scene_export": [vp, vp, sz, C.c_int, vp],
+        "crt_scene_import": [vp, sz, C.c_int, C.POINTER(vp), sz, C.POINTER(vp)],
         "crt_trace_counters_enable": [C.c_int],
         "crt_trace_counters_read": [C.POINTER(u64), C.c_int],
         "crt_debug_tree_sizes": [vp, C.POINTER(u64)],
@@ -236,6 +239,7 @@ class SceneBuilder:
         _ck(lib().crt_builder_new(C.byref(h)))
         self._h = h
         self._keep = []  # instanced Scene objects stay alive at least until commit
+        self._inst = {}  # geom_id -> instanced Scene (what commit() will list as the scene's distinct children)
 
     def __del__(self):
         if getattr(self, "_h", None) and _lib is not None:
@@ -267,6 +271,7 @@ class SceneBuilder:
             end = None if g.transform_end is None else _fptr(g.transform_end.m)
             _ck(L.crt_attach_instance(h, g.scene._h, _fptr(g.transform.m), end, mask, C.byref(gid)))
             self._keep.append(g.scene)
+            self._inst[gid.value] = g.scene
         elif g.kind == "empty":
             _ck(L.crt_attach_empty(h, mask, C.byref(gid)))
         else:
@@ -302,17 +307,49 @@ class SceneBuilder:
             _ck(L.crt_set_empty(h, id))
         else:
             raise CrtError(1, f"unknown geometry kind {g.kind!r}")
+        if g.kind == "instance":
+            self._inst[id] = g.scene
+        else:
+            self._inst.pop(id, None)
 
     @staticmethod
     def empty_geometry() -> Geometry:
         return Geometry.Empty()
 
+    def distinct_children(self) -> list:
+        """The instanced scenes in first-attachment order, each once: the order crt_commit lists a scene's children in and
+        crt_scene_export / crt_scene_import name them by."""
+        seen, out = set(), []
+        for gid in sorted(self._inst):
+            sc = self._inst[gid]
+            if sc._h.value not in seen:
+                seen.add(sc._h.value)
+                out.append(sc)
+        return out
+
+    def discard(self) -> None:
+        """Frees the builder without committing (a rank that receives the committed scene from another one)."""
+        h = self._handle()
+        self._h = None
+        lib().crt_builder_free(h)
+
     def commit(self, flags: int = 0, host_threads: int = 0) -> "Scene":
+        if _commit_override is not None:
+            return _commit_override(self, flags, host_threads)
+        return self.commit_local(flags, host_threads)
+
+    def commit_local(self, flags: int = 0, host_threads: int = 0) -> "Scene":
         h = self._handle()
         self._h = None  # consumed, also on failure
         out = C.c_void_p()
         _ck(lib().crt_commit_ex(h, flags, host_threads, C.byref(out)))
-        return Scene(out)
+        sc = Scene(out)
+        sc._children = self.distinct_children()  # kept alive with the scene on the Python side too
+        return sc
+
+
+# crust_render_b200.distributed.shared_commits installs a function here: (builder, flags, host_threads) -> Scene
+_commit_override = None
 
 
 class Scene:
@@ -327,6 +364,25 @@ class Scene:
             self._h = None
 
     # -- single-ray calls in the reference's shape (scene.rs:354, 370) ---------
+    def export_size(self) -> int:
+        n = C.c_size_t()
+        _ck(lib().crt_scene_export_size(self._h, C.byref(n)))
+        return n.value
+
+    def export_to(self, ptr: int, nbytes: int, on_device: bool, stream: int = 0) -> None:
+        """crt_scene_export into host or device memory at `ptr`."""
+        _ck(lib().crt_scene_export(self._h, C.c_void_p(ptr), nbytes, 1 if on_device else 0, C.c_void_p(stream)))
+
+    @staticmethod
+    def import_from(ptr: int, nbytes: int, on_device: bool, children=()) -> "Scene":
+        """crt_scene_import: `children` are the scenes the exported one instances, in its distinct-children order."""
+        arr = (C.c_void_p * max(1, len(children)))(*[c._h for c in children])
+        out = C.c_void_p()
+        _ck(lib().crt_scene_import(C.c_void_p(ptr), nbytes, 1 if on_device else 0, arr, len(children), C.byref(out)))
+        sc = Scene(out)
+        sc._children = list(children)
+        return sc
+
     def intersect(self, ray: Ray, t_min: float, t_max: float) -> Optional[RayHit]:
         r = make_rays([ray.origin], [ray.dir], t_min, t_max)
         hit = np.zeros(1, dtype=HIT_DTYPE)

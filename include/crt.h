@@ -196,6 +196,17 @@ uint64_t crt_launch_count(void);
 /* Sticky device-side error bits; bit 0 = a traversal stack overflowed (an
  * entry was dropped, results of that launch are not trustworthy).
  * Synchronises the device. */
+/* Replicating a commit without rebuilding it (multi-GPU: the reference builds once per process, scene.rs:226; with one
+ * process per GPU the same tree would be built N times). crt_scene_export writes one committed scene — its flattened
+ * device arrays and host-side metadata — as a flat blob into host (dst_on_device = 0) or device memory; crt_scene_import
+ * turns such a blob into a committed scene on the calling process' device. Scenes instanced by the exported one are not
+ * embedded: the blob names them by their index among the scene's distinct children in first-attachment order, and the
+ * importer passes the handles it obtained for them (import or commit) in that order. The imported scene retains them like
+ * an instance attach does. A device blob can be broadcast with NCCL and is unpacked with device-to-device copies. */
+int crt_scene_export_size(const crt_scene* s, size_t* bytes);
+int crt_scene_export(const crt_scene* s, void* dst, size_t bytes, int dst_on_device, void* stream);
+int crt_scene_import(const void* src, size_t bytes, int src_on_device, crt_scene* const* children, size_t n_children, crt_scene** out);
+
 /* Device-side traversal counters (the reference's `stats` module, bvh.rs:31-136, counts on the CPU): while enabled, every
  * traversal launch runs the counting build of its kernel (slower; never enable it around a timed region).
  * crt_trace_counters_read synchronises the device; out = {rays, BVH4 nodes fetched, popped entries culled by their entry

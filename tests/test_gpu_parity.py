@@ -336,3 +336,63 @@ def test_device_traversal_counters_match_the_reference_counters(gpu, orc):
         # counting launches give the same answers as the plain ones
         h2, _ = p.intersect_n(rays)
         assert h2.tobytes() == hits.tobytes() and np.array_equal(p.occluded_n(rays), occ)
+
+
+def test_scene_export_import_round_trip(gpu, orc):
+    """crt_scene_export / crt_scene_import (build once, share across GPUs): a committed scene rebuilt from its blob — through
+    host memory and through device memory — answers every query bit for bit like the original, for a flat SBVH scene and for
+    an instancing hierarchy (children imported first and handed in by index), and reports the same metadata."""
+    import torch
+
+    def clone(scene, children=(), device_blob=False):
+        n = scene.export_size()
+        if device_blob:
+            blob = torch.empty(n, dtype=torch.uint8, device="cuda")
+            scene.export_to(blob.data_ptr(), n, True, torch.cuda.current_stream().cuda_stream)
+            torch.cuda.synchronize()
+            return gpu.Scene.import_from(blob.data_ptr(), n, True, children)
+        blob = np.empty(n, dtype=np.uint8)
+        scene.export_to(blob.ctypes.data, n, False)
+        return gpu.Scene.import_from(blob.ctypes.data, n, False, children)
+
+    # flat, with spatial-split duplicates and the breadth-first top levels
+    flat = workloads.stress_scene(gpu, grid=3, shards=4000)[0].commit()
+    rays = workloads.ray_batch(1 << 17, workloads.scene_extent(flat.bounds()), seed=3)
+    h0, f0 = flat.intersect_n(rays)
+    for dev in (False, True):
+        c = clone(flat, device_blob=dev)
+        h1, f1 = c.intersect_n(rays)
+        assert h1.tobytes() == h0.tobytes() and np.array_equal(f0, f1)
+        assert np.array_equal(c.occluded_n(rays), flat.occluded_n(rays))
+        assert c.primitive_count() == flat.primitive_count() and c.geometry_count() == flat.geometry_count()
+        assert np.array_equal(c.bounds().minimum, flat.bounds().minimum) and c.memory_footprint().total() == flat.memory_footprint().total()
+    # instancing: two levels, a moving instance, spheres next to meshes; the imported parent points at the imported children
+    inner = gpu.SceneBuilder()
+    v, i = workloads.uv_sphere(np.zeros(3, np.float32), 1.0, 16, 8)
+    inner.attach(Geometry.TriangleMesh(v, i))
+    inner.attach(Geometry.Sphere((0.0, 1.5, 0.0), 0.4))
+    inner = inner.commit()
+    mid = gpu.SceneBuilder()
+    mid.attach(Geometry.Instance(inner, Affine3A.from_translation((-1.5, 0, 0))))
+    mid.attach(Geometry.Instance(inner, Affine3A.from_translation((1.5, 0, 0)), Affine3A.from_translation((1.5, 1.0, 0))))
+    mid = mid.commit()
+    top = gpu.SceneBuilder()
+    for k in range(5):
+        top.attach(Geometry.Instance(mid, Affine3A.from_translation((0.0, 0.0, 4.0 * (k - 2)))))
+    top.attach(Geometry.Instance(inner, Affine3A.from_translation((0.0, 4.0, 0.0))))
+    top.attach(Geometry.Sphere((0.0, -3.0, 0.0), 1.0))
+    top = top.commit()
+    rays = workloads.ray_batch(1 << 16, 9.0, seed=4)
+    time = np.random.default_rng(1).random(len(rays)).astype(np.float32)
+    h0, f0 = top.intersect_n(rays, time)
+    assert (h0["geom_id"] != 0xFFFFFFFF).mean() > 0.05
+    inner2 = clone(inner, device_blob=True)
+    mid2 = clone(mid, [inner2])
+    top2 = clone(top, [mid2, inner2], device_blob=True)
+    del inner, mid  # the clones must not depend on the originals' device memory
+    h1, f1 = top2.intersect_n(rays, time)
+    assert h1.tobytes() == h0.tobytes() and np.array_equal(f0, f1)
+    assert np.array_equal(top2.occluded_n(rays, time), top.occluded_n(rays, time))
+    assert top2.has_motion() and top2.unique_primitive_breakdown().triangles == top.unique_primitive_breakdown().triangles
+    with pytest.raises(gpu.CrtError):
+        clone(top, [mid2])  # wrong number of children

@@ -2,8 +2,8 @@
 """Regenerates profiles/trace_traffic.json — DRAM bytes, L1/L2 behaviour and SIMT efficiency of the five timed traversal
 launches of one bench.py step — from an `ncu --set full` capture of the bench command:
 
-    ncu --set full --clock-control none --import-source on -k regex:trace_kernel --launch-skip <5*(warmup + set-up launches)> \
-        -c 5 -o gpurun_out/bench_trace python bench.py --steps 1 --warmup 1 --no-render --no-cpu-baseline --no-e2e
+    ncu --set full --clock-control none --import-source on -k regex:trace_kernel -c 60 -o gpurun_out/bench_trace \
+        python bench.py --steps 1 --warmup 1 --no-render --no-cpu-baseline --no-e2e
     python tools/trace_traffic.py gpurun_out/bench_trace.ncu-rep [--last 5]
 
 The json is stamped with a hash of the traversal sources (`source_sha`); bench.py only quotes `roofline.traffic` from it
@@ -41,7 +41,10 @@ def main():
         open(a.raw_out, "w").write(txt)
     rows = list(csv.reader(txt.splitlines()))
     hdr, data = rows[0], [r for r in rows[2:] if len(r) == len(rows[0])]
-    data = [r for r in data if "trace_kernel" in r[hdr.index("Kernel Name")]][-a.last:]
+    import re
+    # the plain build of the kernel only: the counting build (last template argument 1) runs once after the timed region
+    plain = re.compile(r"trace_kernel<[^>]*,\s*(?:\(bool\))?(?:0|false)>")
+    data = [r for r in data if plain.search(r[hdr.index("Kernel Name")])][-a.last:]
     if len(data) != len(SETS):
         sys.exit(f"expected {len(SETS)} trace_kernel launches, found {len(data)}")
 
