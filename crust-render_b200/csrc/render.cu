@@ -115,6 +115,7 @@ struct RenderParams {
     Queues q;
     PixelState px;
     unsigned long long* stats;  // crt_ray_stats
+    unsigned int* status;       // sticky device status word (bit 1: a ray segment crossed more volume regions than it can walk)
 };
 
 __device__ __forceinline__ V3 xyz(float4 a) { return v3(a.x, a.y, a.z); }
@@ -325,6 +326,7 @@ __global__ void __launch_bounds__(CRT_SHADE_BLOCK, (VOL ? 4 : CRT_SHADE_MINBLOCK
         const PathSampler v = new_domain(PathSampler{smp.x, smp.y}, k);
         const float time = P.ps.time[path];
         V3 add = splat(0.0f);
+        [[maybe_unused]] bool vol_overflow = false;
         uint2 cnt = P.ps.counts[path];
         if (PASS != SHADE_SCATTER) cnt.x += 1u;  // this entry is one traced closest-hit query (stats.rs:133)
         const Medium* med = medium >= 0 ? &P.materials[medium].medium : nullptr;
@@ -342,7 +344,7 @@ __global__ void __launch_bounds__(CRT_SHADE_BLOCK, (VOL ? 4 : CRT_SHADE_MINBLOCK
                     if (med) emitted *= medium_transmittance(*med, t_surf);
                     if (VOL) {  // tracer.rs:1138-1141
                         Rng rng = sampler_rng(new_domain(v, K_VOLUME));
-                        emitted *= volumes_transmittance(P.volumes, P.n_volumes, ro, rd, kTMin, t_surf, rng);
+                        emitted *= volumes_transmittance(P.volumes, P.n_volumes, ro, rd, kTMin, t_surf, rng, &vol_overflow);
                     }
                     float w = bounce_emission_weight(P, flags, prev_pdf, xyz(pp), geom_id, ro + t_surf * rd);
                     add = beta * (emitted * w);
@@ -366,7 +368,7 @@ __global__ void __launch_bounds__(CRT_SHADE_BLOCK, (VOL ? 4 : CRT_SHADE_MINBLOCK
             if (VOL) {
                 Rng rng = sampler_rng(new_domain(v, K_VOLUME));
                 VolumeEvent ev;
-                volumes_sample_interaction(P.volumes, P.n_volumes, ro, rd, kTMin, fminf(t_surf, t_med), rng, ev);
+                volumes_sample_interaction(P.volumes, P.n_volumes, ro, rd, kTMin, fminf(t_surf, t_med), rng, ev, &vol_overflow);
                 add = beta * ev.emitted;  // segment_emit: already weighted by the walk, not attenuated again (:1552)
                 if (ev.scatter) {
                     // Volume-region scatter vertex (tracer.rs:1184-1244): NEE with the phase function in place of brdf*cos
@@ -592,6 +594,7 @@ __global__ void __launch_bounds__(CRT_SHADE_BLOCK, (VOL ? 4 : CRT_SHADE_MINBLOCK
             }
         }
         P.ps.counts[path] = cnt;
+        if (VOL && vol_overflow) atomicOr(P.status, 2u);
         if (add.x != 0.0f || add.y != 0.0f || add.z != 0.0f) {
             float4 lw = P.ps.L_w[path];
             P.ps.L_w[path] = make_float4(lw.x + add.x, lw.y + add.y, lw.z + add.z, lw.w);
@@ -615,7 +618,9 @@ __global__ void __launch_bounds__(kBlock) nee_resolve_kernel(const RenderParams 
             const uint2 smp = P.ps.sampler[path];
             Rng rng = sampler_rng(new_domain(new_domain(PathSampler{smp.x, smp.y}, k), K_NEE_SHADOW));
             const float4 ra = P.q.srays[2 * (size_t)i], rb = P.q.srays[2 * (size_t)i + 1];
-            V3 tr = volumes_transmittance(P.volumes, P.n_volumes, xyz(ra), xyz(rb), kTMin, rb.w, rng);
+            bool vol_overflow = false;
+            V3 tr = volumes_transmittance(P.volumes, P.n_volumes, xyz(ra), xyz(rb), kTMin, rb.w, rng, &vol_overflow);
+            if (vol_overflow) atomicOr(P.status, 2u);
             c.x *= tr.x;
             c.y *= tr.y;
             c.z *= tr.z;
@@ -926,7 +931,6 @@ int crt_world_set_environment(crt_world* w, uint32_t light_index, uint32_t width
 
 int crt_world_set_volumes(crt_world* w, const crt_volume* volumes, size_t n) {
     if (!w || (n && !volumes)) return crt::set_error(CRT_ERR_INVALID_ARG, "crt_world_set_volumes: null argument");
-    if (n > CRT_MAX_VOLUMES) return crt::set_error(CRT_ERR_INVALID_ARG, "crt_world_set_volumes: at most CRT_MAX_VOLUMES regions");
     for (size_t i = 0; i < n; ++i)
         if (!volume_abi_valid(volumes[i])) return crt::set_error(CRT_ERR_INVALID_ARG, "crt_world_set_volumes: unknown field kind or malformed grid");
     int rc = crt::require_device();
@@ -1254,6 +1258,7 @@ int render_impl(crt_world* w, const crt_camera* camera, const crt_render_setting
     P.n_lights = (int)w->lights.size();
     P.motion = motion ? 1 : 0;
     P.stats = sc.stats;
+    P.status = crt::device_status_word();
     {
         char* p = (char*)sc.paths;
         P.ps.beta_pdf = carve<float4>(p, cap);

@@ -887,6 +887,14 @@ int crt_device_status(uint32_t* bits) {
     return CRT_OK;
 }
 
+int crt_device_status_reset(void) {
+    int rc = ensure_device();
+    if (rc) return rc;
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemset(g_dev.status, 0, sizeof(unsigned int)));
+    return CRT_OK;
+}
+
 // ---- host-buffer path ------------------------------------------------------
 namespace {
 constexpr int kSlots = 3;

@@ -199,12 +199,14 @@ CRT_HD float phase_pdf(const PhaseMix& m, float cos_theta) {  // :320-325
 // ---- Volumes (volume.rs:331-540) --------------------------------------------------------------------------
 struct VolumeSpans {
     int n;
+    bool overflow;  // the segment crosses more regions than the list holds: the excess is ignored (and reported)
     int idx[MAX_VOLUME_REGIONS];
     float a[MAX_VOLUME_REGIONS], b[MAX_VOLUME_REGIONS];
     float majorant, start, end;
 };
 CRT_HD void volumes_active_intervals(const VolumeRegion* regions, int n_regions, V3 ro, V3 rd, float t_eps, float t_max, VolumeSpans& s) {  // :386-410
     s.n = 0;
+    s.overflow = false;
     s.majorant = 0.0f;
     s.start = INFINITY;  // :424-425
     s.end = 0.0f;
@@ -215,6 +217,7 @@ CRT_HD void volumes_active_intervals(const VolumeRegion* regions, int n_regions,
         float t0, t1;
         if (!region_intersect(r, ro, rd, t0, t1)) continue;
         float a = fmaxf(t0, t_eps), b = fminf(t1, t_max);
+        if (b > a && s.n >= MAX_VOLUME_REGIONS) s.overflow = true;
         if (b > a && s.n < MAX_VOLUME_REGIONS) {
             s.idx[s.n] = i;
             s.a[s.n] = a;
@@ -237,9 +240,14 @@ struct VolumeEvent {  // volume.rs:331-362
 };
 
 // Volumes::sample_interaction (:415-487)
-CRT_HD_NOINLINE void volumes_sample_interaction(const VolumeRegion* regions, int n_regions, V3 ro, V3 rd, float t_eps, float t_max, Rng& rng, VolumeEvent& ev) {
+// `overflow` (optional) is set when the segment crosses more than MAX_VOLUME_REGIONS regions at once — the one limit left:
+// a world may hold any number of regions (the reference's Vec, volume.rs:356-366), a single ray segment is walked through
+// at most that many.
+CRT_HD_NOINLINE void volumes_sample_interaction(const VolumeRegion* regions, int n_regions, V3 ro, V3 rd, float t_eps, float t_max, Rng& rng, VolumeEvent& ev,
+                                                bool* overflow = nullptr) {
     VolumeSpans sp;
     volumes_active_intervals(regions, n_regions, ro, rd, t_eps, t_max, sp);
+    if (overflow && sp.overflow) *overflow = true;
     ev.scatter = false;
     ev.weight = splat(1.0f);
     ev.emitted = splat(0.0f);
@@ -297,9 +305,10 @@ CRT_HD_NOINLINE void volumes_sample_interaction(const VolumeRegion* regions, int
 }
 
 // Volumes::transmittance (:493-539)
-CRT_HD_NOINLINE V3 volumes_transmittance(const VolumeRegion* regions, int n_regions, V3 ro, V3 rd, float t_eps, float t_max, Rng& rng) {
+CRT_HD_NOINLINE V3 volumes_transmittance(const VolumeRegion* regions, int n_regions, V3 ro, V3 rd, float t_eps, float t_max, Rng& rng, bool* overflow = nullptr) {
     VolumeSpans sp;
     volumes_active_intervals(regions, n_regions, ro, rd, t_eps, t_max, sp);
+    if (overflow && sp.overflow) *overflow = true;
     if (sp.n == 0 || sp.majorant <= 0.0f) return splat(1.0f);
     bool all_homogeneous = true;
     for (int k = 0; k < sp.n; ++k) all_homogeneous = all_homogeneous && regions[sp.idx[k]].field == FIELD_HOMOGENEOUS;

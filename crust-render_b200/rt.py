@@ -37,7 +37,7 @@ __all__ = [
     "AABB", "Affine3A", "CrtError", "CubicCurveSegment", "CurveSegment", "Geometry", "HIT_DTYPE", "INVALID_ID",
     "MASK_ALL", "MASK_CAMERA", "MASK_INDIRECT", "MASK_SHADOW", "PrimitiveBreakdown", "RAY_DTYPE", "Ray", "RayHit",
     "Scene", "SceneBuilder", "MemoryFootprint", "BuildInfo", "lib", "lib_path", "make_rays", "init", "device_info",
-    "launch_count", "device_status", "trace_counters_enable", "trace_counters_read", "TRACE_COUNTER_NAMES", "l2_persist_info", "COMMIT_KEEP_HOST_TREE", "COMMIT_HOST_ONLY", "COMMIT_DEVICE_BUILD",
+    "launch_count", "device_status", "device_status_reset", "trace_counters_enable", "trace_counters_read", "TRACE_COUNTER_NAMES", "l2_persist_info", "COMMIT_KEEP_HOST_TREE", "COMMIT_HOST_ONLY", "COMMIT_DEVICE_BUILD",
 ]
 
 COMMIT_KEEP_HOST_TREE = 0x1
@@ -128,6 +128,7 @@ def lib() -> C.CDLL:
         "crt_intersect1": [vp, vp, C.c_float, u32, vp, C.POINTER(C.c_int), C.POINTER(C.c_int)],
         "crt_occluded1": [vp, vp, C.c_float, u32, C.POINTER(C.c_int)],
         "crt_device_status": [u32p],
+        "crt_device_status_reset": [],
         "crt_scene_export_size": [vp, C.POINTER(sz)],
         "crt_scene_export": [vp, vp, sz, C.c_int, vp],
         "crt_scene_import": [vp, sz, C.c_int, C.POINTER(vp), sz, C.POINTER(vp)],
@@ -193,6 +194,10 @@ def device_info() -> dict:
 
 def launch_count() -> int:
     return int(lib().crt_launch_count())
+
+
+def device_status_reset() -> None:
+    _ck(lib().crt_device_status_reset())
 
 
 TRACE_COUNTER_NAMES = ("rays", "nodes_fetched", "entries_culled_on_pop", "leaves_entered", "triangle_records", "other_records", "instance_descents")

@@ -25,7 +25,8 @@ What is reproduced, with the reference lines it follows:
     per authored span, widths by vertex / curve / constant, as one Instance over its own committed scene;
   * volumes: a prim carrying `crust:volume:type` (homogeneous | smoke | grid) imports as a VolumeRegion only, never
     as geometry (:190-209, 427-503).
-Not reproduced: Ptex, external-file references / payloads / variants (the stage is not composed: arcs resolve only to prims
+Composition across files (subLayers, variant selections, references and payloads into other layers) happens before the
+import, in usd/compose.py (the reference gets it from openusd, :271-300). Not reproduced: Ptex (internal arcs resolve to prims
 of the same layer, which covers every bundled sample).
 """
 from __future__ import annotations
@@ -767,13 +768,8 @@ def world_from_meshes(api, meshes, settings: RenderSettings):
 def load_scene(api, path: str, **overrides):
     """`Scene::from_usd` (scene.rs:67-85 -> usd_import.rs:287-424). Returns (world, camera, settings);
     keyword overrides replace RenderSettings fields (the CLI's -s / --strategy / --filter flags)."""
-    with open(path, "rb") as f:
-        magic = f.read(8)
-    if magic == b"PXR-USDC":
-        from . import usdc
-        stage = usdc.load(path)
-    else:
-        stage = usda.load(path)
+    from .compose import load_composed
+    stage = load_composed(path)  # the layer stack with variant selections, external references and payloads flattened in
     return import_stage(api, stage, path, **overrides)
 
 

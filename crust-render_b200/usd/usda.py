@@ -6,7 +6,8 @@ enough for prim hierarchies, typed attributes (scalars, tuples, arrays, matrices
 paths), relationships, `custom` attributes, prim metadata (`active`, `instanceable`, `kind`,
 `apiSchemas`) and `.timeSamples` (the earliest sample stands in for the default, like
 `attr.get()` without a time code does for single-sample attributes). Composition arcs
-(references, payloads, variants, sublayers) are parsed but not composed.
+(references, payloads, variants, sublayers) are parsed here — external targets as `Ref(asset, path)`, variant sets as
+`Prim.variant_sets` — and composed by `usd/compose.py`.
 """
 from __future__ import annotations
 
@@ -40,6 +41,14 @@ class Attribute:
         return v
 
 
+@dataclass(frozen=True)
+class Ref:
+    """A reference / payload target: `@layer.usda@</Prim>` (either part may be empty: an internal path, or a layer's
+    defaultPrim)."""
+    asset: str
+    path: str = ""
+
+
 @dataclass
 class Prim:
     specifier: str          # def | over | class
@@ -51,6 +60,8 @@ class Prim:
     relationships: Dict[str, List[str]] = field(default_factory=dict)
     children: List["Prim"] = field(default_factory=list)
     parent: Optional["Prim"] = None
+    # variantSet name -> variant name -> the variant's body as an `over` of this prim (properties, children, metadata)
+    variant_sets: Dict[str, Dict[str, "Prim"]] = field(default_factory=dict)
 
     def attr(self, name: str):
         a = self.attributes.get(name)
@@ -224,7 +235,13 @@ class _Parser:
         if k in ("str", "str3"):
             return _unquote(v)
         if k == "asset":
-            return v.strip("@")
+            a = v.strip("@")
+            if self.lx.peek()[0] == "path":  # @layer@</Prim>: an external composition target
+                tgt = Ref(a, self.lx.next()[1].strip("<>"))
+                if self.lx.peek()[1] == "(":
+                    self.metadata_block()  # layer offset: not applied (no animation is read)
+                return tgt
+            return a
         if k == "path":
             return v
         if k == "ident":
@@ -353,27 +370,37 @@ class _Parser:
             if v in ("def", "over", "class"):
                 p.children.append(self.prim(p))
             elif v == "variantSet":
-                self.skip_variant_set()
+                self.variant_set(p)
             else:
                 self.property(p)
         return p
 
-    def skip_variant_set(self):
+    def variant_set(self, p: Prim):
+        """variantSet "name" = { "variant" (metadata) { properties and child prims } ... }"""
         lx = self.lx
         lx.next()
-        lx.next()
+        set_name = _unquote(lx.next()[1])
         lx.expect("=")
-        depth = 0
-        while True:
+        lx.expect("{")
+        variants = p.variant_sets.setdefault(set_name, {})
+        while not lx.accept("}"):
             k, v = lx.next()
-            if v == "{":
-                depth += 1
-            elif v == "}":
-                depth -= 1
-                if depth == 0:
-                    return
-            elif k == "eof":
+            if k == "eof":
                 raise SyntaxError("usda: unterminated variantSet")
+            body = Prim("over", "", p.name, p.path, parent=p.parent)
+            if lx.peek()[1] == "(":
+                body.metadata = self.metadata_block()
+            lx.expect("{")
+            while not lx.accept("}"):
+                k2, v2 = lx.peek()
+                if v2 in ("def", "over", "class"):
+                    child = self.prim(body)
+                    body.children.append(child)
+                elif v2 == "variantSet":
+                    self.variant_set(body)
+                else:
+                    self.property(body)
+            variants[_unquote(v)] = body
 
     def property(self, p: Prim):
         lx = self.lx

@@ -215,6 +215,8 @@ int crt_trace_counters_enable(int on);
 int crt_trace_counters_read(uint64_t out[7], int reset);
 
 int crt_device_status(uint32_t* bits);
+/* Clears the sticky bits (synchronises the device). */
+int crt_device_status_reset(void);
 
 /* ---- debug / test support (needs CRT_COMMIT_KEEP_HOST_TREE) ---------------
  * Canonical view of the host tree for builder-equivalence tests:

@@ -162,7 +162,9 @@ typedef struct crt_volume {
 } crt_volume;
 /* Scene::with_volumes (tracer.rs:167-170): replaces the world's volume regions (n = 0 clears them). Regions live
  * outside the BVH; the integrator delta-tracks through them on every segment and ratio-tracks shadow rays.
- * At most CRT_MAX_VOLUMES regions (the reference has no cap; the device keeps a fixed span list per ray). */
+ * Any number of regions, like the reference's Vec (volume.rs:356-366). The one limit left is per ray: a single segment is
+ * walked through at most CRT_MAX_VOLUMES regions that it crosses at once; regions beyond that are ignored for that
+ * segment and bit 1 of crt_device_status() is set. */
 int crt_world_set_volumes(crt_world* w, const crt_volume* volumes, size_t n);
 
 /* Renderer::render_with_stats (tracer.rs:194-212): one non-guided pass. `framebuffer` is a DEVICE

@@ -477,7 +477,6 @@ struct VolumesHandle {
 }  // namespace
 int orc_world_set_volumes(void* w, const crt_volume* v, size_t n) {
     orcr::World& W = ((WorldHandle*)w)->world;
-    if (n > CRT_MAX_VOLUMES) return 1;
     for (size_t i = 0; i < n; ++i)
         if (!shade::volume_abi_valid(v[i])) return 1;
     set_volumes(W.volumes, W.grids, v, n);

@@ -5,6 +5,8 @@ relative-MSE tolerance": the tolerance stated here is relMSE <= 1e-6 with <= 1% 
 than 1e-3 relative (measured on B200: relMSE 4e-12 .. 1.2e-7, see profiles/r01_render_parity.jsonl).
 Differences come from CUDA's vs glibc's transcendental functions and the forward-vs-backward
 summation order; a handful of paths per million flip a discrete decision (lobe pick, roulette)."""
+import math
+
 import numpy as np
 import pytest
 
@@ -188,8 +190,39 @@ def test_volumes_can_be_replaced_and_cleared(gpu, orc):
     wg.with_volumes(scenes.volume_slab(orc, "furnace", spp=4)[0].volumes)
     c, _ = gpu.Renderer(cam, wg, st).render_with_stats()
     assert a.tobytes() == c.tobytes()
-    with pytest.raises(gpu.CrtError):
-        wg.with_volumes(scenes.volume_slab(orc, "furnace", spp=4)[0].volumes * 17)  # CRT_MAX_VOLUMES
+
+
+def test_any_number_of_volume_regions(gpu, orc):
+    """`Volumes` holds a Vec of regions with no cap (volume.rs:356-366). 48 regions tiled side by side under the 1-degree
+    camera of the slab probe (a ray crosses one or two of them) render like the oracle and like one wide slab; the one limit
+    left is per ray — a segment that crosses more than CRT_MAX_VOLUMES regions at once walks the first 16 and sets bit 1 of
+    the device status word."""
+    from crust_render_b200.render_types import DensityField, VolumeRegion
+
+    def tiles(n):
+        out = []
+        for k in range(n):
+            m = np.eye(4, dtype=np.float32)
+            m[0, 3] = -12.0 + 0.5 * k + 0.25  # 0.5-wide columns next to each other along x (column-vector l2w)
+            out.append(VolumeRegion(m, (0.25, 50.0, 0.5), (0,) * 3, (0.7,) * 3, 0.0, (0,) * 3, 1.0, DensityField.Homogeneous()))
+        return out
+
+    wg, cam, st = scenes.volume_slab(gpu, "absorb", spp=16)
+    wo = scenes.volume_slab(orc, "absorb", spp=16)[0]
+    one, _ = gpu.Renderer(cam, wg, st).render_with_stats()
+    wg.with_volumes(tiles(48))
+    wo.with_volumes(tiles(48))
+    many, sm = gpu.Renderer(cam, wg, st).render_with_stats()
+    ref, so = orc.Renderer(cam, wo, st).render_with_stats()
+    compare(many, ref)
+    stats_close(sm, so)
+    assert abs(float(many[..., :3].mean()) - math.exp(-0.7)) < 2e-3 and abs(float(one[..., :3].mean()) - math.exp(-0.7)) < 2e-3
+    assert gpu.device_status() == 0
+    wg.with_volumes(scenes.volume_slab(orc, "furnace", spp=4)[0].volumes * 17)  # 17 coincident regions: every ray crosses them all
+    gpu.Renderer(cam, wg, st).render_with_stats()
+    assert gpu.device_status() & 2
+    gpu.device_status_reset()
+    assert gpu.device_status() == 0
 
 
 @pytest.mark.parametrize("name", ["instancing", "nested_instancing", "curves"])
