@@ -1,5 +1,7 @@
-// Device-side BVH4 build for sm_100a: an alternative commit() path for
-// triangle-only static scenes that constructs the whole acceleration structure on the GPU.
+// Device-side BVH4 build for sm_100a: an alternative commit() path that constructs the whole
+// acceleration structure on the GPU — over triangle meshes (expanded on the device) and over every other primitive kind
+// (spheres, curve segments, cubic spans, instances incl. moving ones: boxes and leaf records prepared on the host exactly as
+// the host build prepares them, host_build.cpp expand_other_prims, then sorted and grouped on the device with the triangles).
 //
 // The reference builds its tree on the host (crates/crust-rt/src/bvh.rs:300-327, 1059-1375: binned SAH +
 // SBVH, then a collapse to BVH4); csrc/host_build.cpp restates that build exactly and stays the default,
@@ -76,8 +78,17 @@ struct BuildArrays {
     uint32_t *is_root4, *id4;
     int *frontier_a, *frontier_b;
     unsigned int* counters;      // [0] valid triangles, [1] next frontier size, [2] leaves, [3] valid references,
-                                 // [4..5] sum of quantised triangle extents (u64), [8..13] bounds as ordered ints
+                                 // [4..5] sum of quantised triangle extents (u64), [8..13] bounds as ordered ints,
+                                 // [16..17] sum of the triangle box diagonals (double), [18] largest diagonal (float bits)
+    // primitives that are not triangles: indices [n_tris, n_tris + n_other) of the per-primitive arrays
+    uint32_t n_tris;
+    const uint32_t* other_rec_off;  // n_other + 1 offsets (16-byte units) into other_recs
+    const float4* other_recs;       // their leaf records as the host flattener writes them (without REC_LAST)
+    uint32_t* other_pos;            // out: where each one's record landed in the leaf stream
+    uint32_t* rec_size;             // per sorted reference: size of its record in 16-byte units ...
+    uint32_t* rec_at;               // ... and its exclusive prefix sum = where a leaf that starts with it begins
 };
+constexpr int kCounters = 24;
 
 __device__ __forceinline__ unsigned int f2ord(float f) {
     unsigned int u = __float_as_uint(f);
@@ -146,8 +157,31 @@ __global__ void __launch_bounds__(kB) tri_setup_kernel(uint32_t n, MeshTable mt,
     r = BR(tmp).Reduce(hi.x, cub::Max()); __syncthreads(); if (threadIdx.x == 0) atomicMax(A.counters + 11, f2ord(r));
     r = BR(tmp).Reduce(hi.y, cub::Max()); __syncthreads(); if (threadIdx.x == 0) atomicMax(A.counters + 12, f2ord(r));
     r = BR(tmp).Reduce(hi.z, cub::Max()); __syncthreads(); if (threadIdx.x == 0) atomicMax(A.counters + 13, f2ord(r));
+    // scene.rs:446-455 primitive extents (the host sums f32 diagonals in input order; here a double sum of the same terms)
+    float diag = 0.0f;
+    if (valid) {
+        float ex = hi.x - lo.x, ey = hi.y - lo.y, ez = hi.z - lo.z;
+        diag = sqrtf((ex * ex + ey * ey) + ez * ez);
+    }
+    typedef cub::BlockReduce<double, kB> BRD;
+    __shared__ typename BRD::TempStorage tmpd;
+    __syncthreads();
+    double dsum = BRD(tmpd).Sum((double)diag);
+    if (threadIdx.x == 0 && dsum != 0.0) atomicAdd((double*)(A.counters + 16), dsum);
+    r = BR(tmp).Reduce(diag, cub::Max()); __syncthreads(); if (threadIdx.x == 0) atomicMax(A.counters + 18, __float_as_uint(r));
     unsigned int v = __syncthreads_count(valid);
     if (threadIdx.x == 0 && v) atomicAdd(A.counters + 0, v);
+}
+
+// Boxes and ids of the primitives that are not triangles, prepared on the host, into their slots behind the triangles.
+__global__ void __launch_bounds__(kB) other_setup_kernel(uint32_t n_other, const float4* __restrict__ lo, const float4* __restrict__ hi,
+                                                         const uint2* __restrict__ ids, BuildArrays A) {
+    uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_other) return;
+    const uint32_t i = A.n_tris + j;
+    A.lo[i] = lo[j];
+    A.hi[i] = hi[j];
+    A.prim_ids[i] = ids[j];
 }
 
 // Mean triangle size, deterministically: longest AABB side of every valid triangle, quantised against the scene
@@ -176,7 +210,7 @@ __global__ void __launch_bounds__(kB) count_kernel(uint32_t n, float cell, float
     if (lo.w != 0.0f) {
         float ex = hi.x - lo.x, ey = hi.y - lo.y, ez = hi.z - lo.z;
         uint32_t nx = 1, ny = 1, nz = 1;
-        if (fmaxf(fmaxf(ex, ey), ez) > split_above) {
+        if (i < A.n_tris && fmaxf(fmaxf(ex, ey), ez) > split_above) {  // only triangles are clipped to cells
             float c = cell;
             for (int it = 0; it < 16; ++it) {  // coarsen until the grid has at most 4096 cells and 64 per axis
                 nx = (uint32_t)fminf(fmaxf(ceilf(ex / c), 1.0f), 64.0f);
@@ -251,6 +285,12 @@ __device__ bool split_candidate(uint32_t r, uint32_t n_tris, float eps, const Bu
             // conservative: interpolated corners carry rounding error; never leave the triangle's own box
             lo = make_float3(fmaxf(lo.x - eps, tlo.x), fmaxf(lo.y - eps, tlo.y), fmaxf(lo.z - eps, tlo.z));
             hi = make_float3(fminf(hi.x + eps, thi.x), fminf(hi.y + eps, thi.y), fminf(hi.z + eps, thi.z));
+            // ... and, like every box the reference makes (aabb.rs:47-58; clip_triangle_aabb, triangle.rs:367-429), never
+            // thinner than the pad: the slab test of a ray whose origin is hundreds of units away rounds by more than the
+            // thickness of an unpadded piece of an axis-aligned triangle, and would step over it
+            if (hi.x - lo.x < kPadDev) lo.x -= kPadDev, hi.x += kPadDev;
+            if (hi.y - lo.y < kPadDev) lo.y -= kPadDev, hi.y += kPadDev;
+            if (hi.z - lo.z < kPadDev) lo.z -= kPadDev, hi.z += kPadDev;
         }
     }
     unsigned long long key = ~0ull;
@@ -381,24 +421,57 @@ __global__ void __launch_bounds__(kB) mark_kernel(int n, const int* __restrict__
         if (expandable(A, n, kids[l])) next[atomicAdd(A.counters + 1, 1u)] = kids[l];
 }
 
-__device__ __forceinline__ void write_leaf_records(const BuildArrays& A, const uint32_t* __restrict__ sorted, float4* __restrict__ leafs, int first, int last) {
+// Record size (16-byte units) of every sorted reference, for the prefix sum that places the leaves.
+__global__ void __launch_bounds__(kB) rec_size_kernel(int n, const uint32_t* __restrict__ sorted, BuildArrays A) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    uint32_t t = A.ref_prim[sorted[j]];
+    A.rec_size[j] = t < A.n_tris ? REC_TRI_Q : A.other_rec_off[t - A.n_tris + 1] - A.other_rec_off[t - A.n_tris];
+}
+
+// The records of the leaf over sorted references [first, last], in the order the traversal expects (host_build.cpp
+// emit_leaf, bvh.rs:1256-1290): its triangles first — packet flags on every 4th and on the last one — then its other
+// primitives; the last record of the leaf carries REC_LAST. Returns the leaf's offset in the record stream.
+__device__ __forceinline__ uint32_t write_leaf_records(const BuildArrays& A, const uint32_t* __restrict__ sorted, float4* __restrict__ leafs, int first, int last) {
+    const uint32_t base = A.rec_at[first];
+    int n_tri = 0, n_other = 0;
+    for (int j = first; j <= last; ++j) {
+        if (A.ref_prim[sorted[j]] < A.n_tris) ++n_tri; else ++n_other;
+    }
+    int ti = 0;
     for (int j = first; j <= last; ++j) {
         uint32_t t = A.ref_prim[sorted[j]];
+        if (t >= A.n_tris) continue;
         float4 a = A.v0[t], b = A.v1[t], c = A.v2[t];
-        int ti = j - first;
         uint32_t flags = REC_TRI | ((uint32_t)(ti & 3) << REC_LANE_SHIFT);
-        if ((ti & 3) == 3 || j == last) flags |= REC_PACKET_END;
-        if (j == last) flags |= REC_LAST;
+        if ((ti & 3) == 3 || ti + 1 == n_tri) flags |= REC_PACKET_END;
+        if (ti + 1 == n_tri && n_other == 0) flags |= REC_LAST;
         // prim.rs:80-83: geometric normal exactly zero (glam cross: a.yzx * b.zxy - a.zxy * b.yzx, no FMA)
         float e1x = b.x - a.x, e1y = b.y - a.y, e1z = b.z - a.z, e2x = c.x - a.x, e2y = c.y - a.y, e2z = c.z - a.z;
         float nx = __fsub_rn(__fmul_rn(e1y, e2z), __fmul_rn(e2y, e1z)), ny = __fsub_rn(__fmul_rn(e1z, e2x), __fmul_rn(e2z, e1x)),
               nz = __fsub_rn(__fmul_rn(e1x, e2y), __fmul_rn(e2x, e1y));
         if (nx == 0.0f && ny == 0.0f && nz == 0.0f) flags |= REC_DEGENERATE;
-        float4* out = leafs + 3 * (size_t)j;
+        float4* out = leafs + base + REC_TRI_Q * (size_t)ti;
         out[0] = make_float4(a.x, a.y, a.z, __uint_as_float(flags));
         out[1] = make_float4(b.x, b.y, b.z, __uint_as_float(t));
         out[2] = make_float4(c.x, c.y, c.z, a.w);
+        ++ti;
     }
+    uint32_t pos = base + REC_TRI_Q * (uint32_t)n_tri;
+    int oi = 0;
+    for (int j = first; j <= last; ++j) {
+        uint32_t t = A.ref_prim[sorted[j]];
+        if (t < A.n_tris) continue;
+        const uint32_t k = t - A.n_tris, r0 = A.other_rec_off[k], r1 = A.other_rec_off[k + 1];
+        for (uint32_t q = r0; q < r1; ++q) {
+            float4 v = A.other_recs[q];
+            if (q == r0 && ++oi == n_other) v.w = __uint_as_float(__float_as_uint(v.w) | REC_LAST);
+            leafs[pos + (q - r0)] = v;
+        }
+        A.other_pos[k] = pos;
+        pos += r1 - r0;
+    }
+    return base;
 }
 
 __global__ void __launch_bounds__(kB) emit_kernel(int n, const uint32_t* __restrict__ sorted, DevNode* __restrict__ nodes, float4* __restrict__ leafs, BuildArrays A) {
@@ -424,8 +497,7 @@ __global__ void __launch_bounds__(kB) emit_kernel(int n, const uint32_t* __restr
             w.child[l] = A.id4[k];
         } else {
             int first = k >= n - 1 ? k - (n - 1) : A.first[k], last = k >= n - 1 ? first : A.last[k];
-            write_leaf_records(A, sorted, leafs, first, last);
-            w.child[l] = CRT_LEAF_BIT | (uint32_t)(3 * first);
+            w.child[l] = CRT_LEAF_BIT | write_leaf_records(A, sorted, leafs, first, last);
             w.flags |= 1u << (4 + l);
             ++n_leaves;
         }
@@ -434,7 +506,7 @@ __global__ void __launch_bounds__(kB) emit_kernel(int n, const uint32_t* __restr
     if (n_leaves) atomicAdd(A.counters + 2, n_leaves);
 }
 
-// n <= kLeafMax triangles: one node with one leaf lane (host_build.cpp run(): bin[0].count > 0)
+// n <= kLeafMax references: one node with one leaf lane (host_build.cpp run(): bin[0].count > 0)
 __global__ void tiny_kernel(int n, const uint32_t* __restrict__ sorted, DevNode* __restrict__ nodes, float4* __restrict__ leafs, BuildArrays A) {
     DevNode w;
     for (int l = 0; l < 4; ++l) {
@@ -449,9 +521,8 @@ __global__ void tiny_kernel(int n, const uint32_t* __restrict__ sorted, DevNode*
         hi = make_float3(fmaxf(hi.x, b.x), fmaxf(hi.y, b.y), fmaxf(hi.z, b.z));
     }
     w.bmin_x[0] = lo.x, w.bmin_y[0] = lo.y, w.bmin_z[0] = lo.z, w.bmax_x[0] = hi.x, w.bmax_y[0] = hi.y, w.bmax_z[0] = hi.z;
-    w.child[0] = CRT_LEAF_BIT | 0u;
     w.flags = 1u | (1u << 4);
-    write_leaf_records(A, sorted, leafs, 0, n - 1);
+    w.child[0] = CRT_LEAF_BIT | write_leaf_records(A, sorted, leafs, 0, n - 1);
     nodes[0] = w;
     A.counters[2] = 1;
 }
@@ -489,12 +560,14 @@ size_t padded(size_t count, size_t elem) { return (std::max<size_t>(count, 1) * 
 }  // namespace
 
 bool device_build_supported(const std::vector<Geom>& geoms) {
+    // every primitive kind; the one thing left to the host build is per-vertex shading normals (prim.rs:77-78: the
+    // importer never supplies them, usd_import.rs:904,960,1051)
     for (const Geom& g : geoms)
-        if (g.type != G_MESH || g.has_normals) return false;
+        if (g.type == G_MESH && g.has_normals) return false;
     return true;
 }
 
-int device_build(const std::vector<Geom>& geoms, crt_scene* s) {
+int device_build(std::vector<Geom>& geoms, ChildInfoFn child_info, crt_scene* s) {
     auto t0 = std::chrono::steady_clock::now();
     const bool trace = getenv("CRT_DEVICE_BUILD_TRACE") != nullptr;  // per-phase wall times on stderr (synchronises)
     const bool trace_sync = trace && atoi(getenv("CRT_DEVICE_BUILD_TRACE")) != 2;  // 2 = host-side times only, no extra synchronisation
@@ -510,7 +583,7 @@ int device_build(const std::vector<Geom>& geoms, crt_scene* s) {
     size_t n_tris = 0, n_v = 0;
     for (size_t g = 0; g < geoms.size(); ++g) {
         const Geom& G = geoms[g];
-        if (G.indices.empty()) continue;
+        if (G.type != G_MESH || G.indices.empty()) continue;
         tri_offset.push_back((uint32_t)n_tris);
         vert_offset.push_back((uint32_t)n_v);
         n_verts.push_back((uint32_t)(G.verts.size() / 3));
@@ -526,19 +599,49 @@ int device_build(const std::vector<Geom>& geoms, crt_scene* s) {
     s->non_empty = false;
     s->features = 0;
     s->desc = DevScene{};
-    if (n_tris == 0) {  // nothing to intersect: the kernels treat n_nodes == 0 as an empty scene
+    // ---- everything that is not a triangle mesh: expanded on the host like the host build does it -----------------------
+    OtherPrims others;
+    {
+        const char* err = nullptr;
+        if (!expand_other_prims(geoms, child_info, (uint32_t)n_tris, others, &err)) return set_error(CRT_ERR_NESTING, err ? err : "commit failed");
+    }
+    const uint32_t M = (uint32_t)others.n;
+    if ((uint64_t)n_tris + M > 0x0FFFFFFFull) return set_error(CRT_ERR_INVALID_ARG, "device build: more than 2^28 primitives");
+    for (size_t k = 0; k < others.inst_prim.size(); ++k) {  // child addresses into the instance records (q4, q5, REC_CHILD_TRIS)
+        const crt_scene* child = others.inst_child[k];
+        const size_t q = others.rec_off[others.inst_prim[k]];
+        const uint64_t d = (uint64_t)(uintptr_t)child->d_desc, cn = (uint64_t)(uintptr_t)child->d_nodes, cl = (uint64_t)(uintptr_t)child->d_leafs;
+        others.recs[4 * (q + 4) + 0] = (uint32_t)(d & 0xFFFFFFFFu), others.recs[4 * (q + 4) + 1] = (uint32_t)(d >> 32);
+        others.recs[4 * (q + 5) + 0] = (uint32_t)(cn & 0xFFFFFFFFu), others.recs[4 * (q + 5) + 1] = (uint32_t)(cn >> 32);
+        others.recs[4 * (q + 5) + 2] = (uint32_t)(cl & 0xFFFFFFFFu), others.recs[4 * (q + 5) + 3] = (uint32_t)(cl >> 32);
+        if (child->desc.has_triangles) others.recs[4 * q + 3] |= REC_CHILD_TRIS;
+    }
+    s->has_motion = others.has_motion;
+    s->instance_depth = others.instance_depth;
+    s->breakdown.spheres = others.counts.spheres, s->breakdown.curve_segments = others.counts.curve_segments;
+    s->breakdown.cubic_curve_spans = others.counts.cubic_curve_spans, s->breakdown.instances = others.counts.instances;
+    uint32_t feat = 0;
+    if (others.counts.spheres) feat |= FEAT_SPHERE;
+    if (others.counts.curve_segments || others.counts.cubic_curve_spans) feat |= FEAT_CURVE;
+    if (others.counts.instances) feat |= FEAT_INSTANCE;
+    for (crt_scene* c : s->children) feat |= c->features;
+    s->features = feat;
+    if (n_tris == 0 && M == 0) {  // nothing to intersect: the kernels treat n_nodes == 0 as an empty scene
         DevScene d{};
         CKB(cudaMalloc((void**)&s->d_desc, sizeof(DevScene)));
         CKB(cudaMemcpy(s->d_desc, &d, sizeof d, cudaMemcpyHostToDevice));
         return CRT_OK;
     }
-    // ---- arena 1: the upload and everything that is per triangle; one pinned buffer for the upload --------------
-    const uint32_t N = (uint32_t)n_tris;
+    // ---- arena 1: the upload and everything that is per primitive; one pinned buffer for the upload --------------
+    const uint32_t NT = (uint32_t)n_tris;       // triangle slots (skipped triangles keep theirs)
+    const uint32_t N = NT + M;                  // primitive slots: triangles, then the others in input order
+    const size_t other_quads = others.recs.size() / 4;
     const size_t tab_words = (size_t)5 * n_meshes + 1;
     size_t scan_tmp = 0;
     CKB(cub::DeviceScan::ExclusiveSum(nullptr, scan_tmp, (uint32_t*)nullptr, (uint32_t*)nullptr, (int)N));
-    const size_t upload_bytes = padded(3 * n_v, 4) + padded(3 * n_tris, 4) + padded(tab_words, 4);
-    const size_t need1 = upload_bytes + 5 * padded(N, 16) + 2 * padded(N, 4) + padded(16, 4) + padded(scan_tmp, 1);
+    const size_t upload_bytes = padded(3 * n_v, 4) + padded(3 * n_tris, 4) + padded(tab_words, 4)  //
+                                + 2 * padded(M, 16) + padded(M, 8) + padded((size_t)M + 1, 4) + padded(other_quads, 16);
+    const size_t need1 = upload_bytes + 5 * padded(N, 16) + 2 * padded(N, 4) + padded(kCounters, 4) + padded(scan_tmp, 1) + padded(M, 4);
     std::lock_guard<std::mutex> arena_lock(g_arena.mu);
     auto grow = [](char*& p, size_t& cap, size_t need) -> cudaError_t {
         if (need <= cap) return cudaSuccess;
@@ -561,14 +664,31 @@ int device_build(const std::vector<Geom>& geoms, crt_scene* s) {
     float* d_verts = dc.take<float>(3 * n_v);
     uint32_t* d_idx = dc.take<uint32_t>(3 * n_tris);
     uint32_t* d_tab = dc.take<uint32_t>(tab_words);
+    float4* d_olo = dc.take<float4>(M);
+    float4* d_ohi = dc.take<float4>(M);
+    uint2* d_oids = dc.take<uint2>(M);
+    uint32_t* d_orec_off = dc.take<uint32_t>((size_t)M + 1);
+    float4* d_orecs = dc.take<float4>(other_quads);
     {
         Carver hc{g_arena.pinned, g_arena.pinned + g_arena.pinned_cap};
         float* h_verts = hc.take<float>(3 * n_v);
         uint32_t* h_idx = hc.take<uint32_t>(3 * n_tris);
         uint32_t* h_tab = hc.take<uint32_t>(tab_words);
+        float* h_olo = (float*)hc.take<float4>(M);
+        float* h_ohi = (float*)hc.take<float4>(M);
+        uint32_t* h_oids = (uint32_t*)hc.take<uint2>(M);
+        uint32_t* h_orec_off = hc.take<uint32_t>((size_t)M + 1);
+        uint32_t* h_orecs = (uint32_t*)hc.take<float4>(other_quads);
+        if (M) {
+            memcpy(h_olo, others.lo.data(), others.lo.size() * 4);
+            memcpy(h_ohi, others.hi.data(), others.hi.size() * 4);
+            memcpy(h_oids, others.ids.data(), others.ids.size() * 4);
+            memcpy(h_orecs, others.recs.data(), others.recs.size() * 4);
+        }
+        memcpy(h_orec_off, others.rec_off.data(), others.rec_off.size() * 4);
         size_t vo = 0, io = 0;
         for (const Geom& G : geoms) {
-            if (G.indices.empty()) continue;
+            if (G.type != G_MESH || G.indices.empty()) continue;
             memcpy(h_verts + vo, G.verts.data(), G.verts.size() * 4);
             memcpy(h_idx + io, G.indices.data(), G.indices.size() * 4);
             vo += G.verts.size();
@@ -588,29 +708,60 @@ int device_build(const std::vector<Geom>& geoms, crt_scene* s) {
     BuildArrays A{};
     A.v0 = dc.take<float4>(N), A.v1 = dc.take<float4>(N), A.v2 = dc.take<float4>(N), A.lo = dc.take<float4>(N), A.hi = dc.take<float4>(N);
     A.cells = dc.take<uint32_t>(N), A.cell_off = dc.take<uint32_t>(N);
-    A.counters = dc.take<unsigned int>(16);
+    A.counters = dc.take<unsigned int>(kCounters);
+    A.n_tris = NT, A.other_rec_off = d_orec_off, A.other_recs = d_orecs, A.other_pos = dc.take<uint32_t>(M);
     void* d_scan = dc.take<char>(scan_tmp);
     uint2* d_prim_ids = nullptr;  // owned by the scene
     CKB(dmalloc(&d_prim_ids, N));
     s->d_prim_ids = d_prim_ids;  // from here on the scene owns it: every error return below frees it with the scene
     A.prim_ids = d_prim_ids;
     {
-        unsigned int init[16] = {0};
+        unsigned int init[kCounters] = {0};
         for (int k = 8; k < 11; ++k) init[k] = 0xFFFFFFFFu;
         CKB(cudaMemcpy(A.counters, init, sizeof init, cudaMemcpyHostToDevice));
     }
     const int grid_t = (int)((N + kB - 1) / kB);
-    tri_setup_kernel<<<grid_t, kB>>>(N, mt, d_verts, d_idx, A);
-    unsigned int h_counters[16];
+    uint64_t launches = 0;
+    if (NT) {
+        tri_setup_kernel<<<(int)((NT + kB - 1) / kB), kB>>>(NT, mt, d_verts, d_idx, A);
+        ++launches;
+    }
+    if (M) {
+        other_setup_kernel<<<(int)((M + kB - 1) / kB), kB>>>(M, d_olo, d_ohi, d_oids, A);
+        ++launches;
+    }
+    unsigned int h_counters[kCounters];
     CKB(cudaMemcpy(h_counters, A.counters, sizeof h_counters, cudaMemcpyDeviceToHost));
-    const uint32_t n_valid = h_counters[0];
-    uint64_t launches = 1;
+    const uint32_t n_valid_tris = h_counters[0];
+    const uint32_t n_valid = n_valid_tris + M;
     s->n_prims = (uint64_t)n_valid;
-    s->breakdown.triangles = (uint64_t)n_valid;
+    s->breakdown.triangles = (uint64_t)n_valid_tris;
     s->non_empty = n_valid > 0;
     Box root{{ord2f(h_counters[8]), ord2f(h_counters[9]), ord2f(h_counters[10])}, {ord2f(h_counters[11]), ord2f(h_counters[12]), ord2f(h_counters[13])}};
+    if (n_valid_tris == 0) root = Box{{INFINITY, INFINITY, INFINITY}, {-INFINITY, -INFINITY, -INFINITY}};  // the counters still hold their sentinels
+    for (uint32_t j = 0; j < M; ++j) {  // the other primitives' boxes join the scene bounds (they are few: on the host)
+        root.lo.x = std::min(root.lo.x, others.lo[4 * j]), root.lo.y = std::min(root.lo.y, others.lo[4 * j + 1]), root.lo.z = std::min(root.lo.z, others.lo[4 * j + 2]);
+        root.hi.x = std::max(root.hi.x, others.hi[4 * j]), root.hi.y = std::max(root.hi.y, others.hi[4 * j + 1]), root.hi.z = std::max(root.hi.z, others.hi[4 * j + 2]);
+    }
+    if (M) {  // the Morton normalisation of split_kernel reads the bounds from the counters
+        auto f2o = [](float f) {
+            unsigned int u;
+            memcpy(&u, &f, 4);
+            return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+        };
+        unsigned int b6[6] = {f2o(root.lo.x), f2o(root.lo.y), f2o(root.lo.z), f2o(root.hi.x), f2o(root.hi.y), f2o(root.hi.z)};
+        CKB(cudaMemcpy(A.counters + 8, b6, sizeof b6, cudaMemcpyHostToDevice));
+    }
     if (n_valid > 0) s->root = root;
-    lap("tri_setup");
+    {  // scene.rs:446-455: mean / max primitive diagonal
+        double tri_sum;
+        float tri_max;
+        memcpy(&tri_sum, h_counters + 16, 8);
+        memcpy(&tri_max, h_counters + 18, 4);
+        s->extent_sum = (float)(tri_sum + (double)others.extent_sum);
+        s->extent_max = std::max(tri_max, others.extent_max);
+    }
+    lap("primitive setup");
 
     DevNode* d_nodes = nullptr;
     float4* d_leafs = nullptr;
@@ -620,10 +771,12 @@ int device_build(const std::vector<Geom>& geoms, crt_scene* s) {
     if (n_valid > 0) {
         // ---- early split clipping: how large is a typical triangle, which ones are much larger -----------------------
         const float scene_extent = std::max(std::max(root.hi.x - root.lo.x, root.hi.y - root.lo.y), std::max(root.hi.z - root.lo.z, 1e-30f));
-        extent_kernel<<<grid_t, kB>>>(N, scene_extent, A);
         unsigned long long ext_sum = 0;
-        CKB(cudaMemcpy(&ext_sum, A.counters + 4, 8, cudaMemcpyDeviceToHost));
-        const float mean_extent = (float)((double)ext_sum / 16777216.0 / (double)n_valid) * scene_extent;
+        if (NT) {
+            extent_kernel<<<(int)((NT + kB - 1) / kB), kB>>>(NT, scene_extent, A);
+            CKB(cudaMemcpy(&ext_sum, A.counters + 4, 8, cudaMemcpyDeviceToHost));
+        }
+        const float mean_extent = n_valid_tris ? (float)((double)ext_sum / 16777216.0 / (double)n_valid_tris) * scene_extent : 0.0f;
         const float cell = std::max(2.0f * mean_extent, scene_extent * (1.0f / 4096.0f));
         count_kernel<<<grid_t, kB>>>(N, cell, 2.0f * cell, A);
         uint32_t last_count = 0, last_off = 0;
@@ -632,7 +785,6 @@ int device_build(const std::vector<Geom>& geoms, crt_scene* s) {
         CKB(cub::DeviceScan::ExclusiveSum(d_scan, scan_bytes, A.cell_off, A.cell_off, (int)N));
         CKB(cudaMemcpy(&last_off, A.cell_off + (N - 1), 4, cudaMemcpyDeviceToHost));
         const uint64_t T64 = (uint64_t)last_off + last_count;
-        // a leaf word is CRT_LEAF_BIT | 3 * first_reference (16-byte units): 3 * T must stay below 2^31
         if (T64 > 0x2AAAAAA0ull) return set_error(CRT_ERR_OOM, "device build: too many split references");
         const uint32_t T = (uint32_t)T64;
         launches += 3;
@@ -648,7 +800,8 @@ int device_build(const std::vector<Geom>& geoms, crt_scene* s) {
         size_t scan_tmp2 = 0;
         CKB(cub::DeviceScan::ExclusiveSum(nullptr, scan_tmp2, (uint32_t*)nullptr, (uint32_t*)nullptr, (int)T));
         const size_t need2 = padded(T, 4) + 2 * padded(T, 16) + 2 * padded(T, 8) + 2 * padded(T, 4) + padded(sort_tmp, 1) + padded(scan_tmp2, 1)  //
-                             + 4 * padded(T, 4) + padded(2 * (size_t)T, 4) + 2 * padded(2 * (size_t)T, 16) + 3 * padded(T, 4) + 2 * padded(T, 4);
+                             + 4 * padded(T, 4) + padded(2 * (size_t)T, 4) + 2 * padded(2 * (size_t)T, 16) + 3 * padded(T, 4) + 2 * padded(T, 4)  //
+                             + 2 * padded(T, 4);
         CKB(grow(g_arena.dev2, g_arena.dev2_cap, need2));
         Carver rc{g_arena.dev2, g_arena.dev2 + g_arena.dev2_cap};
         A.ref_prim = rc.take<uint32_t>(T), A.rlo = rc.take<float4>(T), A.rhi = rc.take<float4>(T);
@@ -667,10 +820,25 @@ int device_build(const std::vector<Geom>& geoms, crt_scene* s) {
         const unsigned long long* d_keys = keys.Current();
         const uint32_t* d_sorted = vals.Current();
         launches += 2;
-        leaf_quads = 3 * (size_t)n + 4;
+        // where every leaf's records go: the record sizes differ by kind, so a prefix sum over the sorted references
+        A.rec_size = rc.take<uint32_t>(T), A.rec_at = rc.take<uint32_t>(T);
+        if (!A.rec_at) return set_error(CRT_ERR_OOM, "device build: scratch arena too small (internal sizing error)");
+        size_t rec_quads = 0;
+        if (n > 0) {
+            rec_size_kernel<<<(n + kB - 1) / kB, kB>>>(n, d_sorted, A);
+            size_t sb = scan_tmp2;
+            CKB(cub::DeviceScan::ExclusiveSum(d_scan2, sb, A.rec_size, A.rec_at, n));
+            uint32_t last_at = 0, last_size = 0;
+            CKB(cudaMemcpy(&last_at, A.rec_at + (n - 1), 4, cudaMemcpyDeviceToHost));
+            CKB(cudaMemcpy(&last_size, A.rec_size + (n - 1), 4, cudaMemcpyDeviceToHost));
+            rec_quads = (size_t)last_at + last_size;
+            launches += 2;
+        }
+        if (rec_quads > 0x7FFFFFF0ull) return set_error(CRT_ERR_OOM, "device build: leaf record stream exceeds the 31-bit offset of a leaf word");
+        leaf_quads = rec_quads + 4;
         CKB(dmalloc(&d_leafs, leaf_quads));
         s->d_leafs = d_leafs;
-        pad_kernel<<<1, 1>>>(d_leafs, 3 * (size_t)n);
+        pad_kernel<<<1, 1>>>(d_leafs, rec_quads);
         if (n <= (int)kLeafMax) {
             CKB(dmalloc(&d_nodes, 1));
             s->d_nodes = d_nodes;
@@ -732,9 +900,22 @@ int device_build(const std::vector<Geom>& geoms, crt_scene* s) {
     s->desc.prim_ids = (const U2*)d_prim_ids;
     s->desc.normals = nullptr;
     s->desc.motion = nullptr;
+    if (!others.motion.empty()) {
+        CKB(cudaMalloc(&s->d_motion, others.motion.size() * sizeof(MotionXform)));
+        CKB(cudaMemcpy(s->d_motion, others.motion.data(), others.motion.size() * sizeof(MotionXform), cudaMemcpyHostToDevice));
+        s->desc.motion = (const MotionXform*)s->d_motion;
+    }
     s->desc.n_nodes = n4;
-    s->desc.has_triangles = n > 0;
-    s->n_nodes = n4, s->n_leaf_quads = n > 0 ? leaf_quads : 0, s->n_prim_ids = N, s->n_normal_floats = 0, s->n_motion = 0;
+    s->desc.has_triangles = n_valid_tris > 0;
+    s->n_nodes = n4, s->n_leaf_quads = n > 0 ? leaf_quads : 0, s->n_prim_ids = N, s->n_normal_floats = 0, s->n_motion = others.motion.size();
+    if (!others.inst_prim.empty()) {  // where the instance records landed (crt_scene_export / import re-point them)
+        std::vector<uint32_t> pos(M);
+        CKB(cudaMemcpy(pos.data(), A.other_pos, (size_t)M * 4, cudaMemcpyDeviceToHost));
+        for (size_t k = 0; k < others.inst_prim.size(); ++k) {
+            s->inst_q.push_back(pos[others.inst_prim[k]]);
+            s->inst_child.push_back((uint32_t)(std::find(s->children.begin(), s->children.end(), others.inst_child[k]) - s->children.begin()));
+        }
+    }
     CKB(cudaMalloc((void**)&s->d_desc, sizeof(DevScene)));
     CKB(cudaMemcpy(s->d_desc, &s->desc, sizeof(DevScene), cudaMemcpyHostToDevice));
     auto t1 = std::chrono::steady_clock::now();
@@ -749,7 +930,7 @@ int device_build(const std::vector<Geom>& geoms, crt_scene* s) {
     s->info.build_seconds = std::chrono::duration<double>(t1 - t_up).count();
     s->footprint.bvh_nodes = s->info.node_bytes;
     s->footprint.leaf_records = s->info.leaf_bytes;
-    s->footprint.prim_table = (uint64_t)N * 8;
+    s->footprint.prim_table = (uint64_t)N * 8 + others.motion.size() * sizeof(MotionXform);
     s->footprint.descriptors = sizeof(DevScene);
     return CRT_OK;
 }

@@ -559,6 +559,73 @@ struct Builder {
     }
 };
 
+// The leaf record of a non-triangle primitive (crt_layout.h), appended to t.leafs; instances also append their motion pair
+// and note where their record sits (child pointers are patched in at upload). `last`: REC_LAST or 0.
+void emit_other_record(const PrimStore& ps, uint32_t pi, uint32_t last, HostTree& t) {
+    auto fbits = [](float f) {
+        uint32_t u;
+        std::memcpy(&u, &f, 4);
+        return u;
+    };
+    auto q = [&](uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+        t.leafs.push_back(a);
+        t.leafs.push_back(b);
+        t.leafs.push_back(c);
+        t.leafs.push_back(d);
+    };
+    auto qf = [&](float a, float b, float c, uint32_t d) { q(fbits(a), fbits(b), fbits(c), d); };
+    switch (ps.kind[pi]) {
+        case P_SPHERE: {
+            const float* s = &ps.sphere[4 * (size_t)ps.data[pi]];
+            qf(s[0], s[1], s[2], REC_SPHERE | last);
+            q(fbits(s[3]), pi, ps.mask[pi], ps.geom_id[pi]);
+            break;
+        }
+        case P_CURVE: {
+            const float* c = &ps.curve[8 * (size_t)ps.data[pi]];
+            qf(c[0], c[1], c[2], REC_CURVE | last);
+            qf(c[3], c[4], c[5], pi);
+            q(fbits(c[6]), fbits(c[7]), ps.mask[pi], 0);
+            break;
+        }
+        case P_CUBIC: {
+            const float* c = &ps.cubic[14 * (size_t)ps.data[pi]];
+            qf(c[0], c[1], c[2], REC_CUBIC | last);
+            qf(c[3], c[4], c[5], pi);
+            qf(c[6], c[7], c[8], ps.mask[pi]);
+            qf(c[9], c[10], c[11], 0);
+            q(fbits(c[12]), fbits(c[13]), 0, 0);
+            q(0, 0, 0, 0);
+            break;
+        }
+        default: {
+            const InstancePrim& I = ps.inst[ps.data[pi]];
+            uint32_t flags = REC_INSTANCE | last;
+            uint32_t motion = 0;
+            if (I.has_end) {
+                flags |= REC_MOTION;
+                motion = (uint32_t)t.motion.size();
+                MotionXform m;
+                const Vec3* a = &I.l2w.x;
+                const Vec3* b = &I.l2w_end.x;
+                for (int k = 0; k < 4; ++k) {
+                    m.l2w[3 * k] = a[k].x, m.l2w[3 * k + 1] = a[k].y, m.l2w[3 * k + 2] = a[k].z;
+                    m.l2w_end[3 * k] = b[k].x, m.l2w_end[3 * k + 1] = b[k].y, m.l2w_end[3 * k + 2] = b[k].z;
+                }
+                t.motion.push_back(m);
+            }
+            t.instance_record_q.push_back((uint32_t)(t.leafs.size() / 4));
+            qf(I.w2l.x.x, I.w2l.x.y, I.w2l.x.z, flags);
+            qf(I.w2l.y.x, I.w2l.y.y, I.w2l.y.z, pi);
+            qf(I.w2l.z.x, I.w2l.z.y, I.w2l.z.z, ps.mask[pi]);
+            qf(I.w2l.t.x, I.w2l.t.y, I.w2l.t.z, motion);
+            q(0, 0, ps.geom_id[pi], ps.data[pi]);  // words 0-1: child descriptor pointer, patched at upload
+            q(0, 0, 0, 0);                         // child node / leaf-record arrays, patched at upload
+            break;
+        }
+    }
+}
+
 // ---- collapse to BVH4 + record emission --------------------------------------
 struct Flattener {
     const PrimStore& ps;
@@ -610,56 +677,7 @@ struct Flattener {
             uint32_t pi = range[i];
             if (ps.kind[pi] == P_TRI) continue;
             const uint32_t last = (++oi == n_other) ? (uint32_t)REC_LAST : 0u;
-            switch (ps.kind[pi]) {
-                case P_SPHERE: {
-                    const float* s = &ps.sphere[4 * (size_t)ps.data[pi]];
-                    qf(s[0], s[1], s[2], REC_SPHERE | last);
-                    q(fbits(s[3]), pi, ps.mask[pi], ps.geom_id[pi]);
-                    break;
-                }
-                case P_CURVE: {
-                    const float* c = &ps.curve[8 * (size_t)ps.data[pi]];
-                    qf(c[0], c[1], c[2], REC_CURVE | last);
-                    qf(c[3], c[4], c[5], pi);
-                    q(fbits(c[6]), fbits(c[7]), ps.mask[pi], 0);
-                    break;
-                }
-                case P_CUBIC: {
-                    const float* c = &ps.cubic[14 * (size_t)ps.data[pi]];
-                    qf(c[0], c[1], c[2], REC_CUBIC | last);
-                    qf(c[3], c[4], c[5], pi);
-                    qf(c[6], c[7], c[8], ps.mask[pi]);
-                    qf(c[9], c[10], c[11], 0);
-                    q(fbits(c[12]), fbits(c[13]), 0, 0);
-                    q(0, 0, 0, 0);
-                    break;
-                }
-                default: {
-                    const InstancePrim& I = ps.inst[ps.data[pi]];
-                    uint32_t flags = REC_INSTANCE | last;
-                    uint32_t motion = 0;
-                    if (I.has_end) {
-                        flags |= REC_MOTION;
-                        motion = (uint32_t)t.motion.size();
-                        MotionXform m;
-                        const Vec3* a = &I.l2w.x;
-                        const Vec3* b = &I.l2w_end.x;
-                        for (int k = 0; k < 4; ++k) {
-                            m.l2w[3 * k] = a[k].x, m.l2w[3 * k + 1] = a[k].y, m.l2w[3 * k + 2] = a[k].z;
-                            m.l2w_end[3 * k] = b[k].x, m.l2w_end[3 * k + 1] = b[k].y, m.l2w_end[3 * k + 2] = b[k].z;
-                        }
-                        t.motion.push_back(m);
-                    }
-                    t.instance_record_q.push_back((uint32_t)(t.leafs.size() / 4));
-                    qf(I.w2l.x.x, I.w2l.x.y, I.w2l.x.z, flags);
-                    qf(I.w2l.y.x, I.w2l.y.y, I.w2l.y.z, pi);
-                    qf(I.w2l.z.x, I.w2l.z.y, I.w2l.z.z, ps.mask[pi]);
-                    qf(I.w2l.t.x, I.w2l.t.y, I.w2l.t.z, motion);
-                    q(0, 0, ps.geom_id[pi], ps.data[pi]);  // words 0-1: child descriptor pointer, patched at upload
-                    q(0, 0, 0, 0);                         // child node / leaf-record arrays, patched at upload
-                    break;
-                }
-            }
+            emit_other_record(ps, pi, last, t);
         }
         t.n_leaves += 1;
         t.n_leaf_refs += n;
@@ -734,26 +752,31 @@ inline Vec3 v3at(const std::vector<float>& a, size_t i) { return V(a[3 * i], a[3
 
 }  // namespace
 
-bool build_host_tree(std::vector<Geom>& geoms, ChildInfoFn child_info, int threads, HostTree& out, const char** err) {
-    auto t0 = std::chrono::steady_clock::now();
+namespace {
+// Runs fn(k) for k in [0, count) on up to `threads` workers (static interleave). Every k writes its own slice of the
+// output arrays, so the result does not depend on the thread count.
+template <class F>
+void parallel_for_n(int threads, size_t count, F&& fn) {
+    const int nt = (int)std::min<size_t>((size_t)threads, count);
+    if (nt <= 1) {
+        for (size_t k = 0; k < count; ++k) fn(k);
+        return;
+    }
+    std::vector<std::thread> pool;
+    for (int w = 1; w < nt; ++w)
+        pool.emplace_back([&, w] {
+            for (size_t k = (size_t)w; k < count; k += (size_t)nt) fn(k);
+        });
+    for (size_t k = 0; k < count; k += (size_t)nt) fn(k);
+    for (auto& th : pool) th.join();
+}
+
+// scene.rs:240-335: geometries -> primitives, ids, normals. `skip_meshes`: triangle meshes contribute nothing and keep their
+// inputs (the device build expands them itself and only needs the other kinds from here); ids are unaffected.
+bool expand_geoms(std::vector<Geom>& geoms, ChildInfoFn child_info, int threads, HostTree& out, const char** err, bool skip_meshes,
+                  std::chrono::steady_clock::time_point t0) {
     PrimStore& ps = out.prims;
-    if (threads <= 0) threads = (int)std::max(1u, std::thread::hardware_concurrency());
-    // Runs fn(k) for k in [0, count) on up to `threads` workers (static interleave). Every k writes its own slice of the
-    // output arrays, so the result does not depend on the thread count.
-    auto parallel_for = [&](size_t count, auto&& fn) {
-        const int nt = (int)std::min<size_t>((size_t)threads, count);
-        if (nt <= 1) {
-            for (size_t k = 0; k < count; ++k) fn(k);
-            return;
-        }
-        std::vector<std::thread> pool;
-        for (int w = 1; w < nt; ++w)
-            pool.emplace_back([&, w] {
-                for (size_t k = (size_t)w; k < count; k += (size_t)nt) fn(k);
-            });
-        for (size_t k = 0; k < count; k += (size_t)nt) fn(k);
-        for (auto& th : pool) th.join();
-    };
+    auto parallel_for = [&](size_t count, auto&& fn) { parallel_for_n(threads, count, fn); };
 
     // scene.rs:240-335, in two passes so that meshes expand in parallel: (1) how many primitives / per-kind records each
     // geometry contributes (a triangle with an out-of-range index is skipped but still consumes its prim_id, :251-253),
@@ -781,6 +804,7 @@ bool build_host_tree(std::vector<Geom>& geoms, ChildInfoFn child_info, int threa
         Slice& c = cnt[gi];
         switch (g.type) {
             case G_MESH: {
+                if (skip_meshes) break;
                 const size_t nv = g.verts.size() / 3, nn = g.normals.size() / 3, nt = g.indices.size() / 3;
                 for (size_t k = 0; k < nt; ++k) {
                     const size_t i0 = g.indices[3 * k], i1 = g.indices[3 * k + 1], i2 = g.indices[3 * k + 2];
@@ -818,6 +842,7 @@ bool build_host_tree(std::vector<Geom>& geoms, ChildInfoFn child_info, int threa
         };
         switch (g.type) {
             case G_MESH: {
+                if (skip_meshes) break;
                 const size_t nv = g.verts.size() / 3, nn = g.normals.size() / 3, nt = g.indices.size() / 3;
                 size_t slot = o.tris, nslot = o.tri_normals;
                 for (size_t k = 0; k < nt; ++k) {
@@ -871,6 +896,7 @@ bool build_host_tree(std::vector<Geom>& geoms, ChildInfoFn child_info, int threa
             }
         }
         // geometry inputs are dead once expanded
+        if (skip_meshes && g.type == G_MESH) return;
         std::vector<float>().swap(g.verts);
         std::vector<uint32_t>().swap(g.indices);
         std::vector<float>().swap(g.normals);
@@ -903,6 +929,23 @@ bool build_host_tree(std::vector<Geom>& geoms, ChildInfoFn child_info, int threa
             if (ps.kind[i] == P_TRI && ps.tri_normal_slot[ps.data[i]] != 0xFFFFFFFFu)
                 std::memcpy(&out.normals[9 * i], &ps.tri_normals[9 * (size_t)ps.tri_normal_slot[ps.data[i]]], 36);
     }
+    return true;
+}
+}  // namespace
+
+bool build_host_tree(std::vector<Geom>& geoms, ChildInfoFn child_info, int threads, HostTree& out, const char** err) {
+    auto t0 = std::chrono::steady_clock::now();
+    if (threads <= 0) threads = (int)std::max(1u, std::thread::hardware_concurrency());
+    if (!expand_geoms(geoms, child_info, threads, out, err, false, t0)) return false;
+    PrimStore& ps = out.prims;
+    auto parallel_for = [&](size_t count, auto&& fn) { parallel_for_n(threads, count, fn); };
+    const bool timing = getenv("CRT_BUILD_TIMING") != nullptr;
+    auto lap = [&](const char* what) {
+        if (timing) fprintf(stderr, "[host build] %-28s %.3f s\n", what, std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
+    };
+    const size_t n = ps.size();
+    const size_t kChunk = (size_t)1 << 16;
+    const size_t n_chunks = (n + kChunk - 1) / kChunk;
     if (n == 0) {  // bvh.rs:310-311
         out.non_empty = false;
         for (int i = 0; i < 4; ++i) {
@@ -942,6 +985,48 @@ bool build_host_tree(std::vector<Geom>& geoms, ChildInfoFn child_info, int threa
     fl.run();
     lap("BVH4 collapse + leaf records");
     out.build_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    return true;
+}
+
+// ---- the non-mesh primitives of a scene, for the device build ---------------------------------------------------------
+bool expand_other_prims(std::vector<Geom>& geoms, ChildInfoFn child_info, uint32_t prim_index_base, OtherPrims& out, const char** err) {
+    HostTree t;
+    if (!expand_geoms(geoms, child_info, 1, t, err, true, std::chrono::steady_clock::now())) return false;
+    const PrimStore& ps = t.prims;
+    const size_t n = ps.size();
+    out.n = n;
+    out.lo.resize(4 * n), out.hi.resize(4 * n), out.ids.resize(2 * n), out.rec_off.resize(n + 1);
+    out.has_motion = t.has_motion;
+    out.instance_depth = t.instance_depth;
+    for (size_t i = 0; i < n; ++i) {
+        const Box b = prim_box(ps, (uint32_t)i);
+        out.lo[4 * i] = b.lo.x, out.lo[4 * i + 1] = b.lo.y, out.lo[4 * i + 2] = b.lo.z, out.lo[4 * i + 3] = 1.0f;  // .w = valid
+        out.hi[4 * i] = b.hi.x, out.hi[4 * i + 1] = b.hi.y, out.hi[4 * i + 2] = b.hi.z, out.hi[4 * i + 3] = 0.0f;
+        out.ids[2 * i] = ps.geom_id[i], out.ids[2 * i + 1] = ps.prim_id[i];
+        Vec3 ext = sub(b.hi, b.lo);
+        const float diag = std::sqrt(dot3(ext, ext));
+        out.extent_sum += diag;
+        out.extent_max = std::max(out.extent_max, diag);
+        const uint32_t at = (uint32_t)(t.leafs.size() / 4);
+        out.rec_off[i] = at;
+        emit_other_record(ps, (uint32_t)i, 0, t);
+        // the record names its primitive by index into the scene's id table: the triangles come first there
+        const size_t word = ps.kind[i] == P_SPHERE ? 4 * (size_t)(at + 1) + 1 : 4 * (size_t)(at + 1) + 3;
+        t.leafs[word] += prim_index_base;
+        switch (ps.kind[i]) {
+            case P_SPHERE: out.counts.spheres++; break;
+            case P_CURVE: out.counts.curve_segments++; break;
+            case P_CUBIC: out.counts.cubic_curve_spans++; break;
+            default:
+                out.counts.instances++;
+                out.inst_prim.push_back((uint32_t)i);
+                out.inst_child.push_back(ps.inst[ps.data[i]].child);
+                break;
+        }
+    }
+    out.rec_off[n] = (uint32_t)(t.leafs.size() / 4);
+    out.recs.swap(t.leafs);
+    out.motion.swap(t.motion);
     return true;
 }
 

@@ -110,6 +110,27 @@ typedef ChildInfo (*ChildInfoFn)(crt_scene*);
 // set when the scene cannot be represented (nesting too deep).
 bool build_host_tree(std::vector<Geom>& geoms, ChildInfoFn child_info, int threads, HostTree& out, const char** err);
 
+// The non-mesh primitives of a scene (spheres, curve segments, cubic spans, instances) expanded exactly like
+// build_host_tree expands them — same ids, same silent skips, same bounds — each with its padded box and its leaf record
+// (crt_layout.h, without REC_LAST; instance records still without child addresses), in input order. For the device build,
+// which expands the triangle meshes itself: `prim_index_base` = number of triangle slots that precede these primitives in
+// the scene's id table. Mesh inputs of `geoms` are left intact; the others are consumed.
+struct OtherPrims {
+    size_t n = 0;
+    std::vector<float> lo, hi;         // 4 floats per primitive (lo.w = 1: valid)
+    std::vector<uint32_t> ids;         // geom_id, prim_id per primitive
+    std::vector<uint32_t> rec_off;     // n + 1 offsets into `recs`, in 16-byte units
+    std::vector<uint32_t> recs;        // 4 words per 16-byte unit
+    std::vector<uint32_t> inst_prim;   // which of the primitives are instances ...
+    std::vector<crt_scene*> inst_child;  // ... and of which scene
+    std::vector<MotionXform> motion;
+    crt_primitive_breakdown counts{};
+    bool has_motion = false;
+    uint32_t instance_depth = 0;
+    float extent_sum = 0, extent_max = 0;
+};
+bool expand_other_prims(std::vector<Geom>& geoms, ChildInfoFn child_info, uint32_t prim_index_base, OtherPrims& out, const char** err);
+
 // Canonical export for builder-equivalence tests (see crt.h crt_debug_*).
 void export_sizes(const HostTree& t, uint64_t out4[4]);
 void export_tree(const HostTree& t, void* nodes, uint32_t* tri_counts, uint32_t* other_counts, uint32_t* refs);

@@ -89,6 +89,6 @@ void scene_device_memory_released(bool had_window);
 
 // device_build.cu
 bool device_build_supported(const std::vector<Geom>& geoms);
-int device_build(const std::vector<Geom>& geoms, crt_scene* s);
+int device_build(std::vector<Geom>& geoms, ChildInfoFn child_info, crt_scene* s);
 
 }  // namespace crt

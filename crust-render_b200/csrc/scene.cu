@@ -408,7 +408,7 @@ int crt_commit_ex(crt_builder* b, uint32_t flags, int host_threads, crt_scene** 
             return fail(CRT_ERR_INVALID_ARG, "commit: instanced scene was committed in a different mode (host-only vs device)");
         }
     if ((flags & CRT_COMMIT_DEVICE_BUILD) && !host_only && !(flags & CRT_COMMIT_KEEP_HOST_TREE) && device_build_supported(b->geoms)) {
-        int rc = device_build(b->geoms, s);
+        int rc = device_build(b->geoms, child_info_of, s);
         crt_builder_free(b);
         if (rc) {
             crt_scene_release(s);

@@ -91,7 +91,7 @@ def test_tiny_and_empty_scenes(gpu, orc, n_tris):
     assert np.array_equal(sg.occluded_n(rays), so.occluded_n(rays, threads=0))
 
 
-def test_deterministic_and_falls_back_for_other_primitives(gpu):
+def test_deterministic_and_falls_back_for_vertex_normals(gpu):
     meshes = W.stress_meshes(grid=2, shards=2000, jitter=False)
     rays = W.ray_batch(1 << 16, 30.0)
     outs = []
@@ -103,11 +103,102 @@ def test_deterministic_and_falls_back_for_other_primitives(gpu):
         bi = s.build_info()
         outs.append((s.intersect_n(rays)[0].tobytes(), bi.wide_nodes, bi.leaves))
     assert outs[0] == outs[1]
+    # the one thing left to the host build: meshes with per-vertex shading normals
     b = gpu.SceneBuilder()
-    b.attach(Geometry.TriangleMesh(*meshes[0]))
+    v, i = meshes[0]
+    b.attach(Geometry.TriangleMesh(v, i, normals=np.tile(np.array([[0, 1, 0]], np.float32), (len(v), 1))))
     b.attach(Geometry.Sphere((0, 0, 0), 1.0))
     s = b.commit(flags=gpu.COMMIT_DEVICE_BUILD)
     assert s.build_info().built_on_device == 0 and s.primitive_breakdown().spheres == 1
+
+
+def _mixed_scene(api, flags=0):
+    """Every primitive kind in one scene: two meshes, spheres, round curves, cubic spans, instances of a mesh BLAS (one of them
+    moving), instances of a scene that itself instances (nesting 2), all with masks."""
+    from crust_render_b200.rt_types import Affine3A, CubicCurveSegment, CurveSegment
+    kw = {"flags": flags} if flags else {}
+    blas = api.SceneBuilder()
+    blas.attach(Geometry.TriangleMesh(*W.uv_sphere((0, 0, 0), 0.5, 16, 8)))
+    blas.attach(Geometry.Sphere((0.0, 0.8, 0.0), 0.25))
+    blas = blas.commit(**kw)
+    mid = api.SceneBuilder()
+    mid.attach(Geometry.Instance(blas, Affine3A.from_translation((-0.7, 0, 0))))
+    mid.attach(Geometry.Instance(blas, Affine3A.from_translation((0.7, 0, 0))))
+    mid = mid.commit(**kw)
+    b = api.SceneBuilder()
+    b.attach(Geometry.TriangleMesh(*W.uv_sphere((-3, 0, 0), 1.0, 24, 12)))
+    b.attach_masked(Geometry.TriangleMesh(*W.uv_sphere((3, 0, 0), 1.0, 24, 12)), 0x5)
+    rng = np.random.default_rng(3)
+    for c in rng.uniform(-4, 4, (40, 3)):
+        b.attach(Geometry.Sphere(c.astype(np.float32), 0.3))
+    b.attach(Geometry.RoundCurves([CurveSegment((-4, -3, k * 0.5), (4, -3, k * 0.5 + 0.2), 0.08, 0.03) for k in range(-6, 7)]))
+    b.attach(Geometry.CubicCurves([CubicCurveSegment(((-4, 3, k), (-1, 4.5, k), (1, 1.5, k), (4, 3, k)), 0.1, 0.05) for k in (-2.0, 0.0, 2.0)]))
+    for k in range(12):
+        t = (float(rng.uniform(-4, 4)), float(rng.uniform(-4, 4)), float(rng.uniform(-4, 4)))
+        end = Affine3A.from_translation((t[0], t[1] + 0.8, t[2])) if k == 3 else None
+        b.attach_masked(Geometry.Instance(blas, Affine3A.from_translation(t), end), 0xFFFFFFFF if k % 4 else 0x3)
+    for k in range(4):
+        b.attach(Geometry.Instance(mid, Affine3A.from_translation((0.0, 0.0, -4.5 + 3.0 * k)) * Affine3A.from_scale((1.0, 1.0 + 0.25 * k, 1.0))))
+    return b.commit(**kw)
+
+
+def test_every_primitive_kind_builds_on_the_device(gpu, orc):
+    """Spheres, curve segments, cubic spans and (nested, moving, masked) instances go through the device build too: their
+    boxes and leaf records are prepared on the host exactly as the host build prepares them and are sorted and grouped on
+    the device together with the triangles. Closest hits are the oracle's except exact-t ties, occlusion is equal."""
+    sg = _mixed_scene(gpu, gpu.COMMIT_DEVICE_BUILD)
+    so = _mixed_scene(orc)
+    bi = sg.build_info()
+    pb, po = sg.primitive_breakdown(), so.primitive_breakdown()
+    assert bi.built_on_device == 1
+    assert (pb.triangles, pb.spheres, pb.curve_segments, pb.cubic_curve_spans, pb.instances) == (po.triangles, po.spheres, po.curve_segments, po.cubic_curve_spans, po.instances)
+    assert sg.has_motion() and sg.geometry_count() == so.geometry_count() and sg.primitive_count() == so.primitive_count()
+    assert np.allclose(sg.bounds().minimum, so.bounds().minimum) and np.allclose(sg.bounds().maximum, so.bounds().maximum)
+    eg, eh = sg.primitive_extents(), _mixed_scene(gpu).primitive_extents()  # scene.rs:446-455: count, scene / mean / max diagonal
+    assert eg[0] == eh[0] and abs(eg[1] - eh[1]) <= 1e-5 * eh[1] and abs(eg[2] - eh[2]) <= 1e-4 * eh[2] and abs(eg[3] - eh[3]) <= 1e-5 * eh[3]
+    rays = W.ray_batch(1 << 17, 9.0, seed=21)
+    time = np.random.default_rng(2).random(len(rays)).astype(np.float32)
+    mask = np.where(np.arange(len(rays)) % 3 == 0, 0x1, 0xFFFFFFFF).astype(np.uint32)
+    hg, fg = sg.intersect_n(rays, time, mask)
+    ho, fo = so.intersect_n(rays, time, mask, threads=0)
+    same, tie = agree(hg, ho)
+    assert (same | tie).all() and same.mean() >= 0.9995 and (hg["geom_id"] != 0xFFFFFFFF).mean() > 0.3
+    assert np.array_equal(fg[same], fo[same])
+    assert np.abs(hg["normal"][same] - ho["normal"][same]).max() <= 1e-5
+    assert np.array_equal(sg.occluded_n(rays, time, mask), so.occluded_n(rays, time, mask, threads=0))
+    # a device-built instancing scene exports / imports like a host-built one
+    import torch
+    n = sg.export_size()
+    blob = torch.empty(n, dtype=torch.uint8, device="cuda")
+    sg.export_to(blob.data_ptr(), n, True, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    clone = gpu.Scene.import_from(blob.data_ptr(), n, True, sg._children)
+    hc, _ = clone.intersect_n(rays, time, mask)
+    assert hc.tobytes() == hg.tobytes()
+    assert gpu.device_status() == 0
+
+
+def test_forty_thousand_instance_tlas_builds_on_the_device(gpu, orc):
+    """BASELINE config 4: the TLAS over PointInstancedMedCity's 40 000 instances (and its prototype BLASes) built on the device."""
+    from crust_render_b200 import scenes
+    import crust_render_b200.rt as rt_mod
+    prev = rt_mod._commit_override
+    rt_mod._commit_override = lambda b, flags, threads: b.commit_local(flags | gpu.COMMIT_DEVICE_BUILD, threads)
+    try:
+        wd, cam, st = scenes.medcity(gpu, width=96, height=54, spp=8, variance_threshold=0.0)
+    finally:
+        rt_mod._commit_override = prev
+    wh = scenes.medcity(gpu, width=96, height=54, spp=8, variance_threshold=0.0)[0]
+    assert wd.scene.build_info().built_on_device == 1 and wd.scene.primitive_breakdown().instances == 40000
+    rays = W.ray_batch(1 << 16, W.scene_extent(wh.scene.bounds()), seed=8)
+    hd, _ = wd.scene.intersect_n(rays)
+    hh, _ = wh.scene.intersect_n(rays)
+    same, tie = agree(hd, hh)
+    assert (same | tie).all() and same.mean() >= 0.99  # the city repeats buildings at identical places: exact-t ties between instances
+    a, sa = gpu.Renderer(cam, wh, st).render_with_stats()
+    b, sb_ = gpu.Renderer(cam, wd, st).render_with_stats()
+    rel = np.abs(a[..., :3] - b[..., :3]) / (np.abs(a[..., :3]) + 1e-3)
+    assert (rel.max(axis=-1) > 1e-3).mean() < 0.01 and sa.camera_rays == sb_.camera_rays
 
 
 def test_render_on_a_device_built_scene(gpu, orc):
