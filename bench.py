@@ -218,6 +218,59 @@ def copy_ceiling(torch, dist, world, dev, h2d_bytes, d2h_bytes, mb=256):
             "method": f"one step's bytes per rank as plain pinned copies in {mb} MB chunks, H2D and D2H on two streams, all {world} rank(s) at once, wall clock, max over ranks, best of 3"}
 
 
+def time_other_scenes(crt, W, torch, stream, grid, with_cpu):
+    """SURVEY 8(d)'s other kernel inputs, timed resident like the main step (best of 3, CUDA events): K2 — the stress scene
+    with identical spheres, i.e. one 9 800-triangle BLAS x grid^2 instances over the flat shards/floor/slab (two-level
+    traversal); K3 — the reference's three throughput-probe scenes (ray_throughput.rs:50-100) with its LCG box rays
+    (:103-116). Beside each: the CPU restatement on one thread (the reference's own figure is per core) and on all, on a
+    2^18-ray sample, with hit agreement on that sample."""
+    import orc
+
+    def gpu_rate(scene, rays, closest):
+        n = len(rays)
+        d_r = torch.from_numpy(rays.view(np.float32).reshape(-1, 8).copy()).cuda()
+        d_o = torch.empty((n, 8), dtype=torch.float32, device="cuda") if closest else torch.empty(n, dtype=torch.uint8, device="cuda")
+        best = None
+        for k in range(4):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            if closest:
+                scene.intersect_ptr(n, d_r.data_ptr(), 0, 0, d_o.data_ptr(), 0, stream.cuda_stream)
+            else:
+                scene.occluded_ptr(n, d_r.data_ptr(), 0, 0, d_o.data_ptr(), stream.cuda_stream)
+            e1.record(stream)
+            torch.cuda.synchronize()
+            if k:
+                best = e0.elapsed_time(e1) if best is None else min(best, e0.elapsed_time(e1))
+        return n / best / 1e3, d_o.cpu().numpy()
+
+    out = {}
+    cases = [("K2 instanced stress", lambda api: W.stress_scene_instanced(api, grid=grid).commit(), 24),
+             ("K3 tri_spheres", lambda api: W.triangle_scene(api).commit(), 22),
+             ("K3 sphere_grid", lambda api: W.sphere_grid_scene(api).commit(), 22),
+             ("K3 instance_scene", lambda api: W.instance_scene(api).commit(), 22)]
+    for name, make, log2 in cases:
+        scene = make(crt)
+        rays = W.ray_batch(1 << log2, W.scene_extent(scene.bounds()))
+        pb = scene.primitive_breakdown()
+        rec = {"rays": len(rays), "top_level_primitives": scene.primitive_count(), "instances": pb.instances}
+        rec["closest_lcg_mrays"], hits = gpu_rate(scene, rays, True)
+        rec["occluded_lcg_mrays"], occ = gpu_rate(scene, rays, False)
+        if with_cpu:
+            o = make(orc)
+            sub = slice(0, None, len(rays) >> 18)
+            oh, _ = o.intersect_n(rays[sub], threads=0)
+            rec["cpu_all_threads_mrays"] = len(oh) / o.last_seconds / 1e6
+            o.intersect_n(rays[sub][: 1 << 16], threads=1)
+            rec["cpu_one_thread_mrays"] = (1 << 16) / o.last_seconds / 1e6
+            g = hits.view(np.uint32).reshape(-1, 8)[sub]
+            rec["oracle_agreement_on_sample"] = float(((g[:, 3] == oh["geom_id"]) & (g[:, 4] == oh["prim_id"]) & (g[:, 0].view(np.float32) == oh["t"])).mean())
+            rec["occlusion_agreement_on_sample"] = float((occ[sub] == o.occluded_n(rays[sub], threads=0)).mean())
+        out[name] = rec
+        del scene
+    return out
+
+
 # ---------------------------------------------------------------------------
 # workload
 # ---------------------------------------------------------------------------

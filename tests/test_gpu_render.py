@@ -142,6 +142,15 @@ def test_config3_openpbr_showcase_at_baseline_size(gpu, orc):
     stats_close(sg, so, tol=2e-3, adaptive=True)
 
 
+def test_config4_medcity_at_baseline_size(gpu, orc):
+    """640x360, up to 128 spp adaptive, depth 32, 40 000 instances: the full config (importer defaults), every pixel."""
+    fg, sg, fo, so, _ = both(gpu, orc, scenes.medcity, width=640, height=360, spp=128)
+    same = fg[..., 3] == fo[..., 3]
+    assert same.mean() >= 0.999
+    compare(fg[same], fo[same])
+    stats_close(sg, so, tol=2e-3, adaptive=True)
+
+
 def test_dome_light_with_environment_map_and_distant_light(gpu, orc):
     """samples/domelight.usda: an importance-sampled lat-long HDRI dome (rotated) plus a 1.5-degree
     distant light; both are found by NEE and by escaping bounce rays with matching MIS densities."""
@@ -216,7 +225,8 @@ def test_any_number_of_volume_regions(gpu, orc):
     ref, so = orc.Renderer(cam, wo, st).render_with_stats()
     compare(many, ref)
     stats_close(sm, so)
-    assert abs(float(many[..., :3].mean()) - math.exp(-0.7)) < 2e-3 and abs(float(one[..., :3].mean()) - math.exp(-0.7)) < 2e-3
+    # the tracker's transmittance estimate is stochastic (weights of 0 or 1 per walk): 16 Ki walks => sigma 0.004
+    assert abs(float(many[..., :3].mean()) - math.exp(-0.7)) < 0.016 and abs(float(one[..., :3].mean()) - math.exp(-0.7)) < 0.016
     assert gpu.device_status() == 0
     wg.with_volumes(scenes.volume_slab(orc, "furnace", spp=4)[0].volumes * 17)  # 17 coincident regions: every ray crosses them all
     gpu.Renderer(cam, wg, st).render_with_stats()
