@@ -69,6 +69,13 @@ struct TraceParams {
 #define CRT_SIGNSEL 1  // slab test with the near / far planes picked by the ray's direction signs (by address) instead of min / max
 #endif
 
+#ifndef CRT_KEY_ORDER
+#define CRT_KEY_ORDER 1  // closest-hit push order from one unsigned key per lane (entry-distance bits | internal-lane bit) for rays with t_min >= 0
+#endif
+#ifndef CRT_KEY_ADDR
+#define CRT_KEY_ADDR 1  // ...and, while the group stays in the shared window, the slots as shared byte addresses from six compares (no masks, no popcounts)
+#endif
+
 #ifndef CRT_LEAF_PREFETCH
 #define CRT_LEAF_PREFETCH 0  // L1 prefetch of a popped leaf's first record(s) while the lane waits for the leaf phase (1: first 128-byte line, 2: two)
 #endif
