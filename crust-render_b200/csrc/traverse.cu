@@ -222,8 +222,7 @@ __global__ void __launch_bounds__(CRT_BLOCK, MinBlocks<ANY_HIT, FEAT, MAXD>::val
                     prim = __float_as_uint(q1.w);
                     lr.set(o, d, true);
                     F3 v0 = xyz(q0), v1 = xyz(q1), v2 = xyz(q2);
-                    TriEval e = tri_eval(lr, v0, v1, v2);
-                    if (e.on_edge) e = tri_eval_f64(lr, v0, v1, v2);
+                    TriEval e = tri_eval_exact(lr, v0, v1, v2);
                     float inv_det = 1.0f / e.det;
                     t = e.t_scaled * inv_det;
                     u = e.e1 * inv_det;
@@ -340,9 +339,12 @@ __global__ void __launch_bounds__(CRT_BLOCK, MinBlocks<ANY_HIT, FEAT, MAXD>::val
             // far-to-near on top of them (bvh.rs:491-505). Branch-free: with g(m,l) = [tn[m] > tn[l]] "before"
             // masks are assembled from the six pair bits, and each lane's slot is its rank
             // among the hit lanes of its own class.
-            uint32_t H = 0;
+            auto hit_mask = [&]() {  // built only on the paths that rank with masks: the hot path below never needs it
+                uint32_t m = 0;
 #pragma unroll
-            for (int l = 0; l < 4; ++l) H |= hit[l] ? (1u << l) : 0u;
+                for (int l = 0; l < 4; ++l) m |= hit[l] ? (1u << l) : 0u;
+                return m;
+            };
             const int base = sp;
 #if CRT_KEY_ORDER
             if (tmin_nonneg) {
@@ -386,6 +388,7 @@ __global__ void __launch_bounds__(CRT_BLOCK, MinBlocks<ANY_HIT, FEAT, MAXD>::val
                 B[1] = (g01 ^ 1u) | (g12 << 2) | (g13 << 3);
                 B[2] = (g02 ^ 1u) | ((g12 ^ 1u) << 1) | (g23 << 3);
                 B[3] = (g03 ^ 1u) | ((g13 ^ 1u) << 1) | ((g23 ^ 1u) << 2);
+                const uint32_t H = hit_mask();
                 const int n_hit = __popc(H);
                 if (base + 4 <= CRT_SSTACK) {  // hot path: every slot is in shared memory
 #pragma unroll
@@ -414,6 +417,7 @@ __global__ void __launch_bounds__(CRT_BLOCK, MinBlocks<ANY_HIT, FEAT, MAXD>::val
             }
 #endif
             // Rays with a negative t_min (entry distances may be negative): ranks per class from float compares.
+            const uint32_t H = hit_mask();
             uint32_t Lm = 0;
 #pragma unroll
             for (int l = 0; l < 4; ++l) Lm |= (cw[l] & CRT_LEAF_BIT) ? (1u << l) : 0u;

@@ -46,6 +46,16 @@ __device__ __forceinline__ F3 cross(F3 a, F3 b) {
 }
 __device__ __forceinline__ F3 normalize(F3 a) { return a * (1.0f / sqrtf(dot(a, a))); }
 __device__ __forceinline__ float pick(F3 v, int k) { return k == 0 ? v.x : (k == 1 ? v.y : v.z); }
+// a / b / c for k = 0 / 1 / 2, as two selects (never a branch: the callers sit in the divergent leaf phase, where nvcc
+// otherwise turns a run of picks by the same axis number into nine divergent branch regions)
+__device__ __forceinline__ float sel3(int k, float a, float b, float c) {
+    float r;
+    asm("{\n\t.reg .pred p0, p1;\n\t.reg .f32 bc;\n\tsetp.eq.s32 p0, %4, 0;\n\tsetp.eq.s32 p1, %4, 1;\n\t"
+        "selp.f32 bc, %2, %3, p1;\n\tselp.f32 %0, %1, bc, p0;\n\t}"
+        : "=f"(r)
+        : "f"(a), "f"(b), "f"(c), "r"(k));
+    return r;
+}
 __device__ __forceinline__ F3 xyz(float4 q) { return {q.x, q.y, q.z}; }
 
 struct Xf {  // glam Affine3A column order
@@ -99,22 +109,24 @@ __device__ __forceinline__ float safe_inv(float d) {  // bvh.rs:662-668
 // derived slab reciprocals and Woop shear (triangle.rs:41-80).
 struct LevelRay {
     F3 o, d, inv;
+    // Shear constants of triangle.rs:41-80 WITHOUT the reference's swap of kx / ky for a direction that is negative along kz:
+    // sx = d[(kz+1)%3] / d[kz], sy = d[(kz+2)%3] / d[kz]. See tri_eval for why the hot path does not need the swap.
     float sx, sy, sz;
-    int kx, ky, kz;
+    int kz;
 #if CRT_SIGNSEL
     // byte offsets, inside a 128-byte node, of the bounds vector holding each axis' near plane: the low faces (0, 16, 32)
     // for a ray travelling in +axis, the high faces (48, 64, 80) otherwise; the far plane is the other one of the pair
     uint32_t near_x, near_y, near_z;
 #endif
     __device__ __forceinline__ uint32_t pack_axes() const {
-        uint32_t w = ((uint32_t)kx & 3u) | (((uint32_t)ky & 3u) << 2) | (((uint32_t)kz & 3u) << 4);  // the axes are unset (garbage) for a level without triangles
+        uint32_t w = (uint32_t)kz & 3u;  // the axis is unset (garbage) for a level without triangles
 #if CRT_SIGNSEL
         w |= (near_x << 8) | (near_y << 16) | (near_z << 24);
 #endif
         return w;
     }
     __device__ __forceinline__ void unpack_axes(uint32_t w) {
-        kx = (int)(w & 3u), ky = (int)((w >> 2) & 3u), kz = (int)((w >> 4) & 3u);
+        kz = (int)(w & 3u);
 #if CRT_SIGNSEL
         near_x = (w >> 8) & 0xFFu, near_y = (w >> 16) & 0xFFu, near_z = w >> 24;
 #endif
@@ -133,16 +145,9 @@ struct LevelRay {
         if (want_shear) {
             float ax = fabsf(dir.x), ay = fabsf(dir.y), az = fabsf(dir.z);
             kz = ax > ay ? (ax > az ? 0 : 2) : (ay > az ? 1 : 2);
-            kx = kz == 2 ? 0 : kz + 1;
-            ky = kx == 2 ? 0 : kx + 1;
-            float dz = pick(dir, kz);
-            if (dz < 0.0f) {
-                int t = kx;
-                kx = ky;
-                ky = t;
-            }
-            sx = pick(dir, kx) / dz;
-            sy = pick(dir, ky) / dz;
+                        float dz = sel3(kz, dir.x, dir.y, dir.z);
+            sx = sel3(kz, dir.y, dir.z, dir.x) / dz;
+            sy = sel3(kz, dir.z, dir.x, dir.y) / dz;
             sz = __frcp_rn(dz);
         }
     }
@@ -152,13 +157,20 @@ struct TriEval {
     float e0, e1, e2, det, t_scaled;
     bool on_edge;
 };
-// Shared front half of triangle.rs:123-136 / 285-298.
+// Shared front half of triangle.rs:123-136 / 285-298, in the frame (kx, ky, kz) = ((kz+1)%3, (kz+2)%3, kz) — the reference's
+// frame before it swaps kx and ky for d[kz] < 0. With the swap every product pair of an edge function trades places, so
+// e0, e1, e2, det and t_scaled all come out exactly negated (IEEE multiplication commutes, a - b = -(b - a), round-to-nearest
+// is symmetric), and everything traversal decides from them is blind to that common sign: the zero tests, mixed_signs, both
+// range tests and t = t_scaled * (1 / det). Only the sign of a zero u / v / t could differ, and the reported hit is
+// re-evaluated once with the swap in place (tri_eval_exact, finalize). Three selects per vertex component instead of
+// picking by three independent axis numbers.
 __device__ __forceinline__ TriEval tri_eval(const LevelRay& r, F3 v0, F3 v1, F3 v2) {
+    const int z = r.kz;
     F3 a = v0 - r.o, b = v1 - r.o, c = v2 - r.o;
-    float akz = pick(a, r.kz), bkz = pick(b, r.kz), ckz = pick(c, r.kz);
-    float ax = pick(a, r.kx) - r.sx * akz, ay = pick(a, r.ky) - r.sy * akz;
-    float bx = pick(b, r.kx) - r.sx * bkz, by = pick(b, r.ky) - r.sy * bkz;
-    float cx = pick(c, r.kx) - r.sx * ckz, cy = pick(c, r.ky) - r.sy * ckz;
+    float akz = sel3(z, a.x, a.y, a.z), bkz = sel3(z, b.x, b.y, b.z), ckz = sel3(z, c.x, c.y, c.z);
+    float ax = sel3(z, a.y, a.z, a.x) - r.sx * akz, ay = sel3(z, a.z, a.x, a.y) - r.sy * akz;
+    float bx = sel3(z, b.y, b.z, b.x) - r.sx * bkz, by = sel3(z, b.z, b.x, b.y) - r.sy * bkz;
+    float cx = sel3(z, c.y, c.z, c.x) - r.sx * ckz, cy = sel3(z, c.z, c.x, c.y) - r.sy * ckz;
     TriEval o;
     o.e0 = bx * cy - by * cx;
     o.e1 = cx * ay - cy * ax;
@@ -168,18 +180,47 @@ __device__ __forceinline__ TriEval tri_eval(const LevelRay& r, F3 v0, F3 v1, F3 
     o.t_scaled = (o.e0 * (r.sz * akz) + o.e1 * (r.sz * bkz)) + o.e2 * (r.sz * ckz);
     return o;
 }
-// The f64 re-evaluation of triangle.rs:141-145 (scalar path, rare).
+// The f64 re-evaluation of triangle.rs:141-145 (scalar path, rare); same frame as tri_eval.
 __device__ __noinline__ TriEval tri_eval_f64(const LevelRay& r, F3 v0, F3 v1, F3 v2) {
+    const int kx = r.kz == 2 ? 0 : r.kz + 1, ky = kx == 2 ? 0 : kx + 1;
     F3 a = v0 - r.o, b = v1 - r.o, c = v2 - r.o;
     float akz = pick(a, r.kz), bkz = pick(b, r.kz), ckz = pick(c, r.kz);
-    float ax = pick(a, r.kx) - r.sx * akz, ay = pick(a, r.ky) - r.sy * akz;
-    float bx = pick(b, r.kx) - r.sx * bkz, by = pick(b, r.ky) - r.sy * bkz;
-    float cx = pick(c, r.kx) - r.sx * ckz, cy = pick(c, r.ky) - r.sy * ckz;
+    float ax = pick(a, kx) - r.sx * akz, ay = pick(a, ky) - r.sy * akz;
+    float bx = pick(b, kx) - r.sx * bkz, by = pick(b, ky) - r.sy * bkz;
+    float cx = pick(c, kx) - r.sx * ckz, cy = pick(c, ky) - r.sy * ckz;
     TriEval o;
     o.e0 = (float)__dsub_rn(__dmul_rn((double)bx, (double)cy), __dmul_rn((double)by, (double)cx));
     o.e1 = (float)__dsub_rn(__dmul_rn((double)cx, (double)ay), __dmul_rn((double)cy, (double)ax));
     o.e2 = (float)__dsub_rn(__dmul_rn((double)ax, (double)by), __dmul_rn((double)ay, (double)bx));
     o.on_edge = false;
+    o.det = (o.e0 + o.e1) + o.e2;
+    o.t_scaled = (o.e0 * (r.sz * akz) + o.e1 * (r.sz * bkz)) + o.e2 * (r.sz * ckz);
+    return o;
+}
+// The reference's own frame (triangle.rs:47-60: kx and ky swapped when d[kz] < 0), for the one evaluation per ray whose
+// (t, u, v) are reported: bit-for-bit the reference's values, signs of zeros included. Once per ray, not in the hot loop.
+__device__ __noinline__ TriEval tri_eval_exact(const LevelRay& r, F3 v0, F3 v1, F3 v2) {
+    int kx = r.kz == 2 ? 0 : r.kz + 1, ky = kx == 2 ? 0 : kx + 1;
+    float sx = r.sx, sy = r.sy;
+    if (pick(r.d, r.kz) < 0.0f) {
+        int t = kx; kx = ky; ky = t;
+        float ts = sx; sx = sy; sy = ts;
+    }
+    F3 a = v0 - r.o, b = v1 - r.o, c = v2 - r.o;
+    float akz = pick(a, r.kz), bkz = pick(b, r.kz), ckz = pick(c, r.kz);
+    float ax = pick(a, kx) - sx * akz, ay = pick(a, ky) - sy * akz;
+    float bx = pick(b, kx) - sx * bkz, by = pick(b, ky) - sy * bkz;
+    float cx = pick(c, kx) - sx * ckz, cy = pick(c, ky) - sy * ckz;
+    TriEval o;
+    o.e0 = bx * cy - by * cx;
+    o.e1 = cx * ay - cy * ax;
+    o.e2 = ax * by - ay * bx;
+    o.on_edge = (o.e0 == 0.0f) | (o.e1 == 0.0f) | (o.e2 == 0.0f);
+    if (o.on_edge) {
+        o.e0 = (float)__dsub_rn(__dmul_rn((double)bx, (double)cy), __dmul_rn((double)by, (double)cx));
+        o.e1 = (float)__dsub_rn(__dmul_rn((double)cx, (double)ay), __dmul_rn((double)cy, (double)ax));
+        o.e2 = (float)__dsub_rn(__dmul_rn((double)ax, (double)by), __dmul_rn((double)ay, (double)bx));
+    }
     o.det = (o.e0 + o.e1) + o.e2;
     o.t_scaled = (o.e0 * (r.sz * akz) + o.e1 * (r.sz * bkz)) + o.e2 * (r.sz * ckz);
     return o;
