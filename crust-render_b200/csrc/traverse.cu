@@ -326,6 +326,31 @@ __global__ void __launch_bounds__(CRT_BLOCK, MinBlocks<ANY_HIT, FEAT, MAXD>::val
         if constexpr (ANY_HIT) {
             // bvh.rs:598-608 — no ordering needed for a boolean answer; queue internal
             // lanes first so leaf lanes (the cheap early exits) pop first.
+#if CRT_SADDR && CRT_KEY_ADDR
+            if (sp + 4 <= CRT_SSTACK) {
+                // Hot path, every slot in shared memory: two running shared-window addresses (internal lanes from the group's
+                // base, leaf lanes above all of them), each advanced by a slot for a hit lane of its class — selects and adds,
+                // no per-lane branch, no bounds test. Same slots as the eight conditional pushes below.
+                uint32_t ib[4], lb[4];
+#pragma unroll
+                for (int l = 0; l < 4; ++l) {
+                    const bool leaf = (cw[l] & CRT_LEAF_BIT) != 0u;
+                    ib[l] = (hit[l] && !leaf) ? kSlotBytes : 0u;
+                    lb[l] = (hit[l] && leaf) ? kSlotBytes : 0u;
+                }
+                const uint32_t b0 = sbase + (uint32_t)sp * kSlotBytes;
+                uint32_t ai = b0, al = b0 + ((ib[0] + ib[1]) + (ib[2] + ib[3]));
+#pragma unroll
+                for (int l = 0; l < 4; ++l) {
+                    const uint32_t at = (cw[l] & CRT_LEAF_BIT) ? al : ai;
+                    if (hit[l]) asm volatile("st.shared.u32 [%0], %1;" ::"r"(at), "r"(cw[l]) : "memory");
+                    ai += ib[l];
+                    al += lb[l];
+                }
+                sp += (int)((al - b0) / kSlotBytes);
+                return;
+            }
+#endif
 #pragma unroll
             for (int l = 0; l < 4; ++l)
                 if (hit[l] && !(cw[l] & CRT_LEAF_BIT)) push(make_entry(cw[l], 0.0f));
