@@ -44,7 +44,10 @@ struct TraceParams {
 #define CRT_MINBLOCKS_INST 5  // variants with instance descent carry more live state (level saves, hit chain): 96 registers without spills beat 64 with (measured 3/4/5/6/8 on B200)
 #endif
 #ifndef CRT_MINBLOCKS_INST1
-#define CRT_MINBLOCKS_INST1 7  // scenes whose instances nest one level deep (the parked top-level ray lives in shared memory): 72 registers with a few spills beat 80 / 96 without (measured 5/6/7/8 on B200, profiles/r02_tune_signsel_d1.jsonl)
+#define CRT_MINBLOCKS_INST1 6  // closest-hit in scenes whose instances nest one level deep (the parked top-level ray lives in shared memory): 80 registers / 6 blocks beat 72 / 7 and 64 / 8 since the triangle test dropped two axis registers (measured 6/7/8 on B200, profiles/r02_tune_after_triselect.jsonl; before that 7 won, r02_tune_signsel_d1.jsonl)
+#endif
+#ifndef CRT_MINBLOCKS_INST1_ANY
+#define CRT_MINBLOCKS_INST1_ANY 8  // any-hit, same scenes: 64 registers with one spilled word
 #endif
 #ifndef CRT_REFILL
 #define CRT_REFILL 16  // a warp refills its idle lanes when fewer than this many are active

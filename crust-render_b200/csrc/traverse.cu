@@ -48,7 +48,7 @@ struct StackCap {
 
 template <bool ANY_HIT, uint32_t FEAT, int MAXD>
 struct MinBlocks {
-    static constexpr int value = MAXD > 1 ? CRT_MINBLOCKS_INST : (MAXD == 1 ? CRT_MINBLOCKS_INST1 : (ANY_HIT ? CRT_MINBLOCKS_ANY : CRT_MINBLOCKS_CLOSEST));
+    static constexpr int value = MAXD > 1 ? CRT_MINBLOCKS_INST : (MAXD == 1 ? (ANY_HIT ? CRT_MINBLOCKS_INST1_ANY : CRT_MINBLOCKS_INST1) : (ANY_HIT ? CRT_MINBLOCKS_ANY : CRT_MINBLOCKS_CLOSEST));
 };
 
 // COUNT: the counting build of the same kernel (crt_trace_counters): what the traversal actually touches, summed over the
@@ -515,7 +515,7 @@ __global__ void __launch_bounds__(CRT_BLOCK, MinBlocks<ANY_HIT, FEAT, MAXD>::val
                     const uint32_t fat = pkt_first + REC_TRI_Q * ln;
                     const float4* fr = leafs + fat;
                     float4 f0 = __ldg(fr), f1 = __ldg(fr + 1), f2 = __ldg(fr + 2);
-                    TriEval e = tri_eval_f64(r, xyz(f0), xyz(f1), xyz(f2));
+                    TriEval e = tri_eval_f64(r.o, r.sx, r.sy, r.sz, r.kz, xyz(f0), xyz(f1), xyz(f2));
                     if (mixed_signs(e) || e.det == 0.0f) continue;
                     if (!in_range_scalar(e, t_min, closest)) continue;
                     if constexpr (ANY_HIT) {

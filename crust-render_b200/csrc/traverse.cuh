@@ -181,9 +181,12 @@ __device__ __forceinline__ TriEval tri_eval(const LevelRay& r, F3 v0, F3 v1, F3 
     return o;
 }
 // The f64 re-evaluation of triangle.rs:141-145 (scalar path, rare); same frame as tri_eval.
-__device__ __noinline__ TriEval tri_eval_f64(const LevelRay& r, F3 v0, F3 v1, F3 v2) {
-    const int kx = r.kz == 2 ? 0 : r.kz + 1, ky = kx == 2 ? 0 : kx + 1;
-    F3 a = v0 - r.o, b = v1 - r.o, c = v2 - r.o;
+// (The ray's fields travel by value: a reference would force the whole LevelRay of the traversal loop to keep a
+// local-memory image, stored again at every refill and instance descent.)
+__device__ __noinline__ TriEval tri_eval_f64(F3 ro, float rsx, float rsy, float rsz, int kz, F3 v0, F3 v1, F3 v2) {
+    const int kx = kz == 2 ? 0 : kz + 1, ky = kx == 2 ? 0 : kx + 1;
+    struct { float sx, sy, sz; int kz; } r = {rsx, rsy, rsz, kz};
+    F3 a = v0 - ro, b = v1 - ro, c = v2 - ro;
     float akz = pick(a, r.kz), bkz = pick(b, r.kz), ckz = pick(c, r.kz);
     float ax = pick(a, kx) - r.sx * akz, ay = pick(a, ky) - r.sy * akz;
     float bx = pick(b, kx) - r.sx * bkz, by = pick(b, ky) - r.sy * bkz;
