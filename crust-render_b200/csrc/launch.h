@@ -47,7 +47,7 @@ struct TraceParams {
 #define CRT_MINBLOCKS_INST1 6  // closest-hit in scenes whose instances nest one level deep (the parked top-level ray lives in shared memory): 80 registers / 6 blocks beat 72 / 7 and 64 / 8 since the triangle test dropped two axis registers (measured 6/7/8 on B200, profiles/r02_tune_after_triselect.jsonl; before that 7 won, r02_tune_signsel_d1.jsonl)
 #endif
 #ifndef CRT_MINBLOCKS_INST1_ANY
-#define CRT_MINBLOCKS_INST1_ANY 8  // any-hit, same scenes: 64 registers with one spilled word
+#define CRT_MINBLOCKS_INST1_ANY 7  // any-hit, same scenes: 72 registers, no spills (8 blocks = 64 registers spills 20 bytes since the record loads are issued together)
 #endif
 #ifndef CRT_REFILL
 #define CRT_REFILL 16  // a warp refills its idle lanes when fewer than this many are active

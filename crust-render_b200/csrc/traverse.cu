@@ -220,9 +220,12 @@ __global__ void __launch_bounds__(CRT_BLOCK, MinBlocks<ANY_HIT, FEAT, MAXD>::val
                 if (kind == REC_TRI) {
                     float4 q1 = __ldg(hit_rec + 1), q2 = __ldg(hit_rec + 2);
                     prim = __float_as_uint(q1.w);
-                    lr.set(o, d, true);
+                    if constexpr (MAXD == 0)
+                        lr = r;  // no instancing: the loop's ray is the hit level's ray, shear constants included
+                    else
+                        lr.set(o, d, true);
                     F3 v0 = xyz(q0), v1 = xyz(q1), v2 = xyz(q2);
-                    TriEval e = tri_eval_exact(lr, v0, v1, v2);
+                    TriEval e = tri_eval_exact(lr.o, lr.d, lr.sx, lr.sy, lr.sz, lr.kz, v0, v1, v2);
                     float inv_det = 1.0f / e.det;
                     t = e.t_scaled * inv_det;
                     u = e.e1 * inv_det;
@@ -479,32 +482,39 @@ __global__ void __launch_bounds__(CRT_BLOCK, MinBlocks<ANY_HIT, FEAT, MAXD>::val
     auto record_test = [&]() {
         const uint32_t at = rec;
         const float4* cur = leafs + at;
-        float4 q0 = __ldg(cur), q1 = __ldg(cur + 1), q2 = __ldg(cur + 2);
+        // The record's first three quads in one round trip. Left alone, the compiler sinks the second and third load below
+        // the kind / mask branches that need only the first, which serialises three L1 latencies per record; so the one
+        // gate the visible-triangle path depends on reads all three (a primitive id is never all ones — the last term is
+        // always true and only there to tie the middle quad in). Every record array is padded by one triangle record: the
+        // over-read past a shorter record's tail stays inside the buffer.
+        const float4 q0 = __ldg(cur), q1 = __ldg(cur + 1), q2 = __ldg(cur + 2);
         const uint32_t flags = __float_as_uint(q0.w);
         const uint32_t kind = flags & REC_KIND_MASK;
-        if (kind == REC_TRI) {
-            rec = (flags & REC_LAST) ? CRT_NO_REC : at + REC_TRI_Q;
-            if constexpr (COUNT) ++c_tris;
-            if (ray_mask & __float_as_uint(q2.w)) {  // triangle.rs:257-271 per-lane visibility
-                TriEval e = tri_eval(r, xyz(q0), xyz(q1), xyz(q2));
-                if (e.on_edge) {
-                    pkt_deferred |= 1u << ((flags >> REC_LANE_SHIFT) & 3u);  // f64 tie-break after the packet's other lanes
-                } else if (!mixed_signs(e) && e.det != 0.0f) {
-                    if constexpr (ANY_HIT) {
-                        if (in_range_packet(e, t_min, closest)) {
-                            any_found = true;
-                            state = DONE;
-                            rec = CRT_NO_REC;
-                            return;
-                        }
-                    } else {
-                        if (in_range_packet(e, t_min, pkt_tmax)) {
-                            float t = e.t_scaled * (1.0f / e.det);
-                            if (!(t > closest) && !(flags & REC_DEGENERATE)) accept(at, t);  // bvh.rs:542, prim.rs:80-83
-                        }
+        const bool tri_visible = (kind == REC_TRI) & ((ray_mask & __float_as_uint(q2.w)) != 0u)  // triangle.rs:257-271 per-lane visibility
+                                 & (__float_as_uint(q1.w) != CRT_INVALID_ID);
+        if (tri_visible) {
+            TriEval e = tri_eval(r, xyz(q0), xyz(q1), xyz(q2));
+            if (e.on_edge) {
+                pkt_deferred |= 1u << ((flags >> REC_LANE_SHIFT) & 3u);  // f64 tie-break after the packet's other lanes
+            } else if (!mixed_signs(e) && e.det != 0.0f) {
+                if constexpr (ANY_HIT) {
+                    if (in_range_packet(e, t_min, closest)) {
+                        any_found = true;
+                        state = DONE;
+                        rec = CRT_NO_REC;
+                        return;
+                    }
+                } else {
+                    if (in_range_packet(e, t_min, pkt_tmax)) {
+                        float t = e.t_scaled * (1.0f / e.det);
+                        if (!(t > closest) && !(flags & REC_DEGENERATE)) accept(at, t);  // bvh.rs:542, prim.rs:80-83
                     }
                 }
             }
+        }
+        if (kind == REC_TRI) {
+            rec = (flags & REC_LAST) ? CRT_NO_REC : at + REC_TRI_Q;
+            if constexpr (COUNT) ++c_tris;
             if (flags & REC_PACKET_END) {
                 // Lanes sitting exactly on an edge: scalar f64 path (bvh.rs:551-561 / 636-643). The packet's first record is
                 // this one minus its lane number.

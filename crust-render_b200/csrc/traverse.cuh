@@ -202,15 +202,14 @@ __device__ __noinline__ TriEval tri_eval_f64(F3 ro, float rsx, float rsy, float 
 }
 // The reference's own frame (triangle.rs:47-60: kx and ky swapped when d[kz] < 0), for the one evaluation per ray whose
 // (t, u, v) are reported: bit-for-bit the reference's values, signs of zeros included. Once per ray, not in the hot loop.
-__device__ __noinline__ TriEval tri_eval_exact(const LevelRay& r, F3 v0, F3 v1, F3 v2) {
-    int kx = r.kz == 2 ? 0 : r.kz + 1, ky = kx == 2 ? 0 : kx + 1;
-    float sx = r.sx, sy = r.sy;
-    if (pick(r.d, r.kz) < 0.0f) {
+__device__ __noinline__ TriEval tri_eval_exact(F3 ro, F3 rd, float sx, float sy, float rsz, int kz, F3 v0, F3 v1, F3 v2) {
+    int kx = kz == 2 ? 0 : kz + 1, ky = kx == 2 ? 0 : kx + 1;
+    if (pick(rd, kz) < 0.0f) {
         int t = kx; kx = ky; ky = t;
         float ts = sx; sx = sy; sy = ts;
     }
-    F3 a = v0 - r.o, b = v1 - r.o, c = v2 - r.o;
-    float akz = pick(a, r.kz), bkz = pick(b, r.kz), ckz = pick(c, r.kz);
+    F3 a = v0 - ro, b = v1 - ro, c = v2 - ro;
+    float akz = pick(a, kz), bkz = pick(b, kz), ckz = pick(c, kz);
     float ax = pick(a, kx) - sx * akz, ay = pick(a, ky) - sy * akz;
     float bx = pick(b, kx) - sx * bkz, by = pick(b, ky) - sy * bkz;
     float cx = pick(c, kx) - sx * ckz, cy = pick(c, ky) - sy * ckz;
@@ -225,7 +224,7 @@ __device__ __noinline__ TriEval tri_eval_exact(const LevelRay& r, F3 v0, F3 v1, 
         o.e2 = (float)__dsub_rn(__dmul_rn((double)ax, (double)by), __dmul_rn((double)ay, (double)bx));
     }
     o.det = (o.e0 + o.e1) + o.e2;
-    o.t_scaled = (o.e0 * (r.sz * akz) + o.e1 * (r.sz * bkz)) + o.e2 * (r.sz * ckz);
+    o.t_scaled = (o.e0 * (rsz * akz) + o.e1 * (rsz * bkz)) + o.e2 * (rsz * ckz);
     return o;
 }
 __device__ __forceinline__ bool mixed_signs(const TriEval& e) {
