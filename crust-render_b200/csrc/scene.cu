@@ -993,10 +993,18 @@ int host_query(const crt_scene* s, bool any_hit, size_t n, const crt_ray* rays, 
         pend[sl].used = false;
         return CRT_OK;
     };
+    // The copies are the bottleneck (PCIe), so what a call adds to the pure copy time is its drain: the last chunk's kernel and
+    // download run after the last upload has finished. The tail is therefore tapered — once less than two chunks remain, each
+    // chunk takes half of what is left (in units of kTail rays) — which shrinks the drain from a 2^20-ray kernel + 32 MB
+    // download to a 2^16-ray one.
+    constexpr size_t kTail = (size_t)1 << 16;
+    static const bool taper = getenv("CRT_HOST_NO_TAPER") == nullptr;  // tuning only
     size_t chunk_no = 0;
-    for (size_t off = 0; off < n; off += kChunk, ++chunk_no) {
+    for (size_t off = 0, cnt = 0; off < n; off += cnt, ++chunk_no) {
         int sl = (int)(chunk_no % kSlots);
-        size_t cnt = std::min(kChunk, n - off);
+        const size_t rem = n - off;
+        cnt = std::min(kChunk, rem);
+        if (taper && rem < 2 * kChunk && rem > kTail) cnt = std::min(cnt, std::max((rem / 2 + kTail - 1) / kTail * kTail, kTail));
         if ((rc = drain(sl))) return rc;
         cudaStream_t st = g_pipe.stream[sl];
         const crt_ray* src_r = rays + off;

@@ -69,6 +69,28 @@ def test_tri_spheres_one_million_rays(gpu, orc):
     _compare_occluded(p, o, rays)
 
 
+def test_mixed_t_min_signs_and_all_shear_frames(gpu, orc):
+    """Both push-order paths of the closest-hit node visit in the same warps — the unsigned-key ranks need t_min >= +0, rays
+    with a negative (or -0.0) t_min take the float / class ranks — and every one of the six (kz, sign d[kz]) shear frames of the
+    triangle test, whose hot path leaves out the reference's kx / ky swap (traverse.cuh tri_eval): bit-identical to the oracle."""
+    for make, extent in ((workloads.triangle_scene, 6.0), (workloads.instance_scene, 7.0)):
+        p, o = _pair(gpu, orc, make)
+        rays = workloads.ray_batch(1 << 18, extent, seed=0xBEEF)
+        rng = np.random.default_rng(11)
+        n = len(rays)
+        rays["tmin"] = rng.choice(np.array([-50.0, -1.0, -0.0, 0.0, 1e-3, 2.0], np.float32), n)  # negative: hits behind the origin count
+        assert _compare_closest(p, o, rays) > 5000
+        _compare_occluded(p, o, rays)
+        # dominant axis and its sign forced per ray: the six frames in equal shares, neighbours in a warp differ
+        d = rays["d"].copy()
+        k = np.arange(n) % 3
+        sgn = np.where((np.arange(n) // 3) % 2 == 0, 1.0, -1.0).astype(np.float32)
+        d[np.arange(n), k] = (np.abs(d).max(1) * np.float32(1.5) + np.float32(0.1)) * sgn
+        rays["d"] = d
+        _compare_closest(p, o, rays)
+        _compare_occluded(p, o, rays)
+
+
 def test_stress_scene_with_spatial_splits(gpu, orc):
     """gen_stress_scene.py at 1/9 size: flat spheres + thin shards (SBVH duplicates) + floor + slab."""
     make = lambda api: workloads.stress_scene(api, grid=2, shards=30000)[0]  # noqa: E731
