@@ -80,5 +80,15 @@ struct alignas(64) DevScene {
     const MotionXform* motion;   // indexed by instance record's motion word
     uint32_t n_nodes;
     uint32_t has_triangles;      // bvh.rs:422-425: shear only derived when packets exist
-    uint32_t pad[4];
+    uint32_t shear_at_top;       // has_triangles, or some instance is a translated copy (identity linear part) of a child with
+                                 // triangles: such a child reuses the top level's shear constants (traverse.cu, depth-1 variant)
+    uint32_t pad[3];
 };
+
+// Instance record (host side, 4 words per quad): true if its world-to-local linear part is the identity, i.e. the instance
+// is a translated copy of its child.
+inline bool rec_is_translated_copy(const uint32_t* rec) {
+    auto is0 = [](uint32_t w) { return (w & 0x7FFFFFFFu) == 0u; };
+    const uint32_t one = 0x3F800000u;
+    return rec[0] == one && is0(rec[1]) && is0(rec[2]) && is0(rec[4]) && rec[5] == one && is0(rec[6]) && is0(rec[8]) && is0(rec[9]) && rec[10] == one;
+}

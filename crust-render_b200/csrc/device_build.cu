@@ -607,6 +607,7 @@ int device_build(std::vector<Geom>& geoms, ChildInfoFn child_info, crt_scene* s)
     }
     const uint32_t M = (uint32_t)others.n;
     if ((uint64_t)n_tris + M > 0x0FFFFFFFull) return set_error(CRT_ERR_INVALID_ARG, "device build: more than 2^28 primitives");
+    bool translated_copy = false;
     for (size_t k = 0; k < others.inst_prim.size(); ++k) {  // child addresses into the instance records (q4, q5, REC_CHILD_TRIS)
         const crt_scene* child = others.inst_child[k];
         const size_t q = others.rec_off[others.inst_prim[k]];
@@ -615,6 +616,7 @@ int device_build(std::vector<Geom>& geoms, ChildInfoFn child_info, crt_scene* s)
         others.recs[4 * (q + 5) + 0] = (uint32_t)(cn & 0xFFFFFFFFu), others.recs[4 * (q + 5) + 1] = (uint32_t)(cn >> 32);
         others.recs[4 * (q + 5) + 2] = (uint32_t)(cl & 0xFFFFFFFFu), others.recs[4 * (q + 5) + 3] = (uint32_t)(cl >> 32);
         if (child->desc.has_triangles) others.recs[4 * q + 3] |= REC_CHILD_TRIS;
+        if (child->desc.has_triangles && rec_is_translated_copy(&others.recs[4 * q])) translated_copy = true;
     }
     s->has_motion = others.has_motion;
     s->instance_depth = others.instance_depth;
@@ -907,6 +909,7 @@ int device_build(std::vector<Geom>& geoms, ChildInfoFn child_info, crt_scene* s)
     }
     s->desc.n_nodes = n4;
     s->desc.has_triangles = n_valid_tris > 0;
+    s->desc.shear_at_top = s->desc.has_triangles || translated_copy;
     s->n_nodes = n4, s->n_leaf_quads = n > 0 ? leaf_quads : 0, s->n_prim_ids = N, s->n_normal_floats = 0, s->n_motion = others.motion.size();
     if (!others.inst_prim.empty()) {  // where the instance records landed (crt_scene_export / import re-point them)
         std::vector<uint32_t> pos(M);

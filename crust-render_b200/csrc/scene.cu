@@ -477,6 +477,7 @@ int crt_commit_ex(crt_builder* b, uint32_t flags, int host_threads, crt_scene** 
         t->leafs[4 * (size_t)(q + 5) + 2] = (uint32_t)(cl & 0xFFFFFFFFu);
         t->leafs[4 * (size_t)(q + 5) + 3] = (uint32_t)(cl >> 32);
         if (child->desc.has_triangles) t->leafs[4 * (size_t)q + 3] |= REC_CHILD_TRIS;
+        if (child->desc.has_triangles && rec_is_translated_copy(&t->leafs[4 * (size_t)q])) s->desc.shear_at_top = 1;
     }
     // The builder's per-geometry references are no longer needed.
     crt_builder_free(b);
@@ -504,6 +505,7 @@ int crt_commit_ex(crt_builder* b, uint32_t flags, int host_threads, crt_scene** 
         s->desc.motion = (const MotionXform*)s->d_motion;
         s->desc.n_nodes = (uint32_t)t->nodes.size();
         s->desc.has_triangles = s->breakdown.triangles != 0;
+        s->desc.shear_at_top |= s->desc.has_triangles;
         if ((rc = upload((void**)&s->d_desc, &s->desc, 1))) {
             delete t;
             crt_scene_release(s);
@@ -622,7 +624,7 @@ struct BlobHeader {
     uint64_t n_nodes, n_leaf_quads, n_prim_ids, n_normal_floats, n_motion, n_children, n_inst;
     uint64_t top_bytes;
     // host-side metadata of crt_scene
-    uint32_t non_empty, has_motion, n_geoms, instance_depth, features, has_triangles;
+    uint32_t non_empty, has_motion, n_geoms, instance_depth, features, has_triangles, shear_at_top, pad_;
     uint64_t n_prims;
     float root[6];
     float extent_sum, extent_max;
@@ -631,7 +633,7 @@ struct BlobHeader {
     crt_memory_footprint footprint;
 };
 constexpr uint32_t kBlobMagic = 0x42545243u;  // "CRTB"
-constexpr uint32_t kBlobVersion = 1;
+constexpr uint32_t kBlobVersion = 2;
 size_t pad16(size_t b) { return (b + 15) & ~(size_t)15; }
 struct BlobLayout {
     size_t nodes, leafs, prim_ids, normals, motion, inst_q, inst_child, total;
@@ -654,7 +656,7 @@ BlobHeader header_of(const crt_scene* s) {
     h.n_nodes = s->n_nodes, h.n_leaf_quads = s->n_leaf_quads, h.n_prim_ids = s->n_prim_ids, h.n_normal_floats = s->n_normal_floats;
     h.n_motion = s->n_motion, h.n_children = s->children.size(), h.n_inst = s->inst_q.size(), h.top_bytes = s->top_bytes;
     h.non_empty = s->non_empty, h.has_motion = s->has_motion, h.n_geoms = s->n_geoms, h.instance_depth = s->instance_depth;
-    h.features = s->features, h.has_triangles = s->desc.has_triangles, h.n_prims = s->n_prims;
+    h.features = s->features, h.has_triangles = s->desc.has_triangles, h.shear_at_top = s->desc.shear_at_top, h.pad_ = 0, h.n_prims = s->n_prims;
     h.root[0] = s->root.lo.x, h.root[1] = s->root.lo.y, h.root[2] = s->root.lo.z, h.root[3] = s->root.hi.x, h.root[4] = s->root.hi.y, h.root[5] = s->root.hi.z;
     h.extent_sum = s->extent_sum, h.extent_max = s->extent_max;
     h.breakdown = s->breakdown, h.info = s->info, h.footprint = s->footprint;
@@ -788,6 +790,7 @@ int crt_scene_import(const void* src, size_t bytes, int src_on_device, crt_scene
     s->desc.motion = (const MotionXform*)s->d_motion;
     s->desc.n_nodes = (uint32_t)h.n_nodes;
     s->desc.has_triangles = h.has_triangles;
+    s->desc.shear_at_top = h.shear_at_top;
     if ((rc = upload((void**)&s->d_desc, &s->desc, 1))) return fail_free(rc);
     *out = s;
     return CRT_OK;

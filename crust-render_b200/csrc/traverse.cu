@@ -604,7 +604,24 @@ __global__ void __launch_bounds__(CRT_BLOCK, MinBlocks<ANY_HIT, FEAT, MAXD>::val
                     ++depth;
                     nodes = (const DevNode*)(((uint64_t)q5.y << 32) | (uint64_t)q5.x);
                     leafs = (const float4*)(((uint64_t)q5.w << 32) | (uint64_t)q5.z);
-                    r.set(xf_point(w2l, r.o), xf_vec(w2l, r.d), (flags & REC_CHILD_TRIS) != 0);  // prim.rs:333-341
+                    const F3 lo = xf_point(w2l, r.o), ld = xf_vec(w2l, r.d);  // prim.rs:333-341
+                    const bool child_tris = (flags & REC_CHILD_TRIS) != 0;
+                    bool same_dir = false;
+                    if constexpr (MAXD == 1) {
+                        // An instance whose linear part is the identity (a translated copy — grids of instances) hands the
+                        // child the parent's direction bit for bit; then everything derived from the direction alone —
+                        // reciprocals, plane offsets and, if the top level computed them, the shear constants — is the
+                        // child's too, and only the origin changes. Decided on the transformed values themselves, not on
+                        // the matrix: any case where they differ (a signed zero, a NaN) takes the full setup.
+                        same_dir = __float_as_uint(ld.x) == __float_as_uint(r.d.x) && __float_as_uint(ld.y) == __float_as_uint(r.d.y) &&
+                                   __float_as_uint(ld.z) == __float_as_uint(r.d.z);
+                    }
+                    if (same_dir) {
+                        r.o = lo;
+                        if (child_tris && p.scene.shear_at_top == 0) r.set_shear(ld);
+                    } else {
+                        r.set(lo, ld, child_tris);
+                    }
                     rec = CRT_NO_REC;
                     push(make_entry(CRT_RETURN_MARK, 0.0f));
                     push(make_entry(0u, t_min));  // committed child scenes are never empty (scene.rs:307-309)
@@ -659,7 +676,7 @@ __global__ void __launch_bounds__(CRT_BLOCK, MinBlocks<ANY_HIT, FEAT, MAXD>::val
                         closest = b.w;
                         time = p.time ? __ldg(p.time + idx) : 0.0f;
                         ray_mask = p.mask ? __ldg(p.mask + idx) : p.mask_uniform;
-                        r.set(f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), p.scene.has_triangles != 0);
+                        r.set(f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), p.scene.shear_at_top != 0);
                         nodes = p.scene.nodes;
                         leafs = (const float4*)p.scene.leafs;
                         cur_scene = nullptr;

@@ -142,14 +142,15 @@ struct LevelRay {
         near_y = inv.y < 0.0f ? 64u : 16u;
         near_z = inv.z < 0.0f ? 80u : 32u;
 #endif
-        if (want_shear) {
-            float ax = fabsf(dir.x), ay = fabsf(dir.y), az = fabsf(dir.z);
-            kz = ax > ay ? (ax > az ? 0 : 2) : (ay > az ? 1 : 2);
-                        float dz = sel3(kz, dir.x, dir.y, dir.z);
-            sx = sel3(kz, dir.y, dir.z, dir.x) / dz;
-            sy = sel3(kz, dir.z, dir.x, dir.y) / dz;
-            sz = __frcp_rn(dz);
-        }
+        if (want_shear) set_shear(dir);
+    }
+    __device__ __forceinline__ void set_shear(F3 dir) {
+        float ax = fabsf(dir.x), ay = fabsf(dir.y), az = fabsf(dir.z);
+        kz = ax > ay ? (ax > az ? 0 : 2) : (ay > az ? 1 : 2);
+        float dz = sel3(kz, dir.x, dir.y, dir.z);
+        sx = sel3(kz, dir.y, dir.z, dir.x) / dz;
+        sy = sel3(kz, dir.z, dir.x, dir.y) / dz;
+        sz = __frcp_rn(dz);
     }
 };
 
