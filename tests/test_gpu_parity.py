@@ -91,6 +91,56 @@ def test_mixed_t_min_signs_and_all_shear_frames(gpu, orc):
         _compare_occluded(p, o, rays)
 
 
+def _copies_scene(api, top_level_triangles: bool):
+    """One 576-triangle sphere instanced 64 times one level deep: translated copies (identity linear part — the child keeps the
+    parent's direction-derived ray setup, traverse.cu), rotations by 0 (cos = 1, sin = 0: identity values reached through a
+    product), true rotations, scales, a moving copy — interleaved so neighbouring rays of a warp take different paths."""
+    inner = api.SceneBuilder()
+    v, i = workloads.uv_sphere(np.zeros(3, np.float32), 1.0, 24, 12)
+    inner.attach(Geometry.TriangleMesh(v, i))
+    inner = inner.commit()
+    b = api.SceneBuilder()
+    k = 0
+    for x in range(4):
+        for y in range(4):
+            for z in range(4):
+                t = Affine3A.from_translation(np.array([x, y, z], np.float32) * np.float32(2.5))
+                kind = k % 5
+                if kind == 0:
+                    xf, end = t, None
+                elif kind == 1:
+                    xf, end = t * Affine3A.from_rotation_y(0.0), None
+                elif kind == 2:
+                    xf, end = t * Affine3A.from_rotation_z(0.3 + 0.1 * k), None
+                elif kind == 3:
+                    xf, end = t * Affine3A.from_scale(np.array([1.0, 0.5, 1.5], np.float32)), None
+                else:
+                    xf, end = t, Affine3A.from_translation(np.array([x, y, z], np.float32) * np.float32(2.5) + np.float32(0.4))
+                b.attach(Geometry.Instance(inner, xf, end))
+                k += 1
+    if top_level_triangles:
+        fv = np.array([[-3, -1.5, -3], [12, -1.5, -3], [12, -1.5, 12], [-3, -1.5, 12]], np.float32)
+        b.attach(Geometry.TriangleMesh(fv, np.array([[0, 1, 2], [0, 2, 3]], np.uint32)))
+    return b
+
+
+@pytest.mark.parametrize("top_level_triangles", [False, True])
+def test_translated_copies_next_to_rotated_and_moving_instances(gpu, orc, top_level_triangles):
+    p, o = _pair(gpu, orc, lambda api: _copies_scene(api, top_level_triangles))
+    rays = workloads.ray_batch(1 << 18, 11.0, seed=0xC0B1E5)
+    rays["o"] += np.float32(3.75)
+    time = np.random.default_rng(3).uniform(0.0, 1.0, len(rays)).astype(np.float32)
+    time[::3] = 0.0  # the reference takes the cached transform at time 0 (prim.rs:345-350)
+    assert _compare_closest(p, o, rays, time=time) > 20000
+    _compare_occluded(p, o, rays, time=time)
+    d = rays["d"].copy()
+    d[::2, 1] = np.float32(-0.0)  # signed zeros in the direction: the copy's direction is compared bit for bit
+    d[1::4, 0] = np.float32(0.0)
+    rays["d"] = d
+    _compare_closest(p, o, rays, time=time)
+    _compare_occluded(p, o, rays, time=time)
+
+
 def test_stress_scene_with_spatial_splits(gpu, orc):
     """gen_stress_scene.py at 1/9 size: flat spheres + thin shards (SBVH duplicates) + floor + slab."""
     make = lambda api: workloads.stress_scene(api, grid=2, shards=30000)[0]  # noqa: E731
