@@ -21,7 +21,14 @@
 //     lanes, near one on top) instead of being intersected inside the node
 //     visit — same order;
 //   * (u, v) and the normal are recomputed once at the end from the winning
-//     record instead of at every accepted hit.
+//     record instead of at every accepted hit;
+//   * the slab planes are picked by the ray's direction signs instead of by
+//     min / max (tests/test_slab_signselect.py);
+//   * during traversal the triangle test works in the shear frame without the
+//     reference's kx / ky swap (tri_eval below, tests/test_tri_frame_symmetry.py);
+//     the reported hit is re-evaluated in the reference's frame (tri_eval_exact);
+//   * for rays with t_min >= +0 the push order comes from unsigned compares of
+//     the entry distances' bit patterns (same order: they are non-negative).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>

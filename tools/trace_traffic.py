@@ -6,8 +6,8 @@ launches of one bench.py step — from an `ncu --set full` capture of the bench 
         python bench.py --steps 1 --warmup 1 --no-render --no-cpu-baseline --no-e2e
     python tools/trace_traffic.py gpurun_out/bench_trace.ncu-rep [--last 5]
 
-The json is stamped with a hash of the traversal sources (`source_sha`); bench.py only quotes `roofline.traffic` from it
-when the hash matches the sources it is running, so the figure cannot silently go stale.
+The json is stamped with a hash of the traversal sources' code, comments and blank lines left out (`source_sha`); bench.py only
+quotes `roofline.traffic` from it when the hash matches the sources it is running, so the figure cannot silently go stale.
 """
 import argparse
 import csv
@@ -22,10 +22,21 @@ SETS = ["closest_lcg", "closest_camera", "closest_bounce", "occluded_lcg", "occl
 KERNEL_SOURCES = ["traverse.cu", "traverse.cuh", "launch.h", "crt_layout.h"]
 
 
-def source_sha() -> str:
+def _code_only(text: str) -> str:
+    """The source without comments and without blank lines / indentation: a comment edit does not make the capture stale."""
+    import re
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    lines = (re.sub(r"//.*$", "", ln).strip() for ln in text.splitlines())  # no string literal of these files holds "//"
+    return "\n".join(ln for ln in lines if ln)
+
+
+def source_sha(read=None) -> str:
+    """Hash of the code (not the comments) of the traversal sources. `read(name)` overrides where a file comes from
+    (tools use it to hash the sources of another commit)."""
     h = hashlib.sha256()
     for name in KERNEL_SOURCES:
-        h.update(open(os.path.join(ROOT, "crust-render_b200", "csrc", name), "rb").read())
+        text = read(name) if read else open(os.path.join(ROOT, "crust-render_b200", "csrc", name), encoding="utf-8").read()
+        h.update(_code_only(text).encode())
     return h.hexdigest()[:16]
 
 
