@@ -46,7 +46,10 @@ namespace {
 
 constexpr int kB = 256;
 constexpr float kPadDev = 1e-4f;  // aabb.rs:50
-constexpr uint32_t kLeafMax = 4;  // bvh.rs:142-167 MIN_LEAF_PACKED: one Tri4 packet per leaf
+#ifndef CRT_DEV_LEAF_MAX
+#define CRT_DEV_LEAF_MAX 4
+#endif
+constexpr uint32_t kLeafMax = CRT_DEV_LEAF_MAX;  // bvh.rs:142-167 MIN_LEAF_PACKED: one Tri4 packet per leaf
 
 struct MeshTable {            // per triangle mesh, device arrays of length n_meshes (+1 for the offsets)
     const uint32_t* tri_offset;   // first flat triangle index of mesh m; [n_meshes] = total
