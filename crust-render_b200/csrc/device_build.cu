@@ -385,6 +385,113 @@ __global__ void __launch_bounds__(kB) refit_kernel(int n, const uint32_t* __rest
     }
 }
 
+// ---- SAH-built top (optional, CRT_DEV_SAH_TOP) -------------------------------------------------------------------------
+// The radix tree's upper levels split where the Morton code changes, wherever the geometry is. The binary nodes holding
+// more than `cluster` references are therefore rebuilt: their children that hold at most `cluster` references ("clusters",
+// a few thousand contiguous runs of the sorted references) go to the host with their boxes, the host builds a binary tree
+// over them with a full-sweep surface-area heuristic, and that tree is written into the slots of the nodes it replaces
+// (a binary tree over K clusters has K - 1 internal nodes — exactly the nodes above them). Below the clusters nothing
+// changes, so leaves still cover contiguous runs; above them only left / right / boxes are read by the later stages.
+struct TopCluster {
+    float lo[3], hi[3];
+    int node, count, first;
+};
+__global__ void __launch_bounds__(kB) top_select_kernel(int n, int cluster, unsigned int cap, BuildArrays A, int* __restrict__ top_ids,
+                                                        TopCluster* __restrict__ clusters, unsigned int* __restrict__ counts) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n - 1 || A.last[i] - A.first[i] + 1 <= cluster) return;
+    const unsigned int at = atomicAdd(counts + 0, 1u);
+    if (at < cap) top_ids[at] = i;  // a lopsided radix tree can have far more such nodes than n / cluster: the caller then keeps it as it is
+    const int kids[2] = {A.left[i], A.right[i]};
+    for (int k = 0; k < 2; ++k) {
+        const int c = kids[k];
+        const int first = c >= n - 1 ? c - (n - 1) : A.first[c];
+        const int cnt = c >= n - 1 ? 1 : A.last[c] - A.first[c] + 1;
+        if (cnt > cluster) continue;
+        TopCluster t;
+        const float4 lo = A.nlo[c], hi = A.nhi[c];
+        t.lo[0] = lo.x, t.lo[1] = lo.y, t.lo[2] = lo.z, t.hi[0] = hi.x, t.hi[1] = hi.y, t.hi[2] = hi.z;
+        t.node = c, t.count = cnt, t.first = first;
+        const unsigned int ct = atomicAdd(counts + 1, 1u);
+        if (ct < cap) clusters[ct] = t;
+    }
+}
+struct TopNode {
+    float lo[3], hi[3];
+    int slot, left, right;
+};
+__global__ void __launch_bounds__(kB) top_apply_kernel(int n, int count, const TopNode* __restrict__ t, BuildArrays A) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const TopNode v = t[i];
+    A.left[v.slot] = v.left, A.right[v.slot] = v.right;
+    A.first[v.slot] = 0, A.last[v.slot] = n - 1;  // only "more than a leaf's worth" is read from these above the clusters
+    A.nlo[v.slot] = make_float4(v.lo[0], v.lo[1], v.lo[2], 0.0f);
+    A.nhi[v.slot] = make_float4(v.hi[0], v.hi[1], v.hi[2], 0.0f);
+    A.parent[v.left] = v.slot, A.parent[v.right] = v.slot;
+}
+
+// Host side: full-sweep SAH over the clusters (cost = area x references on each side, the reference's measure, bvh.rs:811-830).
+struct TopBuilder {
+    const std::vector<TopCluster>& c;
+    const std::vector<int>& slots;  // ascending; slots[0] == 0 is the root
+    std::vector<TopNode> out;
+    size_t next_slot = 0;
+    static float area(const float lo[3], const float hi[3]) {
+        const float ex = hi[0] - lo[0], ey = hi[1] - lo[1], ez = hi[2] - lo[2];
+        return 2.0f * (ex * ey + ey * ez + ez * ex);
+    }
+    int build(std::vector<int>& idx, size_t b, size_t e) {  // returns the binary node id of the subtree over idx[b, e)
+        if (e - b == 1) return c[idx[b]].node;
+        const size_t m = e - b;
+        int best_axis = -1;
+        size_t best_pos = 0;
+        double best_cost = 0.0;
+        {
+        std::vector<float> ra(m);
+        std::vector<long long> rn(m);
+        for (int axis = 0; axis < 3; ++axis) {
+            std::sort(idx.begin() + b, idx.begin() + e, [&](int x, int y) {
+                const float cx = c[x].lo[axis] + c[x].hi[axis], cy = c[y].lo[axis] + c[y].hi[axis];
+                return cx < cy || (cx == cy && c[x].first < c[y].first);
+            });
+            float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+            long long cnt = 0;
+            for (size_t k = m; k-- > 1;) {  // suffix [k, m)
+                const TopCluster& t = c[idx[b + k]];
+                for (int a = 0; a < 3; ++a) lo[a] = std::min(lo[a], t.lo[a]), hi[a] = std::max(hi[a], t.hi[a]);
+                cnt += t.count;
+                ra[k] = area(lo, hi), rn[k] = cnt;
+            }
+            for (int a = 0; a < 3; ++a) lo[a] = INFINITY, hi[a] = -INFINITY;
+            cnt = 0;
+            for (size_t k = 1; k < m; ++k) {  // prefix [0, k)
+                const TopCluster& t = c[idx[b + k - 1]];
+                for (int a = 0; a < 3; ++a) lo[a] = std::min(lo[a], t.lo[a]), hi[a] = std::max(hi[a], t.hi[a]);
+                cnt += t.count;
+                const double cost = (double)area(lo, hi) * (double)cnt + (double)ra[k] * (double)rn[k];
+                if (best_axis < 0 || cost < best_cost) best_axis = axis, best_pos = k, best_cost = cost;
+            }
+        }
+        }  // the sweep's scratch is gone before the recursion
+        if (best_axis != 2)
+            std::sort(idx.begin() + b, idx.begin() + e, [&](int x, int y) {
+                const float cx = c[x].lo[best_axis] + c[x].hi[best_axis], cy = c[y].lo[best_axis] + c[y].hi[best_axis];
+                return cx < cy || (cx == cy && c[x].first < c[y].first);
+            });
+        const size_t me = out.size();
+        out.push_back(TopNode{});
+        out[me].slot = slots[next_slot++];
+        const int l = build(idx, b, b + best_pos), r = build(idx, b + best_pos, e);
+        TopNode& t = out[me];
+        t.left = l, t.right = r;
+        for (int a = 0; a < 3; ++a) t.lo[a] = INFINITY, t.hi[a] = -INFINITY;
+        for (size_t k = b; k < e; ++k)
+            for (int a = 0; a < 3; ++a) t.lo[a] = std::min(t.lo[a], c[idx[k]].lo[a]), t.hi[a] = std::max(t.hi[a], c[idx[k]].hi[a]);
+        return t.slot;
+    }
+};
+
 __device__ __forceinline__ int node_count(const BuildArrays& A, int n, int node) { return node >= n - 1 ? 1 : A.last[node] - A.first[node] + 1; }
 __device__ __forceinline__ bool expandable(const BuildArrays& A, int n, int node) { return node < n - 1 && node_count(A, n, node) > (int)kLeafMax; }
 __device__ __forceinline__ float node_area(const BuildArrays& A, int node) {  // bvh.rs:811-814
@@ -863,6 +970,50 @@ int device_build(std::vector<Geom>& geoms, ChildInfoFn child_info, crt_scene* s)
             karras_kernel<<<grid_n, kB>>>(n, d_keys, A);
             refit_kernel<<<grid_n, kB>>>(n, d_sorted, A);
             lap("karras + refit");
+            static const int top_cluster = [] {
+                const char* e = getenv("CRT_DEV_SAH_TOP");
+                return e ? atoi(e) : 0;
+            }();
+            if (top_cluster >= 8 && n > 4 * top_cluster) {
+                const size_t cap = (size_t)(8 * (size_t)n / (size_t)top_cluster) + 64;  // a balanced tree has about 2 n / cluster of them
+                int* d_top = nullptr;
+                TopCluster* d_cl = nullptr;
+                unsigned int* d_cnt = nullptr;
+                CKB(cudaMalloc(&d_top, cap * sizeof(int)));
+                CKB(cudaMalloc(&d_cl, (cap + 1) * sizeof(TopCluster)));
+                CKB(cudaMalloc(&d_cnt, 8));
+                CKB(cudaMemset(d_cnt, 0, 8));
+                top_select_kernel<<<grid_n, kB>>>(n, top_cluster, (unsigned int)cap, A, d_top, d_cl, d_cnt);
+                unsigned int cnt[2] = {0, 0};
+                CKB(cudaMemcpy(cnt, d_cnt, 8, cudaMemcpyDeviceToHost));
+                if (cnt[0] + 1 != cnt[1]) {
+                    cudaFree(d_top), cudaFree(d_cl), cudaFree(d_cnt);
+                    return set_error(CRT_ERR_INVALID_ARG, "device build: SAH top selection is inconsistent");
+                }
+                if (cnt[1] <= cap) {
+                std::vector<int> slots(cnt[0]);
+                std::vector<TopCluster> cl(cnt[1]);
+                CKB(cudaMemcpy(slots.data(), d_top, slots.size() * sizeof(int), cudaMemcpyDeviceToHost));
+                CKB(cudaMemcpy(cl.data(), d_cl, cl.size() * sizeof(TopCluster), cudaMemcpyDeviceToHost));
+                std::sort(slots.begin(), slots.end());
+                std::sort(cl.begin(), cl.end(), [](const TopCluster& a, const TopCluster& b) { return a.first < b.first; });
+                std::vector<int> idx(cl.size());
+                for (size_t k = 0; k < idx.size(); ++k) idx[k] = (int)k;
+                TopBuilder tb{cl, slots};
+                tb.out.reserve(slots.size());
+                tb.build(idx, 0, idx.size());
+                TopNode* d_tn = nullptr;
+                CKB(cudaMalloc(&d_tn, tb.out.size() * sizeof(TopNode)));
+                CKB(cudaMemcpy(d_tn, tb.out.data(), tb.out.size() * sizeof(TopNode), cudaMemcpyHostToDevice));
+                top_apply_kernel<<<(int)((tb.out.size() + kB - 1) / kB), kB>>>(n, (int)tb.out.size(), d_tn, A);
+                CKB(cudaDeviceSynchronize());
+                cudaFree(d_tn);
+                launches += 1;
+                }
+                cudaFree(d_top), cudaFree(d_cl), cudaFree(d_cnt);
+                launches += 1;
+                lap("SAH top");
+            }
             // level-synchronous marking of the binary nodes that become BVH4 nodes
             int zero = 0;
             CKB(cudaMemcpy(A.frontier_a, &zero, 4, cudaMemcpyHostToDevice));
