@@ -220,3 +220,37 @@ def test_render_on_a_device_built_scene(gpu, orc):
     b, sb_ = gpu.Renderer(cam, world(gpu.COMMIT_DEVICE_BUILD), st).render_with_stats()
     rel = np.abs(a[..., :3] - b[..., :3]) / (np.abs(a[..., :3]) + 1e-3)
     assert (rel.max(axis=-1) > 1e-3).mean() < 0.002 and sa.camera_rays == sb_.camera_rays
+
+
+def test_sah_built_top_keeps_every_hit():
+    """CRT_DEV_SAH_TOP (read once per process, hence the subprocess): the binary nodes above clusters of 64 references are
+    rebuilt by a host SAH and spliced into the radix tree; the probe scene's hits must still be the oracle's."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = r'''
+import sys
+sys.path.insert(0, %r); sys.path.insert(0, %r + "/oracle"); sys.path.insert(0, %r + "/tests")
+import numpy as np
+import crust_render_b200 as gpu
+import orc
+from crust_render_b200 import workloads as W
+from test_gpu_device_build import commit_both, agree
+gpu.init(0)
+meshes = [W.uv_sphere(c, 0.45, 24, 12) for c in [(x * 1.2, y * 1.2, z * 1.2) for x in range(-2, 3) for y in range(-1, 2) for z in range(-2, 3)]]
+plain, so = commit_both(gpu, orc, meshes)
+rays = W.ray_batch(1 << 17, W.scene_extent(so.bounds()))
+hg, _ = plain.intersect_n(rays)
+ho, _ = so.intersect_n(rays, threads=0)
+same, tie = agree(hg, ho)
+assert (same | tie).all() and same.mean() >= 0.9999, same.mean()
+assert np.array_equal(plain.occluded_n(rays), so.occluded_n(rays, threads=0))
+info = plain.build_info()
+assert info.built_on_device == 1
+print("ok", int(info.wide_nodes), float(same.mean()))
+''' % (root, root, root)
+    env = dict(os.environ, CRT_DEV_SAH_TOP="64", CRT_DEVICE_BUILD_TRACE="1")
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    assert "ok" in r.stdout and "SAH top" in r.stderr, r.stderr[-2000:]
