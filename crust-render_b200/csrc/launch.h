@@ -79,6 +79,10 @@ struct TraceParams {
 #define CRT_KEY_ADDR 1  // ...and, while the group stays in the shared window, the slots as shared byte addresses from six compares (no masks, no popcounts)
 #endif
 
+#ifndef CRT_ANY_ORDER
+#define CRT_ANY_ORDER 4  // any-hit visiting order of a node's hit lanes (the answer does not depend on it): 0 lane order, 1 nearest entry first, 2 longest overlap first, 3 farthest first, 4 farthest first for a ray with a finite t_max and nearest first for an open-ended one (measured: profiles/r02_tune_any_hit_order.jsonl)
+#endif
+
 #ifndef CRT_LEAF_PREFETCH
 #define CRT_LEAF_PREFETCH 0  // L1 prefetch of a popped leaf's first record(s) while the lane waits for the leaf phase (1: first 128-byte line, 2: two)
 #endif

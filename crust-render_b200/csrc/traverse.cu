@@ -277,6 +277,7 @@ __global__ void __launch_bounds__(CRT_BLOCK, MinBlocks<ANY_HIT, FEAT, MAXD>::val
     auto node_visit = [&](uint32_t child) {
         if constexpr (COUNT) ++c_nodes;
         float tn[4];
+        [[maybe_unused]] float tf[4];
         bool hit[4];
         uint32_t cw[4];
 #if CRT_SIGNSEL
@@ -303,6 +304,7 @@ __global__ void __launch_bounds__(CRT_BLOCK, MinBlocks<ANY_HIT, FEAT, MAXD>::val
             float near_ = fmaxf(fmaxf(fmaxf(tnx, tny), tnz), t_min);
             float far_ = fminf(fminf(fminf(tfx, tfy), tfz), closest);
             tn[l] = near_;
+            tf[l] = far_;
             hit[l] = near_ <= far_;
         }
 #else
@@ -323,12 +325,48 @@ __global__ void __launch_bounds__(CRT_BLOCK, MinBlocks<ANY_HIT, FEAT, MAXD>::val
             float near_ = fmaxf(fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fminf(t0z, t1z)), t_min);
             float far_ = fminf(fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fmaxf(t0z, t1z)), closest);
             tn[l] = near_;
+            tf[l] = far_;
             hit[l] = (near_ <= far_) & (cw[l] != CRT_EMPTY_LANE);
         }
 #endif
         if constexpr (ANY_HIT) {
             // bvh.rs:598-608 — no ordering needed for a boolean answer; queue internal
             // lanes first so leaf lanes (the cheap early exits) pop first.
+#if CRT_SADDR && CRT_KEY_ADDR && CRT_ANY_ORDER
+            // A boolean answer does not depend on the visiting order, its cost does: the lanes are queued by a per-lane key
+            // (leaf lanes still pop first) — 1: nearest entry first, 2: longest overlap with the ray's range first, 3: farthest first.
+            if (sp + 4 <= CRT_SSTACK && (CRT_ANY_ORDER == 2 || tmin_nonneg)) {
+                uint32_t u[4], hb[4];
+                // 4: a query with a finite far end is a visibility test towards a point (a light): what blocks it for many
+                // origins sits near that point, so its lanes are visited farthest first; an open-ended one nearest first
+                [[maybe_unused]] const uint32_t far_first = closest < __int_as_float(0x7f800000) ? 0x7FFFFFFFu : 0u;
+#pragma unroll
+                for (int l = 0; l < 4; ++l) {
+                    uint32_t k;
+                    if (CRT_ANY_ORDER == 4) k = __float_as_uint(tn[l]) ^ far_first;
+                    else if (CRT_ANY_ORDER == 1) k = __float_as_uint(tn[l]);
+                    else if (CRT_ANY_ORDER == 2) k = 0x7FFFFFFFu - (__float_as_uint(tf[l] - tn[l]) & 0x7FFFFFFFu);
+                    else k = 0x7FFFFFFFu - (__float_as_uint(tn[l]) & 0x7FFFFFFFu);
+                    u[l] = k | (~cw[l] & CRT_LEAF_BIT);
+                    hb[l] = hit[l] ? kSlotBytes : 0u;
+                }
+                const uint32_t nbytes = (hb[0] + hb[1]) + (hb[2] + hb[3]);
+                const uint32_t top = sbase + (uint32_t)sp * kSlotBytes + nbytes - kSlotBytes;
+                uint32_t a0 = top, a1 = top, a2 = top, a3 = top;
+                if (u[0] > u[1]) a0 -= hb[1]; else a1 -= hb[0];
+                if (u[0] > u[2]) a0 -= hb[2]; else a2 -= hb[0];
+                if (u[0] > u[3]) a0 -= hb[3]; else a3 -= hb[0];
+                if (u[1] > u[2]) a1 -= hb[2]; else a2 -= hb[1];
+                if (u[1] > u[3]) a1 -= hb[3]; else a3 -= hb[1];
+                if (u[2] > u[3]) a2 -= hb[3]; else a3 -= hb[2];
+                if (hit[0]) asm volatile("st.shared.u32 [%0], %1;" ::"r"(a0), "r"(cw[0]) : "memory");
+                if (hit[1]) asm volatile("st.shared.u32 [%0], %1;" ::"r"(a1), "r"(cw[1]) : "memory");
+                if (hit[2]) asm volatile("st.shared.u32 [%0], %1;" ::"r"(a2), "r"(cw[2]) : "memory");
+                if (hit[3]) asm volatile("st.shared.u32 [%0], %1;" ::"r"(a3), "r"(cw[3]) : "memory");
+                sp += (int)(nbytes / kSlotBytes);
+                return;
+            }
+#endif
 #if CRT_SADDR && CRT_KEY_ADDR
             if (sp + 4 <= CRT_SSTACK) {
                 // Hot path, every slot in shared memory: two running shared-window addresses (internal lanes from the group's
