@@ -506,11 +506,13 @@ def main():
     launches0 = crt.launch_count()
     barrier()
     e_start.record(stream)
+    torch.cuda.nvtx.range_push("crt_timed_steps")  # `ncu --nvtx --nvtx-include "crt_timed_steps/"` captures exactly these launches
     for k in range(args.steps):
         for j, name in enumerate(SETS):
             ev[k][j][0].record(stream)
             launch(name)
             ev[k][j][1].record(stream)
+    torch.cuda.nvtx.range_pop()
     e_end.record(stream)
     barrier()
     launches = crt.launch_count() - launches0

@@ -2,9 +2,12 @@
 """Regenerates profiles/trace_traffic.json — DRAM bytes, L1/L2 behaviour and SIMT efficiency of the five timed traversal
 launches of one bench.py step — from an `ncu --set full` capture of the bench command:
 
-    ncu --set full --clock-control none --import-source on -k regex:trace_kernel -c 60 -o gpurun_out/bench_trace \
-        python bench.py --steps 1 --warmup 1 --no-render --no-cpu-baseline --no-e2e
-    python tools/trace_traffic.py gpurun_out/bench_trace.ncu-rep [--last 5]
+    ncu --set full --clock-control none --import-source on --nvtx --nvtx-include "crt_timed_steps/" -k regex:trace_kernel \
+        -o /tmp/bench_trace python bench.py --steps 1 --warmup 1 --no-render --no-cpu-baseline --no-e2e
+    python tools/trace_traffic.py /tmp/bench_trace.ncu-rep
+
+(bench.py wraps its timed steps in the NVTX range `crt_timed_steps`, so the capture holds exactly the five timed launches,
+however many launches the set-up made before them; the launch durations are checked to be in the order of the sets' sizes.)
 
 The json is stamped with a hash of the traversal sources' code, comments and blank lines left out (`source_sha`); bench.py only
 quotes `roofline.traffic` from it when the hash matches the sources it is running, so the figure cannot silently go stale.
@@ -82,6 +85,10 @@ def main():
                      "warps_active_pct": col(r, "sm__warps_active.avg.pct_of_peak_sustained_active"),
                      "dram_gb_per_s": (rd + wr) / ms / 1e6, "l2_gb_per_s": None if l2 is None else l2 / ms / 1e6}
     closest = [n for n in SETS if n.startswith("closest")]
+    # the five launches must be the five sets in order: closest-hit kernels first (their name has <false / (bool)0 first), then any-hit
+    kinds = [bool(re.search(r"trace_kernel<(?:\(bool\))?(?:1|true)\b", per[n]["kernel"])) for n in SETS]
+    if kinds != [False, False, False, True, True]:
+        sys.exit(f"the captured launches are not one bench step in order (any-hit flags {kinds}): check the capture window")
     out = {"source": f"{os.path.relpath(a.report, ROOT)} (ncu --set full --clock-control none, the five timed launches of one bench step); regenerate with tools/trace_traffic.py",
            "source_sha": source_sha(), "kernel_sources": KERNEL_SOURCES, "per_launch": per,
            "mean_traffic_per_closest_launch": sum(per[n]["traffic"] for n in closest) / len(closest)}
