@@ -561,31 +561,65 @@ struct Builder {
 
 // The leaf record of a non-triangle primitive (crt_layout.h), appended to t.leafs; instances also append their motion pair
 // and note where their record sits (child pointers are patched in at upload). `last`: REC_LAST or 0.
-void emit_other_record(const PrimStore& ps, uint32_t pi, uint32_t last, HostTree& t) {
-    auto fbits = [](float f) {
-        uint32_t u;
-        std::memcpy(&u, &f, 4);
-        return u;
-    };
-    auto q = [&](uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+// Where a leaf record goes: appended to the tree's vectors (PushSink: device build's host-side preparation), or written at
+// known positions of arrays sized beforehand (CursorSink: the flattener, whose subtrees are emitted in parallel).
+struct PushSink {
+    HostTree& t;
+    void q(uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
         t.leafs.push_back(a);
         t.leafs.push_back(b);
         t.leafs.push_back(c);
         t.leafs.push_back(d);
-    };
-    auto qf = [&](float a, float b, float c, uint32_t d) { q(fbits(a), fbits(b), fbits(c), d); };
+    }
+    uint32_t add_motion(const MotionXform& m) {
+        t.motion.push_back(m);
+        return (uint32_t)(t.motion.size() - 1);
+    }
+    void add_instance() { t.instance_record_q.push_back((uint32_t)(t.leafs.size() / 4)); }
+};
+struct Cur {  // positions in (or, in a dry run, sizes of) the flattened arrays
+    size_t node = 0, quad = 0, motion = 0, inst = 0, leaves = 0, refs = 0;
+};
+template <bool DRY>
+struct CursorSink {
+    HostTree& t;
+    Cur& c;
+    void q(uint32_t a, uint32_t b, uint32_t c4, uint32_t d) {
+        if (!DRY) {
+            uint32_t* w = &t.leafs[4 * c.quad];
+            w[0] = a, w[1] = b, w[2] = c4, w[3] = d;
+        }
+        ++c.quad;
+    }
+    uint32_t add_motion(const MotionXform& m) {
+        if (!DRY) t.motion[c.motion] = m;
+        return (uint32_t)c.motion++;
+    }
+    void add_instance() {
+        if (!DRY) t.instance_record_q[c.inst] = (uint32_t)c.quad;
+        ++c.inst;
+    }
+};
+inline uint32_t fbits_of(float f) {
+    uint32_t u;
+    std::memcpy(&u, &f, 4);
+    return u;
+}
+template <class Sink>
+void emit_other_record_to(const PrimStore& ps, uint32_t pi, uint32_t last, Sink& k) {
+    auto qf = [&](float a, float b, float c, uint32_t d) { k.q(fbits_of(a), fbits_of(b), fbits_of(c), d); };
     switch (ps.kind[pi]) {
         case P_SPHERE: {
             const float* s = &ps.sphere[4 * (size_t)ps.data[pi]];
             qf(s[0], s[1], s[2], REC_SPHERE | last);
-            q(fbits(s[3]), pi, ps.mask[pi], ps.geom_id[pi]);
+            k.q(fbits_of(s[3]), pi, ps.mask[pi], ps.geom_id[pi]);
             break;
         }
         case P_CURVE: {
             const float* c = &ps.curve[8 * (size_t)ps.data[pi]];
             qf(c[0], c[1], c[2], REC_CURVE | last);
             qf(c[3], c[4], c[5], pi);
-            q(fbits(c[6]), fbits(c[7]), ps.mask[pi], 0);
+            k.q(fbits_of(c[6]), fbits_of(c[7]), ps.mask[pi], 0);
             break;
         }
         case P_CUBIC: {
@@ -594,8 +628,8 @@ void emit_other_record(const PrimStore& ps, uint32_t pi, uint32_t last, HostTree
             qf(c[3], c[4], c[5], pi);
             qf(c[6], c[7], c[8], ps.mask[pi]);
             qf(c[9], c[10], c[11], 0);
-            q(fbits(c[12]), fbits(c[13]), 0, 0);
-            q(0, 0, 0, 0);
+            k.q(fbits_of(c[12]), fbits_of(c[13]), 0, 0);
+            k.q(0, 0, 0, 0);
             break;
         }
         default: {
@@ -604,155 +638,32 @@ void emit_other_record(const PrimStore& ps, uint32_t pi, uint32_t last, HostTree
             uint32_t motion = 0;
             if (I.has_end) {
                 flags |= REC_MOTION;
-                motion = (uint32_t)t.motion.size();
                 MotionXform m;
                 const Vec3* a = &I.l2w.x;
                 const Vec3* b = &I.l2w_end.x;
-                for (int k = 0; k < 4; ++k) {
-                    m.l2w[3 * k] = a[k].x, m.l2w[3 * k + 1] = a[k].y, m.l2w[3 * k + 2] = a[k].z;
-                    m.l2w_end[3 * k] = b[k].x, m.l2w_end[3 * k + 1] = b[k].y, m.l2w_end[3 * k + 2] = b[k].z;
+                for (int n = 0; n < 4; ++n) {
+                    m.l2w[3 * n] = a[n].x, m.l2w[3 * n + 1] = a[n].y, m.l2w[3 * n + 2] = a[n].z;
+                    m.l2w_end[3 * n] = b[n].x, m.l2w_end[3 * n + 1] = b[n].y, m.l2w_end[3 * n + 2] = b[n].z;
                 }
-                t.motion.push_back(m);
+                motion = k.add_motion(m);
             }
-            t.instance_record_q.push_back((uint32_t)(t.leafs.size() / 4));
+            k.add_instance();
             qf(I.w2l.x.x, I.w2l.x.y, I.w2l.x.z, flags);
             qf(I.w2l.y.x, I.w2l.y.y, I.w2l.y.z, pi);
             qf(I.w2l.z.x, I.w2l.z.y, I.w2l.z.z, ps.mask[pi]);
             qf(I.w2l.t.x, I.w2l.t.y, I.w2l.t.z, motion);
-            q(0, 0, ps.geom_id[pi], ps.data[pi]);  // words 0-1: child descriptor pointer, patched at upload
-            q(0, 0, 0, 0);                         // child node / leaf-record arrays, patched at upload
+            k.q(0, 0, ps.geom_id[pi], ps.data[pi]);  // words 0-1: child descriptor pointer, patched at upload
+            k.q(0, 0, 0, 0);                         // child node / leaf-record arrays, patched at upload
             break;
         }
     }
 }
 
-// ---- collapse to BVH4 + record emission --------------------------------------
-struct Flattener {
-    const PrimStore& ps;
-    const std::vector<BinNode>& bin;
-    const std::vector<uint32_t>& bidx;
-    HostTree& t;
+void emit_other_record(const PrimStore& ps, uint32_t pi, uint32_t last, HostTree& t) {
+    PushSink k{t};
+    emit_other_record_to(ps, pi, last, k);
+}
 
-    static uint32_t fbits(float f) {
-        uint32_t u;
-        std::memcpy(&u, &f, 4);
-        return u;
-    }
-    void q(uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-        t.leafs.push_back(a);
-        t.leafs.push_back(b);
-        t.leafs.push_back(c);
-        t.leafs.push_back(d);
-    }
-    void qf(float a, float b, float c, uint32_t d) { q(fbits(a), fbits(b), fbits(c), d); }
-
-    // bvh.rs:1256-1290: triangles of the range first (packet order), then the rest.
-    uint32_t emit_leaf(const uint32_t* range, size_t n) {
-        uint32_t first_q = (uint32_t)(t.leafs.size() / 4);
-        size_t n_tri = 0;
-        for (size_t i = 0; i < n; ++i) n_tri += ps.kind[range[i]] == P_TRI;
-        const size_t n_other = n - n_tri;
-        size_t ti = 0;
-        for (size_t i = 0; i < n; ++i) {
-            uint32_t pi = range[i];
-            if (ps.kind[pi] != P_TRI) continue;
-            const float* v = tri_of(ps, pi);
-            uint32_t flags = REC_TRI | ((uint32_t)(ti & 3) << REC_LANE_SHIFT);
-            if ((ti & 3) == 3 || ti + 1 == n_tri) flags |= REC_PACKET_END;
-            if (ti + 1 == n_tri && n_other == 0) flags |= REC_LAST;
-            if (ps.tri_normal_slot[ps.data[pi]] != 0xFFFFFFFFu) {
-                flags |= REC_HAS_NORMALS;
-            } else {  // prim.rs:80-83
-                Vec3 a = V(v[0], v[1], v[2]);
-                Vec3 nrm = cross3(sub(V(v[3], v[4], v[5]), a), sub(V(v[6], v[7], v[8]), a));
-                if (nrm.x == 0.0f && nrm.y == 0.0f && nrm.z == 0.0f) flags |= REC_DEGENERATE;
-            }
-            qf(v[0], v[1], v[2], flags);
-            qf(v[3], v[4], v[5], pi);
-            qf(v[6], v[7], v[8], ps.mask[pi]);
-            ++ti;
-        }
-        size_t oi = 0;
-        for (size_t i = 0; i < n; ++i) {
-            uint32_t pi = range[i];
-            if (ps.kind[pi] == P_TRI) continue;
-            const uint32_t last = (++oi == n_other) ? (uint32_t)REC_LAST : 0u;
-            emit_other_record(ps, pi, last, t);
-        }
-        t.n_leaves += 1;
-        t.n_leaf_refs += n;
-        return CRT_LEAF_BIT | first_q;
-    }
-
-    static void set_lane(DevNode& w, int lane, const Box& b) {  // bvh.rs:243-251
-        w.bmin_x[lane] = b.lo.x, w.bmin_y[lane] = b.lo.y, w.bmin_z[lane] = b.lo.z;
-        w.bmax_x[lane] = b.hi.x, w.bmax_y[lane] = b.hi.y, w.bmax_z[lane] = b.hi.z;
-        w.flags |= 1u << lane;
-    }
-    static DevNode empty_node() {  // bvh.rs:230-241
-        DevNode w;
-        for (int l = 0; l < 4; ++l) {
-            w.bmin_x[l] = w.bmin_y[l] = w.bmin_z[l] = w.bmax_x[l] = w.bmax_y[l] = w.bmax_z[l] = kInf;
-            w.child[l] = CRT_EMPTY_LANE;
-        }
-        w.flags = 0;
-        w.pad[0] = w.pad[1] = w.pad[2] = 0;
-        return w;
-    }
-    // bvh.rs:1328-1375
-    uint32_t node(uint32_t b_idx) {
-        size_t slot = t.nodes.size();
-        t.nodes.push_back(empty_node());
-        uint32_t kids[4] = {b_idx + 1, bin[b_idx].first_or_right, 0, 0};
-        int n_kids = 2;
-        while (n_kids < 4) {
-            int best = -1;
-            float best_a = 0;
-            for (int i = 0; i < n_kids; ++i)
-                if (bin[kids[i]].count == 0) {
-                    float a = area(bin[kids[i]].bbox);
-                    if (best < 0 || a > best_a) best = i, best_a = a;
-                }
-            if (best < 0) break;
-            uint32_t k = kids[best];
-            kids[best] = k + 1;
-            kids[n_kids++] = bin[k].first_or_right;
-        }
-        for (int lane = 0; lane < n_kids; ++lane) {
-            const BinNode& k = bin[kids[lane]];
-            set_lane(t.nodes[slot], lane, k.bbox);
-            uint32_t c;
-            if (k.count > 0) {
-                c = emit_leaf(bidx.data() + k.first_or_right, k.count);
-                t.nodes[slot].flags |= 1u << (4 + lane);
-            } else {
-                c = node(kids[lane]);
-            }
-            t.nodes[slot].child[lane] = c;
-        }
-        return (uint32_t)slot;
-    }
-    void run() {  // bvh.rs:1299-1320
-        t.nodes.reserve(bin.size() / 2 + 1);
-        if (bin[0].count > 0) {
-            t.nodes.push_back(empty_node());
-            set_lane(t.nodes[0], 0, bin[0].bbox);
-            uint32_t c = emit_leaf(bidx.data() + bin[0].first_or_right, bin[0].count);
-            t.nodes[0].child[0] = c;
-            t.nodes[0].flags |= 1u << 4;
-        } else {
-            node(0);
-        }
-        // Kernels may over-read up to one triangle record past a leaf's end.
-        for (int i = 0; i < 4; ++i) q(0, 0, 0, REC_LAST | REC_SPHERE);
-    }
-};
-
-inline Vec3 v3at(const std::vector<float>& a, size_t i) { return V(a[3 * i], a[3 * i + 1], a[3 * i + 2]); }
-
-}  // namespace
-
-namespace {
 // Runs fn(k) for k in [0, count) on up to `threads` workers (static interleave). Every k writes its own slice of the
 // output arrays, so the result does not depend on the thread count.
 template <class F>
@@ -771,6 +682,219 @@ void parallel_for_n(int threads, size_t count, F&& fn) {
     for (auto& th : pool) th.join();
 }
 
+// ---- collapse to BVH4 + record emission --------------------------------------
+// The flattened arrays are in the reference's depth-first order (bvh.rs:1299-1375): a node takes its slot when it is entered,
+// a leaf's records are appended when its lane is reached. Every function below runs either as a dry run, which only advances
+// the cursors (= measures a subtree), or for real, writing at the cursors into arrays sized by a dry run — so subtrees can
+// be measured and then written in parallel, each at its own offsets, and the arrays do not depend on the thread count.
+struct Flattener {
+    const PrimStore& ps;
+    const std::vector<BinNode>& bin;
+    const std::vector<uint32_t>& bidx;
+    HostTree& t;
+    int threads;
+
+    // bvh.rs:1256-1290: triangles of the range first (packet order), then the rest.
+    template <bool DRY>
+    uint32_t emit_leaf(const uint32_t* range, size_t n, Cur& c) {
+        const uint32_t first_q = (uint32_t)c.quad;
+        CursorSink<DRY> k{t, c};
+        size_t n_tri = 0;
+        for (size_t i = 0; i < n; ++i) n_tri += ps.kind[range[i]] == P_TRI;
+        const size_t n_other = n - n_tri;
+        if (DRY) {
+            c.quad += (size_t)REC_TRI_Q * n_tri;
+        } else {
+            size_t ti = 0;
+            for (size_t i = 0; i < n; ++i) {
+                uint32_t pi = range[i];
+                if (ps.kind[pi] != P_TRI) continue;
+                const float* v = tri_of(ps, pi);
+                uint32_t flags = REC_TRI | ((uint32_t)(ti & 3) << REC_LANE_SHIFT);
+                if ((ti & 3) == 3 || ti + 1 == n_tri) flags |= REC_PACKET_END;
+                if (ti + 1 == n_tri && n_other == 0) flags |= REC_LAST;
+                if (ps.tri_normal_slot[ps.data[pi]] != 0xFFFFFFFFu) {
+                    flags |= REC_HAS_NORMALS;
+                } else {  // prim.rs:80-83
+                    Vec3 a = V(v[0], v[1], v[2]);
+                    Vec3 nrm = cross3(sub(V(v[3], v[4], v[5]), a), sub(V(v[6], v[7], v[8]), a));
+                    if (nrm.x == 0.0f && nrm.y == 0.0f && nrm.z == 0.0f) flags |= REC_DEGENERATE;
+                }
+                k.q(fbits_of(v[0]), fbits_of(v[1]), fbits_of(v[2]), flags);
+                k.q(fbits_of(v[3]), fbits_of(v[4]), fbits_of(v[5]), pi);
+                k.q(fbits_of(v[6]), fbits_of(v[7]), fbits_of(v[8]), ps.mask[pi]);
+                ++ti;
+            }
+        }
+        size_t oi = 0;
+        for (size_t i = 0; i < n && oi < n_other; ++i) {
+            uint32_t pi = range[i];
+            if (ps.kind[pi] == P_TRI) continue;
+            const uint32_t last = (++oi == n_other) ? (uint32_t)REC_LAST : 0u;
+            emit_other_record_to(ps, pi, last, k);
+        }
+        c.leaves += 1;
+        c.refs += n;
+        return CRT_LEAF_BIT | first_q;
+    }
+
+    static void set_lane(DevNode& w, int lane, const Box& b) {  // bvh.rs:243-251
+        w.bmin_x[lane] = b.lo.x, w.bmin_y[lane] = b.lo.y, w.bmin_z[lane] = b.lo.z;
+        w.bmax_x[lane] = b.hi.x, w.bmax_y[lane] = b.hi.y, w.bmax_z[lane] = b.hi.z;
+        w.flags |= 1u << lane;
+    }
+    static DevNode empty_node() {  // bvh.rs:230-241
+        DevNode w;
+        for (int l = 0; l < 4; ++l) {
+            w.bmin_x[l] = w.bmin_y[l] = w.bmin_z[l] = w.bmax_x[l] = w.bmax_y[l] = w.bmax_z[l] = kInf;
+            w.child[l] = CRT_EMPTY_LANE;
+        }
+        w.flags = 0;
+        w.pad[0] = w.pad[1] = w.pad[2] = 0;
+        return w;
+    }
+    // The up-to-four lanes of the BVH4 node rooted at binary node b_idx: the internal child with the largest surface area is
+    // expanded first, the first one winning ties (bvh.rs:1328-1356).
+    int lanes_of(uint32_t b_idx, uint32_t kids[4]) const {
+        kids[0] = b_idx + 1, kids[1] = bin[b_idx].first_or_right, kids[2] = kids[3] = 0;
+        int n_kids = 2;
+        while (n_kids < 4) {
+            int best = -1;
+            float best_a = 0;
+            for (int i = 0; i < n_kids; ++i)
+                if (bin[kids[i]].count == 0) {
+                    float a = area(bin[kids[i]].bbox);
+                    if (best < 0 || a > best_a) best = i, best_a = a;
+                }
+            if (best < 0) break;
+            uint32_t k = kids[best];
+            kids[best] = k + 1;
+            kids[n_kids++] = bin[k].first_or_right;
+        }
+        return n_kids;
+    }
+    // A whole subtree, depth first (bvh.rs:1328-1375).
+    template <bool DRY>
+    uint32_t node(uint32_t b_idx, Cur& c) {
+        const size_t slot = c.node++;
+        uint32_t kids[4];
+        const int n_kids = lanes_of(b_idx, kids);
+        DevNode w;
+        if (!DRY) w = empty_node();
+        for (int lane = 0; lane < n_kids; ++lane) {
+            const BinNode& k = bin[kids[lane]];
+            uint32_t ch;
+            if (k.count > 0) {
+                ch = emit_leaf<DRY>(bidx.data() + k.first_or_right, k.count, c);
+                if (!DRY) w.flags |= 1u << (4 + lane);
+            } else {
+                ch = node<DRY>(kids[lane], c);
+            }
+            if (!DRY) set_lane(w, lane, k.bbox), w.child[lane] = ch;
+        }
+        if (!DRY) t.nodes[slot] = w;
+        return (uint32_t)slot;
+    }
+
+    // Subtrees handed to the workers: the internal lanes `kTaskDepth` BVH4 levels below the root, in depth-first order.
+    static constexpr int kTaskDepth = 5;
+    struct Task {
+        uint32_t b_idx;
+        Cur size, base;
+    };
+    void collect(uint32_t b_idx, int depth, std::vector<Task>& tasks) const {
+        uint32_t kids[4];
+        const int n_kids = lanes_of(b_idx, kids);
+        for (int lane = 0; lane < n_kids; ++lane) {
+            if (bin[kids[lane]].count > 0) continue;
+            if (depth + 1 == kTaskDepth) tasks.push_back(Task{kids[lane], Cur{}, Cur{}});
+            else collect(kids[lane], depth + 1, tasks);
+        }
+    }
+    // The levels above the tasks: same walk as node(), except that a task's subtree is stepped over by its measured size
+    // (dry run: to size the arrays; real run: the task's offsets are noted on the way).
+    template <bool DRY>
+    uint32_t top(uint32_t b_idx, int depth, Cur& c, std::vector<Task>& tasks, size_t& next_task) {
+        const size_t slot = c.node++;
+        uint32_t kids[4];
+        const int n_kids = lanes_of(b_idx, kids);
+        DevNode w;
+        if (!DRY) w = empty_node();
+        for (int lane = 0; lane < n_kids; ++lane) {
+            const BinNode& k = bin[kids[lane]];
+            uint32_t ch;
+            if (k.count > 0) {
+                ch = emit_leaf<DRY>(bidx.data() + k.first_or_right, k.count, c);
+                if (!DRY) w.flags |= 1u << (4 + lane);
+            } else if (depth + 1 == kTaskDepth) {
+                Task& tk = tasks[next_task++];
+                ch = (uint32_t)c.node;
+                if (!DRY) tk.base = c;
+                c.node += tk.size.node, c.quad += tk.size.quad, c.motion += tk.size.motion, c.inst += tk.size.inst;
+                c.leaves += tk.size.leaves, c.refs += tk.size.refs;
+            } else {
+                ch = top<DRY>(kids[lane], depth + 1, c, tasks, next_task);
+            }
+            if (!DRY) set_lane(w, lane, k.bbox), w.child[lane] = ch;
+        }
+        if (!DRY) t.nodes[slot] = w;
+        return (uint32_t)slot;
+    }
+
+    void size_arrays(const Cur& total) {
+        t.nodes.resize(total.node);
+        t.leafs.resize(4 * (total.quad + 4));  // + the over-read padding below
+        t.motion.resize(total.motion);
+        t.instance_record_q.resize(total.inst);
+        t.n_leaves += total.leaves;
+        t.n_leaf_refs += total.refs;
+    }
+    void run() {  // bvh.rs:1299-1320
+        Cur total;
+        if (bin[0].count > 0) {
+            emit_leaf<true>(bidx.data() + bin[0].first_or_right, bin[0].count, total);
+            total.node = 1;
+            size_arrays(total);
+            Cur c;
+            c.node = 1;
+            DevNode w = empty_node();
+            set_lane(w, 0, bin[0].bbox);
+            w.child[0] = emit_leaf<false>(bidx.data() + bin[0].first_or_right, bin[0].count, c);
+            w.flags |= 1u << 4;
+            t.nodes[0] = w;
+        } else {
+            std::vector<Task> tasks;
+            if (threads > 1 && bin.size() >= ((size_t)1 << 16)) collect(0, 0, tasks);
+            if (tasks.empty()) {
+                node<true>(0, total);
+                size_arrays(total);
+                Cur c;
+                node<false>(0, c);
+            } else {
+                parallel_for_n(threads, tasks.size(), [&](size_t i) { node<true>(tasks[i].b_idx, tasks[i].size); });
+                size_t next = 0;
+                top<true>(0, 0, total, tasks, next);
+                size_arrays(total);
+                Cur c;
+                next = 0;
+                top<false>(0, 0, c, tasks, next);
+                parallel_for_n(threads, tasks.size(), [&](size_t i) {
+                    Cur at = tasks[i].base;
+                    node<false>(tasks[i].b_idx, at);
+                });
+            }
+        }
+        // Kernels may over-read up to one triangle record past a leaf's end.
+        uint32_t* pad = &t.leafs[t.leafs.size() - 16];
+        for (int i = 0; i < 4; ++i) pad[4 * i] = pad[4 * i + 1] = pad[4 * i + 2] = 0, pad[4 * i + 3] = REC_LAST | REC_SPHERE;
+    }
+};
+
+inline Vec3 v3at(const std::vector<float>& a, size_t i) { return V(a[3 * i], a[3 * i + 1], a[3 * i + 2]); }
+
+}  // namespace
+
+namespace {
 // scene.rs:240-335: geometries -> primitives, ids, normals. `skip_meshes`: triangle meshes contribute nothing and keep their
 // inputs (the device build expands them itself and only needs the other kinds from here); ids are unaffected.
 bool expand_geoms(std::vector<Geom>& geoms, ChildInfoFn child_info, int threads, HostTree& out, const char** err, bool skip_meshes,
@@ -980,8 +1104,7 @@ bool build_host_tree(std::vector<Geom>& geoms, ChildInfoFn child_info, int threa
     out.non_empty = true;
     out.root = root;
 
-    out.leafs.reserve(bin.indices.size() * 12 + 16);
-    Flattener fl{ps, bin.nodes, bin.indices, out};
+    Flattener fl{ps, bin.nodes, bin.indices, out, threads};
     fl.run();
     lap("BVH4 collapse + leaf records");
     out.build_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();

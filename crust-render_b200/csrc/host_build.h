@@ -12,6 +12,7 @@
 #include <atomic>
 #include <cstdint>
 #include <memory>
+#include <utility>
 #include <vector>
 
 #include "crt.h"
@@ -20,6 +21,25 @@
 struct crt_scene;
 
 namespace crt {
+
+// std::allocator whose value-initialisation is default-initialisation: resize() of the big flattened arrays leaves the new
+// memory untouched, so its pages are first touched by the threads that fill them (in parallel) instead of being zeroed by one.
+template <class T>
+struct DefaultInitAlloc : std::allocator<T> {
+    template <class U>
+    struct rebind {
+        using other = DefaultInitAlloc<U>;
+    };
+    using std::allocator<T>::allocator;
+    template <class U, class... A>
+    void construct(U* p, A&&... a) {
+        if constexpr (sizeof...(A) == 0)
+            ::new ((void*)p) U;
+        else
+            ::new ((void*)p) U(std::forward<A>(a)...);
+    }
+};
+using WordVec = std::vector<uint32_t, DefaultInitAlloc<uint32_t>>;
 
 struct Vec3 {
     float x, y, z;
@@ -85,8 +105,8 @@ struct HostTree {
     bool has_motion = false;
     uint32_t instance_depth = 0;  // deepest nesting below this scene
     // device-layout arrays (host copies; freed after upload unless kept)
-    std::vector<DevNode> nodes;
-    std::vector<uint32_t> leafs;  // 4 words per 16-byte unit
+    std::vector<DevNode, DefaultInitAlloc<DevNode>> nodes;
+    WordVec leafs;  // 4 words per 16-byte unit
     std::vector<uint32_t> prim_ids;  // 2 words per primitive
     std::vector<float> normals;      // 9 per primitive index when any mesh has normals
     std::vector<MotionXform> motion;
@@ -120,7 +140,7 @@ struct OtherPrims {
     std::vector<float> lo, hi;         // 4 floats per primitive (lo.w = 1: valid)
     std::vector<uint32_t> ids;         // geom_id, prim_id per primitive
     std::vector<uint32_t> rec_off;     // n + 1 offsets into `recs`, in 16-byte units
-    std::vector<uint32_t> recs;        // 4 words per 16-byte unit
+    WordVec recs;        // 4 words per 16-byte unit
     std::vector<uint32_t> inst_prim;   // which of the primitives are instances ...
     std::vector<crt_scene*> inst_child;  // ... and of which scene
     std::vector<MotionXform> motion;

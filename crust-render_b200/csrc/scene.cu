@@ -105,7 +105,8 @@ int ensure_device() {
 // copy the first `budget` bytes' worth of nodes are re-ordered breadth-first from the root (the rest keep their DFS order
 // behind them) and child words are renumbered: same tree, same child lanes, same visiting order — only addresses change.
 // Returns the size of the breadth-first prefix in bytes (0 when the tree is smaller than two nodes or the feature is off).
-size_t top_levels_first(const std::vector<DevNode>& nodes, size_t budget, std::vector<DevNode>& out) {
+template <class NodeVec>
+size_t top_levels_first(const NodeVec& nodes, size_t budget, std::vector<DevNode>& out) {
     const size_t n = nodes.size();
     size_t n_top = std::min(n, budget / sizeof(DevNode));
     if (n_top < 2) return 0;
