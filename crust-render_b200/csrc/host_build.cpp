@@ -482,7 +482,8 @@ struct Builder {
             }
         }
         const size_t count = refs.size();
-        if (count <= min_leaf_for(refs, par) || depth >= kMaxDepth) return emit_leaf(out, bbox, refs);
+        // (the kind scan behind min_leaf_for only matters for a node that small: it is a pass of scattered loads otherwise)
+        if ((count <= std::max(kMinLeaf, kMinLeafPacked) && count <= min_leaf_for(refs, par)) || depth >= kMaxDepth) return emit_leaf(out, bbox, refs);
 
         ObjSplit obj{};
         const bool have_obj = object_split(refs, obj, par);
@@ -528,7 +529,7 @@ struct Builder {
             if (l.empty() || r.empty()) {  // degenerate chop: bvh.rs:1130-1134, 1173-1196
                 l.insert(l.end(), r.begin(), r.end());
                 std::vector<Ref>().swap(r);
-                if (have_obj && l.size() > min_leaf_for(l, par)) {
+                if (have_obj && (l.size() > std::max(kMinLeaf, kMinLeafPacked) || l.size() > min_leaf_for(l, par))) {
                     std::vector<Ref> a, b;
                     stable_split(l, obj, a, b, par);
                     if (a.empty() || b.empty()) {
