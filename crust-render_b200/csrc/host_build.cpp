@@ -797,8 +797,10 @@ struct Flattener {
         return (uint32_t)slot;
     }
 
-    // Subtrees handed to the workers: the internal lanes `kTaskDepth` BVH4 levels below the root, in depth-first order.
-    static constexpr int kTaskDepth = 5;
+    // Subtrees handed to the workers: the internal lanes `kTaskDepth` BVH4 levels below the root, in depth-first order
+    // (trees of 2^16 binary nodes or more; CRT_FLATTEN_TASK_DEPTH / CRT_FLATTEN_PAR_MIN move both for the tests).
+    int kTaskDepth = getenv("CRT_FLATTEN_TASK_DEPTH") ? std::max(1, atoi(getenv("CRT_FLATTEN_TASK_DEPTH"))) : 5;
+    size_t kParMin = getenv("CRT_FLATTEN_PAR_MIN") ? (size_t)atoll(getenv("CRT_FLATTEN_PAR_MIN")) : ((size_t)1 << 16);
     struct Task {
         uint32_t b_idx;
         Cur size, base;
@@ -865,7 +867,7 @@ struct Flattener {
             t.nodes[0] = w;
         } else {
             std::vector<Task> tasks;
-            if (threads > 1 && bin.size() >= ((size_t)1 << 16)) collect(0, 0, tasks);
+            if (threads > 1 && bin.size() >= kParMin) collect(0, 0, tasks);
             if (tasks.empty()) {
                 node<true>(0, total);
                 size_arrays(total);

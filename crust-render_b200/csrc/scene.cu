@@ -1075,6 +1075,23 @@ int crt_debug_tree_sizes(const crt_scene* s, uint64_t out4[4]) {
     export_sizes(*s->host, out4);
     return CRT_OK;
 }
+int crt_debug_host_array(const crt_scene* s, int which, uint32_t* out, uint64_t capacity_words, uint64_t* n_words) {
+    if (!s || !n_words) return fail(CRT_ERR_INVALID_ARG, "null argument");
+    if (!s->host) return fail(CRT_ERR_INVALID_ARG, "scene was not committed with CRT_COMMIT_KEEP_HOST_TREE");
+    const HostTree& t = *s->host;
+    const void* src = nullptr;
+    uint64_t words = 0;
+    switch (which) {
+        case 0: src = t.nodes.data(), words = t.nodes.size() * (sizeof(DevNode) / 4); break;
+        case 1: src = t.leafs.data(), words = t.leafs.size(); break;
+        case 2: src = t.motion.data(), words = t.motion.size() * (sizeof(MotionXform) / 4); break;
+        case 3: src = t.instance_record_q.data(), words = t.instance_record_q.size(); break;
+        default: return fail(CRT_ERR_INVALID_ARG, "crt_debug_host_array: which must be 0..3");
+    }
+    *n_words = words;
+    if (out && words) memcpy(out, src, (size_t)std::min(capacity_words, words) * 4);
+    return CRT_OK;
+}
 int crt_debug_tree_export(const crt_scene* s, void* nodes, uint32_t* tri_counts, uint32_t* other_counts, uint32_t* refs) {
     if (!s || !nodes || !tri_counts || !other_counts || !refs) return fail(CRT_ERR_INVALID_ARG, "null argument");
     if (!s->host) return fail(CRT_ERR_INVALID_ARG, "scene was not committed with CRT_COMMIT_KEEP_HOST_TREE");

@@ -136,6 +136,7 @@ def lib() -> C.CDLL:
         "crt_trace_counters_read": [C.POINTER(u64), C.c_int],
         "crt_debug_tree_sizes": [vp, C.POINTER(u64)],
         "crt_debug_tree_export": [vp, vp, u32p, u32p, u32p],
+        "crt_debug_host_array": [vp, C.c_int, u32p, u64, C.POINTER(u64)],
         # include/crt_render.h
         "crt_world_new": [vp, vp, sz, vp, sz, vp, sz, C.POINTER(vp)],
         "crt_world_set_environment": [vp, u32, u32, u32, vp, vp],
@@ -501,3 +502,17 @@ class Scene:
         u32p = C.POINTER(C.c_uint32)
         _ck(lib().crt_debug_tree_export(self._h, _ptr(nodes), tri.ctypes.data_as(u32p), oth.ctypes.data_as(u32p), refs.ctypes.data_as(u32p)))
         return {"nodes": nodes, "tri_counts": tri, "other_counts": oth, "refs": refs, "binary_nodes": n_bin}
+
+    def debug_host_arrays(self):
+        """The flattened host arrays word for word (needs COMMIT_KEEP_HOST_TREE): wide nodes, leaf records, motion pairs,
+        instance record offsets."""
+        out = {}
+        u32p = C.POINTER(C.c_uint32)
+        for which, name in enumerate(("nodes", "leafs", "motion", "instance_record_q")):
+            n = C.c_uint64(0)
+            _ck(lib().crt_debug_host_array(self._h, which, None, 0, C.byref(n)))
+            a = np.zeros(int(n.value), dtype=np.uint32)
+            if n.value:
+                _ck(lib().crt_debug_host_array(self._h, which, a.ctypes.data_as(u32p), n.value, C.byref(n)))
+            out[name] = a
+        return out

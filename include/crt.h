@@ -227,6 +227,11 @@ int crt_debug_tree_sizes(const crt_scene* s, uint64_t out4[4]);
  * count of triangle and other references; refs: primitive indices leaf by leaf. */
 int crt_debug_tree_export(const crt_scene* s, void* nodes, uint32_t* tri_counts, uint32_t* other_counts,
                           uint32_t* refs);
+/* The flattened host arrays as 32-bit words, for tests that compare two commits of the same scene word for word (instance
+ * records hold zeros where the upload patches device pointers in): which = 0 wide nodes (32 words each), 1 leaf records
+ * (4 words per 16-byte unit, padding included), 2 motion pairs (24 words each), 3 instance record offsets. Returns the
+ * number of words through *n_words; copies min(capacity_words, *n_words) words when `out` is not NULL. */
+int crt_debug_host_array(const crt_scene* s, int which, uint32_t* out, uint64_t capacity_words, uint64_t* n_words);
 
 #ifdef __cplusplus
 }

@@ -153,3 +153,57 @@ def test_builder_is_consumed_by_commit(crt):  # scene.rs:226 commit(self)
     b.commit(flags=crt.COMMIT_HOST_ONLY)
     with pytest.raises(crt.CrtError):
         b.attach(Geometry.Sphere((0, 0, 0), 1.0))
+
+
+@pytest.mark.parametrize("threads,depth", [(2, 1), (3, 2), (8, 3)])
+def test_parallel_collapse_writes_the_sequential_arrays(crt, orc, threads, depth, monkeypatch):
+    """The BVH4 collapse measures subtrees in a dry run and then writes them in parallel at their offsets (host_build.cpp
+    Flattener; normally from 2^16 binary nodes up, subtrees five levels below the root). Forced onto small scenes of every
+    record kind — triangles with and without normals, spheres, both curve kinds, masked / moving instances — the wide nodes,
+    the leaf record stream, the motion pairs and the instance record offsets must equal the one-thread commit's word for
+    word, and the tree the oracle's."""
+    def mixed(api):
+        b = api.SceneBuilder()
+        v, i = workloads.uv_sphere((0, 0, 0), 1.0, 48, 24)
+        b.attach(Geometry.TriangleMesh(v, i))
+        v2, i2 = workloads.uv_sphere((2.5, 0.2, 0), 0.7, 24, 12)
+        b.attach(Geometry.TriangleMesh(v2, i2, normals=(v2 - np.array([2.5, 0.2, 0], np.float32)) / np.float32(0.7)))
+        for k in range(40):
+            b.attach(Geometry.Sphere(np.array([k * 0.3 - 6, 2.0, (k % 5) * 0.4], np.float32), 0.1 + 0.01 * k))
+        segs = [CurveSegment(np.array([k * 0.2, -2, 0], np.float32), np.array([k * 0.2 + 0.1, -1.5, 0.3], np.float32), 0.05, 0.02) for k in range(30)]
+        b.attach(Geometry.RoundCurves(segs))
+        cub = [CubicCurveSegment(np.array([[k, 3, 0], [k + 0.3, 3.5, 0.2], [k + 0.6, 3.2, -0.2], [k + 0.9, 3.6, 0]], np.float32), 0.04, 0.01) for k in range(12)]
+        b.attach(Geometry.CubicCurves(cub))
+        return b
+
+    def instanced(api):
+        inner = api.SceneBuilder()
+        v, i = workloads.uv_sphere((0, 0, 0), 1.0, 12, 6)
+        inner.attach(Geometry.TriangleMesh(v, i))
+        inner = inner.commit(flags=crt.COMMIT_KEEP_HOST_TREE | crt.COMMIT_HOST_ONLY) if api is crt else inner.commit()
+        b = api.SceneBuilder()
+        for k in range(300):
+            t = Affine3A.from_translation(np.array([k % 10, (k // 10) % 10, k // 100], np.float32) * np.float32(2.5))
+            end = Affine3A.from_translation(np.array([k % 10, (k // 10) % 10, k // 100], np.float32) * np.float32(2.5) + np.float32(0.3)) if k % 3 == 0 else None
+            g = Geometry.Instance(inner, t * Affine3A.from_rotation_y(0.1 * k), end)
+            if k % 7 == 0:
+                b.attach_masked(g, 0x5)
+            else:
+                b.attach(g)
+        fv = np.array([[-3, -2, -3], [30, -2, -3], [30, -2, 30], [-3, -2, 30]], np.float32)
+        b.attach(Geometry.TriangleMesh(fv, np.array([[0, 1, 2], [0, 2, 3]], np.uint32)))
+        return b
+
+    for make in (mixed, instanced, _mesh(*workloads.diagonal_shards(3000))):
+        seq, o = _commit_pair(crt, orc, make, threads=1)
+        monkeypatch.setenv("CRT_FLATTEN_PAR_MIN", "1")
+        monkeypatch.setenv("CRT_FLATTEN_TASK_DEPTH", str(depth))
+        par, _ = _commit_pair(crt, orc, make, threads=threads)
+        monkeypatch.delenv("CRT_FLATTEN_PAR_MIN")
+        monkeypatch.delenv("CRT_FLATTEN_TASK_DEPTH")
+        _assert_same_tree(seq, o)
+        _assert_same_tree(par, o)
+        a, b = seq.debug_host_arrays(), par.debug_host_arrays()
+        for k in a:
+            assert np.array_equal(a[k], b[k]), k
+        assert len(a["leafs"]) > 0
