@@ -168,7 +168,10 @@ int crt_build_info_of(const crt_scene* s, crt_build_info* out);
  * scene.rs:354 intersect / :370 occluded, batched. DEVICE pointers; work is
  * enqueued on `stream` (a cudaStream_t, NULL = default stream) and the call
  * returns without synchronising. `time`, `mask`, `front_face` may be NULL
- * (time 0, CRT_MASK_ALL, not written). */
+ * (time 0, CRT_MASK_ALL, not written).
+ * Occlusion answers do not depend on the order in which the tree is walked, but their cost does: a ray with a finite
+ * tmax (a segment towards a light) has the children of a node visited farthest first, an open-ended one nearest first
+ * (DESIGN.md §3.1). Give shadow rays their real far end rather than INFINITY. */
 int crt_intersect_n(const crt_scene* s, size_t n, const crt_ray* rays, const float* time, const uint32_t* mask,
                     crt_hit* hits, uint8_t* front_face, void* stream);
 int crt_occluded_n(const crt_scene* s, size_t n, const crt_ray* rays, const float* time, const uint32_t* mask,
