@@ -975,43 +975,44 @@ int device_build(std::vector<Geom>& geoms, ChildInfoFn child_info, crt_scene* s)
                 return e ? atoi(e) : 0;
             }();
             if (top_cluster >= 8 && n > 4 * top_cluster) {
+                struct DevBuf {  // freed on every way out of this block
+                    void* p = nullptr;
+                    ~DevBuf() {
+                        if (p) cudaFree(p);
+                    }
+                };
                 const size_t cap = (size_t)(8 * (size_t)n / (size_t)top_cluster) + 64;  // a balanced tree has about 2 n / cluster of them
-                int* d_top = nullptr;
-                TopCluster* d_cl = nullptr;
-                unsigned int* d_cnt = nullptr;
-                CKB(cudaMalloc(&d_top, cap * sizeof(int)));
-                CKB(cudaMalloc(&d_cl, (cap + 1) * sizeof(TopCluster)));
-                CKB(cudaMalloc(&d_cnt, 8));
+                DevBuf b_top, b_cl, b_cnt, b_tn;
+                CKB(cudaMalloc(&b_top.p, cap * sizeof(int)));
+                CKB(cudaMalloc(&b_cl.p, (cap + 1) * sizeof(TopCluster)));
+                CKB(cudaMalloc(&b_cnt.p, 8));
+                int* d_top = (int*)b_top.p;
+                TopCluster* d_cl = (TopCluster*)b_cl.p;
+                unsigned int* d_cnt = (unsigned int*)b_cnt.p;
                 CKB(cudaMemset(d_cnt, 0, 8));
                 top_select_kernel<<<grid_n, kB>>>(n, top_cluster, (unsigned int)cap, A, d_top, d_cl, d_cnt);
                 unsigned int cnt[2] = {0, 0};
                 CKB(cudaMemcpy(cnt, d_cnt, 8, cudaMemcpyDeviceToHost));
-                if (cnt[0] + 1 != cnt[1]) {
-                    cudaFree(d_top), cudaFree(d_cl), cudaFree(d_cnt);
-                    return set_error(CRT_ERR_INVALID_ARG, "device build: SAH top selection is inconsistent");
-                }
-                if (cnt[1] <= cap) {
-                std::vector<int> slots(cnt[0]);
-                std::vector<TopCluster> cl(cnt[1]);
-                CKB(cudaMemcpy(slots.data(), d_top, slots.size() * sizeof(int), cudaMemcpyDeviceToHost));
-                CKB(cudaMemcpy(cl.data(), d_cl, cl.size() * sizeof(TopCluster), cudaMemcpyDeviceToHost));
-                std::sort(slots.begin(), slots.end());
-                std::sort(cl.begin(), cl.end(), [](const TopCluster& a, const TopCluster& b) { return a.first < b.first; });
-                std::vector<int> idx(cl.size());
-                for (size_t k = 0; k < idx.size(); ++k) idx[k] = (int)k;
-                TopBuilder tb{cl, slots};
-                tb.out.reserve(slots.size());
-                tb.build(idx, 0, idx.size());
-                TopNode* d_tn = nullptr;
-                CKB(cudaMalloc(&d_tn, tb.out.size() * sizeof(TopNode)));
-                CKB(cudaMemcpy(d_tn, tb.out.data(), tb.out.size() * sizeof(TopNode), cudaMemcpyHostToDevice));
-                top_apply_kernel<<<(int)((tb.out.size() + kB - 1) / kB), kB>>>(n, (int)tb.out.size(), d_tn, A);
-                CKB(cudaDeviceSynchronize());
-                cudaFree(d_tn);
+                if (cnt[0] + 1 != cnt[1]) return set_error(CRT_ERR_INVALID_ARG, "device build: SAH top selection is inconsistent");
                 launches += 1;
+                if (cnt[1] <= cap) {  // else: a lopsided radix tree with far more large nodes than expected keeps its own top
+                    std::vector<int> slots(cnt[0]);
+                    std::vector<TopCluster> cl(cnt[1]);
+                    CKB(cudaMemcpy(slots.data(), d_top, slots.size() * sizeof(int), cudaMemcpyDeviceToHost));
+                    CKB(cudaMemcpy(cl.data(), d_cl, cl.size() * sizeof(TopCluster), cudaMemcpyDeviceToHost));
+                    std::sort(slots.begin(), slots.end());  // the kernel appended them in no particular order
+                    std::sort(cl.begin(), cl.end(), [](const TopCluster& a, const TopCluster& b) { return a.first < b.first; });
+                    std::vector<int> idx(cl.size());
+                    for (size_t k = 0; k < idx.size(); ++k) idx[k] = (int)k;
+                    TopBuilder tb{cl, slots};
+                    tb.out.reserve(slots.size());
+                    tb.build(idx, 0, idx.size());
+                    CKB(cudaMalloc(&b_tn.p, tb.out.size() * sizeof(TopNode)));
+                    CKB(cudaMemcpy(b_tn.p, tb.out.data(), tb.out.size() * sizeof(TopNode), cudaMemcpyHostToDevice));
+                    top_apply_kernel<<<(int)((tb.out.size() + kB - 1) / kB), kB>>>(n, (int)tb.out.size(), (const TopNode*)b_tn.p, A);
+                    CKB(cudaDeviceSynchronize());
+                    launches += 1;
                 }
-                cudaFree(d_top), cudaFree(d_cl), cudaFree(d_cnt);
-                launches += 1;
                 lap("SAH top");
             }
             // level-synchronous marking of the binary nodes that become BVH4 nodes
